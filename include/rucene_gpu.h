@@ -1,0 +1,183 @@
+/*
+ * rucene_gpu.h — C ABI of the B200 query-evaluation engine (librucene_gpu.so).
+ *
+ * The reference (zhihu/rucene) has no FFI for this path: the hot path sits behind Rust
+ * traits.  Each entry point below names the reference interface it replaces; paths are
+ * relative to /root/reference/src/core/.  A Rust shim implementing `IndexSearcher<C>` binds
+ * exactly these symbols.
+ *
+ * Conventions: plain pointers and sizes, no exceptions across the boundary; every function
+ * returns 0 on success or a negative RG_E* code, with a message in rg_last_error().
+ * Handles are engine-owned; output buffers are caller-owned.  There is NO CPU fallback:
+ * without a CUDA device every compute entry point fails with RG_ENODEVICE.
+ */
+#ifndef RUCENE_GPU_H
+#define RUCENE_GPU_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RG_OK 0
+#define RG_EINVAL (-1)      /* bad argument / corrupt index bytes */
+#define RG_ENODEVICE (-2)   /* no usable CUDA device */
+#define RG_ECUDA (-3)       /* CUDA runtime error */
+#define RG_EUNSUPPORTED (-4)/* plan shape outside the accelerated path: caller falls back to
+                               DefaultIndexSearcher (searcher.rs:487-525) */
+#define RG_ENOMEM (-5)      /* candidate arena exhausted: split the batch */
+
+#define RG_NO_MORE_DOCS 0x7fffffff /* search/mod.rs:59 */
+
+typedef struct rg_engine rg_engine;
+typedef struct rg_batch rg_batch;
+typedef struct rg_blockset rg_blockset;
+
+typedef struct {
+    int32_t device;            /* CUDA ordinal; -1 = current device */
+    uint64_t cand_arena_bytes; /* candidate arena for exact top-k replay; 0 = default */
+    uint32_t range_postings;   /* target postings per (query, docid-range) work item; 0 = default */
+    uint32_t flags;            /* reserved */
+} rg_config;
+
+/* Per-term, per-segment handle == BlockTermState
+ * (codec/postings/blocktree/mod.rs:33-59; filled by lucene50_decode_term,
+ * codec/postings/posting_reader.rs:264-306).  doc_freq==0: term absent in the segment
+ * (Weight::create_scorer returns None, search/query/mod.rs:139). */
+typedef struct {
+    int32_t doc_freq;
+    int32_t singleton_doc_id; /* docid when doc_freq==1, else -1 */
+    int64_t total_term_freq;
+    int64_t doc_start_fp;     /* into the .doc file */
+    int64_t skip_offset;      /* relative to doc_start_fp; -1 when doc_freq<=128 */
+} rg_term_state;
+
+/* BooleanClause occur (search/query/boolean_query.rs:30-36: must/should/must_not lists). */
+enum { RG_MUST = 0, RG_SHOULD = 1, RG_MUST_NOT = 2 };
+
+/* One TermQuery leaf of the plan, with what TermWeight carries after
+ * BM25Similarity::compute_weight (search/similarity/bm25_similarity.rs:151-177):
+ *   weight   = idf * boost                       (:363-366)
+ *   cache_id = which 256-entry norm cache (:161-165) registered by rg_norm_cache_set. */
+typedef struct {
+    int32_t occur;
+    uint32_t term_id;
+    float weight;
+    uint32_t cache_id;
+} rg_clause;
+
+/* flags */
+#define RG_Q_BOOLEAN 1u /* built by BooleanQuery::build (boolean_query.rs:40-87); without it
+                           the query is a bare TermQuery and n_clauses must be 1 */
+typedef struct {
+    uint32_t clause_begin; /* index into the clause array */
+    uint32_t n_clauses;
+    int32_t min_should_match; /* as passed to BooleanQuery::build */
+    uint32_t flags;
+} rg_query;
+
+/* ScoreDoc (search/sort_field/collapse_top_docs.rs:22-27), global docid = doc + doc_base
+ * (search/collector/top_docs.rs:89). */
+typedef struct {
+    int32_t doc;
+    float score;
+} rg_hit;
+
+#define RG_MODE_SEARCH 0          /* IndexSearcher::search, searcher.rs:487-525 */
+#define RG_MODE_SEARCH_PARALLEL 1 /* search_parallel, searcher.rs:527-630: one TopDocs heap per
+                                     leaf, merged in leaf order (top_docs.rs:157-172) */
+typedef struct {
+    uint32_t k;    /* TopDocsCollector::new(k), search/collector/top_docs.rs:107-113 */
+    float k1;      /* BM25Similarity k1, bm25_similarity.rs:45 */
+    uint32_t mode; /* RG_MODE_* */
+    uint32_t reserved;
+} rg_search_params;
+
+/* ---------------------------------------------------------------- engine ---------- */
+int rg_engine_create(const rg_config* cfg, rg_engine** out);
+void rg_engine_destroy(rg_engine* e);
+/* Message for the last failure on this thread (engine may be NULL). */
+const char* rg_last_error(rg_engine* e);
+/* Launch on this cudaStream_t (e.g. torch's current stream); NULL = the engine's own stream. */
+int rg_engine_set_stream(rg_engine* e, void* cuda_stream);
+/* Number of this library's kernels launched so far (bench.py's gpu_launches). */
+uint64_t rg_engine_launch_count(rg_engine* e);
+/* Device-side timing of the last rg_batch_run / rg_blockset_decode, CUDA events on the launch
+ * stream.  Returns milliseconds, <0 if nothing was timed. */
+float rg_engine_last_kernel_ms(rg_engine* e, const char* which);
+
+/* ---------------------------------------------------------------- index ---------- */
+/* Replaces Lucene50PostingsReader::open + LeafReader::{postings,norm_values,live_docs}
+ * (codec/postings/posting_reader.rs:85-158, index/reader/leaf_reader.rs:92-104).
+ * doc_file: the whole `.doc` file (IndexHeader, ForUtil table, term regions, footer) of a
+ * DocsAndFreqs field.  norms: max_doc bytes (Lucene53 norms, bytes_per_value==1) or NULL.
+ * live_docs: FixedBitSet words (bit doc&63 of word doc>>6) or NULL for "all live".
+ * terms[term_id]: the segment's BlockTermState per engine-wide term id (doc_freq 0 = absent).
+ * Segments must be uploaded in leaf order with seg_ord 0,1,2...; doc_base as in
+ * LeafReaderContext (leaf_reader.rs:195-202). Host buffers may be freed on return. */
+int rg_segment_upload(rg_engine* e, uint32_t seg_ord, int32_t doc_base, int32_t max_doc,
+                      const uint8_t* doc_file, size_t doc_len, const uint8_t* norms,
+                      const uint64_t* live_docs, const rg_term_state* terms, uint32_t n_terms);
+/* BM25SimWeight.cache (bm25_similarity.rs:161-165), one per (field, k1, b, avgdl). */
+int rg_norm_cache_set(rg_engine* e, uint32_t cache_id, const float cache[256]);
+/* Bytes of device memory held by segment images. */
+uint64_t rg_engine_index_bytes(rg_engine* e);
+
+/* ---------------------------------------------------------------- search ---------- */
+/* IndexSearcher::search for a batch of queries against all uploaded segments with a
+ * TopDocsCollector::new(k) each (searcher.rs:487-525, collector/top_docs.rs).
+ * out_hits[n_queries*k] (row i = TopDocs::score_docs() of query i, descending score, exactly
+ * the reference's order incl. ties), out_counts[i] = hits in row i, out_total_hits[i] =
+ * TopDocs::total_hits().  Host buffers; H2D/D2H happen inside. */
+int rg_search_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries,
+                    const rg_clause* clauses, uint32_t n_clauses, const rg_search_params* p,
+                    rg_hit* out_hits, uint32_t* out_counts, uint64_t* out_total_hits);
+
+/* The same in three steps, so the evaluation can be timed with inputs resident in HBM. */
+int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
+                     const rg_clause* clauses, uint32_t n_clauses, const rg_search_params* p,
+                     rg_batch** out);
+int rg_batch_run(rg_engine* e, rg_batch* b);   /* kernels only, asynchronous on the stream */
+int rg_batch_fetch(rg_engine* e, rg_batch* b, rg_hit* out_hits, uint32_t* out_counts,
+                   uint64_t* out_total_hits); /* synchronises */
+void rg_batch_destroy(rg_engine* e, rg_batch* b);
+/* Statistics of a prepared batch: [0]=work items, [1]=postings in scope (sum of df over scored
+ * clauses), [2]=algorithmic bytes the evaluation must read (encoded blocks + tails + tables
+ * touched + norms), [3]=candidates emitted by the last run, [4]=kernels per run. */
+int rg_batch_stats(rg_engine* e, rg_batch* b, uint64_t out[8]);
+
+/* Sharded mode (one segment per GPU).  After rg_batch_run with RG_MODE_SEARCH_PARALLEL the
+ * per-query leaf record {uint32 n; uint32 pad; uint64 total_hits; rg_hit heap[k]} (heap-array
+ * order == BinaryHeap::into_vec, top_docs.rs:203-213) lives on the device: */
+int rg_batch_leaf_records(rg_engine* e, rg_batch* b, void** dev_ptr, size_t* record_bytes);
+/* finish_parallel (top_docs.rs:157-172) on the device: records_all holds n_leaves consecutive
+ * arrays of n_queries records (leaf order), e.g. the output of one all-gather. Host outputs. */
+int rg_merge_leaf_records(rg_engine* e, const void* dev_records_all, uint32_t n_leaves,
+                          uint32_t n_queries, uint32_t k, rg_hit* out_hits, uint32_t* out_counts,
+                          uint64_t* out_total_hits);
+
+/* ---------------------------------------------------------------- block codec ----- */
+/* ForUtil::read_block over a raw block stream (codec/postings/for_util.rs:187-243;
+ * SIMD128Packer::unpack util/packed/packed_simd.rs:126-252 when doc_version>0, else
+ * BulkOperationPacked / BulkOperationPackedSingleBlock::decode_byte_to_int,
+ * util/packed/packed_misc.rs:2655-2680, 2829-2841).  forutil_table: the 32 vints of the .doc
+ * header ((format_id<<5)|(bpv-1), for_util.rs:128-139).  offsets[i]: byte offset of block i's
+ * header byte.  out: n_blocks*128 int32.  Host buffers; copies happen inside. */
+int rg_forutil_decode(rg_engine* e, const uint8_t* stream, size_t len, const uint64_t* offsets,
+                      uint32_t n_blocks, int doc_version, const int32_t forutil_table[32],
+                      int32_t* out);
+/* Staged variant: blocks are parsed once, their payload bytes copied unchanged into 16-byte
+ * aligned slots in HBM; decode then runs with everything resident. */
+int rg_blockset_stage(rg_engine* e, const uint8_t* stream, size_t len, const uint64_t* offsets,
+                      uint32_t n_blocks, int doc_version, const int32_t forutil_table[32],
+                      rg_blockset** out);
+int rg_blockset_decode(rg_engine* e, rg_blockset* bs); /* async; output stays on the device */
+int rg_blockset_fetch(rg_engine* e, rg_blockset* bs, int32_t* out); /* synchronises */
+/* [0]=encoded bytes read per decode (sum of 1+16*b or 1+vint), [1]=bytes written (512/block) */
+int rg_blockset_stats(rg_engine* e, rg_blockset* bs, uint64_t out[4]);
+void rg_blockset_destroy(rg_engine* e, rg_blockset* bs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
