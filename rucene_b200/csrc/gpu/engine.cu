@@ -1,0 +1,733 @@
+// engine.cu — engine lifecycle, segment upload (parse `.doc`, build the HBM index image) and the
+// ForUtil block-decode entry points of include/rucene_gpu.h.
+//
+// Upload replaces what Lucene50PostingsReader::open + BlockDocIterator::reset/refill_docs +
+// Lucene50SkipReader do lazily per query (codec/postings/posting_reader.rs:85-158,460-561;
+// codec/postings/skip_reader.rs:460-511): headers are parsed once, every block's payload bytes
+// are copied UNCHANGED into a 16-byte aligned slot, and level 0 of the skip list becomes the
+// flat `blk_last` table (last docid per block).
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <memory>
+#include <thread>
+
+#include "engine.hpp"
+
+namespace rg {
+
+thread_local std::string g_last_error;
+
+int translate_exception() {
+    try {
+        throw;
+    } catch (const CudaError& e) {
+        g_last_error = e.what();
+        return (e.code == cudaErrorNoDevice || e.code == cudaErrorInsufficientDriver) ? RG_ENODEVICE
+                                                                                       : RG_ECUDA;
+    } catch (const ArgError& e) {
+        g_last_error = e.what();
+        return RG_EINVAL;
+    } catch (const Unsupported& e) {
+        g_last_error = e.what();
+        return RG_EUNSUPPORTED;
+    } catch (const OutOfArena& e) {
+        g_last_error = e.what();
+        return RG_ENOMEM;
+    } catch (const std::bad_alloc&) {
+        g_last_error = "host allocation failed";
+        return RG_ENOMEM;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return RG_EINVAL;
+    }
+}
+
+namespace {
+
+// ---------------------------------------------------------------- host byte reader
+struct In {
+    const uint8_t* p;
+    size_t len, pos;
+    In(const uint8_t* b, size_t l, size_t at = 0) : p(b), len(l), pos(at) {}
+    uint8_t u8() {
+        if (pos >= len) throw ArgError("`.doc` truncated");
+        return p[pos++];
+    }
+    int32_t vint() {
+        uint32_t v = 0;
+        for (int shift = 0; shift < 35; shift += 7) {
+            uint8_t b = u8();
+            v |= (uint32_t)(b & 0x7f) << shift;
+            if (!(b & 0x80)) return (int32_t)v;
+        }
+        throw ArgError("invalid vint");
+    }
+    int64_t vlong() {
+        uint64_t v = 0;
+        for (int shift = 0; shift < 63; shift += 7) {
+            uint8_t b = u8();
+            v |= (uint64_t)(b & 0x7f) << shift;
+            if (!(b & 0x80)) return (int64_t)v;
+        }
+        throw ArgError("invalid vlong");
+    }
+    uint32_t be32() {
+        uint32_t v = 0;
+        for (int i = 0; i < 4; i++) v = (v << 8) | u8();
+        return v;
+    }
+    const uint8_t* take(size_t n) {
+        if (pos + n > len) throw ArgError("`.doc` truncated");
+        const uint8_t* r = p + pos;
+        pos += n;
+        return r;
+    }
+};
+
+struct DocHeader {
+    int version = 0;
+    uint32_t sb_mask = 0;
+    int enc_size[33];  // payload bytes for num_bits b (index b)
+    size_t body_start = 0;
+};
+
+void format_sizes(int version, const int32_t table[32], DocHeader& h) {
+    h.version = version;
+    h.sb_mask = 0;
+    h.enc_size[0] = 0;
+    for (int i = 0; i < 32; i++) {
+        int code = table[i];
+        int fmt = code >> 5, bpv = (code & 31) + 1;
+        if (fmt != 0 && fmt != 1) throw ArgError("ForUtil table: invalid format id");
+        if (version > 0) {
+            h.enc_size[i + 1] = 16 * (i + 1);  // SIMD_ENCODE_SIZE, for_util.rs:44-52
+        } else {
+            if (bpv != i + 1)
+                throw Unsupported("ForUtil table widens bits_per_value (non-COMPACT writer)");
+            if (fmt == 1) {
+                h.sb_mask |= 1u << i;
+                int per = 64 / bpv;
+                h.enc_size[i + 1] = ((kBlock + per - 1) / per) * 8;
+            } else {
+                h.enc_size[i + 1] = (kBlock * bpv + 7) / 8;
+            }
+        }
+    }
+}
+
+// codec/codec_util.rs:46-57,75-124 + for_util.rs:120-148
+DocHeader parse_doc_header(const uint8_t* file, size_t len) {
+    In in(file, len);
+    if (in.be32() != 0x3FD76C17u) throw ArgError("`.doc`: bad codec magic");
+    int n = in.vint();
+    static const char* codec = "Lucene50PostingsWriterDoc";
+    if (n != (int)strlen(codec) || memcmp(in.take((size_t)n), codec, (size_t)n) != 0)
+        throw ArgError("`.doc`: codec name mismatch");
+    int version = (int)in.be32();
+    if (version < 0 || version > 1) throw ArgError("`.doc`: unsupported version");
+    in.take(16);
+    int sl = in.u8();
+    in.take((size_t)sl);
+    if (in.vint() != 2) throw ArgError("`.doc`: PackedInts version must be 2");
+    int32_t table[32];
+    for (int i = 0; i < 32; i++) table[i] = in.vint();
+    DocHeader h;
+    format_sizes(version, table, h);
+    h.body_start = in.pos;
+    return h;
+}
+
+// scalar host decode of one block part (only for the last block of a term, whose last docid is
+// not in the skip list)
+void host_unpack(const uint8_t* part, int b, int version, uint32_t sb_mask, int32_t* out) {
+    if (version > 0) {
+        const uint32_t mask = b == 32 ? 0xffffffffu : ((1u << b) - 1u);
+        for (int n = 0; n < kBlock; n++) {
+            int lane = n & 3, q = n >> 2;
+            int bit = q * b, j = bit >> 5, s = bit & 31;
+            uint32_t lo, hi = 0;
+            memcpy(&lo, part + 16 * j + 4 * lane, 4);
+            if (s + b > 32) memcpy(&hi, part + 16 * (j + 1) + 4 * lane, 4);
+            uint64_t x = ((uint64_t)hi << 32) | lo;
+            out[n] = (int32_t)((uint32_t)(x >> s) & mask);
+        }
+    } else if ((sb_mask >> (b - 1)) & 1u) {
+        int per = 64 / b;
+        const uint64_t mask = b == 64 ? ~0ull : ((1ull << b) - 1);
+        for (int n = 0; n < kBlock; n++) {
+            int L = n / per, i = n % per;
+            uint64_t x = 0;
+            for (int k = 0; k < 8; k++) x = (x << 8) | part[8 * L + k];
+            out[n] = (int32_t)((x >> (i * b)) & mask);
+        }
+    } else {
+        for (int n = 0; n < kBlock; n++) {
+            uint64_t bit = (uint64_t)n * b;
+            uint32_t v = 0;
+            for (int k = 0; k < b; k++, bit++) v = (v << 1) | ((part[bit >> 3] >> (7 - (bit & 7))) & 1u);
+            out[n] = (int32_t)v;
+        }
+    }
+}
+
+struct BlockSrc {
+    const uint8_t* doc_src;
+    const uint8_t* freq_src;
+    uint16_t doc_sz, freq_sz;  // payload bytes (0 when constant)
+    uint8_t bd, bf;
+    int32_t doc_const, freq_const;
+    int32_t last_doc;
+};
+
+struct TermParse {
+    uint32_t n_blocks = 0;
+    const uint8_t* tail_src = nullptr;
+    uint32_t tail_bytes = 0, tail_n = 0;
+    int32_t tail_base = 0;
+    uint64_t enc_bytes = 0;
+};
+
+inline uint32_t part_units(int sz) { return sz == 0 ? 1u : (uint32_t)((sz + 15) / 16); }
+
+// Walk one term's region (posting_writer.rs:334-351,491-502 layout; skip level 0 per
+// skip_writer.rs:209-226,241-259).
+void parse_term(const uint8_t* file, size_t len, const DocHeader& h, const rg_term_state& ts,
+                std::vector<BlockSrc>& blocks, TermParse& tp) {
+    const int df = ts.doc_freq;
+    tp = TermParse();
+    if (df <= 0) return;
+    if (df == 1) {
+        tp.tail_n = 1;
+        return;
+    }
+    if (ts.doc_start_fp < 0 || (size_t)ts.doc_start_fp > len) throw ArgError("doc_start_fp out of range");
+    In in(file, len, (size_t)ts.doc_start_fp);
+    const uint32_t nb = (uint32_t)(df / kBlock);
+    tp.n_blocks = nb;
+    const size_t first = blocks.size();
+    std::vector<size_t> block_fp(nb + 1);
+    for (uint32_t i = 0; i < nb; i++) {
+        block_fp[i] = in.pos;
+        BlockSrc b{};
+        uint8_t code = in.u8();
+        if (code >> 6) throw Unsupported("EF/BITSET/FULL doc blocks (for_util.rs:337-372) are not accelerated");
+        b.bd = code & 0x3f;
+        if (b.bd > 32) throw ArgError("corrupt doc block header");
+        if (b.bd == 0) {
+            b.doc_const = in.vint();
+        } else {
+            b.doc_sz = (uint16_t)h.enc_size[b.bd];
+            b.doc_src = in.take(b.doc_sz);
+        }
+        code = in.u8();
+        b.bf = code & 0x3f;  // ForUtil::read_block: num_bits = code & 0x3F
+        if (b.bf > 32) throw ArgError("corrupt freq block header");
+        if (b.bf == 0) {
+            b.freq_const = in.vint();
+        } else {
+            b.freq_sz = (uint16_t)h.enc_size[b.bf];
+            b.freq_src = in.take(b.freq_sz);
+        }
+        blocks.push_back(b);
+    }
+    block_fp[nb] = in.pos;
+    // vint tail
+    tp.tail_n = (uint32_t)(df % kBlock);
+    tp.tail_src = file + in.pos;
+    size_t tail_start = in.pos;
+    for (uint32_t i = 0; i < tp.tail_n; i++) {
+        uint32_t code = (uint32_t)in.vint();
+        if (!(code & 1)) in.vint();
+    }
+    tp.tail_bytes = (uint32_t)(in.pos - tail_start);
+    tp.enc_bytes = in.pos - (size_t)ts.doc_start_fp;
+    // last docid of each full block: skip level 0, then a host decode for the uncovered block
+    uint32_t n0 = df > kBlock ? (uint32_t)((df - 1) / kBlock) : 0;
+    int32_t last = 0;
+    if (n0 > 0) {
+        if (ts.skip_offset < 0) throw ArgError("doc_freq > 128 but no skip_offset");
+        In sk(file, len, (size_t)(ts.doc_start_fp + ts.skip_offset));
+        int trimmed = df % kBlock == 0 ? df - 1 : df;  // skip_reader.rs:307-313
+        int levels = 1;
+        for (int64_t x = trimmed / kBlock; x >= 8; x /= 8) levels++;
+        levels = std::min(levels, 10);
+        for (int lv = levels - 1; lv >= 1; lv--) {
+            int64_t length = sk.vlong();
+            sk.take((size_t)length);
+        }
+        int64_t fp = ts.doc_start_fp;
+        for (uint32_t i = 0; i < n0; i++) {
+            last += sk.vint();
+            fp += sk.vlong();
+            if ((size_t)fp != block_fp[i + 1]) throw ArgError("skip data disagrees with block layout");
+            blocks[first + i].last_doc = last;
+        }
+    }
+    for (uint32_t i = n0; i < nb; i++) {  // at most one block
+        const BlockSrc& b = blocks[first + i];
+        int64_t sum = 0;
+        if (b.bd == 0) {
+            sum = (int64_t)b.doc_const * kBlock;
+        } else {
+            int32_t vals[kBlock];
+            host_unpack(b.doc_src, b.bd, h.version, h.sb_mask, vals);
+            for (int k = 0; k < kBlock; k++) sum += vals[k];
+        }
+        last = (int32_t)(last + sum);
+        blocks[first + i].last_doc = last;
+    }
+    tp.tail_base = nb ? last : 0;
+}
+
+int hw_threads() {
+    unsigned n = std::thread::hardware_concurrency();
+    return n ? (int)std::min(n, 64u) : 1;
+}
+
+template <class F>
+void parallel_chunks(size_t n, F&& f) {
+    int nt = (int)std::min<size_t>((size_t)hw_threads(), n);
+    if (nt <= 1) {
+        for (size_t i = 0; i < n; i++) f(i);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    std::atomic<int> code{0};
+    std::string msg;
+    std::vector<std::thread> ts;
+    for (int t = 0; t < nt; t++)
+        ts.emplace_back([&] {
+            for (;;) {
+                size_t i = next.fetch_add(1);
+                if (i >= n || code.load()) break;
+                try {
+                    f(i);
+                } catch (...) {
+                    int c = translate_exception();
+                    int expected = 0;
+                    if (code.compare_exchange_strong(expected, c)) msg = g_last_error;
+                }
+            }
+        });
+    for (auto& t : ts) t.join();
+    if (int c = code.load()) {
+        if (c == RG_EUNSUPPORTED) throw Unsupported(msg);
+        throw ArgError(msg);
+    }
+}
+
+template <class T>
+void upload(DevBuf<T>& dst, const T* src, size_t n, cudaStream_t st) {
+    dst.alloc(n);
+    if (n) RG_CUDA_CHECK(cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
+}
+
+}  // namespace
+
+void build_segment(rg_engine* e, Segment& seg, int32_t doc_base, int32_t max_doc,
+                   const uint8_t* file, size_t len, const uint8_t* norms, const uint64_t* live,
+                   const rg_term_state* terms, uint32_t n_terms) {
+    const DocHeader h = parse_doc_header(file, len);
+    // pass 1: parse term regions in parallel chunks
+    const size_t n_chunks = std::max<size_t>(1, std::min<size_t>(256, (n_terms + 63) / 64));
+    struct Chunk {
+        uint32_t t0, t1;
+        std::vector<BlockSrc> blocks;
+        std::vector<TermParse> tp;
+        uint64_t blk_base = 0, unit_base = 0, tail_base = 0, units = 0, tail_bytes = 0;
+    };
+    std::vector<Chunk> chunks(n_chunks);
+    {
+        // balance by doc_freq
+        uint64_t total = 0;
+        for (uint32_t t = 0; t < n_terms; t++) total += (uint64_t)std::max(terms[t].doc_freq, 0) + 16;
+        uint64_t per = total / n_chunks + 1, acc = 0;
+        size_t c = 0;
+        chunks[0].t0 = 0;
+        for (uint32_t t = 0; t < n_terms; t++) {
+            acc += (uint64_t)std::max(terms[t].doc_freq, 0) + 16;
+            if (acc >= per && c + 1 < n_chunks) {
+                chunks[c].t1 = t + 1;
+                c++;
+                chunks[c].t0 = t + 1;
+                acc = 0;
+            }
+        }
+        chunks[c].t1 = n_terms;
+        for (size_t i = c + 1; i < n_chunks; i++) chunks[i].t0 = chunks[i].t1 = n_terms;
+    }
+    parallel_chunks(n_chunks, [&](size_t ci) {
+        Chunk& ch = chunks[ci];
+        ch.tp.resize(ch.t1 - ch.t0);
+        for (uint32_t t = ch.t0; t < ch.t1; t++) {
+            parse_term(file, len, h, terms[t], ch.blocks, ch.tp[t - ch.t0]);
+        }
+        for (const BlockSrc& b : ch.blocks) ch.units += part_units(b.doc_sz) + part_units(b.freq_sz);
+        for (const TermParse& tp : ch.tp) ch.tail_bytes += tp.tail_bytes;
+    });
+    uint64_t n_blocks = 0, units = 0, tail_bytes = 0;
+    for (Chunk& ch : chunks) {
+        ch.blk_base = n_blocks;
+        ch.unit_base = units;
+        ch.tail_base = tail_bytes;
+        n_blocks += ch.blocks.size();
+        units += ch.units;
+        tail_bytes += ch.tail_bytes;
+    }
+    if (units + 8 >= (1ull << 32)) throw Unsupported("segment image exceeds 64 GiB of block payload");
+    if (n_blocks >= (1ull << 32) || tail_bytes >= (1ull << 32)) throw Unsupported("segment too large");
+    // pass 2: fill the host staging image
+    std::vector<uint4> h_arena(units + 8);
+    std::vector<int32_t> h_last(n_blocks + 1);
+    std::vector<BlockDesc> h_desc(n_blocks + 1);
+    std::vector<uint8_t> h_tails(tail_bytes + 16);
+    std::vector<TermDev> h_terms(n_terms);
+    seg.host_terms.assign(n_terms, TermHost());
+    parallel_chunks(n_chunks, [&](size_t ci) {
+        Chunk& ch = chunks[ci];
+        uint64_t blk = ch.blk_base, unit = ch.unit_base, tail = ch.tail_base;
+        size_t bi = 0;
+        for (uint32_t t = ch.t0; t < ch.t1; t++) {
+            const TermParse& tp = ch.tp[t - ch.t0];
+            const rg_term_state& ts = terms[t];
+            TermDev td{};
+            td.blk_begin = (uint32_t)blk;
+            td.n_blocks = tp.n_blocks;
+            td.tail_off = (uint32_t)tail;
+            td.tail_n = tp.tail_n;
+            td.doc_freq = std::max(ts.doc_freq, 0);
+            td.tail_base = tp.tail_base;
+            td.singleton_doc = ts.doc_freq == 1 ? ts.singleton_doc_id : -1;
+            td.singleton_freq = ts.doc_freq == 1 ? (int32_t)ts.total_term_freq : 0;
+            h_terms[t] = td;
+            seg.host_terms[t].doc_freq = td.doc_freq;
+            seg.host_terms[t].n_blocks = tp.n_blocks;
+            seg.host_terms[t].enc_bytes = tp.enc_bytes;
+            for (uint32_t i = 0; i < tp.n_blocks; i++, bi++, blk++) {
+                const BlockSrc& b = ch.blocks[bi];
+                const uint32_t du = part_units(b.doc_sz), fu = part_units(b.freq_sz);
+                uint8_t* dst = reinterpret_cast<uint8_t*>(&h_arena[unit]);
+                if (b.bd) memcpy(dst, b.doc_src, b.doc_sz);
+                else memcpy(dst, &b.doc_const, 4);
+                uint8_t* fdst = dst + 16 * (size_t)du;
+                if (b.bf) memcpy(fdst, b.freq_src, b.freq_sz);
+                else memcpy(fdst, &b.freq_const, 4);
+                h_last[blk] = b.last_doc;
+                h_desc[blk].off16 = (uint32_t)unit;
+                h_desc[blk].bits = (uint32_t)b.bd | ((uint32_t)b.bf << 8) | (du << 16);
+                unit += du + fu;
+            }
+            if (tp.tail_bytes) {
+                memcpy(&h_tails[tail], tp.tail_src, tp.tail_bytes);
+                tail += tp.tail_bytes;
+            }
+        }
+    });
+    cudaStream_t st = e->stream;
+    upload(seg.arena, h_arena.data(), h_arena.size(), st);
+    upload(seg.blk_last, h_last.data(), h_last.size(), st);
+    upload(seg.blk_desc, h_desc.data(), h_desc.size(), st);
+    upload(seg.tails, h_tails.data(), h_tails.size(), st);
+    upload(seg.terms, h_terms.data(), h_terms.size(), st);
+    if (norms) upload(seg.norms, norms, (size_t)max_doc, st);
+    if (live) upload(seg.live, live, ((size_t)max_doc + 63) / 64, st);
+    RG_CUDA_CHECK(cudaStreamSynchronize(st));
+    seg.doc_base = doc_base;
+    seg.max_doc = max_doc;
+    seg.dev.arena = seg.arena.p;
+    seg.dev.blk_last = seg.blk_last.p;
+    seg.dev.blk_desc = seg.blk_desc.p;
+    seg.dev.tails = seg.tails.p;
+    seg.dev.terms = seg.terms.p;
+    seg.dev.norms = seg.norms.p;
+    seg.dev.live = seg.live.p;
+    seg.dev.doc_base = doc_base;
+    seg.dev.max_doc = max_doc;
+    seg.dev.n_terms = n_terms;
+    seg.dev.version = h.version;
+    seg.dev.sb_mask = h.sb_mask;
+    seg.device_bytes = seg.arena.bytes() + seg.blk_last.bytes() + seg.blk_desc.bytes() +
+                       seg.tails.bytes() + seg.terms.bytes() + seg.norms.bytes() + seg.live.bytes();
+}
+
+}  // namespace rg
+
+using namespace rg;
+
+void rg_engine::sync_tables() {
+    if (segs_dirty) {
+        std::vector<SegDev> h(segs.size());
+        for (size_t i = 0; i < segs.size(); i++) h[i] = segs[i].dev;
+        d_segs.alloc(std::max<size_t>(1, h.size()));
+        if (!h.empty())
+            RG_CUDA_CHECK(cudaMemcpyAsync(d_segs.p, h.data(), h.size() * sizeof(SegDev),
+                                          cudaMemcpyHostToDevice, stream));
+        RG_CUDA_CHECK(cudaStreamSynchronize(stream));
+        segs_dirty = false;
+    }
+    if (caches_dirty) {
+        d_caches.alloc(std::max<size_t>(256, h_caches.size()));
+        if (!h_caches.empty())
+            RG_CUDA_CHECK(cudaMemcpyAsync(d_caches.p, h_caches.data(), h_caches.size() * sizeof(float),
+                                          cudaMemcpyHostToDevice, stream));
+        RG_CUDA_CHECK(cudaStreamSynchronize(stream));
+        caches_dirty = false;
+    }
+}
+
+struct rg_blockset {
+    DevBuf<uint4> arena;
+    DevBuf<BlockDesc> desc;
+    DevBuf<int32_t> out;
+    uint32_t n_blocks = 0;
+    int version = 0;
+    uint32_t sb_mask = 0;
+    uint64_t enc_bytes = 0;
+};
+
+#define RG_TRY try {
+#define RG_CATCH \
+    }            \
+    catch (...) { return translate_exception(); }
+
+extern "C" {
+
+const char* rg_last_error(rg_engine*) { return g_last_error.c_str(); }
+
+int rg_engine_create(const rg_config* cfg, rg_engine** out) {
+    RG_TRY
+    if (!out) throw ArgError("out is null");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0) {
+        g_last_error = std::string("no CUDA device: ") + cudaGetErrorString(ce) +
+                       " (librucene_gpu has no CPU fallback)";
+        cudaGetLastError();
+        return RG_ENODEVICE;
+    }
+    std::unique_ptr<rg_engine> e(new rg_engine());
+    if (cfg) e->cfg = *cfg;
+    int dev = e->cfg.device;
+    if (dev < 0) RG_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev >= count) throw ArgError("device ordinal out of range");
+    RG_CUDA_CHECK(cudaSetDevice(dev));
+    e->device = dev;
+    RG_CUDA_CHECK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    e->stream = e->own_stream;
+    RG_CUDA_CHECK(cudaEventCreate(&e->ev0));
+    RG_CUDA_CHECK(cudaEventCreate(&e->ev1));
+    if (e->cfg.range_postings == 0) e->cfg.range_postings = 1u << 18;
+    *out = e.release();
+    return RG_OK;
+    RG_CATCH
+}
+
+void rg_engine_destroy(rg_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+int rg_engine_set_stream(rg_engine* e, void* s) {
+    RG_TRY
+    if (!e) throw ArgError("engine is null");
+    e->stream = s ? reinterpret_cast<cudaStream_t>(s) : e->own_stream;
+    return RG_OK;
+    RG_CATCH
+}
+
+uint64_t rg_engine_launch_count(rg_engine* e) { return e ? e->launches : 0; }
+
+float rg_engine_last_kernel_ms(rg_engine* e, const char* which) {
+    if (!e || !which) return -1.f;
+    std::string w(which);
+    if (w == "decode") return e->last_decode_ms;
+    if (w == "eval") return e->last_eval_ms;
+    if (w == "replay") return e->last_replay_ms;
+    if (w == "run") return e->last_run_ms;
+    return -1.f;
+}
+
+uint64_t rg_engine_index_bytes(rg_engine* e) {
+    uint64_t b = 0;
+    if (e)
+        for (auto& s : e->segs) b += s.device_bytes;
+    return b;
+}
+
+int rg_segment_upload(rg_engine* e, uint32_t seg_ord, int32_t doc_base, int32_t max_doc,
+                      const uint8_t* doc_file, size_t doc_len, const uint8_t* norms,
+                      const uint64_t* live_docs, const rg_term_state* terms, uint32_t n_terms) {
+    RG_TRY
+    if (!e || !doc_file || (!terms && n_terms)) throw ArgError("null argument");
+    if (seg_ord != e->segs.size()) throw ArgError("segments must be uploaded in leaf order (seg_ord == #uploaded)");
+    if (seg_ord >= 65535) throw ArgError("too many segments");
+    if (max_doc <= 0 || doc_base < 0) throw ArgError("bad max_doc/doc_base");
+    RG_CUDA_CHECK(cudaSetDevice(e->device));
+    Segment seg;
+    build_segment(e, seg, doc_base, max_doc, doc_file, doc_len, norms, live_docs, terms, n_terms);
+    e->segs.push_back(std::move(seg));
+    e->segs_dirty = true;
+    return RG_OK;
+    RG_CATCH
+}
+
+int rg_norm_cache_set(rg_engine* e, uint32_t cache_id, const float cache[256]) {
+    RG_TRY
+    if (!e || !cache) throw ArgError("null argument");
+    if (cache_id >= 4096) throw ArgError("cache_id out of range");
+    if (e->h_caches.size() < (size_t)(cache_id + 1) * 256) e->h_caches.resize((size_t)(cache_id + 1) * 256, 0.f);
+    memcpy(&e->h_caches[(size_t)cache_id * 256], cache, 256 * sizeof(float));
+    e->caches_dirty = true;
+    return RG_OK;
+    RG_CATCH
+}
+
+// ---------------------------------------------------------------- block codec entry points
+static void table_to_header(int doc_version, const int32_t forutil_table[32], DocHeader& h) {
+    if (!forutil_table) throw ArgError("forutil_table is null");
+    if (doc_version < 0 || doc_version > 1) throw ArgError("doc_version must be 0 or 1");
+    format_sizes(doc_version, forutil_table, h);
+}
+
+int rg_forutil_decode(rg_engine* e, const uint8_t* stream, size_t len, const uint64_t* offsets,
+                      uint32_t n_blocks, int doc_version, const int32_t forutil_table[32],
+                      int32_t* out) {
+    RG_TRY
+    if (!e || !stream || !offsets || !out) throw ArgError("null argument");
+    RG_CUDA_CHECK(cudaSetDevice(e->device));
+    DocHeader h;
+    table_to_header(doc_version, forutil_table, h);
+    for (uint32_t i = 0; i < n_blocks; i++) {  // bounds + header validation on the host
+        if (offsets[i] >= len) throw ArgError("block offset out of range");
+        int b = stream[offsets[i]] & 0x3f;
+        if (b > 32) throw ArgError("corrupt block header");
+        size_t need = b ? (size_t)1 + (size_t)h.enc_size[b] : 2;
+        if (offsets[i] + need > len) throw ArgError("block runs past the end of the stream");
+    }
+    DevBuf<uint8_t> d_stream;
+    DevBuf<uint64_t> d_off;
+    DevBuf<int32_t> d_out;
+    d_stream.alloc(len + 64);
+    d_off.alloc(std::max<uint32_t>(n_blocks, 1));
+    d_out.alloc((size_t)std::max<uint32_t>(n_blocks, 1) * kBlock);
+    cudaStream_t st = e->stream;
+    RG_CUDA_CHECK(cudaMemsetAsync(d_stream.p + len, 0, 64, st));
+    RG_CUDA_CHECK(cudaMemcpyAsync(d_stream.p, stream, len, cudaMemcpyHostToDevice, st));
+    RG_CUDA_CHECK(cudaMemcpyAsync(d_off.p, offsets, (size_t)n_blocks * 8, cudaMemcpyHostToDevice, st));
+    RG_CUDA_CHECK(cudaEventRecord(e->ev0, st));
+    launch_decode_raw(st, d_stream.p, d_off.p, n_blocks, d_out.p, h.version, h.sb_mask);
+    RG_CUDA_CHECK(cudaGetLastError());
+    if (n_blocks) e->launches++;
+    RG_CUDA_CHECK(cudaEventRecord(e->ev1, st));
+    RG_CUDA_CHECK(cudaMemcpyAsync(out, d_out.p, (size_t)n_blocks * kBlock * 4, cudaMemcpyDeviceToHost, st));
+    RG_CUDA_CHECK(cudaStreamSynchronize(st));
+    RG_CUDA_CHECK(cudaEventElapsedTime(&e->last_decode_ms, e->ev0, e->ev1));
+    return RG_OK;
+    RG_CATCH
+}
+
+int rg_blockset_stage(rg_engine* e, const uint8_t* stream, size_t len, const uint64_t* offsets,
+                      uint32_t n_blocks, int doc_version, const int32_t forutil_table[32],
+                      rg_blockset** out) {
+    RG_TRY
+    if (!e || !stream || !offsets || !out) throw ArgError("null argument");
+    RG_CUDA_CHECK(cudaSetDevice(e->device));
+    DocHeader h;
+    table_to_header(doc_version, forutil_table, h);
+    std::unique_ptr<rg_blockset> bs(new rg_blockset());
+    bs->n_blocks = n_blocks;
+    bs->version = h.version;
+    bs->sb_mask = h.sb_mask;
+    std::vector<BlockDesc> desc(std::max<uint32_t>(n_blocks, 1));
+    uint64_t units = 0;
+    for (uint32_t i = 0; i < n_blocks; i++) {
+        if (offsets[i] >= len) throw ArgError("block offset out of range");
+        int b = stream[offsets[i]] & 0x3f;
+        if (b > 32) throw ArgError("corrupt block header");
+        int sz = b ? h.enc_size[b] : 0;
+        if (offsets[i] + 1 + (size_t)(b ? sz : 1) > len) throw ArgError("block runs past the end of the stream");
+        desc[i].off16 = (uint32_t)units;
+        desc[i].bits = (uint32_t)b | (part_units(sz) << 16);
+        units += part_units(sz);
+        if (units >= (1ull << 32)) throw Unsupported("block set exceeds 64 GiB");
+    }
+    std::vector<uint4> arena(units + 8);
+    parallel_chunks((n_blocks + 65535) / 65536, [&](size_t c) {
+        uint32_t end = (uint32_t)std::min<uint64_t>(n_blocks, (c + 1) * 65536ull);
+        for (uint32_t i = (uint32_t)(c * 65536ull); i < end; i++) {
+            const uint8_t* p = stream + offsets[i];
+            int b = p[0] & 0x3f;
+            uint8_t* dst = reinterpret_cast<uint8_t*>(&arena[desc[i].off16]);
+            if (b) {
+                memcpy(dst, p + 1, (size_t)h.enc_size[b]);
+            } else {
+                In in(stream, len, (size_t)offsets[i] + 1);
+                int32_t v = in.vint();
+                memcpy(dst, &v, 4);
+            }
+        }
+    });
+    for (uint32_t i = 0; i < n_blocks; i++) {
+        int b = desc[i].bits & 0xff;
+        if (b) bs->enc_bytes += 1 + (uint64_t)h.enc_size[b];
+        else {
+            In in(stream, len, (size_t)offsets[i] + 1);
+            size_t p0 = in.pos;
+            in.vint();
+            bs->enc_bytes += 1 + (in.pos - p0);
+        }
+    }
+    cudaStream_t st = e->stream;
+    upload(bs->arena, arena.data(), arena.size(), st);
+    upload(bs->desc, desc.data(), desc.size(), st);
+    bs->out.alloc((size_t)std::max<uint32_t>(n_blocks, 1) * kBlock);
+    RG_CUDA_CHECK(cudaStreamSynchronize(st));
+    *out = bs.release();
+    return RG_OK;
+    RG_CATCH
+}
+
+int rg_blockset_decode(rg_engine* e, rg_blockset* bs) {
+    RG_TRY
+    if (!e || !bs) throw ArgError("null argument");
+    cudaStream_t st = e->stream;
+    RG_CUDA_CHECK(cudaEventRecord(e->ev0, st));
+    launch_decode_staged(st, bs->arena.p, bs->desc.p, bs->n_blocks, bs->out.p, bs->version, bs->sb_mask);
+    RG_CUDA_CHECK(cudaGetLastError());
+    if (bs->n_blocks) e->launches++;
+    RG_CUDA_CHECK(cudaEventRecord(e->ev1, st));
+    return RG_OK;
+    RG_CATCH
+}
+
+int rg_blockset_fetch(rg_engine* e, rg_blockset* bs, int32_t* out) {
+    RG_TRY
+    if (!e || !bs || !out) throw ArgError("null argument");
+    cudaStream_t st = e->stream;
+    RG_CUDA_CHECK(cudaMemcpyAsync(out, bs->out.p, (size_t)bs->n_blocks * kBlock * 4, cudaMemcpyDeviceToHost, st));
+    RG_CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&e->last_decode_ms, e->ev0, e->ev1);
+    cudaGetLastError();
+    return RG_OK;
+    RG_CATCH
+}
+
+int rg_blockset_stats(rg_engine*, rg_blockset* bs, uint64_t out[4]) {
+    if (!bs || !out) return RG_EINVAL;
+    out[0] = bs->enc_bytes;
+    out[1] = (uint64_t)bs->n_blocks * 512;
+    out[2] = bs->n_blocks;
+    out[3] = bs->arena.bytes() + bs->desc.bytes();
+    return RG_OK;
+}
+
+void rg_blockset_destroy(rg_engine*, rg_blockset* bs) { delete bs; }
+
+}  // extern "C"

@@ -1,0 +1,161 @@
+// engine.hpp — host-side engine state and kernel launch prototypes (internal).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace rg {
+
+struct CudaError : std::runtime_error {
+    cudaError_t code;
+    CudaError(cudaError_t e, const char* expr, const char* file, int line)
+        : std::runtime_error(std::string(cudaGetErrorString(e)) + " at " + file + ":" +
+                             std::to_string(line) + " (" + expr + ")"),
+          code(e) {}
+};
+struct ArgError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+struct Unsupported : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+struct OutOfArena : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p;
+            n = o.n;
+            o.p = nullptr;
+            o.n = 0;
+        }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(size_t count) {
+        release();
+        if (count == 0) return;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+        if (e != cudaSuccess) throw CudaError(e, "cudaMalloc", __FILE__, __LINE__);
+        n = count;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// host-side view of a term (for planning and byte accounting)
+struct TermHost {
+    int32_t doc_freq = 0;
+    uint32_t n_blocks = 0;
+    uint64_t enc_bytes = 0;  // encoded block bytes incl. header bytes + vint tail bytes
+};
+
+struct Segment {
+    SegDev dev{};
+    DevBuf<uint4> arena;
+    DevBuf<int32_t> blk_last;
+    DevBuf<BlockDesc> blk_desc;
+    DevBuf<uint8_t> tails;
+    DevBuf<TermDev> terms;
+    DevBuf<uint8_t> norms;
+    DevBuf<uint64_t> live;
+    std::vector<TermHost> host_terms;
+    int32_t doc_base = 0, max_doc = 0;
+    uint64_t device_bytes = 0;
+};
+
+// kernel launchers (decode_kernels.cu)
+void launch_decode_staged(cudaStream_t st, const uint4* arena, const BlockDesc* desc,
+                          uint32_t n_blocks, int32_t* out, int version, uint32_t sb_mask);
+void launch_decode_raw(cudaStream_t st, const uint8_t* stream, const uint64_t* offsets,
+                       uint32_t n_blocks, int32_t* out, int version, uint32_t sb_mask);
+
+// query kernels (query_kernels.cu)
+struct EvalParams {
+    const SegDev* segs;
+    const WorkItem* items;
+    const ItemClause* clauses;
+    const float* caches;       // n_caches * 256
+    uint32_t n_items;
+    uint32_t k;
+    float k1;
+    // outputs / scratch
+    rg_hit* cand_arena;        // slot array; slot 0.. ; run = header slot + entries
+    uint32_t arena_slots;
+    uint32_t* arena_next;      // bump pointer (slots)
+    uint32_t* item_head;       // first run header slot per item (0xffffffff none)
+    uint32_t* item_matches;    // matches per item (total_hits contribution)
+    uint32_t* item_theta;      // ordered-uint running k-th best, chained item -> item+1
+    uint32_t* error_flag;      // bit0: arena exhausted
+};
+void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n);
+void launch_eval_and(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n);
+
+struct ReplayParams {
+    const rg_hit* cand_arena;
+    const uint32_t* item_head;
+    const uint32_t* item_matches;
+    const uint32_t* group_item_begin;  // n_groups+1 : items of heap group g
+    const uint32_t* group_query;       // query of group g
+    uint32_t n_groups;
+    uint32_t k;
+    // outputs: sorted hits per group or leaf records
+    rg_hit* out_hits;        // [n_groups * k] sorted (descending) — used when !leaf_records
+    uint32_t* out_counts;
+    unsigned long long* out_total;
+    uint8_t* leaf_records;   // non-null: write {u32 n; u32 pad; u64 total; rg_hit heap[k]} per group
+};
+void launch_heap_replay(cudaStream_t st, const ReplayParams& p);
+// finish_parallel over leaf records laid out [leaf][query]
+void launch_merge_leaf_records(cudaStream_t st, const uint8_t* records, uint32_t n_leaves,
+                               uint32_t n_queries, uint32_t k, rg_hit* out_hits,
+                               uint32_t* out_counts, unsigned long long* out_total);
+
+inline size_t leaf_record_bytes(uint32_t k) { return 16 + (size_t)k * sizeof(rg_hit); }
+
+extern thread_local std::string g_last_error;
+int translate_exception();  // maps the in-flight exception to an RG_E* code + g_last_error
+
+}  // namespace rg
+
+// the opaque handle of include/rucene_gpu.h
+struct rg_engine {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    rg_config cfg{};
+    std::vector<rg::Segment> segs;
+    rg::DevBuf<rg::SegDev> d_segs;
+    bool segs_dirty = true;
+    rg::DevBuf<float> d_caches;   // n_caches * 256
+    std::vector<float> h_caches;
+    bool caches_dirty = true;
+    rg::DevBuf<rg_hit> cand_arena;
+    uint64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_decode_ms = -1.f, last_eval_ms = -1.f, last_replay_ms = -1.f, last_run_ms = -1.f;
+    void sync_tables();  // (re)upload SegDev array and norm caches when dirty
+};
+
+namespace rg {
+
+}  // namespace rg
