@@ -101,7 +101,7 @@ struct EvalParams {
     // outputs / scratch
     rg_hit* cand_arena;        // slot array; slot 0.. ; run = header slot + entries
     uint32_t arena_slots;
-    uint32_t* arena_next;      // bump pointer (slots)
+    unsigned long long* arena_next;  // bump pointer (slots)
     uint32_t* item_head;       // first run header slot per item (0xffffffff none)
     uint32_t* item_matches;    // matches per item (total_hits contribution)
     uint32_t* item_theta;      // ordered-uint running k-th best, chained item -> item+1
@@ -130,7 +130,7 @@ void launch_merge_leaf_records(cudaStream_t st, const uint8_t* records, uint32_t
                                uint32_t n_queries, uint32_t k, rg_hit* out_hits,
                                uint32_t* out_counts, unsigned long long* out_total);
 
-inline size_t leaf_record_bytes(uint32_t k) { return 16 + (size_t)k * sizeof(rg_hit); }
+__host__ __device__ inline size_t leaf_record_bytes(uint32_t k) { return 16 + (size_t)k * sizeof(rg_hit); }
 
 extern thread_local std::string g_last_error;
 int translate_exception();  // maps the in-flight exception to an RG_E* code + g_last_error

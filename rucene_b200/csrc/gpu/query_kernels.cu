@@ -1,0 +1,871 @@
+// query_kernels.cu — the fused query-evaluation kernels (sm_100a, integer/HBM-bound work).
+//
+//   k_eval_or   : TermQuery / pure-SHOULD BooleanQuery.  One CTA per (query, segment, docid
+//                 range).  Posting blocks are decoded warp-per-block straight from the HBM image,
+//                 docids rebuilt with a warp scan, BM25 computed per posting and accumulated into
+//                 a shared-memory window of 4096 docids, term after term in clause order — the
+//                 f32 summation order of DisjunctionSumScorer::score_sum
+//                 (search/scorer/disjunction_scorer.rs:211-225).  The window is then scanned in
+//                 docid order: every present doc is a match (total_hits), and docs that can still
+//                 enter the top-k heap are appended to the query's candidate list.
+//   k_eval_and  : pure-MUST BooleanQuery (ConjunctionScorer, search/scorer/conjunction_scorer.rs).
+//                 The cheapest list leads (stable sort by cost, :30); 8 lead blocks per step are
+//                 decoded, every lead doc locates its block in each other list via the level-0
+//                 skip table (galloping binary search), that block is decoded once per warp into
+//                 shared memory, membership is a 7-step binary search and the freq is extracted
+//                 lazily by random access into the freq block.  Scores add in cost order
+//                 (lead1 + lead2 + others, :87-95).
+//   k_heap_replay: exact TopDocsCollector semantics (search/collector/top_docs.rs:67-95 over std
+//                 BinaryHeap, util/external/binary_heap.rs:121-210) — one warp per heap replays
+//                 add_doc over the candidate lists in collection order and pops the result.
+//
+// Exactness of the candidate lists: a doc changes the heap iff fewer than
+// k earlier docs score >= it.  Each CTA keeps theta = k-th best score of docs it has already
+// passed (plus what earlier ranges of the same heap chain published), a lower bound of the heap
+// root at that point; docs with score <= theta can never enter, everything else is emitted in
+// docid order.  The replay over that superset is bit-identical to the reference, ties included.
+#include "engine.hpp"
+#include "unpack.cuh"
+
+namespace rg {
+
+constexpr int kEvalThreads = 256;
+constexpr int kEvalWarps = kEvalThreads / 32;
+constexpr int kWin = 4096;              // docids per accumulator window (k_eval_or)
+constexpr int kWinSteps = kWin / kEvalThreads;  // 16 slots per lane
+constexpr int kNewcMax = 512;           // candidate scores fed to the theta tracker per window
+constexpr int kMaxK = 1024;             // theta tracking / replay heap capacity
+constexpr uint32_t kNone = 0xffffffffu;
+constexpr uint32_t kRunMin = 256;       // minimum candidate run length (slots)
+constexpr uint32_t kSent = 0x7fc0dead;  // "no posting yet" marker in the accumulator window (a NaN)
+
+// ------------------------------------------------------------------------------------------
+// candidate emission + theta tracking (shared by both evaluation kernels)
+// ------------------------------------------------------------------------------------------
+struct EmitShared {
+    float topk[kMaxK];
+    float newc[kNewcMax];
+    uint32_t warp_c[kEvalWarps], warp_m[kEvalWarps];
+    uint32_t newc_n;
+    uint32_t topk_n;
+    float theta_local;
+    uint32_t theta_in;  // ordered-uint theta inherited from earlier ranges of the chain
+    uint32_t run_slot, run_cap, run_cnt;
+    uint32_t write_base;
+    uint32_t matches;
+    uint32_t overflow;
+};
+
+__device__ __forceinline__ void emit_init(EmitShared& es) {
+    if (threadIdx.x == 0) {
+        es.newc_n = 0;
+        es.topk_n = 0;
+        es.theta_local = -INFINITY;
+        es.theta_in = 0;
+        es.run_slot = kNone;
+        es.run_cap = 0;
+        es.run_cnt = 0;
+        es.write_base = 0;
+        es.matches = 0;
+        es.overflow = 0;
+    }
+}
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// warp 0: fold this window's candidate scores into the running top-k and publish theta
+__device__ void theta_update(EmitShared& es, uint32_t k, uint32_t* theta_out) {
+    const int lane = lane_id();
+    const uint32_t n_new = min(es.newc_n, (uint32_t)kNewcMax);
+    uint32_t n = es.topk_n;
+    float theta = es.theta_local;
+    int argmin = 0;
+    auto recompute = [&]() {
+        float m = INFINITY;
+        int mi = 0;
+        for (uint32_t j = lane; j < k; j += 32) {
+            float v = es.topk[j];
+            if (v < m) {
+                m = v;
+                mi = (int)j;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            float om = __shfl_xor_sync(0xffffffffu, m, o);
+            int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+            if (om < m || (om == m && oi < mi)) {
+                m = om;
+                mi = oi;
+            }
+        }
+        theta = m;
+        argmin = mi;
+    };
+    if (k <= (uint32_t)kMaxK) {
+        if (n == k && n_new) recompute();
+        for (uint32_t i = 0; i < n_new; i++) {
+            const float x = es.newc[i];
+            if (n < k) {
+                if (lane == 0) es.topk[n] = x;
+                n++;
+                __syncwarp();
+                if (n == k) recompute();
+            } else if (x > theta) {
+                if (lane == 0) es.topk[argmin] = x;
+                __syncwarp();
+                recompute();
+            }
+        }
+    }
+    if (lane == 0) {
+        es.topk_n = n;
+        es.theta_local = (n == k && k <= (uint32_t)kMaxK) ? theta : -INFINITY;
+        uint32_t ord = es.theta_in;
+        if (es.theta_local != -INFINITY) ord = max(ord, float_to_ordered(es.theta_local));
+        if (ord > kOrderedNegInf) atomicMax(theta_out, ord);
+    }
+}
+
+// One emission step.  Slot order = (warp, step, lane) ascending == docid order.  `present`
+// marks matches; inherited_theta is thread 0's prefetched copy of the previous item's theta.
+template <int STEPS>
+__device__ void emit_window(EmitShared& es, const EvalParams& p, uint32_t item_idx, int doc_base,
+                            const bool (&present)[STEPS], const int (&doc)[STEPS],
+                            const float (&score)[STEPS], uint32_t inherited_theta) {
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    float te = es.theta_local;
+    if (es.theta_in > kOrderedNegInf) te = fmaxf(te, ordered_to_float(es.theta_in));
+    const bool open = te == -INFINITY;
+    uint32_t cmask[STEPS];
+    uint32_t nm = 0, nc = 0;
+#pragma unroll
+    for (int s = 0; s < STEPS; s++) {
+        const uint32_t pm = __ballot_sync(0xffffffffu, present[s]);
+        cmask[s] = __ballot_sync(0xffffffffu, present[s] && (open || score[s] > te));
+        nm += __popc(pm);
+        nc += __popc(cmask[s]);
+    }
+    if (lane == 0) {
+        es.warp_m[warp] = nm;
+        es.warp_c[warp] = nc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tc = 0, tm = 0;
+        for (int w = 0; w < kEvalWarps; w++) {
+            const uint32_t c = es.warp_c[w];
+            es.warp_c[w] = tc;
+            tc += c;
+            tm += es.warp_m[w];
+        }
+        es.matches += tm;
+        es.newc_n = 0;
+        es.theta_in = max(es.theta_in, inherited_theta);
+        if (tc > 0 && !es.overflow) {
+            CandRun* hdr = reinterpret_cast<CandRun*>(p.cand_arena);
+            if (es.run_slot == kNone || es.run_cnt + tc > es.run_cap) {
+                const uint32_t cap = max(tc, kRunMin);
+                const unsigned long long slot64 = atomicAdd(p.arena_next, (unsigned long long)cap + 1ull);
+                const uint32_t slot = (uint32_t)slot64;
+                if (slot64 + cap + 1ull > (unsigned long long)p.arena_slots) {
+                    atomicOr(p.error_flag, 1u);
+                    es.overflow = 1;
+                } else {
+                    if (es.run_slot == kNone) p.item_head[item_idx] = slot;
+                    else hdr[es.run_slot] = CandRun{slot, es.run_cnt};
+                    es.run_slot = slot;
+                    es.run_cap = cap;
+                    es.run_cnt = 0;
+                }
+            }
+            if (!es.overflow) {
+                es.write_base = es.run_slot + 1 + es.run_cnt;
+                es.run_cnt += tc;
+                hdr[es.run_slot] = CandRun{kNone, es.run_cnt};
+            }
+        }
+    }
+    __syncthreads();
+    if (nc && !es.overflow) {
+        uint32_t pos = es.write_base + es.warp_c[warp];
+        const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int s = 0; s < STEPS; s++) {
+            if ((cmask[s] >> lane) & 1u) {
+                p.cand_arena[pos + __popc(cmask[s] & lt)] = rg_hit{doc[s] + doc_base, score[s]};
+                const uint32_t i = atomicAdd(&es.newc_n, 1u);
+                if (i < (uint32_t)kNewcMax) es.newc[i] = score[s];
+            }
+            pos += __popc(cmask[s]);
+        }
+    }
+    __syncthreads();
+    if (warp == 0) theta_update(es, p.k, p.item_theta + item_idx);
+}
+
+// first index in [lo, hi) with a[i] >= key (hi if none)
+__device__ __forceinline__ uint32_t lower_bound_i32(const int32_t* __restrict__ a, uint32_t lo,
+                                                    uint32_t hi, int32_t key) {
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(a + mid) < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+// same, galloping forward from `hint` (<= answer)
+__device__ __forceinline__ uint32_t lower_bound_gallop(const int32_t* __restrict__ a, uint32_t hint,
+                                                       uint32_t n, int32_t key) {
+    uint32_t lo = hint, step = 1, hi = hint;
+    while (hi < n && __ldg(a + hi) < key) {
+        lo = hi + 1;
+        hi += step;
+        step <<= 1;
+    }
+    return lower_bound_i32(a, lo, min(hi, n), key);
+}
+
+struct TermCtx {
+    const int32_t* blk_last;   // this term's slice of the level-0 skip table
+    const BlockDesc* blk_desc;
+    const float* cache;
+    uint32_t nb;               // full blocks
+    uint32_t cur;              // first block not fully consumed
+    uint32_t next_cur;
+    uint32_t tail_n;           // postings in the (decoded) tail, 0 = no tail in scope
+    uint32_t tail_pos;
+    uint32_t tail_next;
+    int32_t tail_base;
+    float w1;                  // weight * (k1 + 1)
+};
+
+// Decode a term's vint tail (or singleton) into shared memory: absolute docids + freqs.
+// codec/postings/posting_reader.rs:308-333 (read_vint_block), :545-547 (singleton).
+__device__ void decode_tail(const SegDev& seg, const TermDev& td, int32_t* docs, int32_t* freqs) {
+    if (td.doc_freq == 1) {
+        docs[0] = td.singleton_doc;
+        freqs[0] = td.singleton_freq;
+        return;
+    }
+    const uint8_t* p = seg.tails + td.tail_off;
+    uint32_t pos = 0;
+    int32_t acc = td.tail_base;
+    for (uint32_t i = 0; i < td.tail_n; i++) {
+        const uint32_t code = (uint32_t)read_vint(p, pos);
+        acc += (int32_t)(code >> 1);
+        docs[i] = acc;
+        freqs[i] = (code & 1u) ? 1 : read_vint(p, pos);
+    }
+}
+
+__device__ __forceinline__ bool is_live(const SegDev& seg, int doc) {
+    if (!seg.live) return true;
+    return (seg.live[doc >> 6] >> (doc & 63)) & 1ull;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_eval_or
+// ------------------------------------------------------------------------------------------
+struct OrShared {
+    uint32_t acc[kWin];
+    int32_t tail_docs[kMaxTerms][kBlock];
+    int32_t tail_freqs[kMaxTerms][kBlock];
+    TermCtx term[kMaxTerms];
+    EmitShared emit;
+    int32_t next_doc;
+};
+
+__global__ void __launch_bounds__(kEvalThreads)
+k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    OrShared& sh = *reinterpret_cast<OrShared*>(smem_raw);
+    const uint32_t item_idx = item_ids[blockIdx.x];
+    const WorkItem it = p.items[item_idx];
+    const SegDev seg = p.segs[it.seg];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const int T = it.n_terms;
+    const int lo = it.lo, hi = it.hi;
+
+    emit_init(sh.emit);
+    for (int i = threadIdx.x; i < kWin; i += kEvalThreads) sh.acc[i] = kSent;
+    if ((int)threadIdx.x < T) {
+        const ItemClause c = p.clauses[it.clause_begin + threadIdx.x];
+        const TermDev td = seg.terms[c.term_id];
+        TermCtx& tc = sh.term[threadIdx.x];
+        tc.blk_last = seg.blk_last + td.blk_begin;
+        tc.blk_desc = seg.blk_desc + td.blk_begin;
+        tc.cache = p.caches + (size_t)c.cache_id * 256;
+        tc.nb = td.n_blocks;
+        tc.cur = lower_bound_i32(tc.blk_last, 0, td.n_blocks, lo);
+        tc.next_cur = tc.cur;
+        tc.tail_base = td.tail_base;
+        const bool tail_in_scope = td.tail_n > 0 && (td.n_blocks == 0 || hi - 1 > td.tail_base);
+        tc.tail_n = tail_in_scope ? td.tail_n : 0;
+        tc.tail_pos = 0;
+        tc.tail_next = 0;
+        tc.w1 = __fmul_rn(c.weight, __fadd_rn(p.k1, 1.0f));
+    }
+    __syncthreads();
+    for (int t = warp; t < T; t += kEvalWarps) {
+        TermCtx& tc = sh.term[t];
+        if (tc.tail_n) {
+            if (lane == 0) {
+                const ItemClause c = p.clauses[it.clause_begin + t];
+                decode_tail(seg, seg.terms[c.term_id], sh.tail_docs[t], sh.tail_freqs[t]);
+                uint32_t pos = 0;
+                while (pos < tc.tail_n && sh.tail_docs[t][pos] < lo) pos++;
+                tc.tail_pos = pos;
+                tc.tail_next = pos;
+            }
+        }
+    }
+    const uint32_t* theta_prev = (it.flags & 1u) ? nullptr : p.item_theta + (item_idx - 1);
+    __syncthreads();
+
+    long long w0 = lo;
+    while (w0 < hi) {
+        const int win0 = (int)w0;
+        const int win1 = (int)min((long long)hi, w0 + kWin);
+        uint32_t inherited = 0;
+        if (threadIdx.x == 0) {
+            sh.next_doc = kNoMoreDocs;
+            if (theta_prev) inherited = ld_volatile_u32(theta_prev);
+        }
+        __syncthreads();
+        for (int t = 0; t < T; t++) {
+            TermCtx& tc = sh.term[t];
+            const uint32_t nb = tc.nb;
+            const float w1 = tc.w1;
+            const float* cache = tc.cache;
+            int my_next = kNoMoreDocs;
+            uint32_t my_cur = 0;
+            for (uint32_t b = tc.cur + warp;; b += kEvalWarps) {
+                if (b > nb) break;
+                const int prev_last = b == 0 ? -1 : __ldg(tc.blk_last + b - 1);
+                if (b == nb && tc.tail_n == 0) break;
+                if (prev_last >= win1 - 1) {
+                    my_next = min(my_next, prev_last + 1);
+                    break;
+                }
+                if (b == nb) {  // vint tail / singleton, already decoded in shared memory
+                    uint32_t consumed = 0;
+                    for (uint32_t j = tc.tail_pos + lane; j < tc.tail_n; j += 32) {
+                        const int d = sh.tail_docs[t][j];
+                        if (d >= win1) {
+                            my_next = min(my_next, d);
+                            break;
+                        }
+                        consumed = j + 1;
+                        if (d >= win0) {
+                            const float f = (float)sh.tail_freqs[t][j];
+                            const float nrm = seg.norms ? __ldg(cache + __ldg(seg.norms + d)) : p.k1;
+                            const float s = bm25_score(w1, f, nrm);
+                            const uint32_t old = sh.acc[d - win0];
+                            const float prev = old == kSent ? 0.0f : __uint_as_float(old);
+                            sh.acc[d - win0] = __float_as_uint(__fadd_rn(prev, s));
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) consumed = max(consumed, __shfl_xor_sync(0xffffffffu, consumed, o));
+                    if (lane == 0 && consumed > tc.tail_pos) atomicMax(&tc.tail_next, consumed);
+                    break;
+                }
+                const BlockDesc bd = tc.blk_desc[b];
+                const uint4* part = seg.arena + bd.off16;
+                const int4 dl = unpack4(part, (int)(bd.bits & 0xff), lane, seg.version, seg.sb_mask);
+                const int4 dd = deltas_to_docs(dl, b == 0 ? 0 : prev_last);
+                const int docs[4] = {dd.x, dd.y, dd.z, dd.w};
+                bool in_win = false;
+#pragma unroll
+                for (int i = 0; i < 4; i++) in_win |= docs[i] >= win0 && docs[i] < win1;
+                if (__any_sync(0xffffffffu, in_win)) {
+                    const int4 fr = unpack4(part + ((bd.bits >> 16) & 0xff), (int)((bd.bits >> 8) & 0xff),
+                                            lane, seg.version, seg.sb_mask);
+                    const int fq[4] = {fr.x, fr.y, fr.z, fr.w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int d = docs[i];
+                        if (d >= win0 && d < win1) {
+                            const float nrm = seg.norms ? __ldg(cache + __ldg(seg.norms + d)) : p.k1;
+                            const float s = bm25_score(w1, (float)fq[i], nrm);
+                            const uint32_t old = sh.acc[d - win0];
+                            const float prev = old == kSent ? 0.0f : __uint_as_float(old);
+                            sh.acc[d - win0] = __float_as_uint(__fadd_rn(prev, s));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (docs[i] >= win1) my_next = min(my_next, docs[i]);
+                if (dd.w < win1 && lane == 31) my_cur = b + 1;  // whole block consumed
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) my_next = min(my_next, __shfl_xor_sync(0xffffffffu, my_next, o));
+            my_cur = __shfl_sync(0xffffffffu, my_cur, 31);
+            if (lane == 0) {
+                if (my_next != kNoMoreDocs) atomicMin(&sh.next_doc, my_next);
+                if (my_cur) atomicMax(&tc.next_cur, my_cur);
+            }
+            __syncthreads();  // accumulator hand-over to the next clause (clause-order f32 sums)
+        }
+        if ((int)threadIdx.x < T) {
+            TermCtx& tc = sh.term[threadIdx.x];
+            tc.cur = max(tc.cur, tc.next_cur);
+            tc.tail_pos = max(tc.tail_pos, tc.tail_next);
+        }
+        // scan the window in docid order
+        bool present[kWinSteps];
+        int doc[kWinSteps];
+        float score[kWinSteps];
+        const int span = win1 - win0;
+#pragma unroll
+        for (int s = 0; s < kWinSteps; s++) {
+            const int idx = warp * (kWin / kEvalWarps) + s * 32 + lane;
+            const uint32_t v = sh.acc[idx];
+            sh.acc[idx] = kSent;
+            doc[s] = win0 + idx;
+            score[s] = __uint_as_float(v);
+            present[s] = v != kSent && idx < span && is_live(seg, win0 + idx);
+        }
+        emit_window<kWinSteps>(sh.emit, p, item_idx, seg.doc_base, present, doc, score, inherited);
+        __syncthreads();
+        const int nd = sh.next_doc;
+        if (nd == kNoMoreDocs) break;
+        w0 = nd;
+        __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) p.item_matches[item_idx] = sh.emit.matches;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_eval_and
+// ------------------------------------------------------------------------------------------
+constexpr int kAndSlots = kEvalWarps * kBlock;  // 1024 lead docs per step
+constexpr int kAndSteps = kBlock / 32;          // 4 slots per lane
+
+struct AndShared {
+    int32_t ldoc[kAndSlots];
+    float lscore[kAndSlots];
+    int32_t slab_docs[kEvalWarps][kBlock];
+    int32_t slab_freqs[kEvalWarps][kBlock];
+    TermCtx term[kMaxTerms];
+    uint32_t term_id[kMaxTerms];
+    uint32_t hint[kEvalWarps][kMaxTerms];  // per-warp galloping hints into the skip tables
+    EmitShared emit;
+};
+
+__global__ void __launch_bounds__(kEvalThreads)
+k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    AndShared& sh = *reinterpret_cast<AndShared*>(smem_raw);
+    const uint32_t item_idx = item_ids[blockIdx.x];
+    const WorkItem it = p.items[item_idx];
+    const SegDev seg = p.segs[it.seg];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const int T = it.n_terms;
+    const int lo = it.lo, hi = it.hi;
+
+    emit_init(sh.emit);
+    if ((int)threadIdx.x < T) {
+        const ItemClause c = p.clauses[it.clause_begin + threadIdx.x];
+        const TermDev td = seg.terms[c.term_id];
+        TermCtx& tc = sh.term[threadIdx.x];
+        sh.term_id[threadIdx.x] = c.term_id;
+        tc.blk_last = seg.blk_last + td.blk_begin;
+        tc.blk_desc = seg.blk_desc + td.blk_begin;
+        tc.cache = p.caches + (size_t)c.cache_id * 256;
+        tc.nb = td.n_blocks;
+        tc.cur = lower_bound_i32(tc.blk_last, 0, td.n_blocks, lo);
+        tc.next_cur = 0;
+        tc.tail_base = td.tail_base;
+        tc.tail_n = td.tail_n;
+        tc.tail_pos = 0;
+        tc.tail_next = 0;
+        tc.w1 = __fmul_rn(c.weight, __fadd_rn(p.k1, 1.0f));
+    }
+    const uint32_t* theta_prev = (it.flags & 1u) ? nullptr : p.item_theta + (item_idx - 1);
+    __syncthreads();
+
+    const TermCtx& lead = sh.term[0];
+    const uint32_t lead_nb = lead.nb;
+    const bool lead_has_tail = lead.tail_n > 0 && (lead_nb == 0 || hi - 1 > lead.tail_base);
+    if (lane < kMaxTerms) sh.hint[warp][lane] = 0;
+    __syncwarp();
+
+    for (uint32_t b0 = lead.cur;; b0 += kEvalWarps) {
+        // ---- 1. decode this step's lead blocks (one per warp; pseudo-block lead_nb = vint tail)
+        if (b0 > lead_nb || (b0 == lead_nb && !lead_has_tail)) break;
+        {
+            const int first_prev = b0 == 0 ? -1 : __ldg(lead.blk_last + b0 - 1);
+            if (first_prev >= hi - 1) break;
+        }
+        uint32_t inherited = 0;
+        if (threadIdx.x == 0 && theta_prev) inherited = ld_volatile_u32(theta_prev);
+        const uint32_t b = b0 + warp;
+        int4 ld = make_int4(kNoMoreDocs, kNoMoreDocs, kNoMoreDocs, kNoMoreDocs);
+        float4 ls = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float lw1 = lead.w1;
+        if (b < lead_nb) {
+            const int prev_last = b == 0 ? -1 : __ldg(lead.blk_last + b - 1);
+            if (prev_last < hi - 1) {
+                const BlockDesc bd = lead.blk_desc[b];
+                const uint4* part = seg.arena + bd.off16;
+                const int4 dl = unpack4(part, (int)(bd.bits & 0xff), lane, seg.version, seg.sb_mask);
+                const int4 dd = deltas_to_docs(dl, b == 0 ? 0 : prev_last);
+                const int4 fr = unpack4(part + ((bd.bits >> 16) & 0xff), (int)((bd.bits >> 8) & 0xff), lane,
+                                        seg.version, seg.sb_mask);
+                const int docs[4] = {dd.x, dd.y, dd.z, dd.w};
+                const int fq[4] = {fr.x, fr.y, fr.z, fr.w};
+                int od[4];
+                float os[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int d = docs[i];
+                    const bool ok = d >= lo && d < hi;
+                    od[i] = ok ? d : kNoMoreDocs;
+                    float s = 0.f;
+                    if (ok) {
+                        const float nrm = seg.norms ? __ldg(lead.cache + __ldg(seg.norms + d)) : p.k1;
+                        s = bm25_score(lw1, (float)fq[i], nrm);
+                    }
+                    os[i] = s;
+                }
+                ld = make_int4(od[0], od[1], od[2], od[3]);
+                ls = make_float4(os[0], os[1], os[2], os[3]);
+            }
+            reinterpret_cast<int4*>(sh.ldoc + warp * kBlock)[lane] = ld;
+            reinterpret_cast<float4*>(sh.lscore + warp * kBlock)[lane] = ls;
+        } else {
+            reinterpret_cast<int4*>(sh.ldoc + warp * kBlock)[lane] = ld;
+            reinterpret_cast<float4*>(sh.lscore + warp * kBlock)[lane] = ls;
+            __syncwarp();
+            if (b == lead_nb && lead_has_tail) {
+                if (lane == 0) {
+                    decode_tail(seg, seg.terms[sh.term_id[0]], sh.slab_docs[warp], sh.slab_freqs[warp]);
+                }
+                __syncwarp();
+                for (uint32_t j = lane; j < lead.tail_n; j += 32) {
+                    const int d = sh.slab_docs[warp][j];
+                    if (d >= lo && d < hi) {
+                        const float nrm = seg.norms ? __ldg(lead.cache + __ldg(seg.norms + d)) : p.k1;
+                        sh.ldoc[warp * kBlock + j] = d;
+                        sh.lscore[warp * kBlock + j] = bm25_score(lw1, (float)sh.slab_freqs[warp][j], nrm);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // ---- 2. every other clause, in cost order; each warp works on its own 128 lead slots
+        for (int t = 1; t < T; t++) {
+            const TermCtx& tc = sh.term[t];
+            const uint32_t nb = tc.nb;
+            const float w1 = tc.w1;
+            for (int r = 0; r < kAndSteps; r++) {
+                const int slot = warp * kBlock + r * 32 + lane;
+                int d = sh.ldoc[slot];
+                bool pending = d != kNoMoreDocs;
+                uint32_t bi = 0;
+                if (pending) {
+                    bi = lower_bound_gallop(tc.blk_last, min(sh.hint[warp][t], nb), nb, d);
+                    if (bi == nb && !(tc.tail_n > 0 && (nb == 0 || d > tc.tail_base))) {
+                        pending = false;  // beyond the last posting of this clause
+                        sh.ldoc[slot] = kNoMoreDocs;
+                    }
+                }
+                uint32_t pend_mask = __ballot_sync(0xffffffffu, pending);
+                __syncwarp();
+                if (pend_mask) {
+                    const int last_lane = 31 - __clz(pend_mask);
+                    const uint32_t hb = __shfl_sync(0xffffffffu, bi, last_lane);
+                    if (lane == 0) sh.hint[warp][t] = hb;
+                }
+                __syncwarp();
+                while (pend_mask) {
+                    const int leader = __ffs(pend_mask) - 1;
+                    const uint32_t cb = __shfl_sync(0xffffffffu, bi, leader);
+                    const bool full_block = cb < nb;
+                    BlockDesc bd{};
+                    if (full_block) {
+                        bd = tc.blk_desc[cb];
+                        const int base = cb == 0 ? 0 : __ldg(tc.blk_last + cb - 1);
+                        const uint4* part = seg.arena + bd.off16;
+                        const int4 dl = unpack4(part, (int)(bd.bits & 0xff), lane, seg.version, seg.sb_mask);
+                        const int4 dd = deltas_to_docs(dl, base);
+                        reinterpret_cast<int4*>(sh.slab_docs[warp])[lane] = dd;
+                    } else if (lane == 0) {
+                        decode_tail(seg, seg.terms[sh.term_id[t]], sh.slab_docs[warp], sh.slab_freqs[warp]);
+                    }
+                    __syncwarp();
+                    const int n_in = cb < nb ? kBlock : (int)tc.tail_n;
+                    const bool mine = pending && bi == cb;
+                    if (mine) {
+                        int l = 0, h = n_in;
+                        while (l < h) {
+                            const int m = (l + h) >> 1;
+                            if (sh.slab_docs[warp][m] < d) l = m + 1;
+                            else h = m;
+                        }
+                        if (l < n_in && sh.slab_docs[warp][l] == d) {
+                            int f;
+                            if (full_block) {
+                                f = extract1(seg.arena + bd.off16 + ((bd.bits >> 16) & 0xff),
+                                             (int)((bd.bits >> 8) & 0xff), l, seg.version, seg.sb_mask);
+                            } else {
+                                f = sh.slab_freqs[warp][l];
+                            }
+                            const float nrm = seg.norms ? __ldg(tc.cache + __ldg(seg.norms + d)) : p.k1;
+                            sh.lscore[slot] = __fadd_rn(sh.lscore[slot], bm25_score(w1, (float)f, nrm));
+                        } else {
+                            sh.ldoc[slot] = kNoMoreDocs;
+                        }
+                        pending = false;
+                    }
+                    __syncwarp();
+                    pend_mask = __ballot_sync(0xffffffffu, pending);
+                }
+            }
+            __syncwarp();
+        }
+        // ---- 3. surviving lead docs are the matches of this step, in docid order
+        bool present[kAndSteps];
+        int doc[kAndSteps];
+        float score[kAndSteps];
+#pragma unroll
+        for (int s = 0; s < kAndSteps; s++) {
+            const int slot = warp * kBlock + s * 32 + lane;
+            doc[s] = sh.ldoc[slot];
+            score[s] = sh.lscore[slot];
+            present[s] = doc[s] != kNoMoreDocs && is_live(seg, doc[s]);
+        }
+        emit_window<kAndSteps>(sh.emit, p, item_idx, seg.doc_base, present, doc, score, inherited);
+        __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) p.item_matches[item_idx] = sh.emit.matches;
+}
+
+// ------------------------------------------------------------------------------------------
+// exact TopDocsCollector heap (one lane drives it; the warp pre-filters)
+// ------------------------------------------------------------------------------------------
+struct Heap {
+    rg_hit* data;  // shared memory, capacity k
+    uint32_t n;
+    uint32_t k;
+    // reversed PartialOrd on score only (sort_field/collapse_top_docs.rs:54-60):
+    //   a <= b  <=>  a.score >= b.score
+    __device__ static bool le(const rg_hit& a, const rg_hit& b) { return a.score >= b.score; }
+    __device__ static bool ge(const rg_hit& a, const rg_hit& b) { return a.score <= b.score; }
+    __device__ void sift_up(uint32_t start, uint32_t pos) {
+        const rg_hit e = data[pos];
+        while (pos > start) {
+            const uint32_t parent = (pos - 1) / 2;
+            if (le(e, data[parent])) break;
+            data[pos] = data[parent];
+            pos = parent;
+        }
+        data[pos] = e;
+    }
+    __device__ void sift_down_range(uint32_t pos, uint32_t end) {
+        const rg_hit e = data[pos];
+        uint32_t child = 2 * pos + 1;
+        while (child < end) {
+            const uint32_t right = child + 1;
+            if (right < end && le(data[child], data[right])) child = right;
+            if (ge(e, data[child])) break;
+            data[pos] = data[child];
+            pos = child;
+            child = 2 * pos + 1;
+        }
+        data[pos] = e;
+    }
+    __device__ void sift_down_to_bottom(uint32_t pos) {
+        const uint32_t end = n, start = pos;
+        const rg_hit e = data[pos];
+        uint32_t child = 2 * pos + 1;
+        while (child < end) {
+            const uint32_t right = child + 1;
+            if (right < end && le(data[child], data[right])) child = right;
+            data[pos] = data[child];
+            pos = child;
+            child = 2 * pos + 1;
+        }
+        data[pos] = e;
+        sift_up(start, pos);
+    }
+    __device__ void add_doc(const rg_hit& h) {  // top_docs.rs:67-76
+        if (n < k) {
+            data[n] = h;
+            n++;
+            sift_up(0, n - 1);
+        } else if (n > 0 && data[0].score < h.score) {
+            data[0] = h;
+            sift_down_range(0, n);
+        }
+    }
+    __device__ rg_hit pop() {
+        rg_hit item = data[n - 1];
+        n--;
+        if (n > 0) {
+            const rg_hit top = data[0];
+            data[0] = item;
+            item = top;
+            sift_down_to_bottom(0);
+        }
+        return item;
+    }
+};
+
+constexpr int kReplayWarps = 4;
+
+// warp-cooperative: feed `cnt` candidates starting at `src` (global memory) through add_doc
+__device__ void replay_run(Heap& hp, const rg_hit* __restrict__ src, uint32_t cnt) {
+    const int lane = lane_id();
+    for (uint32_t base = 0; base < cnt; base += 32) {
+        const uint32_t i = base + lane;
+        const bool has = i < cnt;
+        rg_hit c = has ? src[i] : rg_hit{0, 0.f};
+        uint32_t pending = __ballot_sync(0xffffffffu, has);
+        while (pending) {
+            const uint32_t n = hp.n;
+            const float root = n ? hp.data[0].score : 0.f;
+            const bool ok = has && ((pending >> lane) & 1u) && (n < hp.k || root < c.score);
+            const uint32_t acc = __ballot_sync(0xffffffffu, ok);
+            if (!acc) break;
+            const int l = __ffs(acc) - 1;
+            rg_hit pick;
+            pick.doc = __shfl_sync(0xffffffffu, c.doc, l);
+            pick.score = __shfl_sync(0xffffffffu, c.score, l);
+            if (lane == 0) hp.add_doc(pick);
+            __syncwarp();
+            hp.n = __shfl_sync(0xffffffffu, hp.n, 0);
+            pending &= ~((2u << l) - 1u);
+        }
+    }
+}
+
+// top_docs(): pop min(total_hits, len) times and reverse (top_docs.rs:55-65)
+__device__ void finish_sorted(Heap& hp, unsigned long long total, rg_hit* out, uint32_t* out_count,
+                              unsigned long long* out_total) {
+    if (lane_id() == 0) {
+        const uint32_t n = (uint32_t)min((unsigned long long)hp.n, total);
+        for (uint32_t i = 0; i < n; i++) out[n - 1 - i] = hp.pop();
+        *out_count = n;
+        *out_total = total;
+    }
+}
+
+__global__ void __launch_bounds__(kReplayWarps * 32)
+k_heap_replay(ReplayParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t g = blockIdx.x * kReplayWarps + warp;
+    if (g >= p.n_groups) return;
+    Heap hp;
+    hp.data = reinterpret_cast<rg_hit*>(smem_raw) + (size_t)warp * p.k;
+    hp.n = 0;
+    hp.k = p.k;
+    unsigned long long total = 0;
+    const CandRun* hdr = reinterpret_cast<const CandRun*>(p.cand_arena);
+    for (uint32_t item = p.group_item_begin[g]; item < p.group_item_begin[g + 1]; item++) {
+        total += p.item_matches[item];
+        uint32_t run = p.item_head[item];
+        while (run != kNone) {
+            const CandRun h = hdr[run];
+            replay_run(hp, p.cand_arena + run + 1, h.count);
+            run = h.next;
+        }
+    }
+    __syncwarp();
+    const uint32_t q = p.group_query[g];
+    if (p.leaf_records) {
+        // LeafTopDocs { docs: heap.into_vec(), total_hits } (top_docs.rs:203-213)
+        uint8_t* rec = p.leaf_records + (size_t)q * leaf_record_bytes(p.k);
+        if (lane == 0) {
+            reinterpret_cast<uint32_t*>(rec)[0] = hp.n;
+            reinterpret_cast<uint32_t*>(rec)[1] = 0;
+            reinterpret_cast<unsigned long long*>(rec)[1] = total;
+        }
+        rg_hit* dst = reinterpret_cast<rg_hit*>(rec + 16);
+        for (uint32_t i = lane; i < hp.n; i += 32) dst[i] = hp.data[i];
+    } else {
+        finish_sorted(hp, total, p.out_hits + (size_t)q * p.k, p.out_counts + q, p.out_total + q);
+    }
+}
+
+// finish_parallel (top_docs.rs:157-172): leaves in leaf order, each leaf's docs in heap-array
+// order through add_doc; total_hits summed.
+__global__ void __launch_bounds__(kReplayWarps * 32)
+k_merge_leaf_records(const uint8_t* __restrict__ records, uint32_t n_leaves, uint32_t n_queries,
+                     uint32_t k, rg_hit* out_hits, uint32_t* out_counts, unsigned long long* out_total) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x * kReplayWarps + warp;
+    if (q >= n_queries) return;
+    Heap hp;
+    hp.data = reinterpret_cast<rg_hit*>(smem_raw) + (size_t)warp * k;
+    hp.n = 0;
+    hp.k = k;
+    unsigned long long total = 0;
+    const size_t rb = leaf_record_bytes(k);
+    for (uint32_t leaf = 0; leaf < n_leaves; leaf++) {
+        const uint8_t* rec = records + ((size_t)leaf * n_queries + q) * rb;
+        const uint32_t n = reinterpret_cast<const uint32_t*>(rec)[0];
+        total += reinterpret_cast<const unsigned long long*>(rec)[1];
+        replay_run(hp, reinterpret_cast<const rg_hit*>(rec + 16), min(n, k));
+    }
+    __syncwarp();
+    finish_sorted(hp, total, out_hits + (size_t)q * k, out_counts + q, out_total + q);
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n) {
+    if (!n) return;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_eval_or, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrShared));
+        attr_set = true;
+    }
+    k_eval_or<<<n, kEvalThreads, sizeof(OrShared), st>>>(p, item_ids);
+}
+void launch_eval_and(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n) {
+    if (!n) return;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_eval_and, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AndShared));
+        attr_set = true;
+    }
+    k_eval_and<<<n, kEvalThreads, sizeof(AndShared), st>>>(p, item_ids);
+}
+void launch_heap_replay(cudaStream_t st, const ReplayParams& p) {
+    if (!p.n_groups) return;
+    const size_t smem = (size_t)kReplayWarps * p.k * sizeof(rg_hit);
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaFuncSetAttribute(k_heap_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = smem;
+    }
+    k_heap_replay<<<(p.n_groups + kReplayWarps - 1) / kReplayWarps, kReplayWarps * 32, smem, st>>>(p);
+}
+void launch_merge_leaf_records(cudaStream_t st, const uint8_t* records, uint32_t n_leaves,
+                               uint32_t n_queries, uint32_t k, rg_hit* out_hits,
+                               uint32_t* out_counts, unsigned long long* out_total) {
+    if (!n_queries) return;
+    const size_t smem = (size_t)kReplayWarps * k * sizeof(rg_hit);
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaFuncSetAttribute(k_merge_leaf_records, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = smem;
+    }
+    k_merge_leaf_records<<<(n_queries + kReplayWarps - 1) / kReplayWarps, kReplayWarps * 32, smem, st>>>(
+        records, n_leaves, n_queries, k, out_hits, out_counts, out_total);
+}
+
+}  // namespace rg

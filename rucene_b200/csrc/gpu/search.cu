@@ -1,13 +1,399 @@
-// search.cu — (stub, replaced by the real planner) batch search entry points.
+// search.cu — batch planning and the search entry points of include/rucene_gpu.h.
+//
+// Host side of IndexSearcher::search for a batch (search/searcher.rs:487-525): what
+// BooleanQuery::build / BooleanWeight::create_scorer decide per (query, leaf)
+// (search/query/boolean_query.rs:40-87,196-279) becomes a list of work items
+// (query, segment, docid range) evaluated by k_eval_or / k_eval_and, followed by the exact
+// TopDocsCollector replay.  Plan shapes outside the accelerated path return RG_EUNSUPPORTED so
+// the caller can fall through to DefaultIndexSearcher, exactly like an unsupported Query would.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+
 #include "engine.hpp"
+
 using namespace rg;
-extern "C" {
-int rg_search_batch(rg_engine*, const rg_query*, uint32_t, const rg_clause*, uint32_t, const rg_search_params*, rg_hit*, uint32_t*, uint64_t*) { g_last_error = "not built yet"; return RG_EUNSUPPORTED; }
-int rg_batch_prepare(rg_engine*, const rg_query*, uint32_t, const rg_clause*, uint32_t, const rg_search_params*, rg_batch**) { return RG_EUNSUPPORTED; }
-int rg_batch_run(rg_engine*, rg_batch*) { return RG_EUNSUPPORTED; }
-int rg_batch_fetch(rg_engine*, rg_batch*, rg_hit*, uint32_t*, uint64_t*) { return RG_EUNSUPPORTED; }
-void rg_batch_destroy(rg_engine*, rg_batch*) {}
-int rg_batch_stats(rg_engine*, rg_batch*, uint64_t*) { return RG_EUNSUPPORTED; }
-int rg_batch_leaf_records(rg_engine*, rg_batch*, void**, size_t*) { return RG_EUNSUPPORTED; }
-int rg_merge_leaf_records(rg_engine*, const void*, uint32_t, uint32_t, uint32_t, rg_hit*, uint32_t*, uint64_t*) { return RG_EUNSUPPORTED; }
+
+struct rg_batch {
+    uint32_t n_queries = 0, k = 0, mode = 0;
+    float k1 = 1.2f;
+    uint32_t n_items = 0, n_or = 0, n_and = 0, n_groups = 0, n_leaves = 0;
+    DevBuf<WorkItem> items;
+    DevBuf<ItemClause> clauses;
+    DevBuf<uint32_t> or_ids, and_ids;
+    DevBuf<uint32_t> group_item_begin, group_out;
+    DevBuf<uint32_t> item_head, item_matches, item_theta;
+    DevBuf<unsigned long long> arena_next;  // [0] bump pointer, [1] error flag (as u32 view)
+    DevBuf<rg_hit> out_hits;
+    DevBuf<uint32_t> out_counts;
+    DevBuf<unsigned long long> out_total;
+    DevBuf<uint8_t> leaf_records;
+    uint64_t postings = 0, algo_bytes = 0;
+    uint32_t kernels_per_run = 0;
+    bool ran = false;
+};
+
+namespace {
+
+struct HostPlan {
+    std::vector<WorkItem> items;
+    std::vector<ItemClause> clauses;
+    std::vector<uint32_t> or_ids, and_ids;
+    std::vector<uint32_t> group_item_begin, group_out;
+    uint64_t postings = 0, algo_bytes = 0;
+};
+
+struct QShape {
+    int type = -1;  // kTypeOr / kTypeAnd
+    std::vector<uint32_t> clause_idx;  // indices into the caller's clause array, evaluation order
+};
+
+// BooleanQuery::build + BooleanWeight::create_scorer wiring for the accelerated shapes.
+QShape classify(const rg_query& q, const rg_clause* clauses, uint32_t n_clauses_total) {
+    if ((uint64_t)q.clause_begin + q.n_clauses > n_clauses_total) throw ArgError("query clause range out of bounds");
+    QShape s;
+    if (!(q.flags & RG_Q_BOOLEAN)) {
+        if (q.n_clauses != 1) throw ArgError("a bare TermQuery has exactly one clause");
+        s.type = kTypeOr;  // TermScorer == one-clause disjunction: 0.0f + s == s
+        s.clause_idx.push_back(q.clause_begin);
+        return s;
+    }
+    std::vector<uint32_t> musts, shoulds, must_nots;
+    for (uint32_t i = 0; i < q.n_clauses; i++) {
+        const rg_clause& c = clauses[q.clause_begin + i];
+        if (c.occur == RG_MUST) musts.push_back(q.clause_begin + i);
+        else if (c.occur == RG_SHOULD) shoulds.push_back(q.clause_begin + i);
+        else if (c.occur == RG_MUST_NOT) must_nots.push_back(q.clause_begin + i);
+        else throw ArgError("unknown occur");
+    }
+    int32_t msm = q.min_should_match > 0 ? q.min_should_match : (musts.empty() ? 1 : 0);
+    if (musts.size() + shoulds.size() + must_nots.size() == 0)
+        throw ArgError("boolean query should at least contain one inner query!");
+    if (!must_nots.empty())
+        throw Unsupported("MUST_NOT clauses (ReqNotScorer) are not accelerated yet");
+    if (!musts.empty() && !shoulds.empty())
+        throw Unsupported("MUST+SHOULD (ReqOptScorer) is not accelerated yet");
+    if (musts.size() + shoulds.size() == 1) {  // collapses to the clause itself (:66-75)
+        s.type = kTypeOr;
+        s.clause_idx = musts.empty() ? shoulds : musts;
+        return s;
+    }
+    if (!musts.empty()) {
+        if (musts.size() > (size_t)kMaxTerms) throw Unsupported("more than 9 MUST clauses");
+        s.type = kTypeAnd;
+        s.clause_idx = musts;
+        return s;
+    }
+    if (shoulds.size() >= 10) throw Unsupported(">= 10 SHOULD clauses use DisiPriorityQueue");
+    if (msm > 1) throw Unsupported("min_should_match > 1 is not accelerated yet");
+    s.type = kTypeOr;
+    s.clause_idx = shoulds;
+    return s;
 }
+
+void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const rg_clause* clauses,
+                uint32_t n_clauses, uint32_t mode, HostPlan& hp) {
+    const uint32_t n_caches = (uint32_t)(e->h_caches.size() / 256);
+    const uint64_t range_postings = e->cfg.range_postings;
+    const uint32_t n_segs = (uint32_t)e->segs.size();
+    for (uint32_t qi = 0; qi < n_queries; qi++) {
+        const QShape shape = classify(queries[qi], clauses, n_clauses);
+        for (uint32_t ci : shape.clause_idx)
+            if (clauses[ci].cache_id >= n_caches) throw ArgError("clause refers to an unset norm cache");
+        bool group_open = false;
+        for (uint32_t si = 0; si < n_segs; si++) {
+            const Segment& seg = e->segs[si];
+            // resolve clauses against this leaf
+            std::vector<uint32_t> present;
+            bool dead = false;
+            for (uint32_t ci : shape.clause_idx) {
+                const uint32_t t = clauses[ci].term_id;
+                const int32_t df = t < seg.host_terms.size() ? seg.host_terms[t].doc_freq : 0;
+                if (df > 0) present.push_back(ci);
+                else if (shape.type == kTypeAnd) dead = true;  // create_scorer -> None (:201-206)
+            }
+            const bool new_group = mode == RG_MODE_SEARCH_PARALLEL || !group_open;
+            if (dead || present.empty()) continue;
+            uint64_t cost = 0, bytes = 0, total_df = 0;
+            if (shape.type == kTypeAnd) {
+                // ConjunctionScorer::new: stable sort by cost() = doc_freq (:30)
+                std::stable_sort(present.begin(), present.end(), [&](uint32_t a, uint32_t b) {
+                    return seg.host_terms[clauses[a].term_id].doc_freq < seg.host_terms[clauses[b].term_id].doc_freq;
+                });
+                cost = (uint64_t)seg.host_terms[clauses[present[0]].term_id].doc_freq;
+                const TermHost& lead = seg.host_terms[clauses[present[0]].term_id];
+                bytes = lead.enc_bytes + cost;
+                for (size_t i = 1; i < present.size(); i++) {  // upper bound: min(list, one block per lead doc)
+                    const TermHost& th = seg.host_terms[clauses[present[i]].term_id];
+                    const uint64_t per_block = th.n_blocks ? th.enc_bytes / th.n_blocks : th.enc_bytes;
+                    bytes += std::min<uint64_t>(th.enc_bytes, cost * per_block);
+                }
+                total_df = cost;
+            } else {
+                for (uint32_t ci : present) {
+                    const TermHost& th = seg.host_terms[clauses[ci].term_id];
+                    cost += (uint64_t)th.doc_freq;
+                    bytes += th.enc_bytes + 12ull * th.n_blocks;  // + skip table / descriptors
+                }
+                bytes += cost;  // one norm byte per scored posting
+                total_df = cost;
+            }
+            hp.postings += total_df;
+            hp.algo_bytes += bytes;
+            const uint32_t clause_begin = (uint32_t)hp.clauses.size();
+            for (uint32_t ci : present)
+                hp.clauses.push_back(ItemClause{clauses[ci].term_id, clauses[ci].weight, clauses[ci].cache_id, 0});
+            uint64_t R = (cost + range_postings - 1) / range_postings;
+            R = std::max<uint64_t>(1, std::min<uint64_t>(R, (uint64_t)(seg.max_doc + kBlock - 1) / kBlock));
+            if (new_group) {
+                // SEARCH: one heap per query over all its leaves; SEARCH_PARALLEL: one per leaf
+                hp.group_out.push_back(mode == RG_MODE_SEARCH_PARALLEL ? si * n_queries + qi : qi);
+                group_open = true;
+            }
+            for (uint64_t r = 0; r < R; r++) {
+                WorkItem it{};
+                it.query = qi;
+                it.seg = (uint16_t)si;
+                it.type = (uint8_t)shape.type;
+                it.n_terms = (uint8_t)present.size();
+                it.lo = (int32_t)((uint64_t)seg.max_doc * r / R);
+                it.hi = (int32_t)((uint64_t)seg.max_doc * (r + 1) / R);
+                it.clause_begin = clause_begin;
+                it.flags = (r == 0 && new_group) ? 1u : 0u;
+                const uint32_t idx = (uint32_t)hp.items.size();
+                hp.items.push_back(it);
+                (shape.type == kTypeAnd ? hp.and_ids : hp.or_ids).push_back(idx);
+            }
+        }
+    }
+    // heap groups = contiguous item runs starting at chain-start items
+    for (uint32_t i = 0; i < hp.items.size(); i++)
+        if (hp.items[i].flags & 1u) hp.group_item_begin.push_back(i);
+    hp.group_item_begin.push_back((uint32_t)hp.items.size());
+    if (hp.group_item_begin.size() != hp.group_out.size() + 1) throw ArgError("internal: group bookkeeping mismatch");
+}
+
+template <class T>
+void up(DevBuf<T>& d, const std::vector<T>& h, cudaStream_t st) {
+    d.alloc(std::max<size_t>(1, h.size()));
+    if (!h.empty()) RG_CUDA_CHECK(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+}
+
+void ensure_arena(rg_engine* e) {
+    if (e->cand_arena.p) return;
+    size_t free_b = 0, total_b = 0;
+    RG_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    uint64_t want = e->cfg.cand_arena_bytes ? e->cfg.cand_arena_bytes : std::min<uint64_t>(4ull << 30, free_b / 8);
+    want = std::min<uint64_t>(want, (uint64_t)0xfffffff0u * sizeof(rg_hit));
+    want = std::max<uint64_t>(want, 1ull << 20);
+    e->cand_arena.alloc(want / sizeof(rg_hit));
+}
+
+}  // namespace
+
+#define RG_TRY try {
+#define RG_CATCH \
+    }            \
+    catch (...) { return translate_exception(); }
+
+extern "C" {
+
+int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
+                     const rg_clause* clauses, uint32_t n_clauses, const rg_search_params* p,
+                     rg_batch** out) {
+    RG_TRY
+    if (!e || !p || !out || (n_queries && !queries) || (n_clauses && !clauses)) throw ArgError("null argument");
+    *out = nullptr;
+    if (p->k == 0) throw ArgError("k must be >= 1");
+    if (p->k > 1024) throw Unsupported("k > 1024 is not accelerated");
+    if (p->mode != RG_MODE_SEARCH && p->mode != RG_MODE_SEARCH_PARALLEL) throw ArgError("bad mode");
+    if (e->segs.empty()) throw ArgError("no segment uploaded");
+    RG_CUDA_CHECK(cudaSetDevice(e->device));
+    e->sync_tables();
+    ensure_arena(e);
+    HostPlan hp;
+    plan_batch(e, queries, n_queries, clauses, n_clauses, p->mode, hp);
+    std::unique_ptr<rg_batch> b(new rg_batch());
+    b->n_queries = n_queries;
+    b->k = p->k;
+    b->mode = p->mode;
+    b->k1 = p->k1;
+    b->n_items = (uint32_t)hp.items.size();
+    b->n_or = (uint32_t)hp.or_ids.size();
+    b->n_and = (uint32_t)hp.and_ids.size();
+    b->n_groups = (uint32_t)hp.group_out.size();
+    b->n_leaves = (uint32_t)e->segs.size();
+    b->postings = hp.postings;
+    b->algo_bytes = hp.algo_bytes + (uint64_t)n_queries * p->k * sizeof(rg_hit);
+    cudaStream_t st = e->stream;
+    up(b->items, hp.items, st);
+    up(b->clauses, hp.clauses, st);
+    up(b->or_ids, hp.or_ids, st);
+    up(b->and_ids, hp.and_ids, st);
+    up(b->group_item_begin, hp.group_item_begin, st);
+    up(b->group_out, hp.group_out, st);
+    b->item_head.alloc(std::max<uint32_t>(1, b->n_items));
+    b->item_matches.alloc(std::max<uint32_t>(1, b->n_items));
+    b->item_theta.alloc(std::max<uint32_t>(1, b->n_items));
+    b->arena_next.alloc(2);
+    b->out_hits.alloc((size_t)std::max<uint32_t>(1, n_queries) * p->k);
+    b->out_counts.alloc(std::max<uint32_t>(1, n_queries));
+    b->out_total.alloc(std::max<uint32_t>(1, n_queries));
+    if (p->mode == RG_MODE_SEARCH_PARALLEL)
+        b->leaf_records.alloc((size_t)b->n_leaves * std::max<uint32_t>(1, n_queries) * leaf_record_bytes(p->k));
+    b->kernels_per_run = (b->n_or ? 1 : 0) + (b->n_and ? 1 : 0) + (b->n_groups ? 1 : 0) +
+                         (p->mode == RG_MODE_SEARCH_PARALLEL ? 1 : 0);
+    RG_CUDA_CHECK(cudaStreamSynchronize(st));
+    *out = b.release();
+    return RG_OK;
+    RG_CATCH
+}
+
+int rg_batch_run(rg_engine* e, rg_batch* b) {
+    RG_TRY
+    if (!e || !b) throw ArgError("null argument");
+    cudaStream_t st = e->stream;
+    RG_CUDA_CHECK(cudaEventRecord(e->ev0, st));
+    RG_CUDA_CHECK(cudaMemsetAsync(b->item_head.p, 0xff, b->item_head.bytes(), st));
+    RG_CUDA_CHECK(cudaMemsetAsync(b->item_matches.p, 0, b->item_matches.bytes(), st));
+    RG_CUDA_CHECK(cudaMemsetAsync(b->item_theta.p, 0, b->item_theta.bytes(), st));
+    RG_CUDA_CHECK(cudaMemsetAsync(b->arena_next.p, 0, b->arena_next.bytes(), st));
+    RG_CUDA_CHECK(cudaMemsetAsync(b->out_hits.p, 0, b->out_hits.bytes(), st));
+    RG_CUDA_CHECK(cudaMemsetAsync(b->out_counts.p, 0, b->out_counts.bytes(), st));
+    RG_CUDA_CHECK(cudaMemsetAsync(b->out_total.p, 0, b->out_total.bytes(), st));
+    if (b->leaf_records.p) RG_CUDA_CHECK(cudaMemsetAsync(b->leaf_records.p, 0, b->leaf_records.bytes(), st));
+    EvalParams ep{};
+    ep.segs = e->d_segs.p;
+    ep.items = b->items.p;
+    ep.clauses = b->clauses.p;
+    ep.caches = e->d_caches.p;
+    ep.n_items = b->n_items;
+    ep.k = b->k;
+    ep.k1 = b->k1;
+    ep.cand_arena = e->cand_arena.p;
+    ep.arena_slots = (uint32_t)std::min<size_t>(e->cand_arena.n, 0xfffffff0u);
+    ep.arena_next = b->arena_next.p;
+    ep.item_head = b->item_head.p;
+    ep.item_matches = b->item_matches.p;
+    ep.item_theta = b->item_theta.p;
+    ep.error_flag = reinterpret_cast<uint32_t*>(b->arena_next.p + 1);
+    launch_eval_or(st, ep, b->or_ids.p, b->n_or);
+    RG_CUDA_CHECK(cudaGetLastError());
+    launch_eval_and(st, ep, b->and_ids.p, b->n_and);
+    RG_CUDA_CHECK(cudaGetLastError());
+    ReplayParams rp{};
+    rp.cand_arena = e->cand_arena.p;
+    rp.item_head = b->item_head.p;
+    rp.item_matches = b->item_matches.p;
+    rp.group_item_begin = b->group_item_begin.p;
+    rp.group_query = b->group_out.p;
+    rp.n_groups = b->n_groups;
+    rp.k = b->k;
+    rp.out_hits = b->out_hits.p;
+    rp.out_counts = b->out_counts.p;
+    rp.out_total = b->out_total.p;
+    rp.leaf_records = b->mode == RG_MODE_SEARCH_PARALLEL ? b->leaf_records.p : nullptr;
+    launch_heap_replay(st, rp);
+    RG_CUDA_CHECK(cudaGetLastError());
+    if (b->mode == RG_MODE_SEARCH_PARALLEL && b->n_leaves >= 1) {
+        launch_merge_leaf_records(st, b->leaf_records.p, b->n_leaves, b->n_queries, b->k, b->out_hits.p,
+                                  b->out_counts.p, b->out_total.p);
+        RG_CUDA_CHECK(cudaGetLastError());
+    }
+    e->launches += b->kernels_per_run;
+    RG_CUDA_CHECK(cudaEventRecord(e->ev1, st));
+    b->ran = true;
+    return RG_OK;
+    RG_CATCH
+}
+
+int rg_batch_fetch(rg_engine* e, rg_batch* b, rg_hit* out_hits, uint32_t* out_counts,
+                   uint64_t* out_total_hits) {
+    RG_TRY
+    if (!e || !b || !out_hits || !out_counts || !out_total_hits) throw ArgError("null argument");
+    if (!b->ran) throw ArgError("rg_batch_fetch before rg_batch_run");
+    cudaStream_t st = e->stream;
+    unsigned long long flags[2] = {0, 0};
+    RG_CUDA_CHECK(cudaMemcpyAsync(out_hits, b->out_hits.p, (size_t)b->n_queries * b->k * sizeof(rg_hit), cudaMemcpyDeviceToHost, st));
+    RG_CUDA_CHECK(cudaMemcpyAsync(out_counts, b->out_counts.p, (size_t)b->n_queries * 4, cudaMemcpyDeviceToHost, st));
+    RG_CUDA_CHECK(cudaMemcpyAsync(out_total_hits, b->out_total.p, (size_t)b->n_queries * 8, cudaMemcpyDeviceToHost, st));
+    RG_CUDA_CHECK(cudaMemcpyAsync(flags, b->arena_next.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    RG_CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&e->last_run_ms, e->ev0, e->ev1);
+    cudaGetLastError();
+    if (flags[1] & 1ull) throw OutOfArena("candidate arena exhausted: split the batch or raise cand_arena_bytes");
+    return RG_OK;
+    RG_CATCH
+}
+
+void rg_batch_destroy(rg_engine*, rg_batch* b) { delete b; }
+
+int rg_batch_stats(rg_engine* e, rg_batch* b, uint64_t out[8]) {
+    RG_TRY
+    if (!e || !b || !out) throw ArgError("null argument");
+    unsigned long long used = 0;
+    if (b->ran) {
+        RG_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        RG_CUDA_CHECK(cudaMemcpy(&used, b->arena_next.p, 8, cudaMemcpyDeviceToHost));
+    }
+    out[0] = b->n_items;
+    out[1] = b->postings;
+    out[2] = b->algo_bytes;
+    out[3] = used;
+    out[4] = b->kernels_per_run;
+    out[5] = used;
+    out[6] = b->n_or;
+    out[7] = b->n_and;
+    return RG_OK;
+    RG_CATCH
+}
+
+int rg_search_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries,
+                    const rg_clause* clauses, uint32_t n_clauses, const rg_search_params* p,
+                    rg_hit* out_hits, uint32_t* out_counts, uint64_t* out_total_hits) {
+    rg_batch* b = nullptr;
+    int rc = rg_batch_prepare(e, queries, n_queries, clauses, n_clauses, p, &b);
+    if (rc != RG_OK) return rc;
+    rc = rg_batch_run(e, b);
+    if (rc == RG_OK) rc = rg_batch_fetch(e, b, out_hits, out_counts, out_total_hits);
+    rg_batch_destroy(e, b);
+    return rc;
+}
+
+int rg_batch_leaf_records(rg_engine* e, rg_batch* b, void** dev_ptr, size_t* record_bytes) {
+    RG_TRY
+    if (!e || !b || !dev_ptr || !record_bytes) throw ArgError("null argument");
+    if (b->mode != RG_MODE_SEARCH_PARALLEL) throw ArgError("leaf records exist only in RG_MODE_SEARCH_PARALLEL");
+    *dev_ptr = b->leaf_records.p;
+    *record_bytes = leaf_record_bytes(b->k);
+    return RG_OK;
+    RG_CATCH
+}
+
+int rg_merge_leaf_records(rg_engine* e, const void* dev_records_all, uint32_t n_leaves,
+                          uint32_t n_queries, uint32_t k, rg_hit* out_hits, uint32_t* out_counts,
+                          uint64_t* out_total_hits) {
+    RG_TRY
+    if (!e || !dev_records_all || !out_hits || !out_counts || !out_total_hits) throw ArgError("null argument");
+    if (k == 0 || k > 1024) throw ArgError("k out of range");
+    cudaStream_t st = e->stream;
+    DevBuf<rg_hit> d_hits;
+    DevBuf<uint32_t> d_counts;
+    DevBuf<unsigned long long> d_total;
+    d_hits.alloc((size_t)std::max<uint32_t>(1, n_queries) * k);
+    d_counts.alloc(std::max<uint32_t>(1, n_queries));
+    d_total.alloc(std::max<uint32_t>(1, n_queries));
+    RG_CUDA_CHECK(cudaMemsetAsync(d_hits.p, 0, d_hits.bytes(), st));
+    launch_merge_leaf_records(st, static_cast<const uint8_t*>(dev_records_all), n_leaves, n_queries, k,
+                              d_hits.p, d_counts.p, d_total.p);
+    RG_CUDA_CHECK(cudaGetLastError());
+    e->launches++;
+    RG_CUDA_CHECK(cudaMemcpyAsync(out_hits, d_hits.p, (size_t)n_queries * k * sizeof(rg_hit), cudaMemcpyDeviceToHost, st));
+    RG_CUDA_CHECK(cudaMemcpyAsync(out_counts, d_counts.p, (size_t)n_queries * 4, cudaMemcpyDeviceToHost, st));
+    RG_CUDA_CHECK(cudaMemcpyAsync(out_total_hits, d_total.p, (size_t)n_queries * 8, cudaMemcpyDeviceToHost, st));
+    RG_CUDA_CHECK(cudaStreamSynchronize(st));
+    return RG_OK;
+    RG_CATCH
+}
+
+}  // extern "C"

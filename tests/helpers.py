@@ -76,3 +76,34 @@ def distinct_query_terms(rng, n_terms, n_queries, t_min, t_max):
                 s.append(c)
         out.append(s)
     return out
+
+
+def to_queries(specs):
+    """specs (see oracle_binding.make_queries) -> rucene_b200.search Query objects."""
+    from rucene_b200 import search as S
+    out = []
+    for s in specs:
+        if s[0] == "term":
+            out.append(S.TermQuery.new(S.Term.new("body", s[1]), s[2] if len(s) > 2 else 1.0, None))
+        else:
+            musts, shoulds, nots = [], [], []
+            for cl in s[1]:
+                q = S.TermQuery.new(S.Term.new("body", cl[1]), cl[2] if len(cl) > 2 else 1.0, None)
+                (musts if cl[0] == ob.MUST else shoulds if cl[0] == ob.SHOULD else nots).append(q)
+            out.append(S.BooleanQuery.build(musts, shoulds, [], nots, s[2] if len(s) > 2 else 0))
+    return out
+
+
+def assert_same_topdocs(got, want, label=""):
+    """got/want: (hits, counts, total) triples; bit-exact docids, scores, order and total_hits."""
+    gh, gc, gt = got
+    wh, wc, wt = want
+    assert np.array_equal(gt, wt), (label, "total_hits", np.nonzero(gt != wt)[0][:5], gt[:5], wt[:5])
+    assert np.array_equal(gc, wc), (label, "counts")
+    for i in range(len(gc)):
+        n = int(wc[i])
+        if not np.array_equal(gh[i][:n]["doc"], wh[i][:n]["doc"]):
+            j = int(np.nonzero(gh[i][:n]["doc"] != wh[i][:n]["doc"])[0][0])
+            raise AssertionError((label, "query", i, "rank", j, gh[i][j], wh[i][j]))
+        assert np.array_equal(gh[i][:n]["score"].view(np.uint32), wh[i][:n]["score"].view(np.uint32)), \
+            (label, "scores of query", i)

@@ -1,0 +1,146 @@
+"""GPU parity: IndexSearcher::search through the C ABI vs the oracle — TopDocs identical
+(docids bit-exact, BM25 scores bit-exact f32 — tighter than the 1e-5 relative the north star
+allows —, same order under ties, same total_hits)."""
+import numpy as np
+import pytest
+
+import helpers
+import oracle_binding as ob
+from rucene_b200 import codec, engine, search
+
+pytestmark = pytest.mark.gpu
+
+DFS = [0, 1, 2, 100, 127, 128, 129, 255, 256, 257, 1000, 5000, 20000, 40000, 59000]
+
+
+def _mixed_specs(rng, n_terms, n, kinds=("term", "and", "or")):
+    specs = []
+    for i in range(n):
+        kind = kinds[i % len(kinds)]
+        if kind == "term":
+            specs.append(("term", int(rng.integers(0, n_terms))))
+        else:
+            t = int(rng.integers(2, 6))
+            terms = rng.choice(n_terms, size=t, replace=False)
+            occ = ob.MUST if kind == "and" else ob.SHOULD
+            specs.append(("bool", [(occ, int(x)) for x in terms], 0))
+    return specs
+
+
+def _run_both(segs, specs, k, mode=0, range_postings=0, threads=4):
+    ix = helpers.oracle_index(segs)
+    q, c = ob.make_queries(specs)
+    want = ix.search_batch(q, c, k, parallel_mode=mode, n_threads=threads)
+    s = search.GpuIndexSearcher(search.IndexReader(segs), range_postings=range_postings)
+    try:
+        got = s.search_batch(helpers.to_queries(specs), k, mode=mode)
+    finally:
+        s.engine.close()
+    return got, want
+
+
+@pytest.mark.parametrize("version", [1, 0])
+@pytest.mark.parametrize("k", [1, 10, 100])
+def test_small_index_every_shape(version, k):
+    rng = np.random.default_rng(1000 + version)
+    seg, _ = helpers.build_segment(rng, 60000, DFS, doc_version=version, dense_terms=(11,))
+    specs = [("term", t) for t in range(len(DFS))]
+    specs += _mixed_specs(rng, len(DFS), 90, kinds=("and", "or"))
+    specs += [("bool", [(ob.SHOULD, 12, 2.0), (ob.SHOULD, 3, 0.5)], 0),
+              ("bool", [(ob.MUST, 14), (ob.MUST, 13), (ob.MUST, 12), (ob.MUST, 11)], 0),
+              ("bool", [(ob.MUST, 14), (ob.MUST, 0)], 0),
+              ("bool", [(ob.SHOULD, 0), (ob.SHOULD, 1)], 0),
+              ("bool", [(ob.SHOULD, 7)], 0), ("bool", [(ob.MUST, 9)], 0)]
+    got, want = _run_both([seg], specs, k)
+    helpers.assert_same_topdocs(got, want, "v%d k%d" % (version, k))
+
+
+def test_ranges_split_queries_across_ctas():
+    """Tiny range_postings forces many (query, docid-range) work items per query: candidate
+    lists, theta chaining and the replay must still reproduce the sequential collector."""
+    rng = np.random.default_rng(7)
+    seg, _ = helpers.build_segment(rng, 200000, [150000, 90000, 30000, 5000, 300, 1])
+    specs = _mixed_specs(rng, 6, 60)
+    for rp in (1 << 18, 4096, 700):
+        got, want = _run_both([seg], specs, 10, range_postings=rp)
+        helpers.assert_same_topdocs(got, want, "range_postings=%d" % rp)
+
+
+def test_score_ties_follow_heap_layout():
+    """All postings share freq and norm => massive score ties; which docs survive and in what
+    order is decided by the BinaryHeap layout, not by docid."""
+    max_doc = 50000
+    w = codec.PostingsWriter(doc_version=1, max_doc=max_doc)
+    rng = np.random.default_rng(3)
+    for df in (30000, 12000, 700):
+        docs = np.sort(rng.choice(max_doc, df, replace=False)).astype(np.int32)
+        w.add_term(docs, np.ones(df, np.int32))
+    seg = w.finish(norms=np.full(max_doc, 120, np.uint8))
+    specs = [("term", 0), ("term", 1), ("term", 2),
+             ("bool", [(ob.SHOULD, 0), (ob.SHOULD, 1)], 0),
+             ("bool", [(ob.MUST, 0), (ob.MUST, 1)], 0),
+             ("bool", [(ob.SHOULD, 0), (ob.SHOULD, 1), (ob.SHOULD, 2)], 0)]
+    for k in (3, 10, 100):
+        for rp in (0, 2000):
+            got, want = _run_both([seg], specs, k, range_postings=rp)
+            helpers.assert_same_topdocs(got, want, "ties k=%d rp=%d" % (k, rp))
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_multi_segment_and_live_docs(mode):
+    """Several leaves on one GPU: sequential-leaf collector (mode 0) and search_parallel's
+    per-leaf heaps merged in leaf order (mode 1); statistics from the largest leaf only."""
+    rng = np.random.default_rng(11 + mode)
+    dfs = [0, 1, 90, 128, 400, 3000, 9000, 20000]
+    segs = []
+    for s, md in enumerate((30000, 52000, 41000)):
+        d = list(dfs)
+        if s == 1:
+            d[4] = 0      # term absent from the largest leaf (the one that supplies doc_freq)
+        if s == 2:
+            d[6] = 0
+        seg, _ = helpers.build_segment(rng, md, d, live_fraction=0.8 if s != 0 else None)
+        segs.append(seg)
+    specs = [("term", t) for t in range(len(dfs))] + _mixed_specs(rng, len(dfs), 60, kinds=("and", "or"))
+    got, want = _run_both(segs, specs, 10, mode=mode, range_postings=3000)
+    helpers.assert_same_topdocs(got, want, "mode %d" % mode)
+
+
+def test_synthetic_zipf_index_c3_c4_shapes():
+    """Scaled-down BASELINE configs 3 and 4: Zipfian synthetic segment, log-uniform query terms."""
+    seg = codec.synth_segment(0x5EED0001, 300000, 5000, doc_version=1)
+    rng = np.random.default_rng(0x5EED0003)
+    and_q = helpers.distinct_query_terms(rng, 5000, 48, 2, 2)
+    or_q = helpers.distinct_query_terms(rng, 5000, 48, 5, 5)
+    specs = [("bool", [(ob.MUST, t) for t in ts], 0) for ts in and_q]
+    specs += [("bool", [(ob.SHOULD, t) for t in ts], 0) for ts in or_q]
+    got, want = _run_both([seg], specs, 10)
+    helpers.assert_same_topdocs(got, want, "k=10")
+    got, want = _run_both([seg], specs, 100, range_postings=20000)
+    helpers.assert_same_topdocs(got, want, "k=100")
+
+
+def test_reference_style_api():
+    """Reads like examples/example.rs:111-117."""
+    rng = np.random.default_rng(5)
+    seg, posts = helpers.build_segment(rng, 10000, [1666, 40, 7])
+    reader = search.IndexReader([seg], term_ids={("body", b"hello"): 0, ("body", b"world"): 1})
+    searcher = search.GpuIndexSearcher(reader)
+    try:
+        query = search.TermQuery.new(search.Term.new("body", b"hello"), 1.0, None)
+        collector = search.TopDocsCollector.new(10)
+        searcher.search(query, collector)
+        top = collector.top_docs()
+        assert top.total_hits() == 1666 and len(top.score_docs()) == 10
+        scores = [d.score for d in top.score_docs()]
+        assert scores == sorted(scores, reverse=True)
+        collector = search.TopDocsCollector.new(10)
+        searcher.search(search.TermQuery.new(search.Term.new("body", b"absent"), 1.0, None), collector)
+        assert collector.top_docs().total_hits() == 0 and collector.top_docs().score_docs() == []
+        q = search.BooleanQuery.build([query], [search.TermQuery.new(search.Term.new("body", b"world"))], [], [], 0)
+        with pytest.raises(engine.Unsupported):   # MUST+SHOULD (ReqOptScorer) is a "next" row
+            searcher.search(q, search.TopDocsCollector.new(10))
+        with pytest.raises(search.IllegalArgument):
+            search.BooleanQuery.build([], [], [], [], 0)
+    finally:
+        searcher.engine.close()
