@@ -404,6 +404,8 @@ void build_segment(rg_engine* e, Segment& seg, int32_t doc_base, int32_t max_doc
             seg.host_terms[t].doc_freq = td.doc_freq;
             seg.host_terms[t].n_blocks = tp.n_blocks;
             seg.host_terms[t].enc_bytes = tp.enc_bytes;
+            seg.host_terms[t].tail_n = tp.tail_n;
+            seg.host_terms[t].tail_base = tp.tail_base;
             for (uint32_t i = 0; i < tp.n_blocks; i++, bi++, blk++) {
                 const BlockSrc& b = ch.blocks[bi];
                 const uint32_t du = part_units(b.doc_sz), fu = part_units(b.freq_sz);
@@ -518,7 +520,9 @@ int rg_engine_create(const rg_config* cfg, rg_engine** out) {
     e->stream = e->own_stream;
     RG_CUDA_CHECK(cudaEventCreate(&e->ev0));
     RG_CUDA_CHECK(cudaEventCreate(&e->ev1));
-    if (e->cfg.range_postings == 0) e->cfg.range_postings = 1u << 18;
+    RG_CUDA_CHECK(cudaEventCreate(&e->ev2));
+    RG_CUDA_CHECK(cudaEventCreate(&e->ev3));
+    if (e->cfg.range_postings == 0) e->cfg.range_postings = 1u << 15;  // one warp per work item
     *out = e.release();
     return RG_OK;
     RG_CATCH
@@ -530,6 +534,8 @@ void rg_engine_destroy(rg_engine* e) {
     cudaDeviceSynchronize();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->ev2) cudaEventDestroy(e->ev2);
+    if (e->ev3) cudaEventDestroy(e->ev3);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }

@@ -67,6 +67,8 @@ struct TermHost {
     int32_t doc_freq = 0;
     uint32_t n_blocks = 0;
     uint64_t enc_bytes = 0;  // encoded block bytes incl. header bytes + vint tail bytes
+    uint32_t tail_n = 0;     // postings in the vint tail (1 for a singleton)
+    int32_t tail_base = 0;   // last doc of the last full block
 };
 
 struct Segment {
@@ -107,7 +109,8 @@ struct EvalParams {
     uint32_t* item_theta;      // ordered-uint running k-th best, chained item -> item+1
     uint32_t* error_flag;      // bit0: arena exhausted
 };
-void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n);
+void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n,
+                    uint32_t max_terms);
 void launch_eval_and(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n);
 
 struct ReplayParams {
@@ -151,7 +154,7 @@ struct rg_engine {
     bool caches_dirty = true;
     rg::DevBuf<rg_hit> cand_arena;
     uint64_t launches = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     float last_decode_ms = -1.f, last_eval_ms = -1.f, last_replay_ms = -1.f, last_run_ms = -1.f;
     void sync_tables();  // (re)upload SegDev array and norm caches when dirty
 };

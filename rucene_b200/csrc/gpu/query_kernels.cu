@@ -24,6 +24,8 @@
 // passed (plus what earlier ranges of the same heap chain published), a lower bound of the heap
 // root at that point; docs with score <= theta can never enter, everything else is emitted in
 // docid order.  The replay over that superset is bit-identical to the reference, ties included.
+#include <algorithm>
+
 #include "engine.hpp"
 #include "unpack.cuh"
 
@@ -31,7 +33,7 @@ namespace rg {
 
 constexpr int kEvalThreads = 256;
 constexpr int kEvalWarps = kEvalThreads / 32;
-constexpr int kWin = 4096;              // docids per accumulator window (k_eval_or)
+constexpr int kWin = 2048;              // docids per accumulator window (k_eval_or)
 constexpr int kWinSteps = kWin / kEvalThreads;  // 16 slots per lane
 constexpr int kNewcMax = 512;           // candidate scores fed to the theta tracker per window
 constexpr int kMaxK = 1024;             // theta tracking / replay heap capacity
@@ -269,178 +271,341 @@ __device__ __forceinline__ bool is_live(const SegDev& seg, int doc) {
 }
 
 // ------------------------------------------------------------------------------------------
-// k_eval_or
+// k_eval_or  — one WARP per work item, no block-level synchronisation at all.
 // ------------------------------------------------------------------------------------------
-struct OrShared {
-    uint32_t acc[kWin];
-    int32_t tail_docs[kMaxTerms][kBlock];
-    int32_t tail_freqs[kMaxTerms][kBlock];
-    TermCtx term[kMaxTerms];
-    EmitShared emit;
-    int32_t next_doc;
+// A work item is a (query, segment, docid range) of ~32K postings.  Every clause is a *cached
+// block stream*: its current 128-posting block lives decoded AND scored in shared memory
+// (docids + BM25 scores), so each block is unpacked, prefix-summed and scored exactly once.
+// The warp walks the range in windows of kWw docids that always start at a real posting:
+//   for clause t = 0..T-1 (clause order): consume the stream's postings < window end, 32 per
+//       step, "acc[d] = acc[d] + s" in the warp-private accumulator window — pair order ==
+//       clause order == DisjunctionSumScorer::score_sum's f32 order; refill the stream (decode the
+//       next block / the vint tail) whenever it runs dry;
+//   scan the touched 32-doc steps in docid order -> total_hits, theta filter, candidates;
+//   next window start = min over clauses of their next cached docid (exact).
+constexpr int kOrWarps = 4;
+constexpr int kOrThreads = kOrWarps * 32;
+constexpr int kWw = 1024;            // docids per window
+constexpr int kNewcW = 64;
+
+struct WTerm {
+    const int32_t* blk_last;
+    const BlockDesc* blk_desc;
+    const float* cache;
+    uint32_t nb;        // full blocks
+    uint32_t cur;       // next block to decode (nb = vint tail, nb+1 = exhausted)
+    uint32_t n;         // valid entries in the stream cache
+    uint32_t pos;       // next unconsumed entry
+    uint32_t term_id;
+    float w1;           // weight * (k1 + 1)
 };
 
-__global__ void __launch_bounds__(kEvalThreads)
-k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids) {
+struct WarpShared {            // followed by topk[kcap] floats, then cdocs[T][128], cscores[T][128]
+    uint32_t acc[kWw];
+    WTerm term[kMaxTerms];
+    float newc[kNewcW];
+};
+
+// warp-level candidate emitter state (registers, uniform across lanes)
+struct WEmit {
+    float* topk;       // shared memory, kcap floats
+    uint32_t topk_n;
+    float theta_local;
+    uint32_t theta_in;
+    uint32_t run_slot, run_cap, run_cnt;
+    uint32_t matches;
+    bool overflow;
+};
+
+__device__ __forceinline__ void wtheta_recompute(const WEmit& em, uint32_t k, int lane, float& theta, int& argmin) {
+    float m = INFINITY;
+    int mi = 0;
+    for (uint32_t j = lane; j < k; j += 32) {
+        const float v = em.topk[j];
+        if (v < m) {
+            m = v;
+            mi = (int)j;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, m, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        if (om < m || (om == m && oi < mi)) {
+            m = om;
+            mi = oi;
+        }
+    }
+    theta = m;
+    argmin = mi;
+}
+
+// Emit one 32-doc step (docid order).  `newc`/`newc_n`: this window's candidate scores for the
+// theta tracker.
+__device__ __forceinline__ void wemit_step(WEmit& em, const EvalParams& p, uint32_t item_idx, int lane,
+                                           bool present, int gdoc, float score, float te, bool open,
+                                           float* newc, uint32_t& newc_n) {
+    const uint32_t pm = __ballot_sync(0xffffffffu, present);
+    if (!pm) return;
+    em.matches += __popc(pm);
+    const uint32_t cm = __ballot_sync(0xffffffffu, present && (open || score > te));
+    if (!cm || em.overflow) return;
+    const uint32_t c = __popc(cm);
+    CandRun* hdr = reinterpret_cast<CandRun*>(p.cand_arena);
+    if (em.run_slot == kNone || em.run_cnt + c > em.run_cap) {
+        uint32_t slot = 0;
+        const uint32_t cap = kRunMin;
+        if (lane == 0) {
+            const unsigned long long s64 = atomicAdd(p.arena_next, (unsigned long long)cap + 1ull);
+            slot = (s64 + cap + 1ull > (unsigned long long)p.arena_slots) ? kNone : (uint32_t)s64;
+            if (slot == kNone) atomicOr(p.error_flag, 1u);
+            else if (em.run_slot == kNone) p.item_head[item_idx] = slot;
+            else hdr[em.run_slot] = CandRun{slot, em.run_cnt};
+        }
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot == kNone) {
+            em.overflow = true;
+            return;
+        }
+        em.run_slot = slot;
+        em.run_cap = cap;
+        em.run_cnt = 0;
+    }
+    if ((cm >> lane) & 1u) {
+        const uint32_t r = __popc(cm & ((1u << lane) - 1u));
+        p.cand_arena[em.run_slot + 1 + em.run_cnt + r] = rg_hit{gdoc, score};
+        if (newc_n + r < (uint32_t)kNewcW) newc[newc_n + r] = score;
+    }
+    em.run_cnt += c;
+    newc_n += c;
+    if (lane == 0) hdr[em.run_slot] = CandRun{kNone, em.run_cnt};
+}
+
+__device__ __forceinline__ void wtheta_update(WEmit& em, uint32_t k, uint32_t kcap, int lane,
+                                              const float* newc, uint32_t newc_n, uint32_t* theta_out) {
+    const uint32_t n_new = min(newc_n, (uint32_t)kNewcW);
+    if (n_new == 0 || k > kcap) return;
+    __syncwarp();
+    float theta = em.theta_local;
+    int argmin = 0;
+    uint32_t n = em.topk_n;
+    if (n == k) wtheta_recompute(em, k, lane, theta, argmin);
+    for (uint32_t i = 0; i < n_new; i++) {
+        const float x = newc[i];
+        if (n < k) {
+            if (lane == 0) em.topk[n] = x;
+            n++;
+            __syncwarp();
+            if (n == k) wtheta_recompute(em, k, lane, theta, argmin);
+        } else if (x > theta) {
+            if (lane == 0) em.topk[argmin] = x;
+            __syncwarp();
+            wtheta_recompute(em, k, lane, theta, argmin);
+        }
+    }
+    em.topk_n = n;
+    em.theta_local = n == k ? theta : -INFINITY;
+    if (lane == 0) {
+        uint32_t ord = em.theta_in;
+        if (em.theta_local != -INFINITY) ord = max(ord, float_to_ordered(em.theta_local));
+        if (ord > kOrderedNegInf) atomicMax(theta_out, ord);
+    }
+}
+
+// Refill clause t's stream cache with its next block (or vint tail): unpack, docid scan, norm
+// gather, BM25 — once per block.  Entries outside [lo, hi) are trimmed.  Returns false when the
+// list is exhausted.  Warp-cooperative; all lanes must call it.
+__device__ __noinline__ bool stream_refill(const SegDev& seg, const EvalParams& p, WTerm& tc, int32_t* cd,
+                                           float* cs, int lo, int hi, int lane) {
+    for (;;) {
+        const uint32_t b = tc.cur;
+        if (b > tc.nb) return false;
+        int4 docs, freqs;
+        uint32_t n_in = kBlock;
+        if (b < tc.nb) {
+            const BlockDesc bd = tc.blk_desc[b];
+            const int base = b == 0 ? 0 : __ldg(tc.blk_last + b - 1);
+            const uint4* part = seg.arena + bd.off16;
+            const int4 dl = unpack4(part, (int)(bd.bits & 0xff), lane, seg.version, seg.sb_mask);
+            freqs = unpack4(part + ((bd.bits >> 16) & 0xff), (int)((bd.bits >> 8) & 0xff), lane, seg.version,
+                            seg.sb_mask);
+            docs = deltas_to_docs(dl, base);
+        } else {  // vint tail / singleton (posting_reader.rs:308-333, :545-547): lane 0 decodes
+            const TermDev td = seg.terms[tc.term_id];
+            n_in = td.tail_n;
+            if (n_in == 0) {
+                if (lane == 0) tc.cur = tc.nb + 1;
+                __syncwarp();
+                return false;
+            }
+            if (lane == 0) {
+                int32_t* fq = reinterpret_cast<int32_t*>(cs);
+                decode_tail(seg, td, cd, fq);
+            }
+            __syncwarp();
+            const int i0 = 4 * lane;
+            const int32_t* fq = reinterpret_cast<const int32_t*>(cs);
+            docs = make_int4(i0 < (int)n_in ? cd[i0] : kNoMoreDocs, i0 + 1 < (int)n_in ? cd[i0 + 1] : kNoMoreDocs,
+                             i0 + 2 < (int)n_in ? cd[i0 + 2] : kNoMoreDocs, i0 + 3 < (int)n_in ? cd[i0 + 3] : kNoMoreDocs);
+            freqs = make_int4(i0 < (int)n_in ? fq[i0] : 1, i0 + 1 < (int)n_in ? fq[i0 + 1] : 1,
+                              i0 + 2 < (int)n_in ? fq[i0 + 2] : 1, i0 + 3 < (int)n_in ? fq[i0 + 3] : 1);
+            __syncwarp();
+        }
+        const int d[4] = {docs.x, docs.y, docs.z, docs.w};
+        const int f[4] = {freqs.x, freqs.y, freqs.z, freqs.w};
+        float sc[4];
+        uint32_t below = 0, inside = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const bool ok = d[q] >= lo && d[q] < hi;
+            below += d[q] < lo;
+            inside += ok;
+            float s = 0.f;
+            if (ok) {
+                const float nrm = seg.norms ? __ldg(tc.cache + __ldg(seg.norms + d[q])) : p.k1;
+                s = bm25_score(tc.w1, (float)f[q], nrm);
+            }
+            sc[q] = s;
+        }
+        reinterpret_cast<int4*>(cd)[lane] = docs;
+        reinterpret_cast<float4*>(cs)[lane] = make_float4(sc[0], sc[1], sc[2], sc[3]);
+        below = __reduce_add_sync(0xffffffffu, below);
+        inside = __reduce_add_sync(0xffffffffu, inside);
+        const bool past_end = below + inside < n_in;  // some posting >= hi: nothing further in range
+        if (lane == 0) {
+            tc.pos = below;
+            tc.n = below + inside;
+            tc.cur = past_end ? tc.nb + 1 : b + 1;
+        }
+        __syncwarp();
+        if (inside > 0) return true;
+        if (past_end) return false;
+        // whole block below lo (cannot happen after the initial lower_bound except for tails)
+    }
+}
+
+__global__ void __launch_bounds__(kOrThreads)
+k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, uint32_t warp_bytes,
+          uint32_t kcap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    OrShared& sh = *reinterpret_cast<OrShared*>(smem_raw);
-    const uint32_t item_idx = item_ids[blockIdx.x];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t wid = blockIdx.x * kOrWarps + warp;
+    if (wid >= n_ids) return;
+    unsigned char* base = smem_raw + (size_t)warp * warp_bytes;
+    WarpShared& sh = *reinterpret_cast<WarpShared*>(base);
+    float* topk = reinterpret_cast<float*>(base + sizeof(WarpShared));
+    int32_t* cdocs = reinterpret_cast<int32_t*>(topk + kcap);
+    const uint32_t item_idx = item_ids[wid];
     const WorkItem it = p.items[item_idx];
     const SegDev seg = p.segs[it.seg];
-    const int lane = lane_id(), warp = threadIdx.x >> 5;
     const int T = it.n_terms;
     const int lo = it.lo, hi = it.hi;
+    float* cscores = reinterpret_cast<float*>(cdocs + T * kBlock);
 
-    emit_init(sh.emit);
-    for (int i = threadIdx.x; i < kWin; i += kEvalThreads) sh.acc[i] = kSent;
-    if ((int)threadIdx.x < T) {
-        const ItemClause c = p.clauses[it.clause_begin + threadIdx.x];
+    for (int i = lane; i < kWw; i += 32) sh.acc[i] = kSent;
+    if (lane < T) {
+        const ItemClause c = p.clauses[it.clause_begin + lane];
         const TermDev td = seg.terms[c.term_id];
-        TermCtx& tc = sh.term[threadIdx.x];
+        WTerm& tc = sh.term[lane];
         tc.blk_last = seg.blk_last + td.blk_begin;
         tc.blk_desc = seg.blk_desc + td.blk_begin;
         tc.cache = p.caches + (size_t)c.cache_id * 256;
         tc.nb = td.n_blocks;
         tc.cur = lower_bound_i32(tc.blk_last, 0, td.n_blocks, lo);
-        tc.next_cur = tc.cur;
-        tc.tail_base = td.tail_base;
-        const bool tail_in_scope = td.tail_n > 0 && (td.n_blocks == 0 || hi - 1 > td.tail_base);
-        tc.tail_n = tail_in_scope ? td.tail_n : 0;
-        tc.tail_pos = 0;
-        tc.tail_next = 0;
+        tc.n = 0;
+        tc.pos = 0;
+        tc.term_id = c.term_id;
         tc.w1 = __fmul_rn(c.weight, __fadd_rn(p.k1, 1.0f));
     }
-    __syncthreads();
-    for (int t = warp; t < T; t += kEvalWarps) {
-        TermCtx& tc = sh.term[t];
-        if (tc.tail_n) {
-            if (lane == 0) {
-                const ItemClause c = p.clauses[it.clause_begin + t];
-                decode_tail(seg, seg.terms[c.term_id], sh.tail_docs[t], sh.tail_freqs[t]);
-                uint32_t pos = 0;
-                while (pos < tc.tail_n && sh.tail_docs[t][pos] < lo) pos++;
-                tc.tail_pos = pos;
-                tc.tail_next = pos;
-            }
-        }
+    __syncwarp();
+    long long w0 = kNoMoreDocs;
+    for (int t = 0; t < T; t++) {
+        if (stream_refill(seg, p, sh.term[t], cdocs + t * kBlock, cscores + t * kBlock, lo, hi, lane))
+            w0 = min(w0, (long long)cdocs[t * kBlock + sh.term[t].pos]);
     }
-    const uint32_t* theta_prev = (it.flags & 1u) ? nullptr : p.item_theta + (item_idx - 1);
-    __syncthreads();
 
-    long long w0 = lo;
+    WEmit em;
+    em.topk = topk;
+    em.topk_n = 0;
+    em.theta_local = -INFINITY;
+    em.theta_in = 0;
+    em.run_slot = kNone;
+    em.run_cap = 0;
+    em.run_cnt = 0;
+    em.matches = 0;
+    em.overflow = false;
+    const uint32_t* theta_prev = (it.flags & 1u) ? nullptr : p.item_theta + (item_idx - 1);
+
     while (w0 < hi) {
         const int win0 = (int)w0;
-        const int win1 = (int)min((long long)hi, w0 + kWin);
+        const int win1 = (int)min((long long)hi, w0 + kWw);
         uint32_t inherited = 0;
-        if (threadIdx.x == 0) {
-            sh.next_doc = kNoMoreDocs;
-            if (theta_prev) inherited = ld_volatile_u32(theta_prev);
-        }
-        __syncthreads();
+        if (lane == 0 && theta_prev) inherited = ld_volatile_u32(theta_prev);
+        int next_doc = kNoMoreDocs;
+        uint32_t touched = 0;
+        // ---- clauses in order: drain each stream up to the window end
         for (int t = 0; t < T; t++) {
-            TermCtx& tc = sh.term[t];
-            const uint32_t nb = tc.nb;
-            const float w1 = tc.w1;
-            const float* cache = tc.cache;
-            int my_next = kNoMoreDocs;
-            uint32_t my_cur = 0;
-            for (uint32_t b = tc.cur + warp;; b += kEvalWarps) {
-                if (b > nb) break;
-                const int prev_last = b == 0 ? -1 : __ldg(tc.blk_last + b - 1);
-                if (b == nb && tc.tail_n == 0) break;
-                if (prev_last >= win1 - 1) {
-                    my_next = min(my_next, prev_last + 1);
-                    break;
-                }
-                if (b == nb) {  // vint tail / singleton, already decoded in shared memory
-                    uint32_t consumed = 0;
-                    for (uint32_t j = tc.tail_pos + lane; j < tc.tail_n; j += 32) {
-                        const int d = sh.tail_docs[t][j];
-                        if (d >= win1) {
-                            my_next = min(my_next, d);
-                            break;
-                        }
-                        consumed = j + 1;
-                        if (d >= win0) {
-                            const float f = (float)sh.tail_freqs[t][j];
-                            const float nrm = seg.norms ? __ldg(cache + __ldg(seg.norms + d)) : p.k1;
-                            const float s = bm25_score(w1, f, nrm);
-                            const uint32_t old = sh.acc[d - win0];
-                            const float prev = old == kSent ? 0.0f : __uint_as_float(old);
-                            sh.acc[d - win0] = __float_as_uint(__fadd_rn(prev, s));
-                        }
+            WTerm& tc = sh.term[t];
+            const int32_t* cd = cdocs + t * kBlock;
+            const float* cs = cscores + t * kBlock;
+            uint32_t pos = tc.pos, n = tc.n;
+            for (;;) {
+                if (pos >= n) {
+                    if (tc.cur > tc.nb) break;  // exhausted
+                    if (lane == 0) tc.pos = pos;
+                    __syncwarp();
+                    if (!stream_refill(seg, p, tc, cdocs + t * kBlock, cscores + t * kBlock, lo, hi, lane)) {
+                        pos = n = 0;
+                        break;
                     }
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) consumed = max(consumed, __shfl_xor_sync(0xffffffffu, consumed, o));
-                    if (lane == 0 && consumed > tc.tail_pos) atomicMax(&tc.tail_next, consumed);
-                    break;
+                    pos = tc.pos;
+                    n = tc.n;
                 }
-                const BlockDesc bd = tc.blk_desc[b];
-                const uint4* part = seg.arena + bd.off16;
-                const int4 dl = unpack4(part, (int)(bd.bits & 0xff), lane, seg.version, seg.sb_mask);
-                const int4 dd = deltas_to_docs(dl, b == 0 ? 0 : prev_last);
-                const int docs[4] = {dd.x, dd.y, dd.z, dd.w};
-                bool in_win = false;
-#pragma unroll
-                for (int i = 0; i < 4; i++) in_win |= docs[i] >= win0 && docs[i] < win1;
-                if (__any_sync(0xffffffffu, in_win)) {
-                    const int4 fr = unpack4(part + ((bd.bits >> 16) & 0xff), (int)((bd.bits >> 8) & 0xff),
-                                            lane, seg.version, seg.sb_mask);
-                    const int fq[4] = {fr.x, fr.y, fr.z, fr.w};
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const int d = docs[i];
-                        if (d >= win0 && d < win1) {
-                            const float nrm = seg.norms ? __ldg(cache + __ldg(seg.norms + d)) : p.k1;
-                            const float s = bm25_score(w1, (float)fq[i], nrm);
-                            const uint32_t old = sh.acc[d - win0];
-                            const float prev = old == kSent ? 0.0f : __uint_as_float(old);
-                            sh.acc[d - win0] = __float_as_uint(__fadd_rn(prev, s));
-                        }
-                    }
+                const uint32_t i = pos + lane;
+                const int d = i < n ? cd[i] : kNoMoreDocs;
+                const bool in_win = d < win1;
+                const uint32_t c = __popc(__ballot_sync(0xffffffffu, in_win));  // sorted: a prefix
+                if (in_win) {
+                    const int idx = d - win0;
+                    const uint32_t old = sh.acc[idx];
+                    sh.acc[idx] = __float_as_uint(__fadd_rn(old == kSent ? 0.0f : __uint_as_float(old), cs[i]));
+                    touched |= 1u << (idx >> 5);
                 }
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                    if (docs[i] >= win1) my_next = min(my_next, docs[i]);
-                if (dd.w < win1 && lane == 31) my_cur = b + 1;  // whole block consumed
+                pos += c;
+                if (c < 32 && pos < n) break;  // next cached doc is beyond this window
             }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) my_next = min(my_next, __shfl_xor_sync(0xffffffffu, my_next, o));
-            my_cur = __shfl_sync(0xffffffffu, my_cur, 31);
             if (lane == 0) {
-                if (my_next != kNoMoreDocs) atomicMin(&sh.next_doc, my_next);
-                if (my_cur) atomicMax(&tc.next_cur, my_cur);
+                tc.pos = pos;
+                tc.n = n;
             }
-            __syncthreads();  // accumulator hand-over to the next clause (clause-order f32 sums)
+            if (pos < n) next_doc = min(next_doc, cd[pos]);
+            __syncwarp();
         }
-        if ((int)threadIdx.x < T) {
-            TermCtx& tc = sh.term[threadIdx.x];
-            tc.cur = max(tc.cur, tc.next_cur);
-            tc.tail_pos = max(tc.tail_pos, tc.tail_next);
+        touched = __reduce_or_sync(0xffffffffu, touched);
+        // ---- scan touched 32-doc steps in docid order
+        {
+            em.theta_in = max(em.theta_in, __shfl_sync(0xffffffffu, inherited, 0));
+            float te = em.theta_local;
+            if (em.theta_in > kOrderedNegInf) te = fmaxf(te, ordered_to_float(em.theta_in));
+            const bool open = te == -INFINITY;
+            uint32_t newc_n = 0;
+            while (touched) {
+                const int s = __ffs(touched) - 1;
+                touched &= touched - 1;
+                const int idx = s * 32 + lane;
+                const uint32_t v = sh.acc[idx];
+                sh.acc[idx] = kSent;
+                const bool present = v != kSent && is_live(seg, win0 + idx);
+                wemit_step(em, p, item_idx, lane, present, win0 + idx + seg.doc_base, __uint_as_float(v), te, open,
+                           sh.newc, newc_n);
+            }
+            wtheta_update(em, p.k, kcap, lane, sh.newc, newc_n, p.item_theta + item_idx);
+            __syncwarp();
         }
-        // scan the window in docid order
-        bool present[kWinSteps];
-        int doc[kWinSteps];
-        float score[kWinSteps];
-        const int span = win1 - win0;
-#pragma unroll
-        for (int s = 0; s < kWinSteps; s++) {
-            const int idx = warp * (kWin / kEvalWarps) + s * 32 + lane;
-            const uint32_t v = sh.acc[idx];
-            sh.acc[idx] = kSent;
-            doc[s] = win0 + idx;
-            score[s] = __uint_as_float(v);
-            present[s] = v != kSent && idx < span && is_live(seg, win0 + idx);
-        }
-        emit_window<kWinSteps>(sh.emit, p, item_idx, seg.doc_base, present, doc, score, inherited);
-        __syncthreads();
-        const int nd = sh.next_doc;
-        if (nd == kNoMoreDocs) break;
-        w0 = nd;
-        __syncthreads();
+        if (next_doc == kNoMoreDocs) break;
+        w0 = next_doc;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) p.item_matches[item_idx] = sh.emit.matches;
+    if (lane == 0) p.item_matches[item_idx] = em.matches;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -826,14 +991,20 @@ k_merge_leaf_records(const uint8_t* __restrict__ records, uint32_t n_leaves, uin
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n) {
+void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n,
+                    uint32_t max_terms) {
     if (!n) return;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_eval_or, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrShared));
-        attr_set = true;
+    const uint32_t kcap = (std::min<uint32_t>(p.k, kMaxK) + 31u) & ~31u;
+    size_t wb = sizeof(WarpShared) + (size_t)kcap * sizeof(float) + (size_t)max_terms * kBlock * 8;
+    wb = (wb + 15) & ~size_t(15);
+    const size_t smem = wb * kOrWarps;
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaFuncSetAttribute(k_eval_or, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = smem;
     }
-    k_eval_or<<<n, kEvalThreads, sizeof(OrShared), st>>>(p, item_ids);
+    const uint32_t ctas = (n + kOrWarps - 1) / kOrWarps;
+    k_eval_or<<<ctas, kOrThreads, smem, st>>>(p, item_ids, n, (uint32_t)wb, kcap);
 }
 void launch_eval_and(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n) {
     if (!n) return;

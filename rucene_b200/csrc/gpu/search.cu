@@ -17,10 +17,10 @@ using namespace rg;
 struct rg_batch {
     uint32_t n_queries = 0, k = 0, mode = 0;
     float k1 = 1.2f;
-    uint32_t n_items = 0, n_or = 0, n_and = 0, n_groups = 0, n_leaves = 0;
+    uint32_t n_items = 0, n_or = 0, n_ort = 0, n_and = 0, n_groups = 0, n_leaves = 0, max_or_terms = 1;
     DevBuf<WorkItem> items;
     DevBuf<ItemClause> clauses;
-    DevBuf<uint32_t> or_ids, and_ids;
+    DevBuf<uint32_t> or_ids, ort_ids, and_ids;  // OR items without / with a vint tail in scope
     DevBuf<uint32_t> group_item_begin, group_out;
     DevBuf<uint32_t> item_head, item_matches, item_theta;
     DevBuf<unsigned long long> arena_next;  // [0] bump pointer, [1] error flag (as u32 view)
@@ -28,7 +28,7 @@ struct rg_batch {
     DevBuf<uint32_t> out_counts;
     DevBuf<unsigned long long> out_total;
     DevBuf<uint8_t> leaf_records;
-    uint64_t postings = 0, algo_bytes = 0;
+    uint64_t postings = 0, algo_bytes = 0, h2d_bytes = 0;
     uint32_t kernels_per_run = 0;
     bool ran = false;
 };
@@ -38,9 +38,11 @@ namespace {
 struct HostPlan {
     std::vector<WorkItem> items;
     std::vector<ItemClause> clauses;
-    std::vector<uint32_t> or_ids, and_ids;
+    std::vector<uint32_t> or_ids, ort_ids, and_ids;
+    std::vector<uint32_t> or_rank, ort_rank, and_rank;  // range index of each id (launch-order key)
     std::vector<uint32_t> group_item_begin, group_out;
     uint64_t postings = 0, algo_bytes = 0;
+    uint32_t max_or_terms = 1;
 };
 
 struct QShape {
@@ -162,10 +164,36 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 it.flags = (r == 0 && new_group) ? 1u : 0u;
                 const uint32_t idx = (uint32_t)hp.items.size();
                 hp.items.push_back(it);
-                (shape.type == kTypeAnd ? hp.and_ids : hp.or_ids).push_back(idx);
+                if (shape.type == kTypeAnd) {
+                    hp.and_ids.push_back(idx);
+                    hp.and_rank.push_back((uint32_t)r);
+                } else {
+                    bool tails = false;  // does any clause's vint tail / singleton reach into [lo, hi)?
+                    for (uint32_t ci : present) {
+                        const TermHost& th = seg.host_terms[clauses[ci].term_id];
+                        tails |= th.tail_n > 0 && (th.n_blocks == 0 || it.hi - 1 > th.tail_base);
+                    }
+                    (tails ? hp.ort_ids : hp.or_ids).push_back(idx);
+                    (tails ? hp.ort_rank : hp.or_rank).push_back((uint32_t)r);
+                    hp.max_or_terms = std::max<uint32_t>(hp.max_or_terms, (uint32_t)present.size());
+                }
             }
         }
     }
+    // Launch order: all first ranges, then all second ranges, ... so that by the time range r of a
+    // query starts, its range r-1 has (almost always) finished and published theta; candidate
+    // lists then stay ~k*ln(n) per query instead of per range.  Item order itself is untouched.
+    auto by_rank = [](std::vector<uint32_t>& ids, const std::vector<uint32_t>& rank) {
+        std::vector<uint32_t> perm(ids.size());
+        for (uint32_t i = 0; i < perm.size(); i++) perm[i] = i;
+        std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return rank[a] < rank[b]; });
+        std::vector<uint32_t> out(ids.size());
+        for (uint32_t i = 0; i < perm.size(); i++) out[i] = ids[perm[i]];
+        ids.swap(out);
+    };
+    by_rank(hp.or_ids, hp.or_rank);
+    by_rank(hp.ort_ids, hp.ort_rank);
+    by_rank(hp.and_ids, hp.and_rank);
     // heap groups = contiguous item runs starting at chain-start items
     for (uint32_t i = 0; i < hp.items.size(); i++)
         if (hp.items[i].flags & 1u) hp.group_item_begin.push_back(i);
@@ -220,8 +248,10 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     b->k1 = p->k1;
     b->n_items = (uint32_t)hp.items.size();
     b->n_or = (uint32_t)hp.or_ids.size();
+    b->n_ort = (uint32_t)hp.ort_ids.size();
     b->n_and = (uint32_t)hp.and_ids.size();
     b->n_groups = (uint32_t)hp.group_out.size();
+    b->max_or_terms = hp.max_or_terms;
     b->n_leaves = (uint32_t)e->segs.size();
     b->postings = hp.postings;
     b->algo_bytes = hp.algo_bytes + (uint64_t)n_queries * p->k * sizeof(rg_hit);
@@ -229,9 +259,12 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     up(b->items, hp.items, st);
     up(b->clauses, hp.clauses, st);
     up(b->or_ids, hp.or_ids, st);
+    up(b->ort_ids, hp.ort_ids, st);
     up(b->and_ids, hp.and_ids, st);
     up(b->group_item_begin, hp.group_item_begin, st);
     up(b->group_out, hp.group_out, st);
+    b->h2d_bytes = b->items.bytes() + b->clauses.bytes() + b->or_ids.bytes() + b->ort_ids.bytes() + b->and_ids.bytes() +
+                   b->group_item_begin.bytes() + b->group_out.bytes();
     b->item_head.alloc(std::max<uint32_t>(1, b->n_items));
     b->item_matches.alloc(std::max<uint32_t>(1, b->n_items));
     b->item_theta.alloc(std::max<uint32_t>(1, b->n_items));
@@ -241,7 +274,7 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     b->out_total.alloc(std::max<uint32_t>(1, n_queries));
     if (p->mode == RG_MODE_SEARCH_PARALLEL)
         b->leaf_records.alloc((size_t)b->n_leaves * std::max<uint32_t>(1, n_queries) * leaf_record_bytes(p->k));
-    b->kernels_per_run = (b->n_or ? 1 : 0) + (b->n_and ? 1 : 0) + (b->n_groups ? 1 : 0) +
+    b->kernels_per_run = (b->n_or ? 1 : 0) + (b->n_ort ? 1 : 0) + (b->n_and ? 1 : 0) + (b->n_groups ? 1 : 0) +
                          (p->mode == RG_MODE_SEARCH_PARALLEL ? 1 : 0);
     RG_CUDA_CHECK(cudaStreamSynchronize(st));
     *out = b.release();
@@ -277,10 +310,14 @@ int rg_batch_run(rg_engine* e, rg_batch* b) {
     ep.item_matches = b->item_matches.p;
     ep.item_theta = b->item_theta.p;
     ep.error_flag = reinterpret_cast<uint32_t*>(b->arena_next.p + 1);
-    launch_eval_or(st, ep, b->or_ids.p, b->n_or);
+    RG_CUDA_CHECK(cudaEventRecord(e->ev2, st));
+    launch_eval_or(st, ep, b->or_ids.p, b->n_or, b->max_or_terms);
+    RG_CUDA_CHECK(cudaGetLastError());
+    launch_eval_or(st, ep, b->ort_ids.p, b->n_ort, b->max_or_terms);
     RG_CUDA_CHECK(cudaGetLastError());
     launch_eval_and(st, ep, b->and_ids.p, b->n_and);
     RG_CUDA_CHECK(cudaGetLastError());
+    RG_CUDA_CHECK(cudaEventRecord(e->ev3, st));
     ReplayParams rp{};
     rp.cand_arena = e->cand_arena.p;
     rp.item_head = b->item_head.p;
@@ -320,6 +357,8 @@ int rg_batch_fetch(rg_engine* e, rg_batch* b, rg_hit* out_hits, uint32_t* out_co
     RG_CUDA_CHECK(cudaMemcpyAsync(flags, b->arena_next.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
     RG_CUDA_CHECK(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&e->last_run_ms, e->ev0, e->ev1);
+    cudaEventElapsedTime(&e->last_eval_ms, e->ev2, e->ev3);
+    cudaEventElapsedTime(&e->last_replay_ms, e->ev3, e->ev1);
     cudaGetLastError();
     if (flags[1] & 1ull) throw OutOfArena("candidate arena exhausted: split the batch or raise cand_arena_bytes");
     return RG_OK;
@@ -341,8 +380,8 @@ int rg_batch_stats(rg_engine* e, rg_batch* b, uint64_t out[8]) {
     out[2] = b->algo_bytes;
     out[3] = used;
     out[4] = b->kernels_per_run;
-    out[5] = used;
-    out[6] = b->n_or;
+    out[5] = b->h2d_bytes;
+    out[6] = b->n_or + b->n_ort;
     out[7] = b->n_and;
     return RG_OK;
     RG_CATCH

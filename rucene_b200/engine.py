@@ -121,8 +121,8 @@ class Batch:
         out = np.zeros(8, np.uint64)
         _check(lib().rg_batch_stats(self.engine.h, self.h, _p(out)), self.engine.h)
         return {"items": int(out[0]), "postings": int(out[1]), "algorithmic_bytes": int(out[2]),
-                "candidates": int(out[3]), "kernels_per_run": int(out[4]),
-                "arena_slots_used": int(out[5])}
+                "candidate_slots": int(out[3]), "kernels_per_run": int(out[4]),
+                "h2d_bytes": int(out[5]), "or_items": int(out[6]), "and_items": int(out[7])}
 
     def leaf_records(self):
         ptr, nbytes = C.c_void_p(), C.c_size_t()
