@@ -64,7 +64,7 @@ struct WorkItem {
     uint8_t n_terms;
     int32_t lo, hi;          // docid range [lo, hi) inside the segment
     uint32_t clause_begin;   // into ItemClause[]
-    uint32_t flags;          // bit0: first item of its heap chain (no theta to inherit)
+    uint32_t chain_pos;      // position inside its heap chain (0 = first: no theta to inherit)
 };
 
 struct CandRun {  // header slot of a candidate run in the arena (same size as rg_hit)

@@ -39,6 +39,7 @@ constexpr int kNewcMax = 512;           // candidate scores fed to the theta tra
 constexpr int kMaxK = 1024;             // theta tracking / replay heap capacity
 constexpr uint32_t kNone = 0xffffffffu;
 constexpr uint32_t kRunMin = 256;       // minimum candidate run length (slots)
+constexpr uint32_t kRunFirst = 63;      // first run of a warp-sized work item (most items emit few)
 constexpr uint32_t kSent = 0x7fc0dead;  // "no posting yet" marker in the accumulator window (a NaN)
 
 // ------------------------------------------------------------------------------------------
@@ -354,7 +355,7 @@ __device__ __forceinline__ void wemit_step(WEmit& em, const EvalParams& p, uint3
     CandRun* hdr = reinterpret_cast<CandRun*>(p.cand_arena);
     if (em.run_slot == kNone || em.run_cnt + c > em.run_cap) {
         uint32_t slot = 0;
-        const uint32_t cap = kRunMin;
+        const uint32_t cap = em.run_slot == kNone ? kRunFirst : kRunMin;
         if (lane == 0) {
             const unsigned long long s64 = atomicAdd(p.arena_next, (unsigned long long)cap + 1ull);
             slot = (s64 + cap + 1ull > (unsigned long long)p.arena_slots) ? kNone : (uint32_t)s64;
@@ -415,7 +416,7 @@ __device__ __forceinline__ void wtheta_update(WEmit& em, uint32_t k, uint32_t kc
 // Refill clause t's stream cache with its next block (or vint tail): unpack, docid scan, norm
 // gather, BM25 — once per block.  Entries outside [lo, hi) are trimmed.  Returns false when the
 // list is exhausted.  Warp-cooperative; all lanes must call it.
-__device__ __noinline__ bool stream_refill(const SegDev& seg, const EvalParams& p, WTerm& tc, int32_t* cd,
+__device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParams& p, WTerm& tc, int32_t* cd,
                                            float* cs, int lo, int hi, int lane) {
     for (;;) {
         const uint32_t b = tc.cur;
@@ -534,13 +535,20 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
     em.run_cnt = 0;
     em.matches = 0;
     em.overflow = false;
-    const uint32_t* theta_prev = (it.flags & 1u) ? nullptr : p.item_theta + (item_idx - 1);
+    // theta look-back: the up-to-32 preceding items of this heap chain (each publishes
+    // max(own, inherited)), re-read every 8 windows
+    const bool lb_ok = (uint32_t)lane < it.chain_pos;
+    const uint32_t* theta_lb = p.item_theta + item_idx - 1 - (lb_ok ? lane : 0);
+    uint32_t win_no = 0;
 
     while (w0 < hi) {
         const int win0 = (int)w0;
         const int win1 = (int)min((long long)hi, w0 + kWw);
         uint32_t inherited = 0;
-        if (lane == 0 && theta_prev) inherited = ld_volatile_u32(theta_prev);
+        if ((win_no++ & 7u) == 0 && it.chain_pos) {
+            inherited = lb_ok ? ld_volatile_u32(theta_lb) : 0u;
+            inherited = __reduce_max_sync(0xffffffffu, inherited);
+        }
         int next_doc = kNoMoreDocs;
         uint32_t touched = 0;
         // ---- clauses in order: drain each stream up to the window end
@@ -584,7 +592,7 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
         touched = __reduce_or_sync(0xffffffffu, touched);
         // ---- scan touched 32-doc steps in docid order
         {
-            em.theta_in = max(em.theta_in, __shfl_sync(0xffffffffu, inherited, 0));
+            em.theta_in = max(em.theta_in, inherited);
             float te = em.theta_local;
             if (em.theta_in > kOrderedNegInf) te = fmaxf(te, ordered_to_float(em.theta_in));
             const bool open = te == -INFINITY;
@@ -654,7 +662,7 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
         tc.tail_next = 0;
         tc.w1 = __fmul_rn(c.weight, __fadd_rn(p.k1, 1.0f));
     }
-    const uint32_t* theta_prev = (it.flags & 1u) ? nullptr : p.item_theta + (item_idx - 1);
+    const uint32_t* theta_prev = (it.chain_pos == 0) ? nullptr : p.item_theta + (item_idx - 1);
     __syncthreads();
 
     const TermCtx& lead = sh.term[0];

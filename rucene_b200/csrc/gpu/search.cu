@@ -103,6 +103,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
         for (uint32_t ci : shape.clause_idx)
             if (clauses[ci].cache_id >= n_caches) throw ArgError("clause refers to an unset norm cache");
         bool group_open = false;
+        uint32_t chain_pos = 0;
         for (uint32_t si = 0; si < n_segs; si++) {
             const Segment& seg = e->segs[si];
             // resolve clauses against this leaf
@@ -145,7 +146,10 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
             const uint32_t clause_begin = (uint32_t)hp.clauses.size();
             for (uint32_t ci : present)
                 hp.clauses.push_back(ItemClause{clauses[ci].term_id, clauses[ci].weight, clauses[ci].cache_id, 0});
+            // ranges of ~range_postings postings, at most 256 per (query, leaf): long lists get
+            // longer ranges (a range is one warp's sequential job; there are thousands of warps)
             uint64_t R = (cost + range_postings - 1) / range_postings;
+            R = std::min<uint64_t>(R, 256);
             R = std::max<uint64_t>(1, std::min<uint64_t>(R, (uint64_t)(seg.max_doc + kBlock - 1) / kBlock));
             if (new_group) {
                 // SEARCH: one heap per query over all its leaves; SEARCH_PARALLEL: one per leaf
@@ -161,7 +165,8 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 it.lo = (int32_t)((uint64_t)seg.max_doc * r / R);
                 it.hi = (int32_t)((uint64_t)seg.max_doc * (r + 1) / R);
                 it.clause_begin = clause_begin;
-                it.flags = (r == 0 && new_group) ? 1u : 0u;
+                it.chain_pos = (r == 0 && new_group) ? 0u : chain_pos;
+                chain_pos = it.chain_pos + 1;
                 const uint32_t idx = (uint32_t)hp.items.size();
                 hp.items.push_back(it);
                 if (shape.type == kTypeAnd) {
@@ -196,7 +201,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
     by_rank(hp.and_ids, hp.and_rank);
     // heap groups = contiguous item runs starting at chain-start items
     for (uint32_t i = 0; i < hp.items.size(); i++)
-        if (hp.items[i].flags & 1u) hp.group_item_begin.push_back(i);
+        if (hp.items[i].chain_pos == 0) hp.group_item_begin.push_back(i);
     hp.group_item_begin.push_back((uint32_t)hp.items.size());
     if (hp.group_item_begin.size() != hp.group_out.size() + 1) throw ArgError("internal: group bookkeeping mismatch");
 }
@@ -211,7 +216,7 @@ void ensure_arena(rg_engine* e) {
     if (e->cand_arena.p) return;
     size_t free_b = 0, total_b = 0;
     RG_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-    uint64_t want = e->cfg.cand_arena_bytes ? e->cfg.cand_arena_bytes : std::min<uint64_t>(4ull << 30, free_b / 8);
+    uint64_t want = e->cfg.cand_arena_bytes ? e->cfg.cand_arena_bytes : std::min<uint64_t>(8ull << 30, free_b / 6);
     want = std::min<uint64_t>(want, (uint64_t)0xfffffff0u * sizeof(rg_hit));
     want = std::max<uint64_t>(want, 1ull << 20);
     e->cand_arena.alloc(want / sizeof(rg_hit));
