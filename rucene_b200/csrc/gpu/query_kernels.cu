@@ -590,22 +590,44 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
             __syncwarp();
         }
         touched = __reduce_or_sync(0xffffffffu, touched);
-        // ---- scan touched 32-doc steps in docid order
+        // ---- scan touched docs in docid order, four 32-doc steps (one nibble of `touched`) at a
+        // time: the common case "nothing in these 128 docs can enter the heap" costs ~8
+        // instructions per step
         {
             em.theta_in = max(em.theta_in, inherited);
             float te = em.theta_local;
             if (em.theta_in > kOrderedNegInf) te = fmaxf(te, ordered_to_float(em.theta_in));
             const bool open = te == -INFINITY;
             uint32_t newc_n = 0;
-            while (touched) {
-                const int s = __ffs(touched) - 1;
-                touched &= touched - 1;
-                const int idx = s * 32 + lane;
-                const uint32_t v = sh.acc[idx];
-                sh.acc[idx] = kSent;
-                const bool present = v != kSent && is_live(seg, win0 + idx);
-                wemit_step(em, p, item_idx, lane, present, win0 + idx + seg.doc_base, __uint_as_float(v), te, open,
-                           sh.newc, newc_n);
+            const bool has_live = seg.live != nullptr;
+#pragma unroll 1
+            for (int g = 0; g < 8; g++) {
+                if (!((touched >> (4 * g)) & 0xfu)) continue;
+                const int i0 = g * 128 + lane;
+                uint32_t v[4];
+                bool pr[4];
+                bool any_cand = false;
+                uint32_t cnt = 0;
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                    v[s] = sh.acc[i0 + 32 * s];
+                    pr[s] = v[s] != kSent;
+                }
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                    if (pr[s]) sh.acc[i0 + 32 * s] = kSent;
+                    if (has_live && pr[s]) pr[s] = is_live(seg, win0 + i0 + 32 * s);
+                    cnt += pr[s];
+                    any_cand |= pr[s] && (open || __uint_as_float(v[s]) > te);
+                }
+                if (!__any_sync(0xffffffffu, any_cand)) {
+                    em.matches += __reduce_add_sync(0xffffffffu, cnt);
+                    continue;
+                }
+#pragma unroll 1
+                for (int s = 0; s < 4; s++)
+                    wemit_step(em, p, item_idx, lane, pr[s], win0 + i0 + 32 * s + seg.doc_base, __uint_as_float(v[s]),
+                               te, open, sh.newc, newc_n);
             }
             wtheta_update(em, p.k, kcap, lane, sh.newc, newc_n, p.item_theta + item_idx);
             __syncwarp();
