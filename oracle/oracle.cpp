@@ -1330,6 +1330,36 @@ int orc_search_batch(orc_index* ix, const orc_query* queries, uint32_t n_queries
     ORC_CATCH(-1)
 }
 
+// Per-leaf TopDocsLeafCollector result of ONE segment in the engine's leaf-record layout
+// {u32 n; u32 pad; u64 total_hits; orc_hit heap[k]} (heap-array order == into_vec(),
+// top_docs.rs:203-213).  Weights come from the index-wide statistics segment as usual.
+int orc_search_leaf_records(orc_index* ix, uint32_t seg_i, const orc_query* queries, uint32_t n_queries,
+                            const orc_clause* clauses, uint32_t k, int n_threads, uint8_t* out_records) {
+    ORC_TRY
+    const SegmentData& seg = ix->segs.at(seg_i);
+    const size_t rb = 16 + (size_t)k * sizeof(orc_hit);
+    std::memset(out_records, 0, rb * n_queries);
+    parallel_for(n_queries, n_threads, [&](uint32_t qi) {
+        const orc_query& q = queries[qi];
+        Plan plan;
+        plan.weights.resize(q.n_clauses);
+        for (uint32_t i = 0; i < q.n_clauses; i++)
+            make_weight(*ix, clauses[q.clause_begin + i].term_id, clauses[q.clause_begin + i].boost, plan.weights[i]);
+        TopDocsHeap leaf(k);
+        ScorerPtr scorer = create_scorer(*ix, seg, q, clauses, plan);
+        if (scorer)
+            bulk_score(*scorer, &seg, [&](int32_t doc, Scorer& s) { leaf.collect(doc + seg.doc_base, s.score()); });
+        uint8_t* rec = out_records + rb * qi;
+        uint32_t n = (uint32_t)leaf.data.size();
+        uint64_t total = leaf.total_hits;
+        std::memcpy(rec, &n, 4);
+        std::memcpy(rec + 8, &total, 8);
+        if (n) std::memcpy(rec + 16, leaf.data.data(), n * sizeof(orc_hit));
+    });
+    return 0;
+    ORC_CATCH(-1)
+}
+
 int orc_term_weight(orc_index* ix, uint32_t term_id, float boost, float* out_weight,
                     float* out_idf, float* out_avgdl, float out_cache[256]) {
     ORC_TRY

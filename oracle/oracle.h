@@ -79,6 +79,10 @@ int orc_search_batch(orc_index*, const orc_query* queries, uint32_t n_queries,
                      const orc_clause* clauses, uint32_t k, int parallel_mode,
                      int n_threads, orc_hit* out_hits, uint32_t* out_counts,
                      uint64_t* out_total);
+/* One segment's TopDocsLeafCollector result per query in the engine's leaf-record layout
+ * {u32 n; u32 pad; u64 total_hits; orc_hit heap[k]} (heap-array order, top_docs.rs:203-213). */
+int orc_search_leaf_records(orc_index*, uint32_t seg, const orc_query* queries, uint32_t n_queries,
+                            const orc_clause* clauses, uint32_t k, int n_threads, uint8_t* out_records);
 /* BM25 weight pieces, for host-side cross checks. */
 int orc_term_weight(orc_index*, uint32_t term_id, float boost, float* out_weight,
                     float* out_idf, float* out_avgdl, float out_cache[256]);

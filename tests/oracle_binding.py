@@ -138,6 +138,17 @@ class Index:
             raise OracleError(err())
         return hits, counts, total
 
+    def leaf_records(self, seg, queries, clauses, k, n_threads=1):
+        q = np.ascontiguousarray(queries, dtype=QUERY_DTYPE)
+        c = np.ascontiguousarray(clauses, dtype=CLAUSE_DTYPE)
+        out = np.zeros((len(q), 16 + 8 * k), dtype=np.uint8)
+        lib().orc_search_leaf_records.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                                  C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
+        rc = lib().orc_search_leaf_records(self.h, seg, _p(q), len(q), _p(c), k, n_threads, _p(out))
+        if rc != 0:
+            raise OracleError(err())
+        return out
+
     def term_weight(self, term_id, boost=1.0):
         w, idf, avgdl = C.c_float(), C.c_float(), C.c_float()
         cache = np.zeros(256, dtype=np.float32)

@@ -1,0 +1,23 @@
+"""Sharded mode on real GPUs (needs >= 2 devices; skipped otherwise): BASELINE config 5 in small —
+one segment per GPU, mixed AND/OR batch, NCCL all-gather of per-segment top-k + device merge,
+TopDocs identical to the oracle's leaf-ordered search_parallel."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_one_segment_per_gpu_matches_oracle():
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    world = 2 if n < 4 else 4
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(here, "sharded_gpu_worker.py")]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert p.returncode == 0 and "SHARDED_OK" in p.stdout, p.stdout[-3000:]
