@@ -1,0 +1,54 @@
+// The reference's examples/example.rs:111-117 against the C++ host mirror (searcher.hpp):
+// builds a small synthetic segment with librucene_codec, searches it on the GPU, prints TopDocs
+// as "total_hits\n doc score_bits ..." so the pytest driver can compare with the oracle.
+#include <cstdio>
+#include <cstring>
+
+#include "../../rucene_b200/csrc/host/searcher.hpp"
+#include "rucene_codec.h"
+
+int main() {
+    using namespace rucene;
+    rc_synth_config cfg{0x5EED0001ull, 50000, 500, 1, 2};
+    rc_segment* seg = rc_synth_segment(&cfg);
+    if (!seg) { std::fprintf(stderr, "synth failed: %s\n", rc_last_error()); return 2; }
+    LeafData leaf;
+    leaf.doc_file = rc_segment_doc_file(seg, &leaf.doc_len);
+    leaf.norms = rc_segment_norms(seg);
+    leaf.terms = rc_segment_terms(seg, &leaf.n_terms);
+    int64_t st[8];
+    rc_segment_stats(seg, st);
+    leaf.doc_count = st[0]; leaf.sum_total_term_freq = st[1]; leaf.sum_doc_freq = st[2]; leaf.max_doc = (int32_t)st[3];
+    std::unordered_map<std::string, uint32_t> dict;
+    for (uint32_t t = 0; t < leaf.n_terms; t++) dict["t" + std::to_string(t)] = t;
+    try {
+        GpuIndexSearcher searcher({leaf}, "body", dict);
+        auto q1 = TermQuery::create(Term::create("body", "t5"), 1.0f);
+        auto q2 = BooleanQuery::build({TermQuery::create(Term::create("body", "t3")), TermQuery::create(Term::create("body", "t40"))}, {}, {}, {}, 0);
+        auto q3 = BooleanQuery::build({}, {TermQuery::create(Term::create("body", "t1")), TermQuery::create(Term::create("body", "t77")),
+                                           TermQuery::create(Term::create("body", "nope"))}, {}, {}, 0);
+        for (const QueryPtr& q : {q1, q2, q3}) {
+            TopDocsCollector collector(10);
+            searcher.search(*q, collector);
+            const TopDocs& top = collector.top_docs();
+            std::printf("%llu", (unsigned long long)top.total_hits());
+            for (const ScoreDoc& d : top.score_docs()) {
+                uint32_t bits; std::memcpy(&bits, &d.score, 4);
+                std::printf(" %d:%u", d.doc_id(), bits);
+            }
+            std::printf("\n");
+        }
+        bool threw = false;
+        try {  // MUST + SHOULD (ReqOptScorer) is outside the accelerated path
+            auto q4 = BooleanQuery::build({q1}, {q1}, {}, {}, 0);
+            TopDocsCollector c(10);
+            searcher.search(*q4, c);
+        } catch (const UnsupportedQuery&) { threw = true; }
+        std::printf("unsupported:%d\n", (int)threw);
+    } catch (const Error& e) {
+        std::fprintf(stderr, "error %d: %s\n", e.code, e.what());
+        return 1;
+    }
+    rc_segment_destroy(seg);
+    return 0;
+}
