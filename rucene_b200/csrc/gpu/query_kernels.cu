@@ -416,8 +416,11 @@ __device__ __forceinline__ void wtheta_update(WEmit& em, uint32_t k, uint32_t kc
 // Refill clause t's stream cache with its next block (or vint tail): unpack, docid scan, norm
 // gather, BM25 — once per block.  Entries outside [lo, hi) are trimmed.  Returns false when the
 // list is exhausted.  Warp-cooperative; all lanes must call it.
+// When called while clause t is being drained into the window [win0, win1) the new block's
+// postings below win1 are accumulated straight from registers (no round trip through the cache).
 __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParams& p, WTerm& tc, int32_t* cd,
-                                           float* cs, int lo, int hi, int lane) {
+                                           float* cs, int lo, int hi, int lane, int win0, int win1,
+                                           uint32_t* acc, uint32_t& touched) {
     for (;;) {
         const uint32_t b = tc.cur;
         if (b > tc.nb) return false;
@@ -455,7 +458,10 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
         const int d[4] = {docs.x, docs.y, docs.z, docs.w};
         const int f[4] = {freqs.x, freqs.y, freqs.z, freqs.w};
         float sc[4];
-        uint32_t below = 0, inside = 0;
+        uint32_t below = 0, inside = 0, direct = 0;
+        const float w1 = tc.w1;
+        const float* cache = tc.cache;
+        const uint8_t* norms = seg.norms;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const bool ok = d[q] >= lo && d[q] < hi;
@@ -463,8 +469,15 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
             inside += ok;
             float s = 0.f;
             if (ok) {
-                const float nrm = seg.norms ? __ldg(tc.cache + __ldg(seg.norms + d[q])) : p.k1;
-                s = bm25_score(tc.w1, (float)f[q], nrm);
+                const float nrm = norms ? __ldg(cache + __ldg(norms + d[q])) : p.k1;
+                s = bm25_score(w1, (float)f[q], nrm);
+                if (d[q] < win1) {  // still inside the window being drained: accumulate now
+                    const int idx = d[q] - win0;
+                    const uint32_t old = acc[idx];
+                    acc[idx] = __float_as_uint(__fadd_rn(old == kSent ? 0.0f : __uint_as_float(old), s));
+                    touched |= 1u << (idx >> 5);
+                    direct++;
+                }
             }
             sc[q] = s;
         }
@@ -472,7 +485,10 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
         reinterpret_cast<float4*>(cs)[lane] = make_float4(sc[0], sc[1], sc[2], sc[3]);
         below = __reduce_add_sync(0xffffffffu, below);
         inside = __reduce_add_sync(0xffffffffu, inside);
+        direct = __reduce_add_sync(0xffffffffu, direct);
         const bool past_end = below + inside < n_in;  // some posting >= hi: nothing further in range
+        below += direct;
+        inside -= direct;
         if (lane == 0) {
             tc.pos = below;
             tc.n = below + inside;
@@ -481,11 +497,11 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
         __syncwarp();
         if (inside > 0) return true;
         if (past_end) return false;
-        // whole block below lo (cannot happen after the initial lower_bound except for tails)
+        // whole block consumed (all below lo, or all accumulated directly): decode the next one
     }
 }
 
-__global__ void __launch_bounds__(kOrThreads)
+__global__ void __launch_bounds__(kOrThreads, 4)
 k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, uint32_t warp_bytes,
           uint32_t kcap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -520,8 +536,10 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
     }
     __syncwarp();
     long long w0 = kNoMoreDocs;
+    uint32_t touched = 0;
     for (int t = 0; t < T; t++) {
-        if (stream_refill(seg, p, sh.term[t], cdocs + t * kBlock, cscores + t * kBlock, lo, hi, lane))
+        if (stream_refill(seg, p, sh.term[t], cdocs + t * kBlock, cscores + t * kBlock, lo, hi, lane, 0,
+                          -2147483647 - 1, sh.acc, touched))
             w0 = min(w0, (long long)cdocs[t * kBlock + sh.term[t].pos]);
     }
 
@@ -550,7 +568,7 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
             inherited = __reduce_max_sync(0xffffffffu, inherited);
         }
         int next_doc = kNoMoreDocs;
-        uint32_t touched = 0;
+        touched = 0;
         // ---- clauses in order: drain each stream up to the window end
         for (int t = 0; t < T; t++) {
             WTerm& tc = sh.term[t];
@@ -562,7 +580,8 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                     if (tc.cur > tc.nb) break;  // exhausted
                     if (lane == 0) tc.pos = pos;
                     __syncwarp();
-                    if (!stream_refill(seg, p, tc, cdocs + t * kBlock, cscores + t * kBlock, lo, hi, lane)) {
+                    if (!stream_refill(seg, p, tc, cdocs + t * kBlock, cscores + t * kBlock, lo, hi, lane, win0,
+                                       win1, sh.acc, touched)) {
                         pos = n = 0;
                         break;
                     }
@@ -624,7 +643,7 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                     em.matches += __reduce_add_sync(0xffffffffu, cnt);
                     continue;
                 }
-#pragma unroll 1
+#pragma unroll
                 for (int s = 0; s < 4; s++)
                     wemit_step(em, p, item_idx, lane, pr[s], win0 + i0 + 32 * s + seg.doc_base, __uint_as_float(v[s]),
                                te, open, sh.newc, newc_n);
