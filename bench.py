@@ -51,7 +51,23 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("RUCENE_BENCH_CPU_SAMPLE", 256)))
     ap.add_argument("--range-postings", type=int, default=0)
     ap.add_argument("--no-decode", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--workload", default="c4", choices=["c4", "c3"],
+                    help="c4 (headline): 5-term SHOULD top-100 batch 4096 on 100M docs; c3: 2-term MUST "
+                         "(ConjunctionScorer) top-10 batch 1024 on 10M docs")
+    a = ap.parse_args()
+    if a.workload == "c3":
+        env = os.environ
+        if "RUCENE_BENCH_DOCS" not in env and "--docs" not in sys.argv:
+            a.docs = 10_000_000
+        if "--terms" not in sys.argv:
+            a.terms = 100_000
+        if "--batch" not in sys.argv:
+            a.batch = 1024
+        if "--qterms" not in sys.argv:
+            a.qterms = 2
+        if "--k" not in sys.argv:
+            a.k = 10
+    return a
 
 
 def measured_peaks():
@@ -118,8 +134,8 @@ def gen_queries(n_terms, batch, qterms, seed):
     return out
 
 
-def build_query_arrays(qt, weights_of, engine_mod):
-    """-> rg_query[], rg_clause[] for pure-SHOULD BooleanQuery::build(vec![], shoulds, ...)."""
+def build_query_arrays(qt, weights_of, engine_mod, must=False):
+    """-> rg_query[], rg_clause[] for BooleanQuery::build(musts | shoulds of TermQuery)."""
     batch, qterms = qt.shape
     q = np.zeros(batch, engine_mod.QUERY_DTYPE)
     c = np.zeros(batch * qterms, engine_mod.CLAUSE_DTYPE)
@@ -127,7 +143,7 @@ def build_query_arrays(qt, weights_of, engine_mod):
     q["n_clauses"] = qterms
     q["min_should_match"] = 0
     q["flags"] = engine_mod.Q_BOOLEAN
-    c["occur"] = engine_mod.SHOULD
+    c["occur"] = engine_mod.MUST if must else engine_mod.SHOULD
     c["term_id"] = qt.reshape(-1)
     c["weight"] = weights_of(qt.reshape(-1))
     c["cache_id"] = 0
@@ -142,8 +158,9 @@ def oracle_setup(seg, stats_df, stats, total_max_doc):
     return ob, ix
 
 
-def oracle_queries(ob, qt):
-    specs = [("bool", [(ob.SHOULD, int(t)) for t in row], 0) for row in qt]
+def oracle_queries(ob, qt, must=False):
+    occ = ob.MUST if must else ob.SHOULD
+    specs = [("bool", [(occ, int(t)) for t in row], 0) for row in qt]
     return ob.make_queries(specs)
 
 
@@ -161,7 +178,7 @@ def run_reference(args):
     times = []
     for step in range(args.warmup + args.steps):
         lo = (step * sample) % max(1, args.batch - sample + 1)
-        q, c = oracle_queries(ob, qt[lo:lo + sample])
+        q, c = oracle_queries(ob, qt[lo:lo + sample], args.workload == "c3")
         t0 = time.perf_counter()
         ix.search_batch(q, c, args.k, parallel_mode=0, n_threads=cores)
         dt = time.perf_counter() - t0
@@ -181,8 +198,10 @@ def run_reference(args):
 
 
 def workload_config(args, world):
-    return {"workload": "C4: %d-term SHOULD BooleanQuery (DisjunctionSumScorer) BM25 top-%d, batch %d, "
-                        "%d-doc Zipfian synthetic index, %d terms" % (args.qterms, args.k, args.batch, args.docs, args.terms),
+    kind = ("C3: %d-term MUST BooleanQuery (ConjunctionScorer)" if args.workload == "c3"
+            else "C4: %d-term SHOULD BooleanQuery (DisjunctionSumScorer)") % args.qterms
+    return {"workload": "%s BM25 top-%d, batch %d, %d-doc Zipfian synthetic index, %d terms"
+                        % (kind, args.k, args.batch, args.docs, args.terms),
             "batch": args.batch, "k": args.k, "docs": args.docs, "terms": args.terms,
             "segments": world, "parallelism": "1 docid-range segment per GPU" if world > 1 else "single GPU",
             "cache": "index image (GBs) is larger than the 126 MB L2; no explicit flush"}
@@ -253,7 +272,8 @@ def main():
         return out
 
     qt = gen_queries(args.terms, args.batch, args.qterms, SEED_QUERIES)
-    q, c = build_query_arrays(qt, weights_of, engine)
+    must = args.workload == "c3"
+    q, c = build_query_arrays(qt, weights_of, engine, must)
     mode = engine.MODE_SEARCH_PARALLEL if world > 1 else engine.MODE_SEARCH
 
     def barrier():
@@ -297,6 +317,8 @@ def main():
     ms_step = float(ms_total[0]) / args.steps
     launches = eng.launch_count() - launches0
     result = one_step(fetch=True)
+    if world > 1:
+        batch.fetch()  # populates the per-kernel CUDA-event timings of the last run
     eval_ms = eng.last_kernel_ms("eval")
     replay_ms = eng.last_kernel_ms("replay")
     bstats = batch.stats()
@@ -342,7 +364,7 @@ def main():
     peak, peak_src = measured_peaks()
     algo_bytes = bstats["algorithmic_bytes"]
     achieved = algo_bytes / (eval_ms / 1e3) / 1e9 if eval_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_eval_or", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_eval_and" if must else "k_eval_or", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": eval_ms, "replay_ms": replay_ms,
                 "postings_per_launch": bstats["postings"], "work_items": bstats["items"],
@@ -379,7 +401,7 @@ def main():
         ob, ix = oracle_setup(seg, None, None, args.docs)
         cores = os.cpu_count() or 1
         sample = min(args.cpu_sample, args.batch)
-        oq, oc = oracle_queries(ob, qt[:sample])
+        oq, oc = oracle_queries(ob, qt[:sample], must)
         t0 = time.perf_counter()
         want = ix.search_batch(oq, oc, args.k, parallel_mode=0, n_threads=cores)
         cdt = time.perf_counter() - t0
