@@ -420,7 +420,8 @@ __device__ __forceinline__ void wtheta_update(WEmit& em, uint32_t k, uint32_t kc
 // postings below win1 are accumulated straight from registers (no round trip through the cache).
 __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParams& p, WTerm& tc, int32_t* cd,
                                            float* cs, int lo, int hi, int lane, int win0, int win1,
-                                           uint32_t* acc, uint32_t& touched) {
+                                           uint32_t* acc, uint32_t& touched, uint32_t& hot, uint32_t& my_matches,
+                                           float te) {
     for (;;) {
         const uint32_t b = tc.cur;
         if (b > tc.nb) return false;
@@ -474,8 +475,11 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
                 if (d[q] < win1) {  // still inside the window being drained: accumulate now
                     const int idx = d[q] - win0;
                     const uint32_t old = acc[idx];
-                    acc[idx] = __float_as_uint(__fadd_rn(old == kSent ? 0.0f : __uint_as_float(old), s));
+                    const float sum = __fadd_rn(old == kSent ? 0.0f : __uint_as_float(old), s);
+                    acc[idx] = __float_as_uint(sum);
                     touched |= 1u << (idx >> 5);
+                    if (old == kSent && is_live(seg, d[q])) my_matches++;  // first clause on this doc
+                    if (sum > te) hot |= 1u << (idx >> 5);                // may still enter the heap
                     direct++;
                 }
             }
@@ -536,10 +540,10 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
     }
     __syncwarp();
     long long w0 = kNoMoreDocs;
-    uint32_t touched = 0;
+    uint32_t touched = 0, hot = 0, my_matches = 0;
     for (int t = 0; t < T; t++) {
         if (stream_refill(seg, p, sh.term[t], cdocs + t * kBlock, cscores + t * kBlock, lo, hi, lane, 0,
-                          -2147483647 - 1, sh.acc, touched))
+                          -2147483647 - 1, sh.acc, touched, hot, my_matches, INFINITY))
             w0 = min(w0, (long long)cdocs[t * kBlock + sh.term[t].pos]);
     }
 
@@ -569,6 +573,11 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
         }
         int next_doc = kNoMoreDocs;
         touched = 0;
+        hot = 0;
+        em.theta_in = max(em.theta_in, inherited);
+        float te = em.theta_local;
+        if (em.theta_in > kOrderedNegInf) te = fmaxf(te, ordered_to_float(em.theta_in));
+        const bool open = te == -INFINITY;
         // ---- clauses in order: drain each stream up to the window end
         for (int t = 0; t < T; t++) {
             WTerm& tc = sh.term[t];
@@ -581,7 +590,7 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                     if (lane == 0) tc.pos = pos;
                     __syncwarp();
                     if (!stream_refill(seg, p, tc, cdocs + t * kBlock, cscores + t * kBlock, lo, hi, lane, win0,
-                                       win1, sh.acc, touched)) {
+                                       win1, sh.acc, touched, hot, my_matches, te)) {
                         pos = n = 0;
                         break;
                     }
@@ -595,8 +604,11 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                 if (in_win) {
                     const int idx = d - win0;
                     const uint32_t old = sh.acc[idx];
-                    sh.acc[idx] = __float_as_uint(__fadd_rn(old == kSent ? 0.0f : __uint_as_float(old), cs[i]));
+                    const float sum = __fadd_rn(old == kSent ? 0.0f : __uint_as_float(old), cs[i]);
+                    sh.acc[idx] = __float_as_uint(sum);
                     touched |= 1u << (idx >> 5);
+                    if (old == kSent && is_live(seg, d)) my_matches++;
+                    if (sum > te) hot |= 1u << (idx >> 5);
                 }
                 pos += c;
                 if (c < 32 && pos < n) break;  // next cached doc is beyond this window
@@ -609,44 +621,57 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
             __syncwarp();
         }
         touched = __reduce_or_sync(0xffffffffu, touched);
-        // ---- scan touched docs in docid order, four 32-doc steps (one nibble of `touched`) at a
-        // time: the common case "nothing in these 128 docs can enter the heap" costs ~8
-        // instructions per step
+        hot = __reduce_or_sync(0xffffffffu, hot);
+        // ---- window epilogue.  Matches were counted when a doc was first touched; only 32-doc
+        // steps holding a doc whose (partial) sum exceeded theta are scanned for candidates, the
+        // rest of the touched steps are just re-armed.
         {
-            em.theta_in = max(em.theta_in, inherited);
-            float te = em.theta_local;
-            if (em.theta_in > kOrderedNegInf) te = fmaxf(te, ordered_to_float(em.theta_in));
-            const bool open = te == -INFINITY;
+            uint32_t cold = touched & ~hot;
+            while (cold) {
+                const int s = __ffs(cold) - 1;
+                cold &= cold - 1;
+                sh.acc[s * 32 + lane] = kSent;
+            }
             uint32_t newc_n = 0;
-            const bool has_live = seg.live != nullptr;
-#pragma unroll 1
-            for (int g = 0; g < 8; g++) {
-                if (!((touched >> (4 * g)) & 0xfu)) continue;
-                const int i0 = g * 128 + lane;
-                uint32_t v[4];
-                bool pr[4];
-                bool any_cand = false;
-                uint32_t cnt = 0;
-#pragma unroll
-                for (int s = 0; s < 4; s++) {
-                    v[s] = sh.acc[i0 + 32 * s];
-                    pr[s] = v[s] != kSent;
+            while (hot) {
+                const int s = __ffs(hot) - 1;
+                hot &= hot - 1;
+                const int idx = s * 32 + lane;
+                const uint32_t v = sh.acc[idx];
+                sh.acc[idx] = kSent;
+                const float sc = __uint_as_float(v);
+                const bool cand = v != kSent && (open || sc > te) && is_live(seg, win0 + idx);
+                const uint32_t cm = __ballot_sync(0xffffffffu, cand);
+                if (!cm || em.overflow) continue;
+                const uint32_t c = __popc(cm);
+                CandRun* hdr = reinterpret_cast<CandRun*>(p.cand_arena);
+                if (em.run_slot == kNone || em.run_cnt + c > em.run_cap) {
+                    uint32_t slot = 0;
+                    const uint32_t cap = em.run_slot == kNone ? kRunFirst : kRunMin;
+                    if (lane == 0) {
+                        const unsigned long long s64 = atomicAdd(p.arena_next, (unsigned long long)cap + 1ull);
+                        slot = (s64 + cap + 1ull > (unsigned long long)p.arena_slots) ? kNone : (uint32_t)s64;
+                        if (slot == kNone) atomicOr(p.error_flag, 1u);
+                        else if (em.run_slot == kNone) p.item_head[item_idx] = slot;
+                        else hdr[em.run_slot] = CandRun{slot, em.run_cnt};
+                    }
+                    slot = __shfl_sync(0xffffffffu, slot, 0);
+                    if (slot == kNone) {
+                        em.overflow = true;
+                        continue;
+                    }
+                    em.run_slot = slot;
+                    em.run_cap = cap;
+                    em.run_cnt = 0;
                 }
-#pragma unroll
-                for (int s = 0; s < 4; s++) {
-                    if (pr[s]) sh.acc[i0 + 32 * s] = kSent;
-                    if (has_live && pr[s]) pr[s] = is_live(seg, win0 + i0 + 32 * s);
-                    cnt += pr[s];
-                    any_cand |= pr[s] && (open || __uint_as_float(v[s]) > te);
+                if (cand) {
+                    const uint32_t r = __popc(cm & ((1u << lane) - 1u));
+                    p.cand_arena[em.run_slot + 1 + em.run_cnt + r] = rg_hit{win0 + idx + seg.doc_base, sc};
+                    if (newc_n + r < (uint32_t)kNewcW) sh.newc[newc_n + r] = sc;
                 }
-                if (!__any_sync(0xffffffffu, any_cand)) {
-                    em.matches += __reduce_add_sync(0xffffffffu, cnt);
-                    continue;
-                }
-#pragma unroll
-                for (int s = 0; s < 4; s++)
-                    wemit_step(em, p, item_idx, lane, pr[s], win0 + i0 + 32 * s + seg.doc_base, __uint_as_float(v[s]),
-                               te, open, sh.newc, newc_n);
+                em.run_cnt += c;
+                newc_n += c;
+                if (lane == 0) hdr[em.run_slot] = CandRun{kNone, em.run_cnt};
             }
             wtheta_update(em, p.k, kcap, lane, sh.newc, newc_n, p.item_theta + item_idx);
             __syncwarp();
@@ -654,7 +679,8 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
         if (next_doc == kNoMoreDocs) break;
         w0 = next_doc;
     }
-    if (lane == 0) p.item_matches[item_idx] = em.matches;
+    my_matches = __reduce_add_sync(0xffffffffu, my_matches);
+    if (lane == 0) p.item_matches[item_idx] = my_matches;
 }
 
 // ------------------------------------------------------------------------------------------
