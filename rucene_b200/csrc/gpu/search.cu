@@ -189,11 +189,14 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
     // query starts, its range r-1 has (almost always) finished and published theta; candidate
     // lists then stay ~k*ln(n) per query instead of per range.  Item order itself is untouched.
     auto by_rank = [](std::vector<uint32_t>& ids, const std::vector<uint32_t>& rank) {
-        std::vector<uint32_t> perm(ids.size());
-        for (uint32_t i = 0; i < perm.size(); i++) perm[i] = i;
-        std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return rank[a] < rank[b]; });
+        // stable counting sort on the range index (<= 256 distinct values)
+        uint32_t max_rank = 0;
+        for (uint32_t r : rank) max_rank = std::max(max_rank, r);
+        std::vector<uint32_t> start(max_rank + 2, 0);
+        for (uint32_t r : rank) start[r + 1]++;
+        for (uint32_t r = 0; r <= max_rank; r++) start[r + 1] += start[r];
         std::vector<uint32_t> out(ids.size());
-        for (uint32_t i = 0; i < perm.size(); i++) out[i] = ids[perm[i]];
+        for (size_t i = 0; i < ids.size(); i++) out[start[rank[i]]++] = ids[i];
         ids.swap(out);
     };
     by_rank(hp.or_ids, hp.or_rank);
