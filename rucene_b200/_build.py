@@ -3,9 +3,8 @@
 librucene_gpu.so   : CUDA kernels + the C ABI of include/rucene_gpu.h   (nvcc, sm_100a)
 librucene_codec.so : host write side / BM25 host math / synthetic index (g++)
 
-The CPU oracle (oracle/liboracle.so) is test infrastructure and is built by its own Makefile;
-`build_oracle()` only shells out to it for the callers that are allowed to use it
-(tests/, __graft_entry__, bench.py's cpu_baseline leg).
+(The CPU checker under oracle/ is test infrastructure with its own Makefile; nothing in this
+package builds, loads or mentions it.)
 """
 import os
 import shutil
@@ -58,10 +57,6 @@ def gpu_lib_path():
     return os.path.join(LIB, "librucene_gpu.so")
 
 
-def oracle_lib_path():
-    return os.path.join(ROOT, "oracle", "liboracle.so")
-
-
 def build_codec(force=False):
     srcs = _glob(os.path.join(PKG, "csrc", "codec"), (".cpp",))
     deps = srcs + _glob(os.path.join(PKG, "csrc", "host"), (".hpp",)) + _glob(INC, (".h",))
@@ -84,15 +79,6 @@ def build_gpu(force=False):
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
         _run([nvcc] + NVCC_FLAGS + ["-I" + INC, "-I" + gdir, "-shared", "-o", out] + srcs
              + ["-lcudart"], "build_gpu.log")
-    return out
-
-
-def build_oracle(force=False):
-    odir = os.path.join(ROOT, "oracle")
-    out = oracle_lib_path()
-    deps = [os.path.join(odir, "oracle.cpp"), os.path.join(odir, "oracle.h")]
-    if force or _newer(out, deps):
-        _run(["make", "-C", odir] + (["-B"] if force else []))
     return out
 
 
