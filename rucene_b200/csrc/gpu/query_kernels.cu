@@ -272,27 +272,18 @@ __device__ __forceinline__ bool is_live(const SegDev& seg, int doc) {
 }
 
 // ------------------------------------------------------------------------------------------
-// k_eval_or  — one WARP per work item; presence bitmaps + essential-clause scoring.
+// k_eval_or  — one WARP per work item, no block-level synchronisation at all.
 // ------------------------------------------------------------------------------------------
-// A work item is a (query, segment, docid range).  The warp walks it in windows of kWw docids that
-// always start at a real posting.  Per window:
-//   1. bitmaps: each clause's doc-delta blocks are unpacked and prefix-summed ONCE (freq blocks
-//      are not touched); postings below the window end set a bit in the clause's 1024-bit window
-//      bitmap straight from registers, the rest of the block waits in a 128-docid stream cache.
-//      Lane w owns word w (docs 32w..32w+31) of every bitmap.
-//   2. counts : U = OR of the bitmaps (& live docs); popcount(U) = the docs BulkScorer would have
-//      collected in this window (total_hits), exactly.
-//   3. scoring: only docs that can still enter the top-k heap are scored.  theta is a proven lower
-//      bound of the heap root; clauses are split MaxScore-style: the lowest-weight clauses whose
-//      clause-order f32 sum of w*(k1+1) stays <= theta are non-essential — a doc matching only
-//      those scores <= theta (BM25's tf-norm factor is <= 1, f32 addition is monotone) and could
-//      never replace the heap root (top_docs.rs:72 needs root.score < score).  Docs matching an
-//      essential clause (bitmap E) are compacted over the lanes in docid order and scored exactly:
-//      for each clause present, in clause order from 0.0f (DisjunctionSumScorer::score_sum), the
-//      posting's ordinal = clause cursor + rank of the doc inside the clause's bitmap, its freq is
-//      read by random access into the freq block (extract1), then BM25 with IEEE ops.
-//      theta == -inf (cold start) makes every clause essential, i.e. every doc is scored.
-//   4. emit   : scored docs with score > theta go, in docid order, to the candidate run.
+// A work item is a (query, segment, docid range) of ~32K postings.  Every clause is a *cached
+// block stream*: its current 128-posting block lives decoded AND scored in shared memory
+// (docids + BM25 scores), so each block is unpacked, prefix-summed and scored exactly once.
+// The warp walks the range in windows of kWw docids that always start at a real posting:
+//   for clause t = 0..T-1 (clause order): consume the stream's postings < window end, 32 per
+//       step, "acc[d] = acc[d] + s" in the warp-private accumulator window — pair order ==
+//       clause order == DisjunctionSumScorer::score_sum's f32 order; refill the stream (decode the
+//       next block / the vint tail) whenever it runs dry;
+//   scan the touched 32-doc steps in docid order -> total_hits, theta filter, candidates;
+//   next window start = min over clauses of their next cached docid (exact).
 constexpr int kOrWarps = 4;
 constexpr int kOrThreads = kOrWarps * 32;
 constexpr int kWw = 1024;            // docids per window
@@ -303,28 +294,27 @@ struct WTerm {
     const BlockDesc* blk_desc;
     const float* cache;
     uint32_t nb;        // full blocks
-    uint32_t cblk;      // block held by the stream cache (nb = vint tail)
-    uint32_t n;         // valid entries in the stream cache (docs < hi)
+    uint32_t cur;       // next block to decode (nb = vint tail, nb+1 = exhausted)
+    uint32_t n;         // valid entries in the stream cache
     uint32_t pos;       // next unconsumed entry
     uint32_t term_id;
-    uint32_t last;      // no further block after the cached one
-    uint32_t ord0;      // ordinal (block*128+index) of the first posting of the current window
     float w1;           // weight * (k1 + 1)
 };
 
-struct alignas(16) WarpShared {  // followed by topk[kcap] floats, then cdocs[T][128]
-    uint32_t bits[kMaxTerms][32];
-    uint32_t pre[kMaxTerms][32];   // ordinal of the first posting of word w, per clause
+struct WarpShared {            // followed by topk[kcap] floats, then cdocs[T][128], cscores[T][128]
+    uint32_t acc[kWw];
     WTerm term[kMaxTerms];
     float newc[kNewcW];
 };
 
+// warp-level candidate emitter state (registers, uniform across lanes)
 struct WEmit {
     float* topk;       // shared memory, kcap floats
     uint32_t topk_n;
     float theta_local;
     uint32_t theta_in;
     uint32_t run_slot, run_cap, run_cnt;
+    uint32_t matches;
     bool overflow;
 };
 
@@ -351,8 +341,49 @@ __device__ __forceinline__ void wtheta_recompute(const WEmit& em, uint32_t k, in
     argmin = mi;
 }
 
-__device__ __noinline__ void wtheta_update(WEmit& em, uint32_t k, uint32_t kcap, int lane, const float* newc,
-                                           uint32_t newc_n, uint32_t* theta_out) {
+// Emit one 32-doc step (docid order).  `newc`/`newc_n`: this window's candidate scores for the
+// theta tracker.
+__device__ __forceinline__ void wemit_step(WEmit& em, const EvalParams& p, uint32_t item_idx, int lane,
+                                           bool present, int gdoc, float score, float te, bool open,
+                                           float* newc, uint32_t& newc_n) {
+    const uint32_t pm = __ballot_sync(0xffffffffu, present);
+    if (!pm) return;
+    em.matches += __popc(pm);
+    const uint32_t cm = __ballot_sync(0xffffffffu, present && (open || score > te));
+    if (!cm || em.overflow) return;
+    const uint32_t c = __popc(cm);
+    CandRun* hdr = reinterpret_cast<CandRun*>(p.cand_arena);
+    if (em.run_slot == kNone || em.run_cnt + c > em.run_cap) {
+        uint32_t slot = 0;
+        const uint32_t cap = em.run_slot == kNone ? kRunFirst : kRunMin;
+        if (lane == 0) {
+            const unsigned long long s64 = atomicAdd(p.arena_next, (unsigned long long)cap + 1ull);
+            slot = (s64 + cap + 1ull > (unsigned long long)p.arena_slots) ? kNone : (uint32_t)s64;
+            if (slot == kNone) atomicOr(p.error_flag, 1u);
+            else if (em.run_slot == kNone) p.item_head[item_idx] = slot;
+            else hdr[em.run_slot] = CandRun{slot, em.run_cnt};
+        }
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot == kNone) {
+            em.overflow = true;
+            return;
+        }
+        em.run_slot = slot;
+        em.run_cap = cap;
+        em.run_cnt = 0;
+    }
+    if ((cm >> lane) & 1u) {
+        const uint32_t r = __popc(cm & ((1u << lane) - 1u));
+        p.cand_arena[em.run_slot + 1 + em.run_cnt + r] = rg_hit{gdoc, score};
+        if (newc_n + r < (uint32_t)kNewcW) newc[newc_n + r] = score;
+    }
+    em.run_cnt += c;
+    newc_n += c;
+    if (lane == 0) hdr[em.run_slot] = CandRun{kNone, em.run_cnt};
+}
+
+__device__ __forceinline__ void wtheta_update(WEmit& em, uint32_t k, uint32_t kcap, int lane,
+                                              const float* newc, uint32_t newc_n, uint32_t* theta_out) {
     const uint32_t n_new = min(newc_n, (uint32_t)kNewcW);
     if (n_new == 0 || k > kcap) return;
     __syncwarp();
@@ -382,91 +413,99 @@ __device__ __noinline__ void wtheta_update(WEmit& em, uint32_t k, uint32_t kcap,
     }
 }
 
-// freq of tail entry j (posting_reader.rs:308-333): sequential vint walk; singleton: total_term_freq
-__device__ __noinline__ int tail_freq_at(const SegDev& seg, uint32_t term_id, uint32_t j) {
-    const TermDev td = seg.terms[term_id];
-    if (td.doc_freq == 1) return td.singleton_freq;
-    const uint8_t* p = seg.tails + td.tail_off;
-    uint32_t pos = 0;
-    int f = 1;
-    for (uint32_t i = 0; i <= j; i++) {
-        const uint32_t code = (uint32_t)read_vint(p, pos);
-        f = (code & 1u) ? 1 : read_vint(p, pos);
-    }
-    return f;
-}
-
-// Decode the docids of clause block `b` (b == nb: vint tail / singleton) into the stream cache and
-// set the window bits of its postings below win1 straight from registers.  Doc deltas only.
-// Entries >= hi are cut off; entries < lo (first block of the range only) are skipped.
-__device__ __noinline__ void stream_fill(const SegDev& seg, WTerm& tc, int32_t* cd, uint32_t* bits, uint32_t b,
-                                         int lo, int hi, int win0, int win1, int lane) {
-    int4 docs;
-    uint32_t n_in = kBlock;
-    if (b < tc.nb) {
-        const BlockDesc bd = tc.blk_desc[b];
-        const int base = b == 0 ? 0 : __ldg(tc.blk_last + b - 1);
-        const int4 dl = unpack4(seg.arena + bd.off16, (int)(bd.bits & 0xff), lane, seg.version, seg.sb_mask);
-        docs = deltas_to_docs(dl, base);
-        reinterpret_cast<int4*>(cd)[lane] = docs;
-    } else {
-        const TermDev td = seg.terms[tc.term_id];
-        n_in = td.tail_n;
-        if (lane == 0) {
-            if (td.doc_freq == 1) {
-                cd[0] = td.singleton_doc;
-            } else {
-                const uint8_t* p = seg.tails + td.tail_off;
-                uint32_t pos = 0;
-                int32_t acc = td.tail_base;
-                for (uint32_t i = 0; i < td.tail_n; i++) {
-                    const uint32_t code = (uint32_t)read_vint(p, pos);
-                    acc += (int32_t)(code >> 1);
-                    cd[i] = acc;
-                    if (!(code & 1u)) read_vint(p, pos);
+// Refill clause t's stream cache with its next block (or vint tail): unpack, docid scan, norm
+// gather, BM25 — once per block.  Entries outside [lo, hi) are trimmed.  Returns false when the
+// list is exhausted.  Warp-cooperative; all lanes must call it.
+// When called while clause t is being drained into the window [win0, win1) the new block's
+// postings below win1 are accumulated straight from registers (no round trip through the cache).
+__device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParams& p, WTerm& tc, int32_t* cd,
+                                           float* cs, int lo, int hi, int lane, int win0, int win1,
+                                           uint32_t* acc, uint32_t& touched, uint32_t& hot, uint32_t& my_matches,
+                                           float te) {
+    for (;;) {
+        const uint32_t b = tc.cur;
+        if (b > tc.nb) return false;
+        int4 docs, freqs;
+        uint32_t n_in = kBlock;
+        if (b < tc.nb) {
+            const BlockDesc bd = tc.blk_desc[b];
+            const int base = b == 0 ? 0 : __ldg(tc.blk_last + b - 1);
+            const uint4* part = seg.arena + bd.off16;
+            const int4 dl = unpack4(part, (int)(bd.bits & 0xff), lane, seg.version, seg.sb_mask);
+            freqs = unpack4(part + ((bd.bits >> 16) & 0xff), (int)((bd.bits >> 8) & 0xff), lane, seg.version,
+                            seg.sb_mask);
+            docs = deltas_to_docs(dl, base);
+        } else {  // vint tail / singleton (posting_reader.rs:308-333, :545-547): lane 0 decodes
+            const TermDev td = seg.terms[tc.term_id];
+            n_in = td.tail_n;
+            if (n_in == 0) {
+                if (lane == 0) tc.cur = tc.nb + 1;
+                __syncwarp();
+                return false;
+            }
+            if (lane == 0) {
+                int32_t* fq = reinterpret_cast<int32_t*>(cs);
+                decode_tail(seg, td, cd, fq);
+            }
+            __syncwarp();
+            const int i0 = 4 * lane;
+            const int32_t* fq = reinterpret_cast<const int32_t*>(cs);
+            docs = make_int4(i0 < (int)n_in ? cd[i0] : kNoMoreDocs, i0 + 1 < (int)n_in ? cd[i0 + 1] : kNoMoreDocs,
+                             i0 + 2 < (int)n_in ? cd[i0 + 2] : kNoMoreDocs, i0 + 3 < (int)n_in ? cd[i0 + 3] : kNoMoreDocs);
+            freqs = make_int4(i0 < (int)n_in ? fq[i0] : 1, i0 + 1 < (int)n_in ? fq[i0 + 1] : 1,
+                              i0 + 2 < (int)n_in ? fq[i0 + 2] : 1, i0 + 3 < (int)n_in ? fq[i0 + 3] : 1);
+            __syncwarp();
+        }
+        const int d[4] = {docs.x, docs.y, docs.z, docs.w};
+        const int f[4] = {freqs.x, freqs.y, freqs.z, freqs.w};
+        float sc[4];
+        uint32_t below = 0, inside = 0, direct = 0;
+        const float w1 = tc.w1;
+        const float* cache = tc.cache;
+        const uint8_t* norms = seg.norms;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const bool ok = d[q] >= lo && d[q] < hi;
+            below += d[q] < lo;
+            inside += ok;
+            float s = 0.f;
+            if (ok) {
+                const float nrm = norms ? __ldg(cache + __ldg(norms + d[q])) : p.k1;
+                s = bm25_score(w1, (float)f[q], nrm);
+                if (d[q] < win1) {  // still inside the window being drained: accumulate now
+                    const int idx = d[q] - win0;
+                    const uint32_t old = acc[idx];
+                    const float sum = __fadd_rn(old == kSent ? 0.0f : __uint_as_float(old), s);
+                    acc[idx] = __float_as_uint(sum);
+                    touched |= 1u << (idx >> 5);
+                    if (old == kSent && is_live(seg, d[q])) my_matches++;  // first clause on this doc
+                    if (sum > te) hot |= 1u << (idx >> 5);                // may still enter the heap
+                    direct++;
                 }
             }
+            sc[q] = s;
+        }
+        reinterpret_cast<int4*>(cd)[lane] = docs;
+        reinterpret_cast<float4*>(cs)[lane] = make_float4(sc[0], sc[1], sc[2], sc[3]);
+        below = __reduce_add_sync(0xffffffffu, below);
+        inside = __reduce_add_sync(0xffffffffu, inside);
+        direct = __reduce_add_sync(0xffffffffu, direct);
+        const bool past_end = below + inside < n_in;  // some posting >= hi: nothing further in range
+        below += direct;
+        inside -= direct;
+        if (lane == 0) {
+            tc.pos = below;
+            tc.n = below + inside;
+            tc.cur = past_end ? tc.nb + 1 : b + 1;
         }
         __syncwarp();
-        const int i0 = 4 * lane;
-        docs = make_int4(i0 < (int)n_in ? cd[i0] : kNoMoreDocs, i0 + 1 < (int)n_in ? cd[i0 + 1] : kNoMoreDocs,
-                         i0 + 2 < (int)n_in ? cd[i0 + 2] : kNoMoreDocs, i0 + 3 < (int)n_in ? cd[i0 + 3] : kNoMoreDocs);
+        if (inside > 0) return true;
+        if (past_end) return false;
+        // whole block consumed (all below lo, or all accumulated directly): decode the next one
     }
-    const int d[4] = {docs.x, docs.y, docs.z, docs.w};
-    // window bits: consecutive postings of a lane usually share a word -> merge before the atomic
-    uint32_t below = 0, under = 0, inwin = 0;
-    int cw = -1;
-    uint32_t cm = 0;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        below += d[q] < lo;
-        under += d[q] < hi;
-        if (d[q] >= lo && d[q] < win1) {
-            inwin++;
-            const int r = d[q] - win0;
-            const int w = r >> 5;
-            if (w != cw) {
-                if (cm) atomicOr(bits + cw, cm);
-                cw = w;
-                cm = 0;
-            }
-            cm |= 1u << (r & 31);
-        }
-    }
-    if (cm) atomicOr(bits + cw, cm);
-    below = __reduce_add_sync(0xffffffffu, below);
-    under = __reduce_add_sync(0xffffffffu, under);
-    inwin = __reduce_add_sync(0xffffffffu, inwin);
-    if (lane == 0) {
-        tc.cblk = b;
-        tc.pos = below + inwin;
-        tc.n = under;
-        tc.last = (under < n_in || b >= tc.nb || (b + 1 == tc.nb && seg.terms[tc.term_id].tail_n == 0)) ? 1u : 0u;
-    }
-    __syncwarp();
 }
 
-__global__ void __launch_bounds__(kOrThreads, 6)
+__global__ void __launch_bounds__(kOrThreads, 4)
 k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, uint32_t warp_bytes,
           uint32_t kcap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -482,9 +521,9 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
     const SegDev seg = p.segs[it.seg];
     const int T = it.n_terms;
     const int lo = it.lo, hi = it.hi;
+    float* cscores = reinterpret_cast<float*>(cdocs + T * kBlock);
 
-    for (int t = 0; t < T; t++) sh.bits[t][lane] = 0;
-    bool positive = true;  // MaxScore pruning needs non-negative clause weights
+    for (int i = lane; i < kWw; i += 32) sh.acc[i] = kSent;
     if (lane < T) {
         const ItemClause c = p.clauses[it.clause_begin + lane];
         const TermDev td = seg.terms[c.term_id];
@@ -493,30 +532,19 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
         tc.blk_desc = seg.blk_desc + td.blk_begin;
         tc.cache = p.caches + (size_t)c.cache_id * 256;
         tc.nb = td.n_blocks;
-        tc.cblk = lower_bound_i32(tc.blk_last, 0, td.n_blocks, lo);
+        tc.cur = lower_bound_i32(tc.blk_last, 0, td.n_blocks, lo);
         tc.n = 0;
         tc.pos = 0;
         tc.term_id = c.term_id;
-        tc.last = (tc.cblk > td.n_blocks || (tc.cblk == td.n_blocks && td.tail_n == 0)) ? 1u : 0u;
-        tc.ord0 = 0;
         tc.w1 = __fmul_rn(c.weight, __fadd_rn(p.k1, 1.0f));
-        positive = tc.w1 >= 0.0f;
     }
-    positive = __all_sync(0xffffffffu, positive);
     __syncwarp();
-    // prime the streams (no window yet: win1 = lo sets no bits)
     long long w0 = kNoMoreDocs;
+    uint32_t touched = 0, hot = 0, my_matches = 0;
     for (int t = 0; t < T; t++) {
-        WTerm& tc = sh.term[t];
-        int32_t* cd = cdocs + t * kBlock;
-        uint32_t b = tc.cblk;
-        while (!tc.last || b == tc.cblk) {
-            if (tc.last && tc.n == 0 && (b > tc.nb || (b == tc.nb && seg.terms[tc.term_id].tail_n == 0))) break;
-            stream_fill(seg, tc, cd, sh.bits[t], b, lo, hi, lo, lo, lane);
-            if (tc.pos < tc.n || tc.last) break;
-            b++;
-        }
-        if (tc.pos < tc.n) w0 = min(w0, (long long)cd[tc.pos]);
+        if (stream_refill(seg, p, sh.term[t], cdocs + t * kBlock, cscores + t * kBlock, lo, hi, lane, 0,
+                          -2147483647 - 1, sh.acc, touched, hot, my_matches, INFINITY))
+            w0 = min(w0, (long long)cdocs[t * kBlock + sh.term[t].pos]);
     }
 
     WEmit em;
@@ -527,169 +555,95 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
     em.run_slot = kNone;
     em.run_cap = 0;
     em.run_cnt = 0;
+    em.matches = 0;
     em.overflow = false;
+    // theta look-back: the up-to-32 preceding items of this heap chain (each publishes
+    // max(own, inherited)), re-read every 8 windows
     const bool lb_ok = (uint32_t)lane < it.chain_pos;
     const uint32_t* theta_lb = p.item_theta + item_idx - 1 - (lb_ok ? lane : 0);
-    uint32_t win_no = 0, my_matches = 0;
-    uint32_t ess = (1u << T) - 1u;
-    float ess_te = -INFINITY;
-    const bool has_norms = seg.norms != nullptr;
+    uint32_t win_no = 0;
 
     while (w0 < hi) {
         const int win0 = (int)w0;
         const int win1 = (int)min((long long)hi, w0 + kWw);
+        uint32_t inherited = 0;
         if ((win_no++ & 7u) == 0 && it.chain_pos) {
-            uint32_t inh = lb_ok ? ld_volatile_u32(theta_lb) : 0u;
-            inh = __reduce_max_sync(0xffffffffu, inh);
-            em.theta_in = max(em.theta_in, inh);
+            inherited = lb_ok ? ld_volatile_u32(theta_lb) : 0u;
+            inherited = __reduce_max_sync(0xffffffffu, inherited);
         }
         int next_doc = kNoMoreDocs;
-        // ---- 1. bitmaps
+        touched = 0;
+        hot = 0;
+        em.theta_in = max(em.theta_in, inherited);
+        float te = em.theta_local;
+        if (em.theta_in > kOrderedNegInf) te = fmaxf(te, ordered_to_float(em.theta_in));
+        const bool open = te == -INFINITY;
+        // ---- clauses in order: drain each stream up to the window end
         for (int t = 0; t < T; t++) {
             WTerm& tc = sh.term[t];
-            int32_t* cd = cdocs + t * kBlock;
-            uint32_t* bits = sh.bits[t];
+            const int32_t* cd = cdocs + t * kBlock;
+            const float* cs = cscores + t * kBlock;
             uint32_t pos = tc.pos, n = tc.n;
-            if (lane == 0) tc.ord0 = tc.cblk * kBlock + pos;
-            // leftovers of the cached block
-            while (pos < n) {
+            for (;;) {
+                if (pos >= n) {
+                    if (tc.cur > tc.nb) break;  // exhausted
+                    if (lane == 0) tc.pos = pos;
+                    __syncwarp();
+                    if (!stream_refill(seg, p, tc, cdocs + t * kBlock, cscores + t * kBlock, lo, hi, lane, win0,
+                                       win1, sh.acc, touched, hot, my_matches, te)) {
+                        pos = n = 0;
+                        break;
+                    }
+                    pos = tc.pos;
+                    n = tc.n;
+                }
                 const uint32_t i = pos + lane;
                 const int d = i < n ? cd[i] : kNoMoreDocs;
                 const bool in_win = d < win1;
                 const uint32_t c = __popc(__ballot_sync(0xffffffffu, in_win));  // sorted: a prefix
-                if (in_win) atomicOr(bits + ((d - win0) >> 5), 1u << ((d - win0) & 31));
-                pos += c;
-                if (c < 32) break;
-            }
-            // further blocks that start inside the window
-            if (pos >= n) {
-                if (lane == 0) tc.pos = pos;
-                __syncwarp();
-                while (!tc.last) {
-                    stream_fill(seg, tc, cd, bits, tc.cblk + 1, lo, hi, win0, win1, lane);
-                    if (tc.pos < tc.n) break;
+                if (in_win) {
+                    const int idx = d - win0;
+                    const uint32_t old = sh.acc[idx];
+                    const float sum = __fadd_rn(old == kSent ? 0.0f : __uint_as_float(old), cs[i]);
+                    sh.acc[idx] = __float_as_uint(sum);
+                    touched |= 1u << (idx >> 5);
+                    if (old == kSent && is_live(seg, d)) my_matches++;
+                    if (sum > te) hot |= 1u << (idx >> 5);
                 }
-                pos = tc.pos;
-                n = tc.n;
-            } else if (lane == 0) {
+                pos += c;
+                if (c < 32 && pos < n) break;  // next cached doc is beyond this window
+            }
+            if (lane == 0) {
                 tc.pos = pos;
+                tc.n = n;
             }
             if (pos < n) next_doc = min(next_doc, cd[pos]);
             __syncwarp();
         }
-        // ---- 2. theta, essential split, counts
-        float te = em.theta_local;
-        if (em.theta_in > kOrderedNegInf) te = fmaxf(te, ordered_to_float(em.theta_in));
-        const bool open = te == -INFINITY;
-        if (te != ess_te) {  // theta moved: redo the split (O(T^2), T <= 9)
-            ess_te = te;
-            ess = (1u << T) - 1u;
-            if (!open && positive) {
-                uint32_t non = 0;
-                for (int round = 0; round < T; round++) {
-                    int best = -1;
-                    float bw = INFINITY;
-                    for (int t = 0; t < T; t++)
-                        if (!((non >> t) & 1u) && sh.term[t].w1 < bw) {
-                            bw = sh.term[t].w1;
-                            best = t;
-                        }
-                    const uint32_t trial = non | (1u << best);
-                    float ub = 0.0f;
-                    for (int t = 0; t < T; t++)
-                        if ((trial >> t) & 1u) ub = __fadd_rn(ub, sh.term[t].w1);
-                    if (ub <= te) non = trial;
-                    else break;
-                }
-                ess &= ~non;
+        touched = __reduce_or_sync(0xffffffffu, touched);
+        hot = __reduce_or_sync(0xffffffffu, hot);
+        // ---- window epilogue.  Matches were counted when a doc was first touched; only 32-doc
+        // steps holding a doc whose (partial) sum exceeded theta are scanned for candidates, the
+        // rest of the touched steps are just re-armed.
+        {
+            uint32_t cold = touched & ~hot;
+            while (cold) {
+                const int s = __ffs(cold) - 1;
+                cold &= cold - 1;
+                sh.acc[s * 32 + lane] = kSent;
             }
-        }
-        uint32_t U = 0, E = 0;
-        for (int t = 0; t < T; t++) {
-            const uint32_t bw = sh.bits[t][lane];
-            U |= bw;
-            if ((ess >> t) & 1u) E |= bw;
-        }
-        if (seg.live) {
-            uint32_t lv = 0;
-            const int d0 = win0 + 32 * lane;
-            for (int j = 0; j < 32; j++) {
-                const int d = d0 + j;
-                if (d < win1 && ((seg.live[d >> 6] >> (d & 63)) & 1ull)) lv |= 1u << j;
-            }
-            U &= lv;
-            E &= lv;
-        }
-        my_matches += __popc(U);
-        // ---- 3+4. exact scores of the E docs, compacted over the lanes in docid order
-        const uint32_t ecnt = __popc(E);
-        uint32_t eincl = ecnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, eincl, o);
-            if (lane >= o) eincl += v;
-        }
-        const uint32_t total_e = __shfl_sync(0xffffffffu, eincl, 31);
-        uint32_t newc_n = 0;
-        if (total_e) {
-            // ordinal of the first posting of each word, per clause
-            for (int t = 0; t < T; t++) {
-                const uint32_t cnt = __popc(sh.bits[t][lane]);
-                uint32_t incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                sh.pre[t][lane] = incl - cnt + sh.term[t].ord0;
-            }
-            __syncwarp();
-            for (uint32_t r0 = 0; r0 < total_e; r0 += 32) {
-                const uint32_t r = r0 + lane;
-                const bool act = r < total_e;
-                // word holding the r-th E doc: smallest w with eincl[w] > r
-                int w = 0;
-#pragma unroll
-                for (int step = 16; step; step >>= 1) {
-                    const uint32_t v = __shfl_sync(0xffffffffu, eincl, w + step - 1);
-                    if (v <= r) w += step;
-                }
-                w = min(w, 31);
-                const uint32_t Ew = __shfl_sync(0xffffffffu, E, w);
-                const uint32_t ebase = __shfl_sync(0xffffffffu, eincl - ecnt, w);
-                float score = 0.0f;
-                int doc = 0;
-                if (act) {
-                    // (r - ebase)-th set bit of Ew
-                    uint32_t m = Ew;
-                    for (uint32_t s = r - ebase; s; s--) m &= m - 1;
-                    const int j = __ffs(m) - 1;
-                    doc = win0 + 32 * w + j;
-                    const uint32_t below = (1u << j) - 1u;
-                    const uint32_t nb8 = has_norms ? (uint32_t)__ldg(seg.norms + doc) : 0u;
-                    for (int t = 0; t < T; t++) {
-                        const uint32_t bw = sh.bits[t][w];
-                        if ((bw >> j) & 1u) {
-                            const WTerm& tc = sh.term[t];
-                            const uint32_t ord = sh.pre[t][w] + __popc(bw & below);
-                            const uint32_t b = ord >> 7, idx = ord & 127u;
-                            int f;
-                            if (b < tc.nb) {
-                                const BlockDesc bd = tc.blk_desc[b];
-                                f = extract1(seg.arena + bd.off16 + ((bd.bits >> 16) & 0xff),
-                                             (int)((bd.bits >> 8) & 0xff), (int)idx, seg.version, seg.sb_mask);
-                            } else {
-                                f = tail_freq_at(seg, tc.term_id, idx);
-                            }
-                            const float nrm = has_norms ? __ldg(tc.cache + nb8) : p.k1;
-                            score = __fadd_rn(score, bm25_score(tc.w1, (float)f, nrm));
-                        }
-                    }
-                }
-                const bool cand = act && (open || score > te);
-                const uint32_t cmask = __ballot_sync(0xffffffffu, cand);
-                if (!cmask || em.overflow) continue;
-                const uint32_t c = __popc(cmask);
+            uint32_t newc_n = 0;
+            while (hot) {
+                const int s = __ffs(hot) - 1;
+                hot &= hot - 1;
+                const int idx = s * 32 + lane;
+                const uint32_t v = sh.acc[idx];
+                sh.acc[idx] = kSent;
+                const float sc = __uint_as_float(v);
+                const bool cand = v != kSent && (open || sc > te) && is_live(seg, win0 + idx);
+                const uint32_t cm = __ballot_sync(0xffffffffu, cand);
+                if (!cm || em.overflow) continue;
+                const uint32_t c = __popc(cm);
                 CandRun* hdr = reinterpret_cast<CandRun*>(p.cand_arena);
                 if (em.run_slot == kNone || em.run_cnt + c > em.run_cap) {
                     uint32_t slot = 0;
@@ -711,20 +665,17 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                     em.run_cnt = 0;
                 }
                 if (cand) {
-                    const uint32_t rr = __popc(cmask & ((1u << lane) - 1u));
-                    p.cand_arena[em.run_slot + 1 + em.run_cnt + rr] = rg_hit{doc + seg.doc_base, score};
-                    if (newc_n + rr < (uint32_t)kNewcW) sh.newc[newc_n + rr] = score;
+                    const uint32_t r = __popc(cm & ((1u << lane) - 1u));
+                    p.cand_arena[em.run_slot + 1 + em.run_cnt + r] = rg_hit{win0 + idx + seg.doc_base, sc};
+                    if (newc_n + r < (uint32_t)kNewcW) sh.newc[newc_n + r] = sc;
                 }
                 em.run_cnt += c;
                 newc_n += c;
                 if (lane == 0) hdr[em.run_slot] = CandRun{kNone, em.run_cnt};
             }
+            wtheta_update(em, p.k, kcap, lane, sh.newc, newc_n, p.item_theta + item_idx);
+            __syncwarp();
         }
-        __syncwarp();
-        for (int t = 0; t < T; t++) sh.bits[t][lane] = 0;
-        if (newc_n) wtheta_update(em, p.k, kcap, lane, sh.newc, newc_n, p.item_theta + item_idx);
-        __syncwarp();
-        next_doc = __reduce_min_sync(0xffffffffu, next_doc);
         if (next_doc == kNoMoreDocs) break;
         w0 = next_doc;
     }
@@ -1119,7 +1070,7 @@ void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_i
                     uint32_t max_terms) {
     if (!n) return;
     const uint32_t kcap = (std::min<uint32_t>(p.k, kMaxK) + 31u) & ~31u;
-    size_t wb = sizeof(WarpShared) + (size_t)kcap * sizeof(float) + (size_t)max_terms * kBlock * 4;
+    size_t wb = sizeof(WarpShared) + (size_t)kcap * sizeof(float) + (size_t)max_terms * kBlock * 8;
     wb = (wb + 15) & ~size_t(15);
     const size_t smem = wb * kOrWarps;
     static size_t attr = 0;
