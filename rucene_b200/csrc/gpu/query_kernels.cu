@@ -493,6 +493,7 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
         const bool past_end = below + inside < n_in;  // some posting >= hi: nothing further in range
         below += direct;
         inside -= direct;
+        __syncwarp();  // every lane has read tc.cur / tc.nb above
         if (lane == 0) {
             tc.pos = below;
             tc.n = below + inside;
@@ -587,6 +588,7 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
             for (;;) {
                 if (pos >= n) {
                     if (tc.cur > tc.nb) break;  // exhausted
+                    __syncwarp();  // every lane has read tc.pos / tc.n / tc.cur
                     if (lane == 0) tc.pos = pos;
                     __syncwarp();
                     if (!stream_refill(seg, p, tc, cdocs + t * kBlock, cscores + t * kBlock, lo, hi, lane, win0,
@@ -613,6 +615,7 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                 pos += c;
                 if (c < 32 && pos < n) break;  // next cached doc is beyond this window
             }
+            __syncwarp();  // every lane has read this clause's cursor
             if (lane == 0) {
                 tc.pos = pos;
                 tc.n = n;
