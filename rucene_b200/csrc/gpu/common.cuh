@@ -54,7 +54,7 @@ struct ItemClause {
     uint32_t term_id;
     float weight;      // idf * boost
     uint32_t cache_id;
-    uint32_t pad;
+    uint32_t flags;    // bit0: MUST_NOT clause (ReqNotScorer: excludes, never scores)
 };
 
 struct WorkItem {

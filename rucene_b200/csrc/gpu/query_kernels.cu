@@ -41,6 +41,7 @@ constexpr uint32_t kNone = 0xffffffffu;
 constexpr uint32_t kRunMin = 256;       // minimum candidate run length (slots)
 constexpr uint32_t kRunFirst = 63;      // first run of a warp-sized work item (most items emit few)
 constexpr uint32_t kSent = 0x7fc0dead;  // "no posting yet" marker in the accumulator window (a NaN)
+constexpr uint32_t kExcl = 0x7fc0beef;  // doc matched a MUST_NOT clause (ReqNotScorer): not a hit
 
 // ------------------------------------------------------------------------------------------
 // candidate emission + theta tracking (shared by both evaluation kernels)
@@ -299,9 +300,30 @@ struct WTerm {
     uint32_t pos;       // next unconsumed entry
     uint32_t term_id;
     float w1;           // weight * (k1 + 1)
+    uint32_t is_not;    // MUST_NOT clause: its postings exclude docs (search/scorer/req_not_scorer.rs)
+    uint32_t pad;
 };
 
-struct WarpShared {            // followed by topk[kcap] floats, then cdocs[T][128], cscores[T][128]
+// One posting of a clause lands on window slot idx.  SHOULD clause: clause-order f32 add, first
+// touch counts the match.  MUST_NOT clause (drained after every SHOULD clause of the window): a doc
+// that is present becomes kExcl and its match is taken back.
+__device__ __forceinline__ void accumulate_posting(uint32_t* acc, int idx, float s, bool is_not, bool live,
+                                                   float te, uint32_t& touched, uint32_t& hot,
+                                                   uint32_t& my_matches) {
+    const uint32_t old = acc[idx];
+    if (!is_not) {
+        const float sum = __fadd_rn(old == kSent ? 0.0f : __uint_as_float(old), s);
+        acc[idx] = __float_as_uint(sum);
+        touched |= 1u << (idx >> 5);
+        if (old == kSent && live) my_matches++;
+        if (sum > te) hot |= 1u << (idx >> 5);
+    } else if (old != kSent && old != kExcl) {
+        acc[idx] = kExcl;
+        if (live) my_matches--;
+    }
+}
+
+struct alignas(16) WarpShared {  // followed by topk[kcap] floats, then cdocs[T][128], cscores[T][128]
     uint32_t acc[kWw];
     WTerm term[kMaxTerms];
     float newc[kNewcW];
@@ -473,13 +495,8 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
                 const float nrm = norms ? __ldg(cache + __ldg(norms + d[q])) : p.k1;
                 s = bm25_score(w1, (float)f[q], nrm);
                 if (d[q] < win1) {  // still inside the window being drained: accumulate now
-                    const int idx = d[q] - win0;
-                    const uint32_t old = acc[idx];
-                    const float sum = __fadd_rn(old == kSent ? 0.0f : __uint_as_float(old), s);
-                    acc[idx] = __float_as_uint(sum);
-                    touched |= 1u << (idx >> 5);
-                    if (old == kSent && is_live(seg, d[q])) my_matches++;  // first clause on this doc
-                    if (sum > te) hot |= 1u << (idx >> 5);                // may still enter the heap
+                    accumulate_posting(acc, d[q] - win0, s, tc.is_not != 0, is_live(seg, d[q]), te, touched, hot,
+                                       my_matches);
                     direct++;
                 }
             }
@@ -538,6 +555,7 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
         tc.pos = 0;
         tc.term_id = c.term_id;
         tc.w1 = __fmul_rn(c.weight, __fadd_rn(p.k1, 1.0f));
+        tc.is_not = c.flags & 1u;
     }
     __syncwarp();
     long long w0 = kNoMoreDocs;
@@ -603,15 +621,9 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                 const int d = i < n ? cd[i] : kNoMoreDocs;
                 const bool in_win = d < win1;
                 const uint32_t c = __popc(__ballot_sync(0xffffffffu, in_win));  // sorted: a prefix
-                if (in_win) {
-                    const int idx = d - win0;
-                    const uint32_t old = sh.acc[idx];
-                    const float sum = __fadd_rn(old == kSent ? 0.0f : __uint_as_float(old), cs[i]);
-                    sh.acc[idx] = __float_as_uint(sum);
-                    touched |= 1u << (idx >> 5);
-                    if (old == kSent && is_live(seg, d)) my_matches++;
-                    if (sum > te) hot |= 1u << (idx >> 5);
-                }
+                if (in_win)
+                    accumulate_posting(sh.acc, d - win0, cs[i], tc.is_not != 0, is_live(seg, d), te, touched, hot,
+                                       my_matches);
                 pos += c;
                 if (c < 32 && pos < n) break;  // next cached doc is beyond this window
             }
@@ -643,7 +655,7 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                 const uint32_t v = sh.acc[idx];
                 sh.acc[idx] = kSent;
                 const float sc = __uint_as_float(v);
-                const bool cand = v != kSent && (open || sc > te) && is_live(seg, win0 + idx);
+                const bool cand = v != kSent && v != kExcl && (open || sc > te) && is_live(seg, win0 + idx);
                 const uint32_t cm = __ballot_sync(0xffffffffu, cand);
                 if (!cm || em.overflow) continue;
                 const uint32_t c = __popc(cm);
@@ -699,6 +711,7 @@ struct AndShared {
     int32_t slab_freqs[kEvalWarps][kBlock];
     TermCtx term[kMaxTerms];
     uint32_t term_id[kMaxTerms];
+    uint32_t is_not[kMaxTerms];            // MUST_NOT clauses: a hit kills the lead doc, a miss keeps it
     uint32_t hint[kEvalWarps][kMaxTerms];  // per-warp galloping hints into the skip tables
     EmitShared emit;
 };
@@ -720,6 +733,7 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
         const TermDev td = seg.terms[c.term_id];
         TermCtx& tc = sh.term[threadIdx.x];
         sh.term_id[threadIdx.x] = c.term_id;
+        sh.is_not[threadIdx.x] = c.flags & 1u;
         tc.blk_last = seg.blk_last + td.blk_begin;
         tc.blk_desc = seg.blk_desc + td.blk_begin;
         tc.cache = p.caches + (size_t)c.cache_id * 256;
@@ -809,6 +823,7 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
             const TermCtx& tc = sh.term[t];
             const uint32_t nb = tc.nb;
             const float w1 = tc.w1;
+            const bool neg = sh.is_not[t] != 0;
             for (int r = 0; r < kAndSteps; r++) {
                 const int slot = warp * kBlock + r * 32 + lane;
                 int d = sh.ldoc[slot];
@@ -818,7 +833,7 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
                     bi = lower_bound_gallop(tc.blk_last, min(sh.hint[warp][t], nb), nb, d);
                     if (bi == nb && !(tc.tail_n > 0 && (nb == 0 || d > tc.tail_base))) {
                         pending = false;  // beyond the last posting of this clause
-                        sh.ldoc[slot] = kNoMoreDocs;
+                        if (!neg) sh.ldoc[slot] = kNoMoreDocs;
                     }
                 }
                 uint32_t pend_mask = __ballot_sync(0xffffffffu, pending);
@@ -854,7 +869,9 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
                             if (sh.slab_docs[warp][m] < d) l = m + 1;
                             else h = m;
                         }
-                        if (l < n_in && sh.slab_docs[warp][l] == d) {
+                        if (l < n_in && sh.slab_docs[warp][l] == d && neg) {
+                            sh.ldoc[slot] = kNoMoreDocs;  // ReqNotScorer: excluded
+                        } else if (l < n_in && sh.slab_docs[warp][l] == d) {
                             int f;
                             if (full_block) {
                                 f = extract1(seg.arena + bd.off16 + ((bd.bits >> 16) & 0xff),
@@ -864,7 +881,7 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
                             }
                             const float nrm = seg.norms ? __ldg(tc.cache + __ldg(seg.norms + d)) : p.k1;
                             sh.lscore[slot] = __fadd_rn(sh.lscore[slot], bm25_score(w1, (float)f, nrm));
-                        } else {
+                        } else if (!neg) {
                             sh.ldoc[slot] = kNoMoreDocs;
                         }
                         pending = false;

@@ -47,7 +47,8 @@ struct HostPlan {
 
 struct QShape {
     int type = -1;  // kTypeOr / kTypeAnd
-    std::vector<uint32_t> clause_idx;  // indices into the caller's clause array, evaluation order
+    std::vector<uint32_t> clause_idx;  // scoring clauses (indices into the caller's array), evaluation order
+    std::vector<uint32_t> not_idx;     // MUST_NOT clauses (ReqNotScorer)
 };
 
 // BooleanQuery::build + BooleanWeight::create_scorer wiring for the accelerated shapes.
@@ -71,23 +72,27 @@ QShape classify(const rg_query& q, const rg_clause* clauses, uint32_t n_clauses_
     int32_t msm = q.min_should_match > 0 ? q.min_should_match : (musts.empty() ? 1 : 0);
     if (musts.size() + shoulds.size() + must_nots.size() == 0)
         throw ArgError("boolean query should at least contain one inner query!");
-    if (!must_nots.empty())
-        throw Unsupported("MUST_NOT clauses (ReqNotScorer) are not accelerated yet");
     if (!musts.empty() && !shoulds.empty())
         throw Unsupported("MUST+SHOULD (ReqOptScorer) is not accelerated yet");
-    if (musts.size() + shoulds.size() == 1) {  // collapses to the clause itself (:66-75)
+    if (musts.empty() && shoulds.empty())
+        throw Unsupported("pure MUST_NOT (MatchAllDocsQuery) is not accelerated");
+    if (msm > 1) throw Unsupported("min_should_match > 1 is not accelerated yet");
+    if (musts.size() + shoulds.size() + must_nots.size() > (size_t)kMaxTerms)
+        throw Unsupported("more than 9 clauses");
+    // BooleanWeight::create_scorer (:253-278): ReqNotScorer(must | should, must_not); the excluded
+    // set is the union of the MUST_NOT clauses (DisjunctionSumScorer with needs_scores = false)
+    s.not_idx = must_nots;
+    if (must_nots.empty() && musts.size() + shoulds.size() == 1) {  // collapses to the clause (:66-75)
         s.type = kTypeOr;
         s.clause_idx = musts.empty() ? shoulds : musts;
         return s;
     }
     if (!musts.empty()) {
-        if (musts.size() > (size_t)kMaxTerms) throw Unsupported("more than 9 MUST clauses");
-        s.type = kTypeAnd;
+        s.type = kTypeAnd;  // one MUST + MUST_NOTs also takes the lead-list kernel
         s.clause_idx = musts;
         return s;
     }
     if (shoulds.size() >= 10) throw Unsupported(">= 10 SHOULD clauses use DisiPriorityQueue");
-    if (msm > 1) throw Unsupported("min_should_match > 1 is not accelerated yet");
     s.type = kTypeOr;
     s.clause_idx = shoulds;
     return s;
@@ -117,6 +122,11 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
             }
             const bool new_group = mode == RG_MODE_SEARCH_PARALLEL || !group_open;
             if (dead || present.empty()) continue;
+            std::vector<uint32_t> nots;  // MUST_NOT clauses present in this leaf (:236-251)
+            for (uint32_t ci : shape.not_idx) {
+                const uint32_t t = clauses[ci].term_id;
+                if (t < seg.host_terms.size() && seg.host_terms[t].doc_freq > 0) nots.push_back(ci);
+            }
             uint64_t cost = 0, bytes = 0, total_df = 0;
             if (shape.type == kTypeAnd) {
                 // ConjunctionScorer::new: stable sort by cost() = doc_freq (:30)
@@ -146,6 +156,11 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
             const uint32_t clause_begin = (uint32_t)hp.clauses.size();
             for (uint32_t ci : present)
                 hp.clauses.push_back(ItemClause{clauses[ci].term_id, clauses[ci].weight, clauses[ci].cache_id, 0});
+            for (uint32_t ci : nots) {
+                hp.clauses.push_back(ItemClause{clauses[ci].term_id, 0.0f, clauses[ci].cache_id, 1u});
+                bytes += seg.host_terms[clauses[ci].term_id].enc_bytes;
+            }
+            const uint32_t n_item_terms = (uint32_t)(present.size() + nots.size());
             // ranges of ~range_postings postings, at most 256 per (query, leaf): long lists get
             // longer ranges (a range is one warp's sequential job; there are thousands of warps)
             uint64_t R = (cost + range_postings - 1) / range_postings;
@@ -161,7 +176,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 it.query = qi;
                 it.seg = (uint16_t)si;
                 it.type = (uint8_t)shape.type;
-                it.n_terms = (uint8_t)present.size();
+                it.n_terms = (uint8_t)n_item_terms;
                 it.lo = (int32_t)((uint64_t)seg.max_doc * r / R);
                 it.hi = (int32_t)((uint64_t)seg.max_doc * (r + 1) / R);
                 it.clause_begin = clause_begin;
@@ -178,9 +193,13 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                         const TermHost& th = seg.host_terms[clauses[ci].term_id];
                         tails |= th.tail_n > 0 && (th.n_blocks == 0 || it.hi - 1 > th.tail_base);
                     }
+                    for (uint32_t ci : nots) {
+                        const TermHost& th = seg.host_terms[clauses[ci].term_id];
+                        tails |= th.tail_n > 0 && (th.n_blocks == 0 || it.hi - 1 > th.tail_base);
+                    }
                     (tails ? hp.ort_ids : hp.or_ids).push_back(idx);
                     (tails ? hp.ort_rank : hp.or_rank).push_back((uint32_t)r);
-                    hp.max_or_terms = std::max<uint32_t>(hp.max_or_terms, (uint32_t)present.size());
+                    hp.max_or_terms = std::max<uint32_t>(hp.max_or_terms, n_item_terms);
                 }
             }
         }

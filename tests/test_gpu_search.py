@@ -120,6 +120,29 @@ def test_synthetic_zipf_index_c3_c4_shapes():
     helpers.assert_same_topdocs(got, want, "k=100")
 
 
+def test_must_not_clauses_req_not_scorer():
+    """ReqNotScorer (search/scorer/req_not_scorer.rs; wiring boolean_query.rs:253-278): MUST_NOT with
+    pure-MUST and pure-SHOULD queries, several MUST_NOT clauses, absent clauses, tails, ranges."""
+    rng = np.random.default_rng(21)
+    dfs = [0, 1, 60, 128, 300, 2500, 9000, 26000, 52000]
+    segs = [helpers.build_segment(rng, 70000, dfs, live_fraction=lf)[0] for lf in (None, 0.85)]
+    specs = []
+    for i in range(80):
+        n_pos = int(rng.integers(1, 4))
+        n_neg = int(rng.integers(1, 3))
+        terms = [int(x) for x in rng.choice(len(dfs), size=n_pos + n_neg, replace=False)]
+        occ = ob.MUST if i % 2 else ob.SHOULD
+        specs.append(("bool", [(occ, t) for t in terms[:n_pos]] + [(ob.MUST_NOT, t) for t in terms[n_pos:]], 0))
+    specs += [("bool", [(ob.SHOULD, 8), (ob.MUST_NOT, 7), (ob.MUST_NOT, 6), (ob.MUST_NOT, 0)], 0),
+              ("bool", [(ob.MUST, 7), (ob.MUST, 8), (ob.MUST_NOT, 6), (ob.MUST_NOT, 1)], 0),
+              ("bool", [(ob.MUST, 0), (ob.MUST_NOT, 5)], 0),
+              ("bool", [(ob.SHOULD, 0), (ob.MUST_NOT, 5)], 0)]
+    for k, rp in ((10, 0), (100, 1500)):
+        for mode in (0, 1):
+            got, want = _run_both(segs, specs, k, mode=mode, range_postings=rp)
+            helpers.assert_same_topdocs(got, want, "must_not k=%d rp=%d mode=%d" % (k, rp, mode))
+
+
 def test_reference_style_api():
     """Reads like examples/example.rs:111-117."""
     rng = np.random.default_rng(5)
