@@ -485,22 +485,35 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
         const float w1 = tc.w1;
         const float* cache = tc.cache;
         const uint8_t* norms = seg.norms;
+        const bool neg = tc.is_not != 0;
+        // stage the gathers: 4 norm bytes, then 4 cache entries, then 4 divisions — branch-free, so the
+        // loads of all four postings are in flight together (out-of-range lanes read a safe slot)
+        bool ok[4];
+        float nrm[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            const bool ok = d[q] >= lo && d[q] < hi;
+            ok[q] = d[q] >= lo && d[q] < hi;
             below += d[q] < lo;
-            inside += ok;
-            float s = 0.f;
-            if (ok) {
-                const float nrm = norms ? __ldg(cache + __ldg(norms + d[q])) : p.k1;
-                s = bm25_score(w1, (float)f[q], nrm);
-                if (d[q] < win1) {  // still inside the window being drained: accumulate now
-                    accumulate_posting(acc, d[q] - win0, s, tc.is_not != 0, is_live(seg, d[q]), te, touched, hot,
-                                       my_matches);
-                    direct++;
-                }
+            inside += ok[q];
+        }
+        if (norms) {
+            uint32_t nb8[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) nb8[q] = __ldg(norms + (ok[q] ? d[q] : lo));
+#pragma unroll
+            for (int q = 0; q < 4; q++) nrm[q] = __ldg(cache + nb8[q]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) nrm[q] = p.k1;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) sc[q] = bm25_score(w1, (float)f[q], nrm[q]);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (ok[q] && d[q] < win1) {  // still inside the window being drained: accumulate now
+                accumulate_posting(acc, d[q] - win0, sc[q], neg, is_live(seg, d[q]), te, touched, hot, my_matches);
+                direct++;
             }
-            sc[q] = s;
         }
         reinterpret_cast<int4*>(cd)[lane] = docs;
         reinterpret_cast<float4*>(cs)[lane] = make_float4(sc[0], sc[1], sc[2], sc[3]);
