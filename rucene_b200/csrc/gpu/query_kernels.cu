@@ -1,14 +1,14 @@
 // query_kernels.cu — the fused query-evaluation kernels (sm_100a, integer/HBM-bound work).
 //
-//   k_eval_or   : TermQuery / pure-SHOULD BooleanQuery.  One CTA per (query, segment, docid
-//                 range).  Posting blocks are decoded warp-per-block straight from the HBM image,
-//                 docids rebuilt with a warp scan, BM25 computed per posting and accumulated into
-//                 a shared-memory window of 4096 docids, term after term in clause order — the
-//                 f32 summation order of DisjunctionSumScorer::score_sum
-//                 (search/scorer/disjunction_scorer.rs:211-225).  The window is then scanned in
-//                 docid order: every present doc is a match (total_hits), and docs that can still
-//                 enter the top-k heap are appended to the query's candidate list.
-//   k_eval_and  : pure-MUST BooleanQuery (ConjunctionScorer, search/scorer/conjunction_scorer.rs).
+//   k_eval_or   : TermQuery / pure-SHOULD BooleanQuery (+ MUST_NOT).  One WARP per (query, segment,
+//                 docid range).  Every clause is a cached block stream: a posting block is unpacked,
+//                 prefix-summed (warp scan) and BM25-scored exactly once into shared memory; clauses
+//                 are drained in clause order into a warp-private window of 1024 docids — the f32
+//                 summation order of DisjunctionSumScorer::score_sum
+//                 (search/scorer/disjunction_scorer.rs:211-225).  Matches are counted when a doc is
+//                 first touched (total_hits); only docs whose sum can still beat the top-k heap root
+//                 are scanned and appended, in docid order, to the query's candidate list.
+//   k_eval_and  : pure-MUST BooleanQuery (+ MUST_NOT) (ConjunctionScorer, search/scorer/conjunction_scorer.rs).
 //                 The cheapest list leads (stable sort by cost, :30); 8 lead blocks per step are
 //                 decoded, every lead doc locates its block in each other list via the level-0
 //                 skip table (galloping binary search), that block is decoded once per warp into
@@ -33,8 +33,6 @@ namespace rg {
 
 constexpr int kEvalThreads = 256;
 constexpr int kEvalWarps = kEvalThreads / 32;
-constexpr int kWin = 2048;              // docids per accumulator window (k_eval_or)
-constexpr int kWinSteps = kWin / kEvalThreads;  // 16 slots per lane
 constexpr int kNewcMax = 512;           // candidate scores fed to the theta tracker per window
 constexpr int kMaxK = 1024;             // theta tracking / replay heap capacity
 constexpr uint32_t kNone = 0xffffffffu;
@@ -361,47 +359,6 @@ __device__ __forceinline__ void wtheta_recompute(const WEmit& em, uint32_t k, in
     }
     theta = m;
     argmin = mi;
-}
-
-// Emit one 32-doc step (docid order).  `newc`/`newc_n`: this window's candidate scores for the
-// theta tracker.
-__device__ __forceinline__ void wemit_step(WEmit& em, const EvalParams& p, uint32_t item_idx, int lane,
-                                           bool present, int gdoc, float score, float te, bool open,
-                                           float* newc, uint32_t& newc_n) {
-    const uint32_t pm = __ballot_sync(0xffffffffu, present);
-    if (!pm) return;
-    em.matches += __popc(pm);
-    const uint32_t cm = __ballot_sync(0xffffffffu, present && (open || score > te));
-    if (!cm || em.overflow) return;
-    const uint32_t c = __popc(cm);
-    CandRun* hdr = reinterpret_cast<CandRun*>(p.cand_arena);
-    if (em.run_slot == kNone || em.run_cnt + c > em.run_cap) {
-        uint32_t slot = 0;
-        const uint32_t cap = em.run_slot == kNone ? kRunFirst : kRunMin;
-        if (lane == 0) {
-            const unsigned long long s64 = atomicAdd(p.arena_next, (unsigned long long)cap + 1ull);
-            slot = (s64 + cap + 1ull > (unsigned long long)p.arena_slots) ? kNone : (uint32_t)s64;
-            if (slot == kNone) atomicOr(p.error_flag, 1u);
-            else if (em.run_slot == kNone) p.item_head[item_idx] = slot;
-            else hdr[em.run_slot] = CandRun{slot, em.run_cnt};
-        }
-        slot = __shfl_sync(0xffffffffu, slot, 0);
-        if (slot == kNone) {
-            em.overflow = true;
-            return;
-        }
-        em.run_slot = slot;
-        em.run_cap = cap;
-        em.run_cnt = 0;
-    }
-    if ((cm >> lane) & 1u) {
-        const uint32_t r = __popc(cm & ((1u << lane) - 1u));
-        p.cand_arena[em.run_slot + 1 + em.run_cnt + r] = rg_hit{gdoc, score};
-        if (newc_n + r < (uint32_t)kNewcW) newc[newc_n + r] = score;
-    }
-    em.run_cnt += c;
-    newc_n += c;
-    if (lane == 0) hdr[em.run_slot] = CandRun{kNone, em.run_cnt};
 }
 
 __device__ __forceinline__ void wtheta_update(WEmit& em, uint32_t k, uint32_t kcap, int lane,

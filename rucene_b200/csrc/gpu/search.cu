@@ -17,10 +17,10 @@ using namespace rg;
 struct rg_batch {
     uint32_t n_queries = 0, k = 0, mode = 0;
     float k1 = 1.2f;
-    uint32_t n_items = 0, n_or = 0, n_ort = 0, n_and = 0, n_groups = 0, n_leaves = 0, max_or_terms = 1;
+    uint32_t n_items = 0, n_or = 0, n_and = 0, n_groups = 0, n_leaves = 0, max_or_terms = 1;
     DevBuf<WorkItem> items;
     DevBuf<ItemClause> clauses;
-    DevBuf<uint32_t> or_ids, ort_ids, and_ids;  // OR items without / with a vint tail in scope
+    DevBuf<uint32_t> or_ids, and_ids;  // launch order (range-major) of the OR / AND work items
     DevBuf<uint32_t> group_item_begin, group_out;
     DevBuf<uint32_t> item_head, item_matches, item_theta;
     DevBuf<unsigned long long> arena_next;  // [0] bump pointer, [1] error flag (as u32 view)
@@ -38,8 +38,8 @@ namespace {
 struct HostPlan {
     std::vector<WorkItem> items;
     std::vector<ItemClause> clauses;
-    std::vector<uint32_t> or_ids, ort_ids, and_ids;
-    std::vector<uint32_t> or_rank, ort_rank, and_rank;  // range index of each id (launch-order key)
+    std::vector<uint32_t> or_ids, and_ids;
+    std::vector<uint32_t> or_rank, and_rank;  // range index of each id (launch-order key)
     std::vector<uint32_t> group_item_begin, group_out;
     uint64_t postings = 0, algo_bytes = 0;
     uint32_t max_or_terms = 1;
@@ -188,17 +188,8 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                     hp.and_ids.push_back(idx);
                     hp.and_rank.push_back((uint32_t)r);
                 } else {
-                    bool tails = false;  // does any clause's vint tail / singleton reach into [lo, hi)?
-                    for (uint32_t ci : present) {
-                        const TermHost& th = seg.host_terms[clauses[ci].term_id];
-                        tails |= th.tail_n > 0 && (th.n_blocks == 0 || it.hi - 1 > th.tail_base);
-                    }
-                    for (uint32_t ci : nots) {
-                        const TermHost& th = seg.host_terms[clauses[ci].term_id];
-                        tails |= th.tail_n > 0 && (th.n_blocks == 0 || it.hi - 1 > th.tail_base);
-                    }
-                    (tails ? hp.ort_ids : hp.or_ids).push_back(idx);
-                    (tails ? hp.ort_rank : hp.or_rank).push_back((uint32_t)r);
+                    hp.or_ids.push_back(idx);
+                    hp.or_rank.push_back((uint32_t)r);
                     hp.max_or_terms = std::max<uint32_t>(hp.max_or_terms, n_item_terms);
                 }
             }
@@ -219,7 +210,6 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
         ids.swap(out);
     };
     by_rank(hp.or_ids, hp.or_rank);
-    by_rank(hp.ort_ids, hp.ort_rank);
     by_rank(hp.and_ids, hp.and_rank);
     // heap groups = contiguous item runs starting at chain-start items
     for (uint32_t i = 0; i < hp.items.size(); i++)
@@ -275,7 +265,6 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     b->k1 = p->k1;
     b->n_items = (uint32_t)hp.items.size();
     b->n_or = (uint32_t)hp.or_ids.size();
-    b->n_ort = (uint32_t)hp.ort_ids.size();
     b->n_and = (uint32_t)hp.and_ids.size();
     b->n_groups = (uint32_t)hp.group_out.size();
     b->max_or_terms = hp.max_or_terms;
@@ -286,11 +275,10 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     up(b->items, hp.items, st);
     up(b->clauses, hp.clauses, st);
     up(b->or_ids, hp.or_ids, st);
-    up(b->ort_ids, hp.ort_ids, st);
     up(b->and_ids, hp.and_ids, st);
     up(b->group_item_begin, hp.group_item_begin, st);
     up(b->group_out, hp.group_out, st);
-    b->h2d_bytes = b->items.bytes() + b->clauses.bytes() + b->or_ids.bytes() + b->ort_ids.bytes() + b->and_ids.bytes() +
+    b->h2d_bytes = b->items.bytes() + b->clauses.bytes() + b->or_ids.bytes() + b->and_ids.bytes() +
                    b->group_item_begin.bytes() + b->group_out.bytes();
     b->item_head.alloc(std::max<uint32_t>(1, b->n_items));
     b->item_matches.alloc(std::max<uint32_t>(1, b->n_items));
@@ -301,7 +289,7 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     b->out_total.alloc(std::max<uint32_t>(1, n_queries));
     if (p->mode == RG_MODE_SEARCH_PARALLEL)
         b->leaf_records.alloc((size_t)b->n_leaves * std::max<uint32_t>(1, n_queries) * leaf_record_bytes(p->k));
-    b->kernels_per_run = (b->n_or ? 1 : 0) + (b->n_ort ? 1 : 0) + (b->n_and ? 1 : 0) + (b->n_groups ? 1 : 0) +
+    b->kernels_per_run = (b->n_or ? 1 : 0) + (b->n_and ? 1 : 0) + (b->n_groups ? 1 : 0) +
                          (p->mode == RG_MODE_SEARCH_PARALLEL ? 1 : 0);
     RG_CUDA_CHECK(cudaStreamSynchronize(st));
     *out = b.release();
@@ -339,8 +327,6 @@ int rg_batch_run(rg_engine* e, rg_batch* b) {
     ep.error_flag = reinterpret_cast<uint32_t*>(b->arena_next.p + 1);
     RG_CUDA_CHECK(cudaEventRecord(e->ev2, st));
     launch_eval_or(st, ep, b->or_ids.p, b->n_or, b->max_or_terms);
-    RG_CUDA_CHECK(cudaGetLastError());
-    launch_eval_or(st, ep, b->ort_ids.p, b->n_ort, b->max_or_terms);
     RG_CUDA_CHECK(cudaGetLastError());
     launch_eval_and(st, ep, b->and_ids.p, b->n_and);
     RG_CUDA_CHECK(cudaGetLastError());
@@ -408,7 +394,7 @@ int rg_batch_stats(rg_engine* e, rg_batch* b, uint64_t out[8]) {
     out[3] = used;
     out[4] = b->kernels_per_run;
     out[5] = b->h2d_bytes;
-    out[6] = b->n_or + b->n_ort;
+    out[6] = b->n_or;
     out[7] = b->n_and;
     return RG_OK;
     RG_CATCH
