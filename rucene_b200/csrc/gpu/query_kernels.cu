@@ -410,9 +410,15 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
             const BlockDesc bd = tc.blk_desc[b];
             const int base = b == 0 ? 0 : __ldg(tc.blk_last + b - 1);
             const uint4* part = seg.arena + bd.off16;
-            const int4 dl = unpack4(part, (int)(bd.bits & 0xff), lane, seg.version, seg.sb_mask);
-            freqs = unpack4(part + ((bd.bits >> 16) & 0xff), (int)((bd.bits >> 8) & 0xff), lane, seg.version,
-                            seg.sb_mask);
+            const int bdoc = (int)(bd.bits & 0xff), bfrq = (int)((bd.bits >> 8) & 0xff);
+            int4 dl;
+            if (seg.version > 0 && bdoc > 0 && bfrq > 0) {  // the common case: both parts SIMD128-packed
+                dl = unpack4_simd128(part, bdoc, lane);
+                freqs = unpack4_simd128(part + ((bd.bits >> 16) & 0xff), bfrq, lane);
+            } else {
+                dl = unpack4(part, bdoc, lane, seg.version, seg.sb_mask);
+                freqs = unpack4(part + ((bd.bits >> 16) & 0xff), bfrq, lane, seg.version, seg.sb_mask);
+            }
             docs = deltas_to_docs(dl, base);
         } else {  // vint tail / singleton (posting_reader.rs:308-333, :545-547): lane 0 decodes
             const TermDev td = seg.terms[tc.term_id];
@@ -611,11 +617,15 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
         // steps holding a doc whose (partial) sum exceeded theta are scanned for candidates, the
         // rest of the touched steps are just re-armed.
         {
-            uint32_t cold = touched & ~hot;
-            while (cold) {
-                const int s = __ffs(cold) - 1;
-                cold &= cold - 1;
-                sh.acc[s * 32 + lane] = kSent;
+            const uint32_t cold = touched & ~hot;
+#pragma unroll
+            for (int g = 0; g < kWw / 128; g++) {  // re-arm four 32-doc steps per iteration
+                const uint32_t nib = (cold >> (4 * g)) & 0xfu;
+                if (nib) {
+#pragma unroll
+                    for (int s = 0; s < 4; s++)
+                        if ((nib >> s) & 1u) sh.acc[(4 * g + s) * 32 + lane] = kSent;
+                }
             }
             uint32_t newc_n = 0;
             while (hot) {

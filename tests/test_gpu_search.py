@@ -120,6 +120,17 @@ def test_synthetic_zipf_index_c3_c4_shapes():
     helpers.assert_same_topdocs(got, want, "k=100")
 
 
+def test_large_k_and_many_leaves():
+    """k = 1000 (heap/theta capacity 1024) over five leaves, both collector modes."""
+    rng = np.random.default_rng(31)
+    dfs = [3, 200, 1500, 6000, 15000, 30000]
+    segs = [helpers.build_segment(rng, 40000 + 1000 * i, dfs)[0] for i in range(5)]
+    specs = [("term", 5), ("term", 2)] + _mixed_specs(rng, len(dfs), 22, kinds=("and", "or"))
+    for mode in (0, 1):
+        got, want = _run_both(segs, specs, 1000, mode=mode, range_postings=5000)
+        helpers.assert_same_topdocs(got, want, "k=1000 mode %d" % mode)
+
+
 def test_must_not_clauses_req_not_scorer():
     """ReqNotScorer (search/scorer/req_not_scorer.rs; wiring boolean_query.rs:253-278): MUST_NOT with
     pure-MUST and pure-SHOULD queries, several MUST_NOT clauses, absent clauses, tails, ranges."""
