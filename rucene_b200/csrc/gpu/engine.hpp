@@ -153,6 +153,7 @@ struct rg_engine {
     std::vector<float> h_caches;
     bool caches_dirty = true;
     rg::DevBuf<rg_hit> cand_arena;
+    rg::DevBuf<uint8_t> spare_slab;  // device slab of the last destroyed rg_batch, reused by the next
     uint64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     float last_decode_ms = -1.f, last_eval_ms = -1.f, last_replay_ms = -1.f, last_run_ms = -1.f;

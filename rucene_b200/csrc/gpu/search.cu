@@ -9,25 +9,40 @@
 #include <algorithm>
 #include <cstring>
 #include <memory>
+#include <type_traits>
 
 #include "engine.hpp"
 
 using namespace rg;
 
+// A typed window into the batch's device slab.
+template <class T>
+struct Span {
+    T* p = nullptr;
+    size_t n = 0;
+    size_t bytes() const { return n * sizeof(T); }
+};
+
 struct rg_batch {
     uint32_t n_queries = 0, k = 0, mode = 0;
     float k1 = 1.2f;
     uint32_t n_items = 0, n_or = 0, n_and = 0, n_groups = 0, n_leaves = 0, max_or_terms = 1;
-    DevBuf<WorkItem> items;
-    DevBuf<ItemClause> clauses;
-    DevBuf<uint32_t> or_ids, and_ids;  // launch order (range-major) of the OR / AND work items
-    DevBuf<uint32_t> group_item_begin, group_out;
-    DevBuf<uint32_t> item_head, item_matches, item_theta;
-    DevBuf<unsigned long long> arena_next;  // [0] bump pointer, [1] error flag (as u32 view)
-    DevBuf<rg_hit> out_hits;
-    DevBuf<uint32_t> out_counts;
-    DevBuf<unsigned long long> out_total;
-    DevBuf<uint8_t> leaf_records;
+    // One device allocation per batch (cudaMalloc/cudaFree cost milliseconds each next to a
+    // multi-GB index image; the engine keeps the last slab for the next batch).  Layout:
+    // [plan arrays copied from the host][item_head: 0xff per run][everything zeroed per run].
+    DevBuf<uint8_t> slab;
+    Span<WorkItem> items;
+    Span<ItemClause> clauses;
+    Span<uint32_t> or_ids, and_ids;  // launch order (range-major) of the OR / AND work items
+    Span<uint32_t> group_item_begin, group_out;
+    Span<uint32_t> item_head, item_matches, item_theta;
+    Span<unsigned long long> arena_next;  // [0] bump pointer, [1] error flag (as u32 view)
+    Span<rg_hit> out_hits;
+    Span<uint32_t> out_counts;
+    Span<unsigned long long> out_total;
+    Span<uint8_t> leaf_records;
+    uint8_t* zero_begin = nullptr;
+    size_t zero_bytes = 0;
     uint64_t postings = 0, algo_bytes = 0, h2d_bytes = 0;
     uint32_t kernels_per_run = 0;
     bool ran = false;
@@ -219,8 +234,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
 }
 
 template <class T>
-void up(DevBuf<T>& d, const std::vector<T>& h, cudaStream_t st) {
-    d.alloc(std::max<size_t>(1, h.size()));
+void up(Span<T>& d, const std::vector<T>& h, cudaStream_t st) {
     if (!h.empty()) RG_CUDA_CHECK(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
 }
 
@@ -272,23 +286,54 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     b->postings = hp.postings;
     b->algo_bytes = hp.algo_bytes + (uint64_t)n_queries * p->k * sizeof(rg_hit);
     cudaStream_t st = e->stream;
+    // carve the slab
+    size_t off = 0;
+    auto carve = [&](auto& span, size_t count) {
+        using T = std::remove_reference_t<decltype(*span.p)>;
+        span.n = std::max<size_t>(1, count);
+        span.p = reinterpret_cast<T*>(off);  // offset for now; rebased below
+        off = (off + span.n * sizeof(T) + 255) & ~(size_t)255;
+    };
+    carve(b->items, hp.items.size());
+    carve(b->clauses, hp.clauses.size());
+    carve(b->or_ids, hp.or_ids.size());
+    carve(b->and_ids, hp.and_ids.size());
+    carve(b->group_item_begin, hp.group_item_begin.size());
+    carve(b->group_out, hp.group_out.size());
+    carve(b->item_head, b->n_items);
+    const size_t zero_off = off;
+    carve(b->item_matches, b->n_items);
+    carve(b->item_theta, b->n_items);
+    carve(b->arena_next, 2);
+    carve(b->out_hits, (size_t)std::max<uint32_t>(1, n_queries) * p->k);
+    carve(b->out_counts, n_queries);
+    carve(b->out_total, n_queries);
+    if (p->mode == RG_MODE_SEARCH_PARALLEL)
+        carve(b->leaf_records, (size_t)b->n_leaves * std::max<uint32_t>(1, n_queries) * leaf_record_bytes(p->k));
+    if (e->spare_slab.n >= off) b->slab = std::move(e->spare_slab);
+    else {
+        e->spare_slab.release();
+        b->slab.alloc(off);
+    }
+    auto rebase = [&](auto& span) {
+        using T = std::remove_reference_t<decltype(*span.p)>;
+        span.p = reinterpret_cast<T*>(b->slab.p + reinterpret_cast<size_t>(span.p));
+    };
+    rebase(b->items); rebase(b->clauses); rebase(b->or_ids); rebase(b->and_ids);
+    rebase(b->group_item_begin); rebase(b->group_out); rebase(b->item_head); rebase(b->item_matches);
+    rebase(b->item_theta); rebase(b->arena_next); rebase(b->out_hits); rebase(b->out_counts);
+    rebase(b->out_total);
+    if (p->mode == RG_MODE_SEARCH_PARALLEL) rebase(b->leaf_records);
+    b->zero_begin = b->slab.p + zero_off;
+    b->zero_bytes = off - zero_off;
     up(b->items, hp.items, st);
     up(b->clauses, hp.clauses, st);
     up(b->or_ids, hp.or_ids, st);
     up(b->and_ids, hp.and_ids, st);
     up(b->group_item_begin, hp.group_item_begin, st);
     up(b->group_out, hp.group_out, st);
-    b->h2d_bytes = b->items.bytes() + b->clauses.bytes() + b->or_ids.bytes() + b->and_ids.bytes() +
-                   b->group_item_begin.bytes() + b->group_out.bytes();
-    b->item_head.alloc(std::max<uint32_t>(1, b->n_items));
-    b->item_matches.alloc(std::max<uint32_t>(1, b->n_items));
-    b->item_theta.alloc(std::max<uint32_t>(1, b->n_items));
-    b->arena_next.alloc(2);
-    b->out_hits.alloc((size_t)std::max<uint32_t>(1, n_queries) * p->k);
-    b->out_counts.alloc(std::max<uint32_t>(1, n_queries));
-    b->out_total.alloc(std::max<uint32_t>(1, n_queries));
-    if (p->mode == RG_MODE_SEARCH_PARALLEL)
-        b->leaf_records.alloc((size_t)b->n_leaves * std::max<uint32_t>(1, n_queries) * leaf_record_bytes(p->k));
+    b->h2d_bytes = (hp.items.size() * sizeof(WorkItem)) + hp.clauses.size() * sizeof(ItemClause) +
+                   4 * (hp.or_ids.size() + hp.and_ids.size() + hp.group_item_begin.size() + hp.group_out.size());
     b->kernels_per_run = (b->n_or ? 1 : 0) + (b->n_and ? 1 : 0) + (b->n_groups ? 1 : 0) +
                          (p->mode == RG_MODE_SEARCH_PARALLEL ? 1 : 0);
     RG_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -303,13 +348,7 @@ int rg_batch_run(rg_engine* e, rg_batch* b) {
     cudaStream_t st = e->stream;
     RG_CUDA_CHECK(cudaEventRecord(e->ev0, st));
     RG_CUDA_CHECK(cudaMemsetAsync(b->item_head.p, 0xff, b->item_head.bytes(), st));
-    RG_CUDA_CHECK(cudaMemsetAsync(b->item_matches.p, 0, b->item_matches.bytes(), st));
-    RG_CUDA_CHECK(cudaMemsetAsync(b->item_theta.p, 0, b->item_theta.bytes(), st));
-    RG_CUDA_CHECK(cudaMemsetAsync(b->arena_next.p, 0, b->arena_next.bytes(), st));
-    RG_CUDA_CHECK(cudaMemsetAsync(b->out_hits.p, 0, b->out_hits.bytes(), st));
-    RG_CUDA_CHECK(cudaMemsetAsync(b->out_counts.p, 0, b->out_counts.bytes(), st));
-    RG_CUDA_CHECK(cudaMemsetAsync(b->out_total.p, 0, b->out_total.bytes(), st));
-    if (b->leaf_records.p) RG_CUDA_CHECK(cudaMemsetAsync(b->leaf_records.p, 0, b->leaf_records.bytes(), st));
+    RG_CUDA_CHECK(cudaMemsetAsync(b->zero_begin, 0, b->zero_bytes, st));
     EvalParams ep{};
     ep.segs = e->d_segs.p;
     ep.items = b->items.p;
@@ -378,7 +417,12 @@ int rg_batch_fetch(rg_engine* e, rg_batch* b, rg_hit* out_hits, uint32_t* out_co
     RG_CATCH
 }
 
-void rg_batch_destroy(rg_engine*, rg_batch* b) { delete b; }
+void rg_batch_destroy(rg_engine* e, rg_batch* b) {
+    if (!b) return;
+    // hand the slab back for the next batch (stream-ordered reuse: same engine stream)
+    if (e && b->slab.n > e->spare_slab.n) e->spare_slab = std::move(b->slab);
+    delete b;
+}
 
 int rg_batch_stats(rg_engine* e, rg_batch* b, uint64_t out[8]) {
     RG_TRY
