@@ -48,7 +48,7 @@ struct SegDev {
 };
 
 // ------------------------------------------------------------------ plan (device side)
-enum : uint32_t { kTypeOr = 0, kTypeAnd = 1 };
+enum : uint32_t { kTypeOr = 0, kTypeAnd = 1, kTypeReqOpt = 2 };
 
 struct ItemClause {
     uint32_t term_id;

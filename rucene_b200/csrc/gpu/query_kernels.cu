@@ -692,10 +692,25 @@ struct AndShared {
     TermCtx term[kMaxTerms];
     uint32_t term_id[kMaxTerms];
     uint32_t is_not[kMaxTerms];            // MUST_NOT clauses: a hit kills the lead doc, a miss keeps it
+    uint32_t is_opt[kMaxTerms];            // SHOULD clauses next to a MUST (ReqOptScorer's optional side)
     uint32_t hint[kEvalWarps][kMaxTerms];  // per-warp galloping hints into the skip tables
+    // ReqOptScorer (search/scorer/req_opt_scorer.rs:19-65): optional-side sums per lead slot, the
+    // per-step match masks in docid order, and the scorer's sequential state (thread 0 owns it)
+    float oscore[kAndSlots];
+    uint32_t mmask[kEvalWarps][kAndSteps];
     EmitShared emit;
 };
 
+// A (query, leaf) with MUST and SHOULD clauses.  required = the lead-list conjunction above;
+// optional = DisjunctionSumScorer over the SHOULD clauses present in the leaf, summed in clause
+// order from 0.0f.  score() keeps running (scores_sum, scores_num) over the REQUIRED scores of the
+// docs whose optional side it looked at; after more than 100 of them a doc with
+// 2*req < scores_sum/scores_num returns req alone and leaves the state untouched.  That state is a
+// sequential f32 chain over the collected (live, not excluded) docs of the leaf, so such a work
+// item always covers the whole leaf and one thread replays the chain per step, in docid order.
+constexpr uint32_t kOptScoreThreshold = 100;
+
+template <bool REQOPT>
 __global__ void __launch_bounds__(kEvalThreads)
 k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -714,6 +729,7 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
         TermCtx& tc = sh.term[threadIdx.x];
         sh.term_id[threadIdx.x] = c.term_id;
         sh.is_not[threadIdx.x] = c.flags & 1u;
+        sh.is_opt[threadIdx.x] = (c.flags >> 1) & 1u;
         tc.blk_last = seg.blk_last + td.blk_begin;
         tc.blk_desc = seg.blk_desc + td.blk_begin;
         tc.cache = p.caches + (size_t)c.cache_id * 256;
@@ -734,6 +750,8 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
     const bool lead_has_tail = lead.tail_n > 0 && (lead_nb == 0 || hi - 1 > lead.tail_base);
     if (lane < kMaxTerms) sh.hint[warp][lane] = 0;
     __syncwarp();
+    float ro_sum = 0.0f;    // ReqOptScorer::scores_sum / scores_num (thread 0)
+    uint32_t ro_num = 0;
 
     for (uint32_t b0 = lead.cur;; b0 += kEvalWarps) {
         // ---- 1. decode this step's lead blocks (one per warp; pseudo-block lead_nb = vint tail)
@@ -797,6 +815,10 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
                 }
             }
         }
+        if (REQOPT) {
+#pragma unroll
+            for (int r = 0; r < kAndSteps; r++) sh.oscore[warp * kBlock + r * 32 + lane] = __uint_as_float(kSent);
+        }
         __syncwarp();
         // ---- 2. every other clause, in cost order; each warp works on its own 128 lead slots
         for (int t = 1; t < T; t++) {
@@ -804,6 +826,7 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
             const uint32_t nb = tc.nb;
             const float w1 = tc.w1;
             const bool neg = sh.is_not[t] != 0;
+            const bool opt = REQOPT && sh.is_opt[t] != 0;
             for (int r = 0; r < kAndSteps; r++) {
                 const int slot = warp * kBlock + r * 32 + lane;
                 int d = sh.ldoc[slot];
@@ -813,7 +836,7 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
                     bi = lower_bound_gallop(tc.blk_last, min(sh.hint[warp][t], nb), nb, d);
                     if (bi == nb && !(tc.tail_n > 0 && (nb == 0 || d > tc.tail_base))) {
                         pending = false;  // beyond the last posting of this clause
-                        if (!neg) sh.ldoc[slot] = kNoMoreDocs;
+                        if (!neg && !opt) sh.ldoc[slot] = kNoMoreDocs;
                     }
                 }
                 uint32_t pend_mask = __ballot_sync(0xffffffffu, pending);
@@ -860,8 +883,14 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
                                 f = sh.slab_freqs[warp][l];
                             }
                             const float nrm = seg.norms ? __ldg(tc.cache + __ldg(seg.norms + d)) : p.k1;
-                            sh.lscore[slot] = __fadd_rn(sh.lscore[slot], bm25_score(w1, (float)f, nrm));
-                        } else if (!neg) {
+                            const float sc = bm25_score(w1, (float)f, nrm);
+                            if (opt) {  // DisjunctionSumScorer::score_sum: clause order, from 0.0f
+                                const float o = sh.oscore[slot];
+                                sh.oscore[slot] = __fadd_rn(__float_as_uint(o) == kSent ? 0.0f : o, sc);
+                            } else {
+                                sh.lscore[slot] = __fadd_rn(sh.lscore[slot], sc);
+                            }
+                        } else if (!neg && !opt) {
                             sh.ldoc[slot] = kNoMoreDocs;
                         }
                         pending = false;
@@ -871,6 +900,36 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
                 }
             }
             __syncwarp();
+        }
+        // ---- 2b. ReqOptScorer::score over this step's collected docs, in docid order
+        if (REQOPT) {
+#pragma unroll
+            for (int r = 0; r < kAndSteps; r++) {
+                const int d = sh.ldoc[warp * kBlock + r * 32 + lane];
+                const uint32_t m = __ballot_sync(0xffffffffu, d != kNoMoreDocs && is_live(seg, d));
+                if (lane == 0) sh.mmask[warp][r] = m;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int w = 0; w < kEvalWarps; w++) {
+                    for (int r = 0; r < kAndSteps; r++) {
+                        uint32_t m = sh.mmask[w][r];
+                        while (m) {
+                            const int slot = w * kBlock + r * 32 + __ffs(m) - 1;
+                            m &= m - 1;
+                            const float req = sh.lscore[slot];
+                            if (ro_num > kOptScoreThreshold &&
+                                __fmul_rn(2.0f, req) < __fdiv_rn(ro_sum, __uint2float_rn(ro_num)))
+                                continue;  // required score only; state untouched (:46-49)
+                            ro_sum = __fadd_rn(ro_sum, req);
+                            ro_num++;
+                            const float o = sh.oscore[slot];
+                            if (__float_as_uint(o) != kSent) sh.lscore[slot] = __fadd_rn(req, o);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
         }
         // ---- 3. surviving lead docs are the matches of this step, in docid order
         bool present[kAndSteps];
@@ -1081,14 +1140,16 @@ void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_i
     const uint32_t ctas = (n + kOrWarps - 1) / kOrWarps;
     k_eval_or<<<ctas, kOrThreads, smem, st>>>(p, item_ids, n, (uint32_t)wb, kcap);
 }
-void launch_eval_and(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n) {
+void launch_eval_and(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, bool req_opt) {
     if (!n) return;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_eval_and, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AndShared));
+        cudaFuncSetAttribute(k_eval_and<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AndShared));
+        cudaFuncSetAttribute(k_eval_and<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AndShared));
         attr_set = true;
     }
-    k_eval_and<<<n, kEvalThreads, sizeof(AndShared), st>>>(p, item_ids);
+    if (req_opt) k_eval_and<true><<<n, kEvalThreads, sizeof(AndShared), st>>>(p, item_ids);
+    else k_eval_and<false><<<n, kEvalThreads, sizeof(AndShared), st>>>(p, item_ids);
 }
 void launch_heap_replay(cudaStream_t st, const ReplayParams& p) {
     if (!p.n_groups) return;

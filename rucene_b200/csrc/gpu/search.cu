@@ -26,7 +26,7 @@ struct Span {
 struct rg_batch {
     uint32_t n_queries = 0, k = 0, mode = 0;
     float k1 = 1.2f;
-    uint32_t n_items = 0, n_or = 0, n_and = 0, n_groups = 0, n_leaves = 0, max_or_terms = 1;
+    uint32_t n_items = 0, n_or = 0, n_and = 0, n_ro = 0, n_groups = 0, n_leaves = 0, max_or_terms = 1;
     // One device allocation per batch (cudaMalloc/cudaFree cost milliseconds each next to a
     // multi-GB index image; the engine keeps the last slab for the next batch).  Layout:
     // [plan arrays copied from the host][item_head: 0xff per run][everything zeroed per run].
@@ -34,6 +34,7 @@ struct rg_batch {
     Span<WorkItem> items;
     Span<ItemClause> clauses;
     Span<uint32_t> or_ids, and_ids;  // launch order (range-major) of the OR / AND work items
+    Span<uint32_t> ro_ids;           // MUST+SHOULD (ReqOptScorer) work items: one per (query, leaf)
     Span<uint32_t> group_item_begin, group_out;
     Span<uint32_t> item_head, item_matches, item_theta;
     Span<unsigned long long> arena_next;  // [0] bump pointer, [1] error flag (as u32 view)
@@ -53,7 +54,7 @@ namespace {
 struct HostPlan {
     std::vector<WorkItem> items;
     std::vector<ItemClause> clauses;
-    std::vector<uint32_t> or_ids, and_ids;
+    std::vector<uint32_t> or_ids, and_ids, ro_ids;
     std::vector<uint32_t> or_rank, and_rank;  // range index of each id (launch-order key)
     std::vector<uint32_t> group_item_begin, group_out;
     uint64_t postings = 0, algo_bytes = 0;
@@ -64,6 +65,7 @@ struct QShape {
     int type = -1;  // kTypeOr / kTypeAnd
     std::vector<uint32_t> clause_idx;  // scoring clauses (indices into the caller's array), evaluation order
     std::vector<uint32_t> not_idx;     // MUST_NOT clauses (ReqNotScorer)
+    std::vector<uint32_t> opt_idx;     // SHOULD clauses beside a MUST (ReqOptScorer's optional side), clause order
 };
 
 // BooleanQuery::build + BooleanWeight::create_scorer wiring for the accelerated shapes.
@@ -87,8 +89,6 @@ QShape classify(const rg_query& q, const rg_clause* clauses, uint32_t n_clauses_
     int32_t msm = q.min_should_match > 0 ? q.min_should_match : (musts.empty() ? 1 : 0);
     if (musts.size() + shoulds.size() + must_nots.size() == 0)
         throw ArgError("boolean query should at least contain one inner query!");
-    if (!musts.empty() && !shoulds.empty())
-        throw Unsupported("MUST+SHOULD (ReqOptScorer) is not accelerated yet");
     if (musts.empty() && shoulds.empty())
         throw Unsupported("pure MUST_NOT (MatchAllDocsQuery) is not accelerated");
     if (msm > 1) throw Unsupported("min_should_match > 1 is not accelerated yet");
@@ -103,8 +103,11 @@ QShape classify(const rg_query& q, const rg_clause* clauses, uint32_t n_clauses_
         return s;
     }
     if (!musts.empty()) {
-        s.type = kTypeAnd;  // one MUST + MUST_NOTs also takes the lead-list kernel
+        // one MUST + MUST_NOTs also takes the lead-list kernel; SHOULDs beside a MUST are the
+        // optional side of a ReqOptScorer (:253-262) — per leaf, if any of them exists there
+        s.type = shoulds.empty() ? kTypeAnd : kTypeReqOpt;
         s.clause_idx = musts;
+        s.opt_idx = shoulds;
         return s;
     }
     if (shoulds.size() >= 10) throw Unsupported(">= 10 SHOULD clauses use DisiPriorityQueue");
@@ -122,6 +125,8 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
         const QShape shape = classify(queries[qi], clauses, n_clauses);
         for (uint32_t ci : shape.clause_idx)
             if (clauses[ci].cache_id >= n_caches) throw ArgError("clause refers to an unset norm cache");
+        for (uint32_t ci : shape.opt_idx)
+            if (clauses[ci].cache_id >= n_caches) throw ArgError("clause refers to an unset norm cache");
         bool group_open = false;
         uint32_t chain_pos = 0;
         for (uint32_t si = 0; si < n_segs; si++) {
@@ -133,7 +138,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 const uint32_t t = clauses[ci].term_id;
                 const int32_t df = t < seg.host_terms.size() ? seg.host_terms[t].doc_freq : 0;
                 if (df > 0) present.push_back(ci);
-                else if (shape.type == kTypeAnd) dead = true;  // create_scorer -> None (:201-206)
+                else if (shape.type != kTypeOr) dead = true;  // create_scorer -> None (:201-206)
             }
             const bool new_group = mode == RG_MODE_SEARCH_PARALLEL || !group_open;
             if (dead || present.empty()) continue;
@@ -142,8 +147,15 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 const uint32_t t = clauses[ci].term_id;
                 if (t < seg.host_terms.size() && seg.host_terms[t].doc_freq > 0) nots.push_back(ci);
             }
+            std::vector<uint32_t> opts;  // SHOULD clauses present in this leaf (:217-234)
+            for (uint32_t ci : shape.opt_idx) {
+                const uint32_t t = clauses[ci].term_id;
+                if (t < seg.host_terms.size() && seg.host_terms[t].doc_freq > 0) opts.push_back(ci);
+            }
+            // no SHOULD scorer in this leaf -> the MUST side alone, no ReqOptScorer (:259-266)
+            const int leaf_type = shape.type == kTypeReqOpt && opts.empty() ? (int)kTypeAnd : shape.type;
             uint64_t cost = 0, bytes = 0, total_df = 0;
-            if (shape.type == kTypeAnd) {
+            if (shape.type != kTypeOr) {
                 // ConjunctionScorer::new: stable sort by cost() = doc_freq (:30)
                 std::stable_sort(present.begin(), present.end(), [&](uint32_t a, uint32_t b) {
                     return seg.host_terms[clauses[a].term_id].doc_freq < seg.host_terms[clauses[b].term_id].doc_freq;
@@ -153,6 +165,11 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 bytes = lead.enc_bytes + cost;
                 for (size_t i = 1; i < present.size(); i++) {  // upper bound: min(list, one block per lead doc)
                     const TermHost& th = seg.host_terms[clauses[present[i]].term_id];
+                    const uint64_t per_block = th.n_blocks ? th.enc_bytes / th.n_blocks : th.enc_bytes;
+                    bytes += std::min<uint64_t>(th.enc_bytes, cost * per_block);
+                }
+                for (uint32_t ci : opts) {
+                    const TermHost& th = seg.host_terms[clauses[ci].term_id];
                     const uint64_t per_block = th.n_blocks ? th.enc_bytes / th.n_blocks : th.enc_bytes;
                     bytes += std::min<uint64_t>(th.enc_bytes, cost * per_block);
                 }
@@ -175,12 +192,15 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 hp.clauses.push_back(ItemClause{clauses[ci].term_id, 0.0f, clauses[ci].cache_id, 1u});
                 bytes += seg.host_terms[clauses[ci].term_id].enc_bytes;
             }
-            const uint32_t n_item_terms = (uint32_t)(present.size() + nots.size());
+            for (uint32_t ci : opts)
+                hp.clauses.push_back(ItemClause{clauses[ci].term_id, clauses[ci].weight, clauses[ci].cache_id, 2u});
+            const uint32_t n_item_terms = (uint32_t)(present.size() + nots.size() + opts.size());
             // ranges of ~range_postings postings, at most 256 per (query, leaf): long lists get
             // longer ranges (a range is one warp's sequential job; there are thousands of warps)
             uint64_t R = (cost + range_postings - 1) / range_postings;
             R = std::min<uint64_t>(R, 256);
             R = std::max<uint64_t>(1, std::min<uint64_t>(R, (uint64_t)(seg.max_doc + kBlock - 1) / kBlock));
+            if (leaf_type == (int)kTypeReqOpt) R = 1;  // sequential scorer state: one item per leaf
             if (new_group) {
                 // SEARCH: one heap per query over all its leaves; SEARCH_PARALLEL: one per leaf
                 hp.group_out.push_back(mode == RG_MODE_SEARCH_PARALLEL ? si * n_queries + qi : qi);
@@ -190,7 +210,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 WorkItem it{};
                 it.query = qi;
                 it.seg = (uint16_t)si;
-                it.type = (uint8_t)shape.type;
+                it.type = (uint8_t)leaf_type;
                 it.n_terms = (uint8_t)n_item_terms;
                 it.lo = (int32_t)((uint64_t)seg.max_doc * r / R);
                 it.hi = (int32_t)((uint64_t)seg.max_doc * (r + 1) / R);
@@ -199,7 +219,9 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 chain_pos = it.chain_pos + 1;
                 const uint32_t idx = (uint32_t)hp.items.size();
                 hp.items.push_back(it);
-                if (shape.type == kTypeAnd) {
+                if (leaf_type == (int)kTypeReqOpt) {
+                    hp.ro_ids.push_back(idx);
+                } else if (leaf_type == (int)kTypeAnd) {
                     hp.and_ids.push_back(idx);
                     hp.and_rank.push_back((uint32_t)r);
                 } else {
@@ -280,6 +302,7 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     b->n_items = (uint32_t)hp.items.size();
     b->n_or = (uint32_t)hp.or_ids.size();
     b->n_and = (uint32_t)hp.and_ids.size();
+    b->n_ro = (uint32_t)hp.ro_ids.size();
     b->n_groups = (uint32_t)hp.group_out.size();
     b->max_or_terms = hp.max_or_terms;
     b->n_leaves = (uint32_t)e->segs.size();
@@ -298,6 +321,7 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     carve(b->clauses, hp.clauses.size());
     carve(b->or_ids, hp.or_ids.size());
     carve(b->and_ids, hp.and_ids.size());
+    carve(b->ro_ids, hp.ro_ids.size());
     carve(b->group_item_begin, hp.group_item_begin.size());
     carve(b->group_out, hp.group_out.size());
     carve(b->item_head, b->n_items);
@@ -319,7 +343,7 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
         using T = std::remove_reference_t<decltype(*span.p)>;
         span.p = reinterpret_cast<T*>(b->slab.p + reinterpret_cast<size_t>(span.p));
     };
-    rebase(b->items); rebase(b->clauses); rebase(b->or_ids); rebase(b->and_ids);
+    rebase(b->items); rebase(b->clauses); rebase(b->or_ids); rebase(b->and_ids); rebase(b->ro_ids);
     rebase(b->group_item_begin); rebase(b->group_out); rebase(b->item_head); rebase(b->item_matches);
     rebase(b->item_theta); rebase(b->arena_next); rebase(b->out_hits); rebase(b->out_counts);
     rebase(b->out_total);
@@ -330,11 +354,12 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     up(b->clauses, hp.clauses, st);
     up(b->or_ids, hp.or_ids, st);
     up(b->and_ids, hp.and_ids, st);
+    up(b->ro_ids, hp.ro_ids, st);
     up(b->group_item_begin, hp.group_item_begin, st);
     up(b->group_out, hp.group_out, st);
     b->h2d_bytes = (hp.items.size() * sizeof(WorkItem)) + hp.clauses.size() * sizeof(ItemClause) +
-                   4 * (hp.or_ids.size() + hp.and_ids.size() + hp.group_item_begin.size() + hp.group_out.size());
-    b->kernels_per_run = (b->n_or ? 1 : 0) + (b->n_and ? 1 : 0) + (b->n_groups ? 1 : 0) +
+                   4 * (hp.or_ids.size() + hp.and_ids.size() + hp.ro_ids.size() + hp.group_item_begin.size() + hp.group_out.size());
+    b->kernels_per_run = (b->n_or ? 1 : 0) + (b->n_and ? 1 : 0) + (b->n_ro ? 1 : 0) + (b->n_groups ? 1 : 0) +
                          (p->mode == RG_MODE_SEARCH_PARALLEL ? 1 : 0);
     RG_CUDA_CHECK(cudaStreamSynchronize(st));
     *out = b.release();
@@ -367,7 +392,9 @@ int rg_batch_run(rg_engine* e, rg_batch* b) {
     RG_CUDA_CHECK(cudaEventRecord(e->ev2, st));
     launch_eval_or(st, ep, b->or_ids.p, b->n_or, b->max_or_terms);
     RG_CUDA_CHECK(cudaGetLastError());
-    launch_eval_and(st, ep, b->and_ids.p, b->n_and);
+    launch_eval_and(st, ep, b->and_ids.p, b->n_and, false);
+    RG_CUDA_CHECK(cudaGetLastError());
+    launch_eval_and(st, ep, b->ro_ids.p, b->n_ro, true);
     RG_CUDA_CHECK(cudaGetLastError());
     RG_CUDA_CHECK(cudaEventRecord(e->ev3, st));
     ReplayParams rp{};
@@ -439,7 +466,7 @@ int rg_batch_stats(rg_engine* e, rg_batch* b, uint64_t out[8]) {
     out[4] = b->kernels_per_run;
     out[5] = b->h2d_bytes;
     out[6] = b->n_or;
-    out[7] = b->n_and;
+    out[7] = b->n_and + b->n_ro;
     return RG_OK;
     RG_CATCH
 }

@@ -27,7 +27,10 @@ int main() {
         auto q2 = BooleanQuery::build({TermQuery::create(Term::create("body", "t3")), TermQuery::create(Term::create("body", "t40"))}, {}, {}, {}, 0);
         auto q3 = BooleanQuery::build({}, {TermQuery::create(Term::create("body", "t1")), TermQuery::create(Term::create("body", "t77")),
                                            TermQuery::create(Term::create("body", "nope"))}, {}, {}, 0);
-        for (const QueryPtr& q : {q1, q2, q3}) {
+        // MUST + SHOULD: ReqOptScorer (boolean_query.rs:253-262)
+        auto q4 = BooleanQuery::build({TermQuery::create(Term::create("body", "t2"))},
+                                      {TermQuery::create(Term::create("body", "t9")), TermQuery::create(Term::create("body", "t30"))}, {}, {}, 0);
+        for (const QueryPtr& q : {q1, q2, q3, q4}) {
             TopDocsCollector collector(10);
             searcher.search(*q, collector);
             const TopDocs& top = collector.top_docs();
@@ -39,10 +42,10 @@ int main() {
             std::printf("\n");
         }
         bool threw = false;
-        try {  // MUST + SHOULD (ReqOptScorer) is outside the accelerated path
-            auto q4 = BooleanQuery::build({q1}, {q1}, {}, {}, 0);
+        try {  // min_should_match > 1 is outside the accelerated path
+            auto q5 = BooleanQuery::build({}, {q1, q1}, {}, {}, 2);
             TopDocsCollector c(10);
-            searcher.search(*q4, c);
+            searcher.search(*q5, c);
         } catch (const UnsupportedQuery&) { threw = true; }
         std::printf("unsupported:%d\n", (int)threw);
     } catch (const Error& e) {

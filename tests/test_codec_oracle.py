@@ -135,7 +135,7 @@ def test_synth_segment_is_deterministic_and_zipfian():
     assert (hist > 0).sum() >= 8  # several distinct norm classes
 
 
-def _brute_force(seg_list, postings_list, ix, spec, k):
+def _brute_force(seg_list, postings_list, ix, spec, k, stats=None):
     """Independent numpy model: returns the (doc,score) stream in collection order."""
     stream_d, stream_s = [], []
     doc_base = 0
@@ -179,6 +179,28 @@ def _brute_force(seg_list, postings_list, ix, spec, k):
         if seg.live_docs is not None:
             live = (seg.live_docs[docs >> 6] >> (docs & 63).astype(np.uint64)) & np.uint64(1)
             docs, score = docs[live == 1], score[live == 1]
+        shoulds = [p for p in shoulds if len(p[1])]
+        if musts and shoulds:
+            # ReqOptScorer (req_opt_scorer.rs:43-64): sequential (scores_sum, scores_num) chain over
+            # the collected docs of this leaf; optional side = clause-order sum from 0.0f
+            opt_docs = np.unique(np.concatenate([p[1] for p in shoulds]))
+            opt = np.zeros(len(opt_docs), np.float32)
+            for _occ, d, s in shoulds:
+                pos = np.searchsorted(opt_docs, d)
+                opt[pos] = (opt[pos] + s).astype(np.float32)
+            pos = np.minimum(np.searchsorted(opt_docs, docs), len(opt_docs) - 1)
+            has_opt = opt_docs[pos] == docs
+            ssum, snum = np.float32(0.0), 0
+            for i in range(len(docs)):
+                req = score[i]
+                if snum > 100 and np.float32(2.0) * req < ssum / np.float32(snum):
+                    if stats is not None:
+                        stats["skipped"] = stats.get("skipped", 0) + 1
+                    continue
+                ssum = np.float32(ssum + req)
+                snum += 1
+                if has_opt[i]:
+                    score[i] = np.float32(req + opt[pos[i]])
         stream_d.append(docs + doc_base)
         stream_s.append(score)
         doc_base += seg.max_doc
@@ -215,3 +237,35 @@ def test_oracle_search_matches_brute_force(version, live):
             got = hits[i][:counts[i]]
             assert np.array_equal(got["doc"], want["doc"]), spec
             assert np.array_equal(got["score"].view(np.uint32), want["score"].view(np.uint32)), spec
+
+
+@pytest.mark.parametrize("live", [None, 0.8])
+def test_oracle_req_opt_matches_brute_force(live):
+    """MUST + SHOULD in one query: ReqOptScorer's running-mean skip (req_opt_scorer.rs:19,46-53) as
+    a plain numpy chain — and the skip does fire on this data."""
+    rng = np.random.default_rng(410)
+    dfs = [0, 2, 90, 700, 5000, 14000, 26000, 33000]
+    segs, posts = [], []
+    for s in range(2):
+        seg, p = helpers.build_segment(rng, 36000 + 500 * s, dfs, live_fraction=live)
+        segs.append(seg)
+        posts.append(p)
+    ix = helpers.oracle_index(segs)
+    specs = [("bool", [(ob.MUST, 7), (ob.SHOULD, 6)], 0),
+             ("bool", [(ob.MUST, 6), (ob.MUST, 7), (ob.SHOULD, 5), (ob.SHOULD, 3)], 0),
+             ("bool", [(ob.SHOULD, 4), (ob.MUST, 5), (ob.SHOULD, 7), (ob.SHOULD, 2)], 0),
+             ("bool", [(ob.MUST, 5), (ob.SHOULD, 0)], 0),      # SHOULD absent everywhere: plain MUST
+             ("bool", [(ob.MUST, 0), (ob.SHOULD, 5)], 0),      # MUST absent: no scorer
+             ("bool", [(ob.MUST, 3), (ob.SHOULD, 7, 3.0), (ob.SHOULD, 1)], 1)]
+    q, c = ob.make_queries(specs)
+    stats = {}
+    for k in (10, 100):
+        hits, counts, total = ix.search_batch(q, c, k)
+        for i, spec in enumerate(specs):
+            d, s = _brute_force(segs, posts, ix, spec, k, stats)
+            want, _ = ob.topk_stream(d, s, k)
+            assert total[i] == len(d), spec
+            got = hits[i][:counts[i]]
+            assert np.array_equal(got["doc"], want["doc"]), spec
+            assert np.array_equal(got["score"].view(np.uint32), want["score"].view(np.uint32)), spec
+    assert stats.get("skipped", 0) > 100

@@ -39,13 +39,14 @@ def test_cpp_mirror_matches_oracle():
     seg = codec.synth_segment(0x5EED0001, 50000, 500, doc_version=1, n_threads=2)
     ix = helpers.oracle_index([seg])
     specs = [("term", 5), ("bool", [(ob.MUST, 3), (ob.MUST, 40)], 0),
-             ("bool", [(ob.SHOULD, 1), (ob.SHOULD, 77), (ob.SHOULD, 499999)], 0)]
+             ("bool", [(ob.SHOULD, 1), (ob.SHOULD, 77), (ob.SHOULD, 499999)], 0),
+             ("bool", [(ob.MUST, 2), (ob.SHOULD, 9), (ob.SHOULD, 30)], 0)]
     q, c = ob.make_queries(specs)
     hits, counts, total = ix.search_batch(q, c, 10)
-    for i in range(3):
+    for i in range(4):
         parts = lines[i].split()
         assert int(parts[0]) == total[i]
         got = [tuple(int(x) for x in p.split(":")) for p in parts[1:]]
         want = [(int(h["doc"]), int(np.float32(h["score"]).view(np.uint32))) for h in hits[i][:counts[i]]]
         assert got == want
-    assert lines[3] == "unsupported:1"
+    assert lines[4] == "unsupported:1"

@@ -154,6 +154,44 @@ def test_must_not_clauses_req_not_scorer():
             helpers.assert_same_topdocs(got, want, "must_not k=%d rp=%d mode=%d" % (k, rp, mode))
 
 
+def test_req_opt_scorer_must_plus_should():
+    """MUST + SHOULD in one query -> ReqOptScorer (search/scorer/req_opt_scorer.rs:19-65; wiring
+    boolean_query.rs:253-262), optionally under a ReqNotScorer: the running-mean skip after 100
+    scored docs is sequential state per (query, leaf).  Leaves where no SHOULD term exists fall back
+    to the plain conjunction; leaves where a MUST term is missing produce nothing."""
+    rng = np.random.default_rng(77)
+    dfs = [0, 1, 2, 90, 129, 700, 5000, 14000, 26000, 33000]
+    segs = []
+    for s, lf in enumerate((None, 0.8, None)):
+        d = list(dfs)
+        if s == 2:
+            d[5] = 0       # a SHOULD/MUST term missing from the last leaf
+            d[8] = 0
+        segs.append(helpers.build_segment(rng, 36000 + 700 * s, d, live_fraction=lf)[0])
+    specs = [("bool", [(ob.MUST, 9), (ob.SHOULD, 8)], 0),
+             ("bool", [(ob.MUST, 8), (ob.MUST, 9), (ob.SHOULD, 7), (ob.SHOULD, 5)], 0),
+             ("bool", [(ob.SHOULD, 6), (ob.MUST, 7), (ob.SHOULD, 9), (ob.SHOULD, 2)], 0),
+             ("bool", [(ob.MUST, 7), (ob.SHOULD, 0)], 0),
+             ("bool", [(ob.MUST, 0), (ob.SHOULD, 7)], 0),
+             ("bool", [(ob.MUST, 5), (ob.SHOULD, 9, 3.0), (ob.SHOULD, 1)], 1),
+             ("bool", [(ob.MUST, 9), (ob.SHOULD, 8), (ob.MUST_NOT, 7)], 0),
+             ("bool", [(ob.MUST, 9), (ob.MUST, 7), (ob.SHOULD, 6), (ob.SHOULD, 4), (ob.MUST_NOT, 5), (ob.MUST_NOT, 3)], 0),
+             ("bool", [(ob.MUST, 4), (ob.SHOULD, 9)], 0),       # lead list with a vint tail only + 1 block
+             ("bool", [(ob.MUST, 2), (ob.SHOULD, 3)], 0)]
+    for i in range(40):
+        n_must, n_should = int(rng.integers(1, 3)), int(rng.integers(1, 4))
+        n_not = int(rng.integers(0, 2))
+        terms = [int(x) for x in rng.choice(len(dfs), size=n_must + n_should + n_not, replace=False)]
+        cl = [(ob.MUST, t) for t in terms[:n_must]] + [(ob.SHOULD, t) for t in terms[n_must:n_must + n_should]]
+        cl += [(ob.MUST_NOT, t) for t in terms[n_must + n_should:]]
+        specs.append(("bool", [cl[j] for j in rng.permutation(len(cl))], 0))
+    specs += _mixed_specs(rng, len(dfs), 10, kinds=("and", "or"))   # same batch as the other kernels
+    for k, rp in ((10, 0), (100, 2000)):
+        for mode in (0, 1):
+            got, want = _run_both(segs, specs, k, mode=mode, range_postings=rp)
+            helpers.assert_same_topdocs(got, want, "req_opt k=%d rp=%d mode=%d" % (k, rp, mode))
+
+
 def test_reference_style_api():
     """Reads like examples/example.rs:111-117."""
     rng = np.random.default_rng(5)
@@ -172,7 +210,11 @@ def test_reference_style_api():
         searcher.search(search.TermQuery.new(search.Term.new("body", b"absent"), 1.0, None), collector)
         assert collector.top_docs().total_hits() == 0 and collector.top_docs().score_docs() == []
         q = search.BooleanQuery.build([query], [search.TermQuery.new(search.Term.new("body", b"world"))], [], [], 0)
-        with pytest.raises(engine.Unsupported):   # MUST+SHOULD (ReqOptScorer) is a "next" row
+        collector = search.TopDocsCollector.new(10)   # MUST + SHOULD: ReqOptScorer
+        searcher.search(q, collector)
+        assert collector.top_docs().total_hits() == 1666
+        q = search.BooleanQuery.build([], [query, search.TermQuery.new(search.Term.new("body", b"world"))], [], [], 2)
+        with pytest.raises(engine.Unsupported):   # min_should_match > 1 is a "next" row
             searcher.search(q, search.TopDocsCollector.new(10))
         with pytest.raises(search.IllegalArgument):
             search.BooleanQuery.build([], [], [], [], 0)
