@@ -110,7 +110,7 @@ struct EvalParams {
     uint32_t* error_flag;      // bit0: arena exhausted
 };
 void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n,
-                    uint32_t max_terms);
+                    uint32_t max_terms, bool has_live, bool has_not);
 void launch_eval_and(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, bool req_opt);
 
 struct ReplayParams {

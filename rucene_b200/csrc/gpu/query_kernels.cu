@@ -305,14 +305,13 @@ struct WTerm {
 // One posting of a clause lands on window slot idx.  SHOULD clause: clause-order f32 add, first
 // touch counts the match.  MUST_NOT clause (drained after every SHOULD clause of the window): a doc
 // that is present becomes kExcl and its match is taken back.
+template <bool NOT>
 __device__ __forceinline__ void accumulate_posting(uint32_t* acc, int idx, float s, bool is_not, bool live,
-                                                   float te, uint32_t& touched, uint32_t& hot,
-                                                   uint32_t& my_matches) {
+                                                   float te, uint32_t& hot, uint32_t& my_matches) {
     const uint32_t old = acc[idx];
-    if (!is_not) {
+    if (!NOT || !is_not) {
         const float sum = __fadd_rn(old == kSent ? 0.0f : __uint_as_float(old), s);
         acc[idx] = __float_as_uint(sum);
-        touched |= 1u << (idx >> 5);
         if (old == kSent && live) my_matches++;
         if (sum > te) hot |= 1u << (idx >> 5);
     } else if (old != kSent && old != kExcl) {
@@ -397,18 +396,20 @@ __device__ __forceinline__ void wtheta_update(WEmit& em, uint32_t k, uint32_t kc
 // list is exhausted.  Warp-cooperative; all lanes must call it.
 // When called while clause t is being drained into the window [win0, win1) the new block's
 // postings below win1 are accumulated straight from registers (no round trip through the cache).
+template <bool LIVE, bool NOT>
 __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParams& p, WTerm& tc, int32_t* cd,
                                            float* cs, int lo, int hi, int lane, int win0, int win1,
-                                           uint32_t* acc, uint32_t& touched, uint32_t& hot, uint32_t& my_matches,
-                                           float te) {
+                                           uint32_t* acc, uint32_t& hot, uint32_t& my_matches, float te) {
     for (;;) {
         const uint32_t b = tc.cur;
         if (b > tc.nb) return false;
         int4 docs, freqs;
         uint32_t n_in = kBlock;
+        bool interior = false;  // every posting of the block lies inside [lo, hi)
         if (b < tc.nb) {
             const BlockDesc bd = tc.blk_desc[b];
             const int base = b == 0 ? 0 : __ldg(tc.blk_last + b - 1);
+            interior = (b == 0 ? lo == 0 : base >= lo) && __ldg(tc.blk_last + b) < hi;
             const uint4* part = seg.arena + bd.off16;
             const int bdoc = (int)(bd.bits & 0xff), bfrq = (int)((bd.bits >> 8) & 0xff);
             int4 dl;
@@ -448,16 +449,21 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
         const float w1 = tc.w1;
         const float* cache = tc.cache;
         const uint8_t* norms = seg.norms;
-        const bool neg = tc.is_not != 0;
+        const bool neg = NOT && tc.is_not != 0;
         // stage the gathers: 4 norm bytes, then 4 cache entries, then 4 divisions — branch-free, so the
         // loads of all four postings are in flight together (out-of-range lanes read a safe slot)
         bool ok[4];
         float nrm[4];
+        if (interior) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            ok[q] = d[q] >= lo && d[q] < hi;
-            below += d[q] < lo;
-            inside += ok[q];
+            for (int q = 0; q < 4; q++) ok[q] = true;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                ok[q] = d[q] >= lo && d[q] < hi;
+                below += d[q] < lo;
+                inside += ok[q];
+            }
         }
         if (norms) {
             uint32_t nb8[4];
@@ -474,14 +480,19 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             if (ok[q] && d[q] < win1) {  // still inside the window being drained: accumulate now
-                accumulate_posting(acc, d[q] - win0, sc[q], neg, is_live(seg, d[q]), te, touched, hot, my_matches);
+                accumulate_posting<NOT>(acc, d[q] - win0, sc[q], neg, LIVE ? is_live(seg, d[q]) : true, te, hot,
+                                        my_matches);
                 direct++;
             }
         }
         reinterpret_cast<int4*>(cd)[lane] = docs;
         reinterpret_cast<float4*>(cs)[lane] = make_float4(sc[0], sc[1], sc[2], sc[3]);
-        below = __reduce_add_sync(0xffffffffu, below);
-        inside = __reduce_add_sync(0xffffffffu, inside);
+        if (interior) {
+            inside = kBlock;
+        } else {
+            below = __reduce_add_sync(0xffffffffu, below);
+            inside = __reduce_add_sync(0xffffffffu, inside);
+        }
         direct = __reduce_add_sync(0xffffffffu, direct);
         const bool past_end = below + inside < n_in;  // some posting >= hi: nothing further in range
         below += direct;
@@ -499,6 +510,7 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
     }
 }
 
+template <bool LIVE, bool NOT>
 __global__ void __launch_bounds__(kOrThreads, 4)
 k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, uint32_t warp_bytes,
           uint32_t kcap) {
@@ -535,10 +547,10 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
     }
     __syncwarp();
     long long w0 = kNoMoreDocs;
-    uint32_t touched = 0, hot = 0, my_matches = 0;
+    uint32_t hot = 0, my_matches = 0;
     for (int t = 0; t < T; t++) {
-        if (stream_refill(seg, p, sh.term[t], cdocs + t * kBlock, cscores + t * kBlock, lo, hi, lane, 0,
-                          -2147483647 - 1, sh.acc, touched, hot, my_matches, INFINITY))
+        if (stream_refill<LIVE, NOT>(seg, p, sh.term[t], cdocs + t * kBlock, cscores + t * kBlock, lo, hi, lane, 0,
+                                     -2147483647 - 1, sh.acc, hot, my_matches, INFINITY))
             w0 = min(w0, (long long)cdocs[t * kBlock + sh.term[t].pos]);
     }
 
@@ -567,7 +579,6 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
             inherited = __reduce_max_sync(0xffffffffu, inherited);
         }
         int next_doc = kNoMoreDocs;
-        touched = 0;
         hot = 0;
         em.theta_in = max(em.theta_in, inherited);
         float te = em.theta_local;
@@ -585,8 +596,8 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                     __syncwarp();  // every lane has read tc.pos / tc.n / tc.cur
                     if (lane == 0) tc.pos = pos;
                     __syncwarp();
-                    if (!stream_refill(seg, p, tc, cdocs + t * kBlock, cscores + t * kBlock, lo, hi, lane, win0,
-                                       win1, sh.acc, touched, hot, my_matches, te)) {
+                    if (!stream_refill<LIVE, NOT>(seg, p, tc, cdocs + t * kBlock, cscores + t * kBlock, lo, hi, lane,
+                                                  win0, win1, sh.acc, hot, my_matches, te)) {
                         pos = n = 0;
                         break;
                     }
@@ -598,8 +609,8 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                 const bool in_win = d < win1;
                 const uint32_t c = __popc(__ballot_sync(0xffffffffu, in_win));  // sorted: a prefix
                 if (in_win)
-                    accumulate_posting(sh.acc, d - win0, cs[i], tc.is_not != 0, is_live(seg, d), te, touched, hot,
-                                       my_matches);
+                    accumulate_posting<NOT>(sh.acc, d - win0, cs[i], NOT && tc.is_not != 0,
+                                            LIVE ? is_live(seg, d) : true, te, hot, my_matches);
                 pos += c;
                 if (c < 32 && pos < n) break;  // next cached doc is beyond this window
             }
@@ -611,31 +622,20 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
             if (pos < n) next_doc = min(next_doc, cd[pos]);
             __syncwarp();
         }
-        touched = __reduce_or_sync(0xffffffffu, touched);
         hot = __reduce_or_sync(0xffffffffu, hot);
         // ---- window epilogue.  Matches were counted when a doc was first touched; only 32-doc
-        // steps holding a doc whose (partial) sum exceeded theta are scanned for candidates, the
-        // rest of the touched steps are just re-armed.
+        // steps holding a doc whose (partial) sum exceeded theta are scanned for candidates, then
+        // the whole window is re-armed with eight 16-byte stores per lane.
         {
-            const uint32_t cold = touched & ~hot;
-#pragma unroll
-            for (int g = 0; g < kWw / 128; g++) {  // re-arm four 32-doc steps per iteration
-                const uint32_t nib = (cold >> (4 * g)) & 0xfu;
-                if (nib) {
-#pragma unroll
-                    for (int s = 0; s < 4; s++)
-                        if ((nib >> s) & 1u) sh.acc[(4 * g + s) * 32 + lane] = kSent;
-                }
-            }
             uint32_t newc_n = 0;
             while (hot) {
                 const int s = __ffs(hot) - 1;
                 hot &= hot - 1;
                 const int idx = s * 32 + lane;
                 const uint32_t v = sh.acc[idx];
-                sh.acc[idx] = kSent;
                 const float sc = __uint_as_float(v);
-                const bool cand = v != kSent && v != kExcl && (open || sc > te) && is_live(seg, win0 + idx);
+                const bool cand = v != kSent && (!NOT || v != kExcl) && (open || sc > te) &&
+                                  (LIVE ? is_live(seg, win0 + idx) : true);
                 const uint32_t cm = __ballot_sync(0xffffffffu, cand);
                 if (!cm || em.overflow) continue;
                 const uint32_t c = __popc(cm);
@@ -668,6 +668,10 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                 newc_n += c;
                 if (lane == 0) hdr[em.run_slot] = CandRun{kNone, em.run_cnt};
             }
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < kWw / 128; g++)
+                reinterpret_cast<uint4*>(sh.acc)[g * 32 + lane] = make_uint4(kSent, kSent, kSent, kSent);
             wtheta_update(em, p.k, kcap, lane, sh.newc, newc_n, p.item_theta + item_idx);
             __syncwarp();
         }
@@ -1125,20 +1129,29 @@ k_merge_leaf_records(const uint8_t* __restrict__ records, uint32_t n_leaves, uin
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+template <bool LIVE, bool NOT>
+static void launch_eval_or_t(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, size_t wb,
+                             uint32_t kcap) {
+    const size_t smem = wb * kOrWarps;
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaFuncSetAttribute(k_eval_or<LIVE, NOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = smem;
+    }
+    const uint32_t ctas = (n + kOrWarps - 1) / kOrWarps;
+    k_eval_or<LIVE, NOT><<<ctas, kOrThreads, smem, st>>>(p, item_ids, n, (uint32_t)wb, kcap);
+}
+// has_live: some leaf has deleted docs; has_not: some item of the launch carries a MUST_NOT clause
 void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n,
-                    uint32_t max_terms) {
+                    uint32_t max_terms, bool has_live, bool has_not) {
     if (!n) return;
     const uint32_t kcap = (std::min<uint32_t>(p.k, kMaxK) + 31u) & ~31u;
     size_t wb = sizeof(WarpShared) + (size_t)kcap * sizeof(float) + (size_t)max_terms * kBlock * 8;
     wb = (wb + 15) & ~size_t(15);
-    const size_t smem = wb * kOrWarps;
-    static size_t attr = 0;
-    if (smem > attr) {
-        cudaFuncSetAttribute(k_eval_or, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = smem;
-    }
-    const uint32_t ctas = (n + kOrWarps - 1) / kOrWarps;
-    k_eval_or<<<ctas, kOrThreads, smem, st>>>(p, item_ids, n, (uint32_t)wb, kcap);
+    if (has_live && has_not) launch_eval_or_t<true, true>(st, p, item_ids, n, wb, kcap);
+    else if (has_live) launch_eval_or_t<true, false>(st, p, item_ids, n, wb, kcap);
+    else if (has_not) launch_eval_or_t<false, true>(st, p, item_ids, n, wb, kcap);
+    else launch_eval_or_t<false, false>(st, p, item_ids, n, wb, kcap);
 }
 void launch_eval_and(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, bool req_opt) {
     if (!n) return;

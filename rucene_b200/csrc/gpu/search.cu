@@ -46,6 +46,7 @@ struct rg_batch {
     size_t zero_bytes = 0;
     uint64_t postings = 0, algo_bytes = 0, h2d_bytes = 0;
     uint32_t kernels_per_run = 0;
+    bool or_has_not = false;
     bool ran = false;
 };
 
@@ -59,6 +60,7 @@ struct HostPlan {
     std::vector<uint32_t> group_item_begin, group_out;
     uint64_t postings = 0, algo_bytes = 0;
     uint32_t max_or_terms = 1;
+    bool or_has_not = false;
 };
 
 struct QShape {
@@ -228,6 +230,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                     hp.or_ids.push_back(idx);
                     hp.or_rank.push_back((uint32_t)r);
                     hp.max_or_terms = std::max<uint32_t>(hp.max_or_terms, n_item_terms);
+                    if (!nots.empty()) hp.or_has_not = true;
                 }
             }
         }
@@ -305,6 +308,7 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     b->n_ro = (uint32_t)hp.ro_ids.size();
     b->n_groups = (uint32_t)hp.group_out.size();
     b->max_or_terms = hp.max_or_terms;
+    b->or_has_not = hp.or_has_not;
     b->n_leaves = (uint32_t)e->segs.size();
     b->postings = hp.postings;
     b->algo_bytes = hp.algo_bytes + (uint64_t)n_queries * p->k * sizeof(rg_hit);
@@ -390,7 +394,9 @@ int rg_batch_run(rg_engine* e, rg_batch* b) {
     ep.item_theta = b->item_theta.p;
     ep.error_flag = reinterpret_cast<uint32_t*>(b->arena_next.p + 1);
     RG_CUDA_CHECK(cudaEventRecord(e->ev2, st));
-    launch_eval_or(st, ep, b->or_ids.p, b->n_or, b->max_or_terms);
+    bool has_live = false;
+    for (const Segment& sg : e->segs) has_live = has_live || sg.live.p != nullptr;
+    launch_eval_or(st, ep, b->or_ids.p, b->n_or, b->max_or_terms, has_live, b->or_has_not);
     RG_CUDA_CHECK(cudaGetLastError());
     launch_eval_and(st, ep, b->and_ids.p, b->n_and, false);
     RG_CUDA_CHECK(cudaGetLastError());
