@@ -405,11 +405,14 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
         if (b > tc.nb) return false;
         int4 docs, freqs;
         uint32_t n_in = kBlock;
-        bool interior = false;  // every posting of the block lies inside [lo, hi)
+        bool interior = false;    // every posting of the block lies inside [lo, hi)
+        bool all_direct = false;  // ... and inside the window being drained
         if (b < tc.nb) {
             const BlockDesc bd = tc.blk_desc[b];
             const int base = b == 0 ? 0 : __ldg(tc.blk_last + b - 1);
-            interior = (b == 0 ? lo == 0 : base >= lo) && __ldg(tc.blk_last + b) < hi;
+            const int last = __ldg(tc.blk_last + b);
+            interior = (b == 0 ? lo == 0 : base >= lo) && last < hi;
+            all_direct = interior && last < win1;
             const uint4* part = seg.arena + bd.off16;
             const int bdoc = (int)(bd.bits & 0xff), bfrq = (int)((bd.bits >> 8) & 0xff);
             int4 dl;
@@ -477,6 +480,19 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) sc[q] = bm25_score(w1, (float)f[q], nrm[q]);
+        if (all_direct) {  // the common case for dense clauses: nothing to cache, no cursor arithmetic
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                accumulate_posting<NOT>(acc, d[q] - win0, sc[q], neg, LIVE ? is_live(seg, d[q]) : true, te, hot,
+                                        my_matches);
+            __syncwarp();  // every lane has read tc.cur / tc.nb above
+            if (lane == 0) {
+                tc.pos = tc.n = 0;
+                tc.cur = b + 1;
+            }
+            __syncwarp();
+            continue;
+        }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             if (ok[q] && d[q] < win1) {  // still inside the window being drained: accumulate now
@@ -546,13 +562,16 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
         tc.is_not = c.flags & 1u;
     }
     __syncwarp();
-    long long w0 = kNoMoreDocs;
     uint32_t hot = 0, my_matches = 0;
+    int nd = kNoMoreDocs;  // lane t: next cached docid of clause t (kNoMoreDocs = exhausted)
     for (int t = 0; t < T; t++) {
         if (stream_refill<LIVE, NOT>(seg, p, sh.term[t], cdocs + t * kBlock, cscores + t * kBlock, lo, hi, lane, 0,
-                                     -2147483647 - 1, sh.acc, hot, my_matches, INFINITY))
-            w0 = min(w0, (long long)cdocs[t * kBlock + sh.term[t].pos]);
+                                     -2147483647 - 1, sh.acc, hot, my_matches, INFINITY)) {
+            const int first = cdocs[t * kBlock + sh.term[t].pos];
+            if (lane == t) nd = first;
+        }
     }
+    long long w0 = __reduce_min_sync(0xffffffffu, nd);
 
     WEmit em;
     em.topk = topk;
@@ -578,14 +597,17 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
             inherited = lb_ok ? ld_volatile_u32(theta_lb) : 0u;
             inherited = __reduce_max_sync(0xffffffffu, inherited);
         }
-        int next_doc = kNoMoreDocs;
         hot = 0;
         em.theta_in = max(em.theta_in, inherited);
         float te = em.theta_local;
         if (em.theta_in > kOrderedNegInf) te = fmaxf(te, ordered_to_float(em.theta_in));
         const bool open = te == -INFINITY;
-        // ---- clauses in order: drain each stream up to the window end
-        for (int t = 0; t < T; t++) {
+        // ---- clauses with a posting in this window, in clause order: drain each stream up to the
+        // window end (a sparse clause sits out most windows)
+        uint32_t active = __ballot_sync(0xffffffffu, nd < win1);
+        while (active) {
+            const int t = __ffs(active) - 1;
+            active &= active - 1;
             WTerm& tc = sh.term[t];
             const int32_t* cd = cdocs + t * kBlock;
             const float* cs = cscores + t * kBlock;
@@ -619,9 +641,11 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                 tc.pos = pos;
                 tc.n = n;
             }
-            if (pos < n) next_doc = min(next_doc, cd[pos]);
+            const int nx = pos < n ? cd[pos] : kNoMoreDocs;
+            if (lane == t) nd = nx;
             __syncwarp();
         }
+        const int next_doc = __reduce_min_sync(0xffffffffu, nd);
         hot = __reduce_or_sync(0xffffffffu, hot);
         // ---- window epilogue.  Matches were counted when a doc was first touched; only 32-doc
         // steps holding a doc whose (partial) sum exceeded theta are scanned for candidates, then
