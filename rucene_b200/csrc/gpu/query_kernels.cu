@@ -285,7 +285,7 @@ __device__ __forceinline__ bool is_live(const SegDev& seg, int doc) {
 //   next window start = min over clauses of their next cached docid (exact).
 constexpr int kOrWarps = 4;
 constexpr int kOrThreads = kOrWarps * 32;
-constexpr int kWw = 1024;            // docids per window
+constexpr int kWw = 768;            // docids per window
 constexpr int kNewcW = 64;
 
 struct WTerm {
@@ -527,7 +527,7 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
 }
 
 template <bool LIVE, bool NOT>
-__global__ void __launch_bounds__(kOrThreads, 4)
+__global__ void __launch_bounds__(kOrThreads, 6)
 k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, uint32_t warp_bytes,
           uint32_t kcap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
