@@ -405,12 +405,14 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
         if (b > tc.nb) return false;
         int4 docs, freqs;
         uint32_t n_in = kBlock;
+        uint32_t next_off16 = 0;  // payload of the block after this one (0: none) — prefetched below
         bool interior = false;    // every posting of the block lies inside [lo, hi)
         bool all_direct = false;  // ... and inside the window being drained
         if (b < tc.nb) {
             const BlockDesc bd = tc.blk_desc[b];
             const int base = b == 0 ? 0 : __ldg(tc.blk_last + b - 1);
             const int last = __ldg(tc.blk_last + b);
+            if (b + 1 < tc.nb) next_off16 = tc.blk_desc[b + 1].off16;  // same cache line as bd, almost always
             interior = (b == 0 ? lo == 0 : base >= lo) && last < hi;
             all_direct = interior && last < win1;
             const uint4* part = seg.arena + bd.off16;
@@ -480,6 +482,13 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) sc[q] = bm25_score(w1, (float)f[q], nrm[q]);
+        // pull the next block's payload towards L1 while this one is accumulated (dense clauses come
+        // straight back for it).  Prefetching the norm bytes the next block will probably hit, or
+        // carrying the next descriptor in shared memory, both measured slower.
+        if (next_off16 && lane < 4) {
+            const uint4* np = seg.arena + next_off16 + lane * 8;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(np));
+        }
         if (all_direct) {  // the common case for dense clauses: nothing to cache, no cursor arithmetic
 #pragma unroll
             for (int q = 0; q < 4; q++)

@@ -4,6 +4,7 @@ There is no CPU fallback anywhere in this module: if the CUDA library cannot be 
 no device is present, every entry point raises.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -53,7 +54,8 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    L = C.CDLL(_build.build_gpu())
+    # RUCENE_B200_GPU_LIB: load an alternative build of the same library (kernel A/B measurements)
+    L = C.CDLL(os.environ.get("RUCENE_B200_GPU_LIB") or _build.build_gpu())
     vp = C.c_void_p
     L.rg_last_error.restype = C.c_char_p
     L.rg_last_error.argtypes = [vp]
