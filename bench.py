@@ -390,7 +390,7 @@ def main():
         pass
     roofline = {"bound": "hbm", "kernel": "k_eval_and" if must else "k_eval_or", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "note": "instruction-bound, not HBM-bound: ~4.7 warp instructions per posting (profiles/README.md); "
+                "note": "instruction-bound, not HBM-bound: ~4.5 warp instructions per posting (profiles/README.md); "
                         "DRAM traffic is far below the algorithmic bytes because hot posting blocks hit in L2",
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": eval_ms, "replay_ms": replay_ms,
                 "postings_per_launch": bstats["postings"], "work_items": bstats["items"],
