@@ -110,7 +110,7 @@ struct EvalParams {
     uint32_t* error_flag;      // bit0: arena exhausted
 };
 void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n,
-                    uint32_t max_terms, bool has_live, bool has_not);
+                    uint32_t max_terms, bool has_live, bool has_not, bool has_msm);
 void launch_eval_and(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, bool req_opt);
 
 struct ReplayParams {
@@ -153,6 +153,7 @@ struct rg_engine {
     std::vector<float> h_caches;
     bool caches_dirty = true;
     rg::DevBuf<rg_hit> cand_arena;
+    rg::DevBuf<uint8_t> merge_scratch;  // rg_merge_leaf_records outputs (grow-only)
     rg::DevBuf<uint8_t> spare_slab;  // device slab of the last destroyed rg_batch, reused by the next
     uint64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;

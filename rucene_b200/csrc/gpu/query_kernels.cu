@@ -305,18 +305,31 @@ struct WTerm {
 // One posting of a clause lands on window slot idx.  SHOULD clause: clause-order f32 add, first
 // touch counts the match.  MUST_NOT clause (drained after every SHOULD clause of the window): a doc
 // that is present becomes kExcl and its match is taken back.
-template <bool NOT>
+// MSM (min_should_match > 1, disjunction_scorer.rs:317-329): a per-doc clause counter next to the
+// sums; a doc becomes a match when its counter reaches msm.
+struct MsmCtx {
+    uint8_t* cnt;  // [kWw] clause counters of the window (MSM variants only)
+    uint32_t msm;
+};
+template <bool NOT, bool MSM>
 __device__ __forceinline__ void accumulate_posting(uint32_t* acc, int idx, float s, bool is_not, bool live,
-                                                   float te, uint32_t& hot, uint32_t& my_matches) {
+                                                   float te, uint32_t& hot, uint32_t& my_matches,
+                                                   const MsmCtx& mc) {
     const uint32_t old = acc[idx];
     if (!NOT || !is_not) {
         const float sum = __fadd_rn(old == kSent ? 0.0f : __uint_as_float(old), s);
         acc[idx] = __float_as_uint(sum);
-        if (old == kSent && live) my_matches++;
+        if (MSM) {
+            const uint32_t c = (uint32_t)mc.cnt[idx] + 1u;
+            mc.cnt[idx] = (uint8_t)c;
+            if (c == mc.msm && live) my_matches++;
+        } else if (old == kSent && live) {
+            my_matches++;
+        }
         if (sum > te) hot |= 1u << (idx >> 5);
     } else if (old != kSent && old != kExcl) {
         acc[idx] = kExcl;
-        if (live) my_matches--;
+        if (live && (!MSM || mc.cnt[idx] >= mc.msm)) my_matches--;
     }
 }
 
@@ -396,10 +409,11 @@ __device__ __forceinline__ void wtheta_update(WEmit& em, uint32_t k, uint32_t kc
 // list is exhausted.  Warp-cooperative; all lanes must call it.
 // When called while clause t is being drained into the window [win0, win1) the new block's
 // postings below win1 are accumulated straight from registers (no round trip through the cache).
-template <bool LIVE, bool NOT>
+template <bool LIVE, bool NOT, bool MSM>
 __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParams& p, WTerm& tc, int32_t* cd,
                                            float* cs, int lo, int hi, int lane, int win0, int win1,
-                                           uint32_t* acc, uint32_t& hot, uint32_t& my_matches, float te) {
+                                           uint32_t* acc, uint32_t& hot, uint32_t& my_matches, float te,
+                                           const MsmCtx& mc) {
     for (;;) {
         const uint32_t b = tc.cur;
         if (b > tc.nb) return false;
@@ -492,8 +506,8 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
         if (all_direct) {  // the common case for dense clauses: nothing to cache, no cursor arithmetic
 #pragma unroll
             for (int q = 0; q < 4; q++)
-                accumulate_posting<NOT>(acc, d[q] - win0, sc[q], neg, LIVE ? is_live(seg, d[q]) : true, te, hot,
-                                        my_matches);
+                accumulate_posting<NOT, MSM>(acc, d[q] - win0, sc[q], neg, LIVE ? is_live(seg, d[q]) : true, te,
+                                             hot, my_matches, mc);
             __syncwarp();  // every lane has read tc.cur / tc.nb above
             if (lane == 0) {
                 tc.pos = tc.n = 0;
@@ -505,8 +519,8 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             if (ok[q] && d[q] < win1) {  // still inside the window being drained: accumulate now
-                accumulate_posting<NOT>(acc, d[q] - win0, sc[q], neg, LIVE ? is_live(seg, d[q]) : true, te, hot,
-                                        my_matches);
+                accumulate_posting<NOT, MSM>(acc, d[q] - win0, sc[q], neg, LIVE ? is_live(seg, d[q]) : true, te,
+                                             hot, my_matches, mc);
                 direct++;
             }
         }
@@ -535,7 +549,7 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
     }
 }
 
-template <bool LIVE, bool NOT>
+template <bool LIVE, bool NOT, bool MSM>
 __global__ void __launch_bounds__(kOrThreads, 6)
 k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, uint32_t warp_bytes,
           uint32_t kcap) {
@@ -555,6 +569,12 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
     float* cscores = reinterpret_cast<float*>(cdocs + T * kBlock);
 
     for (int i = lane; i < kWw; i += 32) sh.acc[i] = kSent;
+    MsmCtx mc;
+    mc.cnt = reinterpret_cast<uint8_t*>(cscores + T * kBlock);  // MSM variants reserve kWw more bytes
+    mc.msm = max(1u, (uint32_t)it.type >> 4);  // items without min_should_match in an MSM launch: 1
+    if (MSM) {
+        for (int i = lane; i < kWw / 4; i += 32) reinterpret_cast<uint32_t*>(mc.cnt)[i] = 0u;
+    }
     if (lane < T) {
         const ItemClause c = p.clauses[it.clause_begin + lane];
         const TermDev td = seg.terms[c.term_id];
@@ -574,8 +594,8 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
     uint32_t hot = 0, my_matches = 0;
     int nd = kNoMoreDocs;  // lane t: next cached docid of clause t (kNoMoreDocs = exhausted)
     for (int t = 0; t < T; t++) {
-        if (stream_refill<LIVE, NOT>(seg, p, sh.term[t], cdocs + t * kBlock, cscores + t * kBlock, lo, hi, lane, 0,
-                                     -2147483647 - 1, sh.acc, hot, my_matches, INFINITY)) {
+        if (stream_refill<LIVE, NOT, MSM>(seg, p, sh.term[t], cdocs + t * kBlock, cscores + t * kBlock, lo, hi, lane,
+                                          0, -2147483647 - 1, sh.acc, hot, my_matches, INFINITY, mc)) {
             const int first = cdocs[t * kBlock + sh.term[t].pos];
             if (lane == t) nd = first;
         }
@@ -627,8 +647,8 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                     __syncwarp();  // every lane has read tc.pos / tc.n / tc.cur
                     if (lane == 0) tc.pos = pos;
                     __syncwarp();
-                    if (!stream_refill<LIVE, NOT>(seg, p, tc, cdocs + t * kBlock, cscores + t * kBlock, lo, hi, lane,
-                                                  win0, win1, sh.acc, hot, my_matches, te)) {
+                    if (!stream_refill<LIVE, NOT, MSM>(seg, p, tc, cdocs + t * kBlock, cscores + t * kBlock, lo, hi,
+                                                       lane, win0, win1, sh.acc, hot, my_matches, te, mc)) {
                         pos = n = 0;
                         break;
                     }
@@ -640,8 +660,8 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                 const bool in_win = d < win1;
                 const uint32_t c = __popc(__ballot_sync(0xffffffffu, in_win));  // sorted: a prefix
                 if (in_win)
-                    accumulate_posting<NOT>(sh.acc, d - win0, cs[i], NOT && tc.is_not != 0,
-                                            LIVE ? is_live(seg, d) : true, te, hot, my_matches);
+                    accumulate_posting<NOT, MSM>(sh.acc, d - win0, cs[i], NOT && tc.is_not != 0,
+                                                 LIVE ? is_live(seg, d) : true, te, hot, my_matches, mc);
                 pos += c;
                 if (c < 32 && pos < n) break;  // next cached doc is beyond this window
             }
@@ -668,7 +688,7 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                 const uint32_t v = sh.acc[idx];
                 const float sc = __uint_as_float(v);
                 const bool cand = v != kSent && (!NOT || v != kExcl) && (open || sc > te) &&
-                                  (LIVE ? is_live(seg, win0 + idx) : true);
+                                  (!MSM || mc.cnt[idx] >= mc.msm) && (LIVE ? is_live(seg, win0 + idx) : true);
                 const uint32_t cm = __ballot_sync(0xffffffffu, cand);
                 if (!cm || em.overflow) continue;
                 const uint32_t c = __popc(cm);
@@ -705,6 +725,9 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
 #pragma unroll
             for (int g = 0; g < kWw / 128; g++)
                 reinterpret_cast<uint4*>(sh.acc)[g * 32 + lane] = make_uint4(kSent, kSent, kSent, kSent);
+            if (MSM) {
+                for (int i = lane; i < kWw / 16; i += 32) reinterpret_cast<uint4*>(mc.cnt)[i] = make_uint4(0, 0, 0, 0);
+            }
             wtheta_update(em, p.k, kcap, lane, sh.newc, newc_n, p.item_theta + item_idx);
             __syncwarp();
         }
@@ -1162,29 +1185,33 @@ k_merge_leaf_records(const uint8_t* __restrict__ records, uint32_t n_leaves, uin
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-template <bool LIVE, bool NOT>
+template <bool LIVE, bool NOT, bool MSM>
 static void launch_eval_or_t(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, size_t wb,
                              uint32_t kcap) {
     const size_t smem = wb * kOrWarps;
     static size_t attr = 0;
     if (smem > attr) {
-        cudaFuncSetAttribute(k_eval_or<LIVE, NOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_eval_or<LIVE, NOT, MSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = smem;
     }
     const uint32_t ctas = (n + kOrWarps - 1) / kOrWarps;
-    k_eval_or<LIVE, NOT><<<ctas, kOrThreads, smem, st>>>(p, item_ids, n, (uint32_t)wb, kcap);
+    k_eval_or<LIVE, NOT, MSM><<<ctas, kOrThreads, smem, st>>>(p, item_ids, n, (uint32_t)wb, kcap);
 }
 // has_live: some leaf has deleted docs; has_not: some item of the launch carries a MUST_NOT clause
 void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n,
-                    uint32_t max_terms, bool has_live, bool has_not) {
+                    uint32_t max_terms, bool has_live, bool has_not, bool has_msm) {
     if (!n) return;
     const uint32_t kcap = (std::min<uint32_t>(p.k, kMaxK) + 31u) & ~31u;
     size_t wb = sizeof(WarpShared) + (size_t)kcap * sizeof(float) + (size_t)max_terms * kBlock * 8;
     wb = (wb + 15) & ~size_t(15);
-    if (has_live && has_not) launch_eval_or_t<true, true>(st, p, item_ids, n, wb, kcap);
-    else if (has_live) launch_eval_or_t<true, false>(st, p, item_ids, n, wb, kcap);
-    else if (has_not) launch_eval_or_t<false, true>(st, p, item_ids, n, wb, kcap);
-    else launch_eval_or_t<false, false>(st, p, item_ids, n, wb, kcap);
+    if (has_msm) {  // min_should_match > 1 somewhere in the batch: the one general variant
+        wb += kWw;  // per-doc clause counters
+        wb = (wb + 15) & ~size_t(15);
+        launch_eval_or_t<true, true, true>(st, p, item_ids, n, wb, kcap);
+    } else if (has_live && has_not) launch_eval_or_t<true, true, false>(st, p, item_ids, n, wb, kcap);
+    else if (has_live) launch_eval_or_t<true, false, false>(st, p, item_ids, n, wb, kcap);
+    else if (has_not) launch_eval_or_t<false, true, false>(st, p, item_ids, n, wb, kcap);
+    else launch_eval_or_t<false, false, false>(st, p, item_ids, n, wb, kcap);
 }
 void launch_eval_and(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, bool req_opt) {
     if (!n) return;

@@ -46,7 +46,7 @@ struct rg_batch {
     size_t zero_bytes = 0;
     uint64_t postings = 0, algo_bytes = 0, h2d_bytes = 0;
     uint32_t kernels_per_run = 0;
-    bool or_has_not = false;
+    bool or_has_not = false, or_has_msm = false;
     bool ran = false;
 };
 
@@ -60,13 +60,14 @@ struct HostPlan {
     std::vector<uint32_t> group_item_begin, group_out;
     uint64_t postings = 0, algo_bytes = 0;
     uint32_t max_or_terms = 1;
-    bool or_has_not = false;
+    bool or_has_not = false, or_has_msm = false;
 };
 
 struct QShape {
     int type = -1;  // kTypeOr / kTypeAnd
     std::vector<uint32_t> clause_idx;  // scoring clauses (indices into the caller's array), evaluation order
     std::vector<uint32_t> not_idx;     // MUST_NOT clauses (ReqNotScorer)
+    uint32_t msm = 0;                  // min_should_match when > 1 on a pure-SHOULD shape, else 0
     std::vector<uint32_t> opt_idx;     // SHOULD clauses beside a MUST (ReqOptScorer's optional side), clause order
 };
 
@@ -93,7 +94,6 @@ QShape classify(const rg_query& q, const rg_clause* clauses, uint32_t n_clauses_
         throw ArgError("boolean query should at least contain one inner query!");
     if (musts.empty() && shoulds.empty())
         throw Unsupported("pure MUST_NOT (MatchAllDocsQuery) is not accelerated");
-    if (msm > 1) throw Unsupported("min_should_match > 1 is not accelerated yet");
     if (musts.size() + shoulds.size() + must_nots.size() > (size_t)kMaxTerms)
         throw Unsupported("more than 9 clauses");
     // BooleanWeight::create_scorer (:253-278): ReqNotScorer(must | should, must_not); the excluded
@@ -115,6 +115,11 @@ QShape classify(const rg_query& q, const rg_clause* clauses, uint32_t n_clauses_
     if (shoulds.size() >= 10) throw Unsupported(">= 10 SHOULD clauses use DisiPriorityQueue");
     s.type = kTypeOr;
     s.clause_idx = shoulds;
+    // min_should_match > 1 only ever filters a disjunction that is iterated with next(): the
+    // top-level SHOULD side.  Beside a MUST it sits behind ReqOptScorer::score -> advance(), which
+    // does not look at it (disjunction_scorer.rs:350-363), so those shapes ignore it above.
+    s.msm = msm > 1 ? (uint32_t)msm : 0u;
+    if (s.msm > 15u) throw Unsupported("min_should_match > 15");
     return s;
 }
 
@@ -144,6 +149,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
             }
             const bool new_group = mode == RG_MODE_SEARCH_PARALLEL || !group_open;
             if (dead || present.empty()) continue;
+            if (shape.type == kTypeOr && shape.msm > present.size()) continue;  // nothing can reach msm here
             std::vector<uint32_t> nots;  // MUST_NOT clauses present in this leaf (:236-251)
             for (uint32_t ci : shape.not_idx) {
                 const uint32_t t = clauses[ci].term_id;
@@ -212,7 +218,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 WorkItem it{};
                 it.query = qi;
                 it.seg = (uint16_t)si;
-                it.type = (uint8_t)leaf_type;
+                it.type = (uint8_t)(leaf_type | (shape.type == kTypeOr ? shape.msm << 4 : 0u));
                 it.n_terms = (uint8_t)n_item_terms;
                 it.lo = (int32_t)((uint64_t)seg.max_doc * r / R);
                 it.hi = (int32_t)((uint64_t)seg.max_doc * (r + 1) / R);
@@ -231,6 +237,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                     hp.or_rank.push_back((uint32_t)r);
                     hp.max_or_terms = std::max<uint32_t>(hp.max_or_terms, n_item_terms);
                     if (!nots.empty()) hp.or_has_not = true;
+                    if (shape.msm) hp.or_has_msm = true;
                 }
             }
         }
@@ -309,6 +316,7 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     b->n_groups = (uint32_t)hp.group_out.size();
     b->max_or_terms = hp.max_or_terms;
     b->or_has_not = hp.or_has_not;
+    b->or_has_msm = hp.or_has_msm;
     b->n_leaves = (uint32_t)e->segs.size();
     b->postings = hp.postings;
     b->algo_bytes = hp.algo_bytes + (uint64_t)n_queries * p->k * sizeof(rg_hit);
@@ -396,7 +404,7 @@ int rg_batch_run(rg_engine* e, rg_batch* b) {
     RG_CUDA_CHECK(cudaEventRecord(e->ev2, st));
     bool has_live = false;
     for (const Segment& sg : e->segs) has_live = has_live || sg.live.p != nullptr;
-    launch_eval_or(st, ep, b->or_ids.p, b->n_or, b->max_or_terms, has_live, b->or_has_not);
+    launch_eval_or(st, ep, b->or_ids.p, b->n_or, b->max_or_terms, has_live, b->or_has_not, b->or_has_msm);
     RG_CUDA_CHECK(cudaGetLastError());
     launch_eval_and(st, ep, b->and_ids.p, b->n_and, false);
     RG_CUDA_CHECK(cudaGetLastError());
@@ -506,12 +514,15 @@ int rg_merge_leaf_records(rg_engine* e, const void* dev_records_all, uint32_t n_
     if (!e || !dev_records_all || !out_hits || !out_counts || !out_total_hits) throw ArgError("null argument");
     if (k == 0 || k > 1024) throw ArgError("k out of range");
     cudaStream_t st = e->stream;
-    DevBuf<rg_hit> d_hits;
-    DevBuf<uint32_t> d_counts;
-    DevBuf<unsigned long long> d_total;
-    d_hits.alloc((size_t)std::max<uint32_t>(1, n_queries) * k);
-    d_counts.alloc(std::max<uint32_t>(1, n_queries));
-    d_total.alloc(std::max<uint32_t>(1, n_queries));
+    // grow-only engine scratch: no cudaMalloc/cudaFree on the per-batch path
+    const size_t nq = std::max<uint32_t>(1, n_queries);
+    const size_t hits_b = (nq * k * sizeof(rg_hit) + 255) & ~(size_t)255;
+    const size_t counts_b = (nq * 4 + 255) & ~(size_t)255;
+    const size_t total_b = nq * 8;
+    if (e->merge_scratch.n < hits_b + counts_b + total_b) e->merge_scratch.alloc(hits_b + counts_b + total_b);
+    Span<rg_hit> d_hits{reinterpret_cast<rg_hit*>(e->merge_scratch.p), nq * k};
+    Span<uint32_t> d_counts{reinterpret_cast<uint32_t*>(e->merge_scratch.p + hits_b), nq};
+    Span<unsigned long long> d_total{reinterpret_cast<unsigned long long*>(e->merge_scratch.p + hits_b + counts_b), nq};
     RG_CUDA_CHECK(cudaMemsetAsync(d_hits.p, 0, d_hits.bytes(), st));
     launch_merge_leaf_records(st, static_cast<const uint8_t*>(dev_records_all), n_leaves, n_queries, k,
                               d_hits.p, d_counts.p, d_total.p);

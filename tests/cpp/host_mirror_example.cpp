@@ -42,8 +42,8 @@ int main() {
             std::printf("\n");
         }
         bool threw = false;
-        try {  // min_should_match > 1 is outside the accelerated path
-            auto q5 = BooleanQuery::build({}, {q1, q1}, {}, {}, 2);
+        try {  // FILTER clauses are outside the accelerated path
+            auto q5 = BooleanQuery::build({q1}, {}, {q1}, {}, 0);
             TopDocsCollector c(10);
             searcher.search(*q5, c);
         } catch (const UnsupportedQuery&) { threw = true; }

@@ -173,9 +173,14 @@ def _brute_force(seg_list, postings_list, ix, spec, k, stats=None):
                 continue
             docs = np.unique(np.concatenate([p[1] for p in shoulds]))
             score = np.zeros(len(docs), np.float32)
+            count = np.zeros(len(docs), np.int32)
             for _occ, d, s in shoulds:  # clause order, starting from 0.0f
                 pos = np.searchsorted(docs, d)
                 score[pos] = (score[pos] + s).astype(np.float32)
+                count[pos] += 1
+            msm = spec[2] if kind == "bool" and len(per) > 1 else 0
+            if msm > 1:  # disjunction_scorer.rs:317-329
+                docs, score = docs[count >= msm], score[count >= msm]
         if seg.live_docs is not None:
             live = (seg.live_docs[docs >> 6] >> (docs & 63).astype(np.uint64)) & np.uint64(1)
             docs, score = docs[live == 1], score[live == 1]
@@ -269,3 +274,28 @@ def test_oracle_req_opt_matches_brute_force(live):
             assert np.array_equal(got["doc"], want["doc"]), spec
             assert np.array_equal(got["score"].view(np.uint32), want["score"].view(np.uint32)), spec
     assert stats.get("skipped", 0) > 100
+
+
+def test_oracle_min_should_match_matches_brute_force():
+    rng = np.random.default_rng(420)
+    dfs = [0, 2, 90, 700, 5000, 14000, 26000]
+    segs, posts = [], []
+    for s in range(2):
+        seg, p = helpers.build_segment(rng, 30000 + 500 * s, dfs, live_fraction=0.9 if s else None)
+        segs.append(seg)
+        posts.append(p)
+    ix = helpers.oracle_index(segs)
+    specs = [("bool", [(ob.SHOULD, 6), (ob.SHOULD, 5)], 2),
+             ("bool", [(ob.SHOULD, 6), (ob.SHOULD, 5), (ob.SHOULD, 4), (ob.SHOULD, 3)], 3),
+             ("bool", [(ob.SHOULD, 4), (ob.SHOULD, 0), (ob.SHOULD, 6)], 2),
+             ("bool", [(ob.SHOULD, 3), (ob.SHOULD, 2)], 3)]
+    q, c = ob.make_queries(specs)
+    hits, counts, total = ix.search_batch(q, c, 20)
+    for i, spec in enumerate(specs):
+        d, s = _brute_force(segs, posts, ix, spec, 20)
+        want, _ = ob.topk_stream(d, s, 20)
+        assert total[i] == len(d), spec
+        got = hits[i][:counts[i]]
+        assert np.array_equal(got["doc"], want["doc"]), spec
+        assert np.array_equal(got["score"].view(np.uint32), want["score"].view(np.uint32)), spec
+    assert total[3] == 0 and 0 < total[1] < total[0]

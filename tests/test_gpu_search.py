@@ -192,6 +192,39 @@ def test_req_opt_scorer_must_plus_should():
             helpers.assert_same_topdocs(got, want, "req_opt k=%d rp=%d mode=%d" % (k, rp, mode))
 
 
+def test_min_should_match_greater_than_one():
+    """min_should_match > 1 (disjunction_scorer.rs:317-329): a doc needs that many SHOULD clauses of
+    the leaf.  Only the top-level SHOULD side is filtered; beside a MUST the SHOULD disjunction sits
+    behind ReqOptScorer::score -> advance(), which ignores it (:350-363) — the oracle restates both."""
+    rng = np.random.default_rng(91)
+    dfs = [0, 1, 130, 900, 5000, 14000, 26000, 33000, 36000]
+    segs = []
+    for s, lf in enumerate((None, 0.85)):
+        d = list(dfs)
+        if s == 1:
+            d[5] = 0
+        segs.append(helpers.build_segment(rng, 38000 + 900 * s, d, live_fraction=lf)[0])
+    specs = [("bool", [(ob.SHOULD, 8), (ob.SHOULD, 7)], 2),
+             ("bool", [(ob.SHOULD, 8), (ob.SHOULD, 7), (ob.SHOULD, 6), (ob.SHOULD, 5), (ob.SHOULD, 4)], 3),
+             ("bool", [(ob.SHOULD, 8), (ob.SHOULD, 7), (ob.SHOULD, 6), (ob.SHOULD, 5), (ob.SHOULD, 4)], 5),
+             ("bool", [(ob.SHOULD, 4), (ob.SHOULD, 5), (ob.SHOULD, 0)], 2),
+             ("bool", [(ob.SHOULD, 3), (ob.SHOULD, 2)], 3),                       # msm > clauses: nothing
+             ("bool", [(ob.SHOULD, 8), (ob.MUST_NOT, 7)], 2),                     # one SHOULD, msm 2: nothing
+             ("bool", [(ob.SHOULD, 8), (ob.SHOULD, 6), (ob.SHOULD, 4), (ob.MUST_NOT, 7), (ob.MUST_NOT, 5)], 2),
+             ("bool", [(ob.MUST, 7), (ob.SHOULD, 8), (ob.SHOULD, 6)], 2),         # beside a MUST: ignored
+             ("bool", [(ob.MUST, 7), (ob.MUST, 8)], 2),
+             ("bool", [(ob.SHOULD, 8)], 4)]                                        # collapses to the clause
+    for i in range(30):
+        t = int(rng.integers(2, 6))
+        terms = [int(x) for x in rng.choice(len(dfs), size=t, replace=False)]
+        specs.append(("bool", [(ob.SHOULD, x) for x in terms], int(rng.integers(2, t + 1))))
+    specs += _mixed_specs(rng, len(dfs), 8, kinds=("and", "or"))
+    for k, rp in ((10, 0), (100, 2500)):
+        for mode in (0, 1):
+            got, want = _run_both(segs, specs, k, mode=mode, range_postings=rp)
+            helpers.assert_same_topdocs(got, want, "msm k=%d rp=%d mode=%d" % (k, rp, mode))
+
+
 def test_reference_style_api():
     """Reads like examples/example.rs:111-117."""
     rng = np.random.default_rng(5)
@@ -213,9 +246,8 @@ def test_reference_style_api():
         collector = search.TopDocsCollector.new(10)   # MUST + SHOULD: ReqOptScorer
         searcher.search(q, collector)
         assert collector.top_docs().total_hits() == 1666
-        q = search.BooleanQuery.build([], [query, search.TermQuery.new(search.Term.new("body", b"world"))], [], [], 2)
-        with pytest.raises(engine.Unsupported):   # min_should_match > 1 is a "next" row
-            searcher.search(q, search.TopDocsCollector.new(10))
+        with pytest.raises(engine.Unsupported):   # FILTER clauses are outside the accelerated path
+            searcher.search(search.BooleanQuery.build([query], [], [query], [], 0), search.TopDocsCollector.new(10))
         with pytest.raises(search.IllegalArgument):
             search.BooleanQuery.build([], [], [], [], 0)
     finally:
