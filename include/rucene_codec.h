@@ -34,6 +34,23 @@ rc_writer* rc_writer_create(int doc_version, int32_t max_doc, const uint8_t segm
  * whose postings are docs[0..n) strictly ascending with freqs[i] >= 1. */
 int rc_writer_add_term(rc_writer* w, const int32_t* docs, const int32_t* freqs, int32_t n,
                        rg_term_state* out_state);
+/* Turn on the reference's dormant doc-block encodings for the terms added afterwards
+ * (EfWriterMeta{use_ef, with_pf}, codec/postings/posting_writer.rs:33-57; ForUtil::write_block,
+ * for_util.rs:417-468): a block whose 128 docids fit a FixedBitSet no larger than its PF payload is
+ * written as EncodeType::BITSET, else as EncodeType::EF (Elias-Fano) when that is no larger than PF
+ * (or always, with_pf = 0), else as PF.  The open-source writer never sets use_ef; production
+ * indexes carry these blocks and the reader side handles them (posting_reader.rs:501-561). */
+int rc_writer_set_ef(rc_writer* w, int use_ef, int with_pf);
+/* EliasFanoEncoder pieces, exported so the reference's own unit vectors can be checked
+ * (util/packed/elias_fano_encoder.rs:308-311 num_longs_for_bits, :334-345 pack_value, :46-253
+ * new + encode_next: out_longs = upper | lower | index longs, out_geom = {num_low_bits, n_upper,
+ * n_lower, n_index}). */
+int64_t rc_ef_num_longs_for_bits(int64_t n);
+void rc_ef_pack_value(int64_t value, int64_t* longs, int n_longs, int num_bits, int64_t pack_index);
+int rc_ef_encode(const int64_t* values, int64_t n, int64_t upper_bound, int64_t* out_longs, int cap,
+                 int32_t out_geom[4]);
+/* out[0] full blocks written, out[1] of them EF, out[2] of them BITSET */
+void rc_writer_block_counts(rc_writer* w, uint64_t out[3]);
 int rc_writer_finish(rc_writer* w); /* codec footer (codec/codec_util.rs:110-114) */
 const uint8_t* rc_writer_data(rc_writer* w, size_t* len);
 /* the 32 ForUtil header codes as written (codec/postings/for_util.rs:150-185) */

@@ -595,6 +595,257 @@ using ScorerPtr = std::unique_ptr<Scorer>;
 // ---------------------------------------------------------------------------
 // codec/postings/posting_reader.rs:343-794 — BlockDocIterator (PF blocks)
 // ---------------------------------------------------------------------------
+// util/packed/elias_fano_encoder.rs:24-146,255-262 (read side: geometry + the three long arrays),
+// util/packed/elias_fano_decoder.rs:23-330 (next_value / advance_to_value / current_index),
+// util/bit_set.rs:193-251,351-376,453-460 (FixedBitSet pieces the BITSET blocks use).
+// The open-source writer never emits these blocks (EfWriterMeta.use_ef is never set,
+// posting_writer.rs:46) but the reader handles them (posting_reader.rs:501-561,612-647,649-789).
+// ---------------------------------------------------------------------------
+static const int64_t NO_MORE_VALUES = -1;
+static inline int64_t ushr64(int64_t x, int n) { return (int64_t)((uint64_t)x >> n); }
+static inline int clz64(int64_t x) { return x == 0 ? 64 : __builtin_clzll((uint64_t)x); }
+static inline int ctz64(int64_t x) { return x == 0 ? 64 : __builtin_ctzll((uint64_t)x); }
+static inline int popc64(int64_t x) { return __builtin_popcountll((uint64_t)x); }
+
+struct EliasFanoEncoder {  // as rebuilt by get_encoder / rebuild_not_with_check + deserialize2
+    int64_t num_values = 0, upper_bound = 0;
+    int num_low_bits = 0;
+    int64_t lower_bits_mask = 0;
+    std::vector<int64_t> upper_longs, lower_longs, upper_zero_bit_position_index;
+    int64_t num_encoded = 0, last_encoded = 0;
+    int64_t num_index_entries = 0, index_interval = 256;
+    int n_index_entry_bits = 0;
+    static int64_t num_longs_for_bits(int64_t n) { return ushr64(n + 63, 6); }  // :308-311
+    void rebuild(int64_t nv, int64_t ub) {  // :48-146 and :148-205 agree on every derived field
+        num_values = nv;
+        upper_bound = ub;
+        num_encoded = nv;
+        last_encoded = ub;
+        num_low_bits = 0;
+        if (nv > 0) {
+            int64_t fac = ub / nv;
+            if (fac > 0) num_low_bits = 64 - 1 - clz64(fac);
+        }
+        lower_bits_mask = ushr64(INT64_MAX, 64 - 1 - num_low_bits);
+        lower_longs.assign((size_t)num_longs_for_bits(nv * num_low_bits), 0);
+        upper_longs.assign((size_t)num_longs_for_bits(ushr64(ub, num_low_bits) + nv), 0);
+        int64_t max_high_value = ushr64(ub, num_low_bits);
+        int64_t n_entries = max_high_value / index_interval;
+        num_index_entries = n_entries >= 0 ? n_entries : 0;
+        int64_t max_index_entry = max_high_value + nv - 1;
+        n_index_entry_bits = max_index_entry <= 0 ? 0 : 64 - clz64(max_index_entry);
+        upper_zero_bit_position_index.assign((size_t)num_longs_for_bits(num_index_entries * n_index_entry_bits), 0);
+    }
+    static void read_data2(std::vector<int64_t>& buf, Input& in) {  // :367-374: raw little-endian memory
+        for (auto& x : buf) {
+            uint8_t b[8];
+            in.read_exact(b, 8);
+            uint64_t v = 0;
+            for (int i = 0; i < 8; i++) v |= (uint64_t)b[i] << (8 * i);
+            x = (int64_t)v;
+        }
+    }
+    void deserialize2(Input& in) {  // :278-285
+        num_encoded = num_values;
+        last_encoded = upper_bound;
+        read_data2(upper_longs, in);
+        read_data2(lower_longs, in);
+        read_data2(upper_zero_bit_position_index, in);
+    }
+};
+
+struct EliasFanoDecoder {
+    const EliasFanoEncoder* e = nullptr;
+    int64_t num_encoded = 0, ef_index = -1, set_bit_for_index = -1, num_index_entries = 0, index_mask = 0;
+    int64_t cur_high_long = 0;
+    void refresh(const EliasFanoEncoder* enc) {  // new() :36-46
+        e = enc;
+        num_encoded = enc->num_encoded;
+        ef_index = -1;
+        set_bit_for_index = -1;
+        num_index_entries = enc->num_index_entries;
+        index_mask = ((int64_t)1 << enc->n_index_entry_bits) - 1;
+        cur_high_long = 0;
+    }
+    int64_t current_index() const {  // :60-68
+        if (ef_index < 0) throw Error("index before sequence");
+        if (ef_index >= num_encoded) throw Error("index after sequence");
+        return ef_index;
+    }
+    static int64_t unpack_value(const std::vector<int64_t>& a, int num_bits, int64_t pack_index, int64_t mask) {
+        if (num_bits == 0) return 0;  // :96-108
+        int64_t bit_pos = pack_index * num_bits;
+        size_t index = (size_t)ushr64(bit_pos, 6);
+        int bit_pos_at_index = (int)(bit_pos & 63);
+        int64_t value = ushr64(a.at(index), bit_pos_at_index);
+        if (bit_pos_at_index + num_bits > 64) value |= (int64_t)((uint64_t)a.at(index + 1) << (64 - bit_pos_at_index));
+        return value & mask;
+    }
+    int64_t current_low_value() const { return unpack_value(e->lower_longs, e->num_low_bits, ef_index, e->lower_bits_mask); }
+    int64_t combine(int64_t high, int64_t low) const { return (int64_t)((uint64_t)high << e->num_low_bits) | low; }
+    bool to_after_current_high_bit() {  // :122-134
+        ef_index++;
+        if (ef_index >= num_encoded) return false;
+        set_bit_for_index++;
+        size_t hi = (size_t)ushr64(set_bit_for_index, 6);
+        cur_high_long = ushr64(e->upper_longs.at(hi), (int)(set_bit_for_index & 63));
+        return true;
+    }
+    void to_next_high_long() {  // :136-142
+        set_bit_for_index += 64 - (set_bit_for_index & 63);
+        cur_high_long = e->upper_longs.at((size_t)ushr64(set_bit_for_index, 6));
+    }
+    void to_next_high_value() {  // :143-148
+        while (cur_high_long == 0) to_next_high_long();
+        set_bit_for_index += ctz64(cur_high_long);
+    }
+    int64_t next_value() {  // :154-160
+        if (!to_after_current_high_bit()) return NO_MORE_VALUES;
+        to_next_high_value();
+        return combine(set_bit_for_index - ef_index, current_low_value());
+    }
+    static int select_bit(int64_t x, int r) {  // bit_util.rs:215-248: index of the r-th 1 bit, -1 if none
+        int s = -1;
+        uint64_t u = (uint64_t)x;
+        while (u != 0 && r > 0) {
+            int ntz = __builtin_ctzll(u);
+            u = ntz + 1 >= 64 ? 0 : u >> (ntz + 1);
+            s += ntz + 1;
+            r--;
+        }
+        return r > 0 ? -1 : s;
+    }
+    int64_t advance_to_value(int64_t target) {  // :186-318
+        ef_index++;
+        if (ef_index >= num_encoded) return NO_MORE_VALUES;
+        set_bit_for_index++;
+        size_t high_index = (size_t)ushr64(set_bit_for_index, 6);
+        int64_t upper_long = e->upper_longs.at(high_index);
+        cur_high_long = ushr64(upper_long, (int)(set_bit_for_index & 63));
+        int64_t high_target = ushr64(target, e->num_low_bits);
+        int64_t index_entry_index = (high_target / e->index_interval) - 1;
+        if (index_entry_index >= 0) {
+            if (index_entry_index >= num_index_entries) index_entry_index = num_index_entries - 1;
+            int64_t index_high_value = (index_entry_index + 1) * e->index_interval;
+            if (index_high_value > high_target) throw Error("ef: index_high_value > high_target");
+            if (index_high_value > (set_bit_for_index - ef_index)) {
+                set_bit_for_index = unpack_value(e->upper_zero_bit_position_index, e->n_index_entry_bits,
+                                                 index_entry_index, index_mask);
+                ef_index = set_bit_for_index - index_high_value;
+                high_index = (size_t)ushr64(set_bit_for_index, 6);
+                upper_long = e->upper_longs.at(high_index);
+                cur_high_long = ushr64(upper_long, (int)(set_bit_for_index & 63));
+            }
+            if (!(ef_index < num_encoded)) throw Error("ef: index past the sequence");
+        }
+        int cur_set_bits = popc64(cur_high_long);
+        int cur_clear_bits = 64 - cur_set_bits - (int)(set_bit_for_index & 63);
+        while ((set_bit_for_index - ef_index + cur_clear_bits) < high_target) {
+            ef_index += cur_set_bits;
+            if (ef_index >= num_encoded) return NO_MORE_VALUES;
+            set_bit_for_index += 64 - (set_bit_for_index & 63);
+            high_index++;
+            upper_long = e->upper_longs.at(high_index);
+            cur_high_long = upper_long;
+            cur_set_bits = popc64(cur_high_long);
+            cur_clear_bits = 64 - cur_set_bits;
+        }
+        while (cur_high_long == 0) {
+            set_bit_for_index += 64 - (set_bit_for_index & 63);
+            high_index++;
+            upper_long = e->upper_longs.at(high_index);
+            cur_high_long = upper_long;
+        }
+        int rank = (int)(high_target - (set_bit_for_index - ef_index));
+        if (rank > 64) throw Error("ef: rank > 64");
+        if (rank >= 1) {
+            int clear_bit_for_value = select_bit(~cur_high_long, rank);
+            if (clear_bit_for_value < 0 || clear_bit_for_value > 63) throw Error("ef: select failed");
+            set_bit_for_index += clear_bit_for_value + 1;
+            int one_bits_before_clear_bit = clear_bit_for_value - rank + 1;
+            ef_index += one_bits_before_clear_bit;
+            if (ef_index >= num_encoded) return NO_MORE_VALUES;
+            if ((set_bit_for_index & 63) == 0) {
+                high_index++;
+                upper_long = e->upper_longs.at(high_index);
+                cur_high_long = upper_long;
+            } else {
+                cur_high_long = ushr64(upper_long, (int)(set_bit_for_index & 63));
+            }
+            while (cur_high_long == 0) {
+                set_bit_for_index += 64 - (set_bit_for_index & 63);
+                high_index++;
+                upper_long = e->upper_longs.at(high_index);
+                cur_high_long = upper_long;
+            }
+        }
+        set_bit_for_index += ctz64(cur_high_long);
+        int64_t current_value = combine(set_bit_for_index - ef_index, current_low_value());
+        while (current_value < target) {
+            current_value = next_value();
+            if (current_value == NO_MORE_VALUES) return NO_MORE_VALUES;
+        }
+        return current_value;
+    }
+};
+
+struct FixedBitSet {
+    std::vector<int64_t> bits;
+    size_t num_bits = 0, num_words = 0;
+    static size_t bits2words(size_t n) { return (size_t)((((int32_t)n - 1) >> 6) + 1); }  // :480-484
+    void resize(size_t n) {  // :193-200
+        size_t w = bits2words(n);
+        if (w != bits.size()) {
+            bits.resize(w, 0);
+            num_words = w;
+            num_bits = num_words << 6;
+        }
+    }
+    void clear_all() { std::fill(bits.begin(), bits.end(), 0); }
+    bool get(size_t index) const { return (bits.at(index >> 6) & ((int64_t)1 << (index & 63))) != 0; }
+    int32_t next_set_bit(size_t index) const {  // :351-376
+        size_t i = index >> 6;
+        int64_t word = bits.at(i) >> (index & 63);  // arithmetic shift, as in the reference
+        if (word != 0) return (int32_t)(index + (size_t)ctz64(word));
+        for (;;) {
+            i++;
+            if (i >= num_words) break;
+            word = bits[i];
+            if (word != 0) return (int32_t)((i << 6) + (size_t)ctz64(word));
+        }
+        return NO_MORE_DOCS;
+    }
+    uint32_t count_ones_before_index2(int32_t doc_upto, size_t bit_index, size_t end_index) const {  // :206-251
+        uint32_t count = (uint32_t)doc_upto;
+        if (end_index > bit_index) {
+            size_t start_high = bit_index >> 6, end_high = end_index >> 6;
+            if (start_high < end_high) {
+                uint64_t remain = (uint64_t)bits.at(start_high) >> (bit_index & 63);
+                if (remain != 0) count += (uint32_t)__builtin_popcountll(remain);
+                start_high++;
+                for (size_t i = start_high; i < end_high; i++)
+                    if (bits.at(i) != 0) count += (uint32_t)popc64(bits[i]);
+                size_t low_value = end_index & 63;
+                if (low_value > 0) {
+                    int64_t value = bits.at(end_high) & (int64_t)(((uint64_t)1 << low_value) - 1);
+                    if (value > 0) count += (uint32_t)popc64(value);
+                }
+            } else {
+                size_t end_remain = end_index & 63;
+                if (end_remain > 0) {
+                    int64_t value = bits.at(end_high) & (int64_t)(((uint64_t)1 << end_remain) - 1);
+                    if (value > 0) {
+                        value = value >> (bit_index & 63);
+                        if (value > 0) count += (uint32_t)popc64(value);
+                    }
+                }
+            }
+        }
+        return count;
+    }
+};
+
+// ---------------------------------------------------------------------------
 struct SegmentData;
 
 struct BlockDocIterator {
@@ -619,6 +870,16 @@ struct BlockDocIterator {
     int32_t singleton_doc_id = -1;
     const ForUtil* for_util = nullptr;
     bool use_simd = false;
+    // other block encodings (:394-400)
+    EncodeType encode_type = PF;
+    EliasFanoEncoder ef_encoder;
+    EliasFanoDecoder ef_decoder;
+    bool has_ef_decoder = false;
+    int32_t ef_base_doc = -1;
+    int ef_base_total = 0;
+    FixedBitSet doc_bits;
+    int32_t bits_min_doc = 0;
+    int32_t bits_index = 0;
 
     BlockDocIterator(const Input& file, const ForUtil* fu, bool simd, bool has_freq,
                      const orc_term_state& ts, bool want_freq) {  // :410-458
@@ -646,6 +907,26 @@ struct BlockDocIterator {
         next_skip_doc = BLOCK_SIZE - 1;
         doc_buffer_upto = BLOCK_SIZE;
         skipped = false;
+        encode_type = PF;  // :491-496
+        has_ef_decoder = false;
+        ef_base_doc = -1;
+        doc_bits.clear_all();
+        bits_index = 0;
+    }
+    // ForUtil::read_other_encode_block, for_util.rs:337-372
+    void read_other_encode_block() {
+        if (encode_type == EF) {
+            int64_t upper_bound = doc_in.read_vlong();
+            ef_encoder.rebuild(BLOCK_SIZE, upper_bound);
+            ef_encoder.deserialize2(doc_in);
+            ef_decoder.refresh(&ef_encoder);
+            has_ef_decoder = true;
+        } else if (encode_type == BITSET) {
+            bits_min_doc = doc_in.read_vint();
+            size_t num_longs = doc_in.read_byte();
+            doc_bits.resize(num_longs << 6);
+            EliasFanoEncoder::read_data2(doc_bits.bits, doc_in);
+        }
     }
     void read_vint_block(int num) {  // :308-333
         if (index_has_freq) {
@@ -660,12 +941,15 @@ struct BlockDocIterator {
         }
     }
     void refill_docs() {  // :501-561
+        if (accum > 0) ef_base_doc = accum;  // "EF & PF compatible"
+        ef_base_total = doc_upto;
+        encode_type = PF;
+        bits_index = 0;
         int left = doc_freq - doc_upto;
         if (left >= BLOCK_SIZE) {
-            EncodeType et = PF;
-            for_util->read_block(doc_in, encoded, doc_delta_buffer, &et, use_simd);
-            if (et != PF)
-                throw Error("EF/BITSET/FULL doc blocks are out of scope (SURVEY 8f-2)");
+            for_util->read_block(doc_in, encoded, doc_delta_buffer, &encode_type, use_simd);
+            if (encode_type == FULL) throw Error("EncodeType::FULL is unimplemented in the reference too (:637-639)");
+            read_other_encode_block();
             if (index_has_freq) {
                 if (needs_freq) for_util->read_block(doc_in, encoded, freq_buffer, nullptr, use_simd);
                 else for_util->skip_block(doc_in);
@@ -681,7 +965,16 @@ struct BlockDocIterator {
     int32_t next() {  // :612-647
         if (doc_upto == doc_freq) return doc = NO_MORE_DOCS;
         if (doc_buffer_upto == BLOCK_SIZE) refill_docs();
-        doc = accum + doc_delta_buffer[doc_buffer_upto];
+        if (encode_type == PF) {
+            doc = accum + doc_delta_buffer[doc_buffer_upto];
+        } else if (encode_type == EF) {  // :624-626
+            ef_decoder.e = &ef_encoder;  // (self-pointer: stays valid if the iterator object was moved)
+            doc = (int32_t)ef_decoder.next_value() + 1 + ef_base_doc;
+        } else {  // BITSET :628-633
+            bits_index = doc_bits.next_set_bit((size_t)bits_index);
+            doc = bits_min_doc + bits_index;
+            bits_index += 1;
+        }
         accum = doc;
         doc_upto++;
         freq = freq_buffer[doc_buffer_upto];
@@ -707,13 +1000,42 @@ struct BlockDocIterator {
         }
         if (doc_upto == doc_freq) return doc = NO_MORE_DOCS;
         if (doc_buffer_upto == BLOCK_SIZE) refill_docs();
-        for (;;) {
-            if (doc_buffer_upto >= MAX_DATA_SIZE) throw Error("index out of bounds in advance scan");
-            accum += doc_delta_buffer[doc_buffer_upto];
-            doc_upto++;
-            if (accum >= target) break;
-            doc_buffer_upto++;
-            if (doc_upto == doc_freq) return doc = NO_MORE_DOCS;
+        if (encode_type == PF) {
+            for (;;) {
+                if (doc_buffer_upto >= MAX_DATA_SIZE) throw Error("index out of bounds in advance scan");
+                accum += doc_delta_buffer[doc_buffer_upto];
+                doc_upto++;
+                if (accum >= target) break;
+                doc_buffer_upto++;
+                if (doc_upto == doc_freq) return doc = NO_MORE_DOCS;
+            }
+        } else if (encode_type == EF) {  // :733-744
+            ef_decoder.e = &ef_encoder;
+            int64_t v = ef_decoder.advance_to_value((int64_t)(target - 1 - ef_base_doc));
+            if (v == NO_MORE_VALUES) return doc = NO_MORE_DOCS;
+            doc_buffer_upto = (int)ef_decoder.current_index();
+            doc_upto = ef_base_total + doc_buffer_upto + 1;
+            accum = (int32_t)v + 1 + ef_base_doc;
+        } else {  // BITSET :746-778
+            if (target < bits_min_doc) {
+                accum = bits_min_doc;
+                bits_index = 1;
+                doc_buffer_upto = 0;
+            } else {
+                int32_t index = target - bits_min_doc;
+                if (index >= (int32_t)doc_bits.num_bits) return doc = NO_MORE_DOCS;
+                bool find = doc_bits.get((size_t)index);
+                if (find) {
+                    accum = target;
+                } else {
+                    index = doc_bits.next_set_bit((size_t)index);
+                    if (index == NO_MORE_DOCS) return doc = NO_MORE_DOCS;
+                    accum = bits_min_doc + index;
+                }
+                doc_buffer_upto = (int)doc_bits.count_ones_before_index2(doc_buffer_upto, (size_t)bits_index, (size_t)index);
+                bits_index = index + 1;
+            }
+            doc_upto = ef_base_total + doc_buffer_upto + 1;
         }
         doc = accum;
         freq = freq_buffer[doc_buffer_upto];

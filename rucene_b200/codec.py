@@ -38,6 +38,9 @@ def lib():
     L.rc_writer_create.argtypes = [C.c_int, C.c_int32, u8p, C.c_char_p]
     L.rc_writer_add_term.argtypes = [vp, vp, vp, C.c_int32, C.POINTER(TermState)]
     L.rc_writer_finish.argtypes = [vp]
+    L.rc_writer_set_ef.argtypes = [vp, C.c_int, C.c_int]
+    L.rc_writer_block_counts.argtypes = [vp, vp]
+    L.rc_writer_block_counts.restype = None
     L.rc_writer_data.restype = vp
     L.rc_writer_data.argtypes = [vp, C.POINTER(C.c_size_t)]
     L.rc_writer_forutil_table.argtypes = [vp, i32p]
@@ -148,12 +151,17 @@ def synth_segment(seed, max_doc, n_terms, doc_version=1, n_threads=0):
 class PostingsWriter:
     """Lucene50PostingsWriter for one DocsAndFreqs field (codec/postings/posting_writer.rs)."""
 
-    def __init__(self, doc_version=1, max_doc=1 << 20, segment_id=None, suffix=""):
+    def __init__(self, doc_version=1, max_doc=1 << 20, segment_id=None, suffix="", use_ef=False,
+                 with_pf=True):
+        """use_ef / with_pf: EfWriterMeta (posting_writer.rs:33-57) — the reference's EF / BITSET doc-block
+        encodings, dormant in the open-source writer (off by default here too)."""
         L = lib()
         sid = (C.c_uint8 * 16)(*(segment_id or bytes(range(16))))
         self.h = L.rc_writer_create(doc_version, max_doc, sid, suffix.encode())
         if not self.h:
             raise RuntimeError("rc_writer_create: " + _err())
+        if use_ef:
+            L.rc_writer_set_ef(self.h, 1, 1 if with_pf else 0)
         self.max_doc = max_doc
         self.states = []
         self.sum_ttf = 0
@@ -175,6 +183,12 @@ class PostingsWriter:
         self.sum_ttf += st.total_term_freq
         self.sum_df += st.doc_freq
         return t
+
+    def block_counts(self):
+        """(full blocks written, of them EF, of them BITSET)"""
+        out = np.zeros(3, np.uint64)
+        lib().rc_writer_block_counts(self.h, out.ctypes.data)
+        return tuple(int(x) for x in out)
 
     def finish(self, norms=None, doc_count=None, live_docs=None):
         L = lib()

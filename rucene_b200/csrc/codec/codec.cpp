@@ -168,6 +168,113 @@ int write_block(const int32_t* data, int doc_version, uint8_t* out) {
     return 1 + 16 * b;
 }
 
+// ---- the reference's other doc-block encodings (dormant in the open-source writer:
+// EfWriterMeta.use_ef is never set, posting_writer.rs:46; production indexes carry them).
+// EfWriterMeta, posting_writer.rs:33-57; filled at :335 (ef_upper_doc) and :472 (ef_base_doc).
+struct EfWriterMeta {
+    int32_t ef_base_doc = -1, ef_upper_doc = 0;
+    bool use_ef = false, with_pf = true;
+};
+inline int64_t ushr64(int64_t x, int n) { return (int64_t)((uint64_t)x >> n); }
+inline int64_t num_longs_for_bits(int64_t n) { return ushr64(n + 63, 6); }  // elias_fano_encoder.rs:308-311
+// EliasFanoEncoder::pack_value, elias_fano_encoder.rs:334-345 (the spill word is assigned, not or-ed)
+inline void ef_pack_value(int64_t value, std::vector<int64_t>& a, int num_bits, int64_t pack_index) {
+    if (num_bits == 0) return;
+    int64_t bit_pos = (int64_t)num_bits * pack_index;
+    size_t index = (size_t)ushr64(bit_pos, 6);
+    int at = (int)(bit_pos & 63);
+    a[index] |= (int64_t)((uint64_t)value << at);
+    if (at + num_bits > 64) a[index + 1] = ushr64(value, 64 - at);
+}
+// EliasFanoEncoder::new + encode_next for one block, elias_fano_encoder.rs:46-146,214-253
+struct EfEncoder {
+    int64_t num_values, upper_bound;
+    int num_low_bits = 0;
+    int64_t lower_bits_mask;
+    std::vector<int64_t> upper, lower, index;
+    int64_t num_encoded = 0, last_encoded = 0, num_index_entries, index_interval = 256, current_entry_index = 0;
+    int n_index_entry_bits;
+    EfEncoder(int64_t nv, int64_t ub) : num_values(nv), upper_bound(ub) {
+        if (nv > 0 && ub < 0) throw std::runtime_error("upper_bound should not be negative");
+        int64_t fac = ub / nv;
+        if (fac > 0) num_low_bits = 63 - __builtin_clzll((uint64_t)fac);
+        lower_bits_mask = ushr64(INT64_MAX, 63 - num_low_bits);
+        lower.assign((size_t)num_longs_for_bits(nv * num_low_bits), 0);
+        int64_t high_clear = ushr64(ub > 0 ? ub : 0, num_low_bits);
+        if (high_clear > 2 * nv) throw std::runtime_error("ef: num_high_bits_clear > 2 * num_values");
+        upper.assign((size_t)num_longs_for_bits(high_clear + nv), 0);
+        int64_t max_high_value = ushr64(ub, num_low_bits);
+        int64_t n_entries = max_high_value / index_interval;
+        num_index_entries = n_entries >= 0 ? n_entries : 0;
+        int64_t max_index_entry = max_high_value + nv - 1;
+        n_index_entry_bits = max_index_entry <= 0 ? 0 : 64 - __builtin_clzll((uint64_t)max_index_entry);
+        index.assign((size_t)num_longs_for_bits(num_index_entries * n_index_entry_bits), 0);
+    }
+    int encode_size() const { return (int)((upper.size() + lower.size() + index.size()) << 3); }  // :207-212
+    void encode_next(int64_t x) {
+        if (num_encoded >= num_values) throw std::runtime_error("encode_next called too often");
+        if (last_encoded > x) throw std::runtime_error("ef: value smaller than previous");
+        if (x > upper_bound) throw std::runtime_error("ef: value larger than upper bound");
+        int64_t high_value = ushr64(x, num_low_bits);
+        int64_t bit = num_encoded + high_value;  // encode_upper_bits :313-317
+        upper[(size_t)ushr64(bit, 6)] |= (int64_t)((uint64_t)1 << (bit & 63));
+        ef_pack_value(x & lower_bits_mask, lower, num_low_bits, num_encoded);
+        last_encoded = x;
+        int64_t index_value = (current_entry_index + 1) * index_interval;
+        while (index_value <= high_value) {
+            ef_pack_value(index_value + num_encoded, index, n_index_entry_bits, current_entry_index);
+            current_entry_index++;
+            index_value += index_interval;
+        }
+        num_encoded++;
+    }
+};
+inline void raw_longs(Bytes& o, const std::vector<int64_t>& a) {  // write_data :347-355: raw LE memory
+    for (int64_t x : a)
+        for (int k = 0; k < 8; k++) o.u8((uint8_t)((uint64_t)x >> (8 * k)));
+}
+// ForUtil::write_block with an EfWriterMeta, for_util.rs:396-478 (doc-delta blocks only).
+// Returns false when the block falls through to the PF encoding.
+bool write_block_other(const int32_t* data, int pf_bits, const EfWriterMeta& meta, Bytes& o) {
+    if (!meta.use_ef) return false;
+    const int encoded_size = 16 * pf_bits;  // encoded_sizes[num_bits - 1]
+    EfEncoder ef(kBlock, (int64_t)(meta.ef_upper_doc - meta.ef_base_doc - 1));
+    if (ef.encode_size() > 4 * kBlock) return false;  // MAX_ENCODED_SIZE :33
+    int32_t doc = meta.ef_base_doc < 0 ? 0 : meta.ef_base_doc;
+    int32_t min_doc = INT32_MAX, max_doc = 0;
+    for (int i = 0; i < kBlock; i++) {
+        doc += data[i];
+        max_doc = std::max(max_doc, doc);
+        min_doc = std::min(min_doc, doc);
+        ef.encode_next((int64_t)(doc - meta.ef_base_doc - 1));
+    }
+    // FixedBitSet::resize / encode_size, bit_set.rs:193-204,480-484
+    const size_t num_words = (size_t)((((max_doc - min_doc + 1) - 1) >> 6) + 1);
+    if ((int)(num_words << 3) <= encoded_size) {
+        std::vector<int64_t> bits(num_words, 0);
+        doc = meta.ef_base_doc < 0 ? 0 : meta.ef_base_doc;
+        for (int i = 0; i < kBlock; i++) {
+            doc += data[i];
+            const int32_t b = doc - min_doc;
+            bits[(size_t)b >> 6] |= (int64_t)((uint64_t)1 << (b & 63));
+        }
+        o.u8(2u << 6);  // EncodeType::BITSET
+        o.vint(min_doc);
+        o.u8((uint8_t)num_words);
+        raw_longs(o, bits);
+        return true;
+    }
+    if (!meta.with_pf || ef.encode_size() <= encoded_size) {  // EliasFanoEncoder::serialize :255-262
+        o.u8(1u << 6);  // EncodeType::EF
+        o.vlong(ef.upper_bound);
+        raw_longs(o, ef.upper);
+        raw_longs(o, ef.lower);
+        raw_longs(o, ef.index);
+        return true;
+    }
+    return false;
+}
+
 void write_index_header(Bytes& o, int version, const uint8_t id[16], const char* suffix) {
     static const char* codec = "Lucene50PostingsWriterDoc";
     o.be32(0x3FD76C17u);
@@ -265,6 +372,8 @@ struct PostingsWriter {
     int32_t dbuf[kBlock], fbuf[kBlock];
     int upto = 0;
     int32_t last_doc = 0, last_block_doc = -1;
+    EfWriterMeta ef_meta;
+    uint64_t ef_blocks = 0, bitset_blocks = 0;
     int32_t doc_count = 0;
     int64_t term_fp = 0;
     int64_t ttf = 0;
@@ -278,6 +387,8 @@ struct PostingsWriter {
         upto = 0;
         ttf = 0;
         skip.reset(term_fp);
+        ef_meta.ef_base_doc = -1;  // EfWriterMeta::reset :52-56
+        ef_meta.ef_upper_doc = 0;
     }
     void add_doc(int32_t doc, int32_t freq) {
         if (last_block_doc != -1 && upto == 0)
@@ -292,8 +403,26 @@ struct PostingsWriter {
         ttf += freq;
         if (upto == kBlock) {
             uint8_t tmp[1 + 512];
-            int n = write_block(dbuf, version, tmp);
-            out.raw(tmp, (size_t)n);
+            ef_meta.ef_upper_doc = doc;  // :335
+            bool other = false;
+            if (ef_meta.use_ef) {
+                bool all_equal = true;
+                uint32_t orv = 0;
+                for (int i = 0; i < kBlock; i++) {
+                    all_equal &= dbuf[i] == dbuf[0];
+                    orv |= (uint32_t)dbuf[i];
+                }
+                if (!all_equal) {  // the all-equal shortcut comes first (:402-405)
+                    const size_t before = out.size();
+                    other = write_block_other(dbuf, 32 - __builtin_clz(orv), ef_meta, out);
+                    if (other) (out.v[before] >> 6) == 1 ? ef_blocks++ : bitset_blocks++;
+                }
+            }
+            int n = 0;
+            if (!other) {
+                n = write_block(dbuf, version, tmp);
+                out.raw(tmp, (size_t)n);
+            }
             n = write_block(fbuf, version, tmp);
             out.raw(tmp, (size_t)n);
             blocks_written++;
@@ -302,6 +431,7 @@ struct PostingsWriter {
         if (upto == kBlock) {  // finish_doc
             last_block_doc = last_doc;
             upto = 0;
+            ef_meta.ef_base_doc = last_block_doc;  // :472
         }
     }
     void finish_term(rg_term_state* st) {
@@ -460,6 +590,42 @@ int rc_writer_add_term(rc_writer* w, const int32_t* docs, const int32_t* freqs, 
     w->pw.finish_term(out_state);
     return 0;
     RC_CATCH(-1)
+}
+// test hooks for the reference's own EliasFanoEncoder unit tests (elias_fano_encoder.rs:398-448)
+int64_t rc_ef_num_longs_for_bits(int64_t n) { return num_longs_for_bits(n); }
+void rc_ef_pack_value(int64_t value, int64_t* longs, int n_longs, int num_bits, int64_t pack_index) {
+    std::vector<int64_t> a(longs, longs + n_longs);
+    ef_pack_value(value, a, num_bits, pack_index);
+    std::copy(a.begin(), a.end(), longs);
+}
+int rc_ef_encode(const int64_t* values, int64_t n, int64_t upper_bound, int64_t* out_longs, int cap,
+                 int32_t out_geom[4]) {
+    RC_TRY
+    EfEncoder ef(n, upper_bound);
+    for (int64_t i = 0; i < n; i++) ef.encode_next(values[i]);
+    out_geom[0] = ef.num_low_bits;
+    out_geom[1] = (int32_t)ef.upper.size();
+    out_geom[2] = (int32_t)ef.lower.size();
+    out_geom[3] = (int32_t)ef.index.size();
+    if ((int)(ef.upper.size() + ef.lower.size() + ef.index.size()) > cap) throw std::runtime_error("rc_ef_encode: cap");
+    int64_t* o = out_longs;
+    o = std::copy(ef.upper.begin(), ef.upper.end(), o);
+    o = std::copy(ef.lower.begin(), ef.lower.end(), o);
+    std::copy(ef.index.begin(), ef.index.end(), o);
+    return 0;
+    RC_CATCH(-1)
+}
+int rc_writer_set_ef(rc_writer* w, int use_ef, int with_pf) {
+    RC_TRY
+    w->pw.ef_meta.use_ef = use_ef != 0;
+    w->pw.ef_meta.with_pf = with_pf != 0;
+    return 0;
+    RC_CATCH(-1)
+}
+void rc_writer_block_counts(rc_writer* w, uint64_t out[3]) {
+    out[0] = w->pw.blocks_written;
+    out[1] = w->pw.ef_blocks;
+    out[2] = w->pw.bitset_blocks;
 }
 int rc_writer_finish(rc_writer* w) {
     RC_TRY

@@ -13,9 +13,12 @@ def random_postings(rng, max_doc, df):
     return docs, freqs
 
 
-def build_segment(rng, max_doc, dfs, doc_version=1, live_fraction=None, dense_terms=()):
-    """dfs: list of document frequencies (0 allowed = absent term)."""
-    w = codec.PostingsWriter(doc_version=doc_version, max_doc=max_doc)
+def build_segment(rng, max_doc, dfs, doc_version=1, live_fraction=None, dense_terms=(), use_ef=False,
+                  with_pf=True, counts=None):
+    """dfs: list of document frequencies (0 allowed = absent term).  use_ef/with_pf: write EF / BITSET
+    doc blocks where the reference's (dormant) writer rule picks them; counts: list that receives
+    (blocks, ef_blocks, bitset_blocks)."""
+    w = codec.PostingsWriter(doc_version=doc_version, max_doc=max_doc, use_ef=use_ef, with_pf=with_pf)
     postings = []
     for t, df in enumerate(dfs):
         if df == 0:
@@ -39,6 +42,8 @@ def build_segment(rng, max_doc, dfs, doc_version=1, live_fraction=None, dense_te
         idx = np.nonzero(bits)[0]
         np.bitwise_or.at(words, idx >> 6, np.uint64(1) << (idx & 63).astype(np.uint64))
         live = words
+    if counts is not None:
+        counts.append(w.block_counts())
     seg = w.finish(norms=norms, live_docs=live)
     return seg, postings
 

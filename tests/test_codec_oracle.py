@@ -214,13 +214,16 @@ def _brute_force(seg_list, postings_list, ix, spec, k, stats=None):
     return np.concatenate(stream_d).astype(np.int32), np.concatenate(stream_s)
 
 
-@pytest.mark.parametrize("version,live", [(1, None), (0, None), (1, 0.7)])
-def test_oracle_search_matches_brute_force(version, live):
+@pytest.mark.parametrize("version,live,ef", [(1, None, 0), (0, None, 0), (1, 0.7, 0), (1, None, 1), (0, 0.8, 2)])
+def test_oracle_search_matches_brute_force(version, live, ef):
     rng = np.random.default_rng(300 + version)
     dfs = [0, 1, 3, 100, 128, 129, 500, 2000, 9000, 30000, 45000]
     segs, posts = [], []
     for s in range(2):
-        seg, p = helpers.build_segment(rng, 50000 + 1000 * s, dfs, doc_version=version, live_fraction=live)
+        cnt = []
+        seg, p = helpers.build_segment(rng, 50000 + 1000 * s, dfs, doc_version=version, live_fraction=live,
+                                       use_ef=ef > 0, with_pf=ef != 2, counts=cnt)
+        assert (cnt[0][1] + cnt[0][2] > 0) == (ef > 0)
         segs.append(seg)
         posts.append(p)
     ix = helpers.oracle_index(segs)
@@ -299,3 +302,36 @@ def test_oracle_min_should_match_matches_brute_force():
         assert np.array_equal(got["doc"], want["doc"]), spec
         assert np.array_equal(got["score"].view(np.uint32), want["score"].view(np.uint32)), spec
     assert total[3] == 0 and 0 < total[1] < total[0]
+
+
+def test_elias_fano_encoder_reference_vectors():
+    """The reference's own unit vectors, util/packed/elias_fano_encoder.rs:398-448."""
+    import ctypes as C
+    L = codec.lib()
+    L.rc_ef_num_longs_for_bits.restype = C.c_int64
+    L.rc_ef_num_longs_for_bits.argtypes = [C.c_int64]
+    for n, want in ((5, 1), (31, 1), (32, 1), (33, 1), (65, 2), (128, 2), (129, 3)):   # :399-407
+        assert L.rc_ef_num_longs_for_bits(n) == want
+    L.rc_ef_pack_value.argtypes = [C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int64]
+    L.rc_ef_pack_value.restype = None
+    lv = np.zeros(2, np.int64)                                                          # :414-425
+    L.rc_ef_pack_value(2, lv.ctypes.data, 2, 2, 31)
+    assert lv[0] == np.int64(-0x8000000000000000)
+    lv[:] = 0
+    L.rc_ef_pack_value(0b11111, lv.ctypes.data, 2, 5, 12)
+    assert lv.view(np.uint64)[0] == 0xF000000000000000 and lv[1] == 1
+    # :427-447 encode_upper: EliasFanoEncoder::new(7, 24, 256), high values 0,0,1,1,2 -> 1,3,11,27,91
+    L.rc_ef_encode.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
+    vals = np.array([0, 1, 2, 3, 4, 24, 24], np.int64)
+    out = np.zeros(16, np.int64)
+    geom = np.zeros(4, np.int32)
+    assert L.rc_ef_encode(vals.ctypes.data, 7, 24, out.ctypes.data, 16, geom.ctypes.data) == 0
+    assert geom[0] == 1                       # floor(log2(24 / 7)) — "different from lucene version" (:72-77)
+    assert int(out[0]) & 0x7f == 91
+    assert int(out[0]) == 91 | (1 << (5 + 12)) | (1 << (6 + 12))
+    # :408-412 get_encoder(128, 510901): geometry of a block-sized encoder
+    vals = np.sort(np.random.default_rng(3).choice(510901, 128, replace=False)).astype(np.int64)
+    vals[-1] = 510901
+    out = np.zeros(64, np.int64)
+    assert L.rc_ef_encode(vals.ctypes.data, 128, 510901, out.ctypes.data, 64, geom.ctypes.data) == 0
+    assert list(geom) == [11, 6, 22, 0]       # 510901/128 = 3991 -> 11 low bits; (249 + 128) bits -> 6 longs

@@ -12,13 +12,15 @@ from rucene_b200 import codec
 @settings(max_examples=25, deadline=None)
 @given(seed=st.integers(0, 2**31 - 1), version=st.sampled_from([0, 1]),
        df=st.one_of(st.integers(1, 300), st.sampled_from([127, 128, 129, 1023, 1024, 1025, 8192, 8193, 9000])),
-       density=st.sampled_from([0.9, 0.3, 0.01]))
-def test_random_list_round_trip_and_advance(seed, version, df, density):
+       density=st.sampled_from([0.9, 0.3, 0.01]), ef=st.sampled_from([0, 0, 1, 2]))
+def test_random_list_round_trip_and_advance(seed, version, df, density, ef):
     rng = np.random.default_rng(seed)
     max_doc = max(int(df / density) + 10, df + 10)
     docs = np.sort(rng.choice(max_doc, size=df, replace=False)).astype(np.int32)
     freqs = np.minimum(rng.geometric(0.4, size=df), 10**6).astype(np.int32)
-    w = codec.PostingsWriter(doc_version=version, max_doc=max_doc)
+    # ef: the reference's dormant EF / BITSET doc-block encodings (1: only where no larger than PF, 2: EF
+    # wherever it fits MAX_ENCODED_SIZE) — next() and advance() must see the same posting list
+    w = codec.PostingsWriter(doc_version=version, max_doc=max_doc, use_ef=ef > 0, with_pf=ef != 2)
     w.add_term(docs, freqs)
     seg = w.finish(norms=np.full(max_doc, 100, np.uint8))
     ix = helpers.oracle_index([seg])
