@@ -19,6 +19,7 @@ constexpr int kNoMoreDocs = 0x7fffffff;
 struct BlockDesc {
     uint32_t off16;  // slot offset in 16-byte units
     uint32_t bits;   // [0:8) doc num_bits, [8:16) freq num_bits, [16:24) doc part size in 16B units
+                     // [24:26) doc part EncodeType: 0 PF, 1 EF, 2 BITSET (unpack.cuh: decode_other_docs)
 };
 
 struct TermDev {

@@ -176,9 +176,75 @@ struct BlockSrc {
     const uint8_t* freq_src;
     uint16_t doc_sz, freq_sz;  // payload bytes (0 when constant)
     uint8_t bd, bf;
+    uint8_t enc;     // EncodeType of the doc part: 0 PF, 1 EF, 2 BITSET (for_util.rs:505-513)
+    int32_t hdr[4];  // EF: {num_low_bits, n_upper_longs, n_lower_longs, 0}; BITSET: {min_doc, num_words, 0, 0}
     int32_t doc_const, freq_const;
     int32_t last_doc;
 };
+
+// EliasFanoEncoder geometry of a block (util/packed/elias_fano_encoder.rs:62-123): number of low
+// bits and the sizes of the upper / lower / index long arrays that follow vlong(upper_bound).
+struct EfGeom {
+    int num_low_bits;
+    uint32_t n_upper, n_lower, n_index;
+};
+inline EfGeom ef_geom(int64_t upper_bound) {
+    if (upper_bound < 0) throw ArgError("corrupt EF block: negative upper bound");
+    auto longs_for_bits = [](int64_t n) { return (uint32_t)((uint64_t)(n + 63) >> 6); };
+    EfGeom g{};
+    const int64_t nv = kBlock, fac = upper_bound / nv;
+    g.num_low_bits = fac > 0 ? 63 - __builtin_clzll((uint64_t)fac) : 0;
+    const int64_t max_high = (int64_t)((uint64_t)upper_bound >> g.num_low_bits);
+    g.n_lower = longs_for_bits(nv * g.num_low_bits);
+    g.n_upper = longs_for_bits(max_high + nv);
+    const int64_t n_entries = max_high / 256;  // DEFAULT_INDEX_INTERVAL
+    const int64_t max_index_entry = max_high + nv - 1;
+    const int entry_bits = max_index_entry <= 0 ? 0 : 64 - __builtin_clzll((uint64_t)max_index_entry);
+    g.n_index = longs_for_bits(n_entries * entry_bits);
+    return g;
+}
+inline uint64_t le64(const uint8_t* p) {
+    uint64_t v;
+    memcpy(&v, p, 8);
+    return v;
+}
+// last docid of an EF / BITSET block (host side; only for the one block skip level 0 does not cover)
+int32_t other_block_last_doc(const BlockSrc& b, int32_t ef_base_doc) {
+    if (b.enc == 2) {  // min_doc + highest set bit
+        for (int w = b.hdr[1] - 1; w >= 0; w--) {
+            const uint64_t x = le64(b.doc_src + 8 * (size_t)w);
+            if (x) return b.hdr[0] + 64 * w + 63 - __builtin_clzll(x);
+        }
+        throw ArgError("corrupt BITSET block: no bit set");
+    }
+    // EF: value 127 = ((position of the 128th set upper bit - 127) << L) | low[127]
+    const int L = b.hdr[0];
+    int64_t pos = -1;
+    int seen = 0;
+    for (int w = 0; w < b.hdr[1] && pos < 0; w++) {
+        uint64_t x = le64(b.doc_src + 8 * (size_t)w);
+        while (x) {
+            const int bit = __builtin_ctzll(x);
+            x &= x - 1;
+            if (++seen == kBlock) {
+                pos = 64 * (int64_t)w + bit;
+                break;
+            }
+        }
+    }
+    if (pos < 0) throw ArgError("corrupt EF block: fewer than 128 upper bits");
+    int64_t low = 0;
+    if (L) {
+        const uint8_t* lo = b.doc_src + 8 * (size_t)b.hdr[1];
+        const int64_t bitpos = (int64_t)L * (kBlock - 1);
+        const size_t wi = (size_t)(bitpos >> 6);
+        const int at = (int)(bitpos & 63);
+        uint64_t v = le64(lo + 8 * wi) >> at;
+        if (at + L > 64) v |= le64(lo + 8 * (wi + 1)) << (64 - at);
+        low = (int64_t)(v & ((1ull << L) - 1));
+    }
+    return (int32_t)((((pos - (kBlock - 1)) << L) | low) + 1 + ef_base_doc);
+}
 
 struct TermParse {
     uint32_t n_blocks = 0;
@@ -211,14 +277,30 @@ void parse_term(const uint8_t* file, size_t len, const DocHeader& h, const rg_te
         block_fp[i] = in.pos;
         BlockSrc b{};
         uint8_t code = in.u8();
-        if (code >> 6) throw Unsupported("EF/BITSET/FULL doc blocks (for_util.rs:337-372) are not accelerated");
-        b.bd = code & 0x3f;
-        if (b.bd > 32) throw ArgError("corrupt doc block header");
-        if (b.bd == 0) {
-            b.doc_const = in.vint();
+        b.enc = code >> 6;
+        if (b.enc == 3) throw Unsupported("EncodeType::FULL doc blocks are unimplemented in the reference too");
+        if (b.enc == 1) {  // EF, ForUtil::read_other_encode_block (for_util.rs:346-362)
+            const EfGeom g = ef_geom(in.vlong());
+            b.hdr[0] = g.num_low_bits;
+            b.hdr[1] = (int32_t)g.n_upper;
+            b.hdr[2] = (int32_t)g.n_lower;
+            b.doc_src = in.take(8 * (size_t)(g.n_upper + g.n_lower));
+            in.take(8 * (size_t)g.n_index);  // the skip index inside the block is not needed on the device
+            b.doc_sz = (uint16_t)(16 + 8 * (g.n_upper + g.n_lower));
+        } else if (b.enc == 2) {  // BITSET (:363-368)
+            b.hdr[0] = in.vint();
+            b.hdr[1] = in.u8();
+            b.doc_src = in.take(8 * (size_t)b.hdr[1]);
+            b.doc_sz = (uint16_t)(16 + 8 * b.hdr[1]);
         } else {
-            b.doc_sz = (uint16_t)h.enc_size[b.bd];
-            b.doc_src = in.take(b.doc_sz);
+            b.bd = code & 0x3f;
+            if (b.bd > 32) throw ArgError("corrupt doc block header");
+            if (b.bd == 0) {
+                b.doc_const = in.vint();
+            } else {
+                b.doc_sz = (uint16_t)h.enc_size[b.bd];
+                b.doc_src = in.take(b.doc_sz);
+            }
         }
         code = in.u8();
         b.bf = code & 0x3f;  // ForUtil::read_block: num_bits = code & 0x3F
@@ -266,6 +348,11 @@ void parse_term(const uint8_t* file, size_t len, const DocHeader& h, const rg_te
     }
     for (uint32_t i = n0; i < nb; i++) {  // at most one block
         const BlockSrc& b = blocks[first + i];
+        if (b.enc) {
+            last = other_block_last_doc(b, i == 0 ? -1 : last);
+            blocks[first + i].last_doc = last;
+            continue;
+        }
         int64_t sum = 0;
         if (b.bd == 0) {
             sum = (int64_t)b.doc_const * kBlock;
@@ -410,14 +497,20 @@ void build_segment(rg_engine* e, Segment& seg, int32_t doc_base, int32_t max_doc
                 const BlockSrc& b = ch.blocks[bi];
                 const uint32_t du = part_units(b.doc_sz), fu = part_units(b.freq_sz);
                 uint8_t* dst = reinterpret_cast<uint8_t*>(&h_arena[unit]);
-                if (b.bd) memcpy(dst, b.doc_src, b.doc_sz);
-                else memcpy(dst, &b.doc_const, 4);
+                if (b.enc) {  // 16-byte header, then the raw little-endian longs
+                    memcpy(dst, b.hdr, 16);
+                    memcpy(dst + 16, b.doc_src, (size_t)b.doc_sz - 16);
+                } else if (b.bd) {
+                    memcpy(dst, b.doc_src, b.doc_sz);
+                } else {
+                    memcpy(dst, &b.doc_const, 4);
+                }
                 uint8_t* fdst = dst + 16 * (size_t)du;
                 if (b.bf) memcpy(fdst, b.freq_src, b.freq_sz);
                 else memcpy(fdst, &b.freq_const, 4);
                 h_last[blk] = b.last_doc;
                 h_desc[blk].off16 = (uint32_t)unit;
-                h_desc[blk].bits = (uint32_t)b.bd | ((uint32_t)b.bf << 8) | (du << 16);
+                h_desc[blk].bits = (uint32_t)b.bd | ((uint32_t)b.bf << 8) | (du << 16) | ((uint32_t)b.enc << 24);
                 unit += du + fu;
             }
             if (tp.tail_bytes) {
@@ -435,6 +528,8 @@ void build_segment(rg_engine* e, Segment& seg, int32_t doc_base, int32_t max_doc
     if (norms) upload(seg.norms, norms, (size_t)max_doc, st);
     if (live) upload(seg.live, live, ((size_t)max_doc + 63) / 64, st);
     RG_CUDA_CHECK(cudaStreamSynchronize(st));
+    for (const Chunk& ch : chunks)
+        for (const BlockSrc& b : ch.blocks) seg.has_other_enc = seg.has_other_enc || b.enc != 0;
     seg.doc_base = doc_base;
     seg.max_doc = max_doc;
     seg.dev.arena = seg.arena.p;

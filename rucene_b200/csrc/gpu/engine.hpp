@@ -80,6 +80,7 @@ struct Segment {
     DevBuf<TermDev> terms;
     DevBuf<uint8_t> norms;
     DevBuf<uint64_t> live;
+    bool has_other_enc = false;  // some doc block is EF / BITSET encoded
     std::vector<TermHost> host_terms;
     int32_t doc_base = 0, max_doc = 0;
     uint64_t device_bytes = 0;
@@ -111,7 +112,8 @@ struct EvalParams {
 };
 void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n,
                     uint32_t max_terms, bool has_live, bool has_not, bool has_msm);
-void launch_eval_and(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, bool req_opt);
+void launch_eval_and(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, bool req_opt,
+                     bool has_other_enc);
 
 struct ReplayParams {
     const rg_hit* cand_arena;

@@ -432,14 +432,21 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
             const uint4* part = seg.arena + bd.off16;
             const int bdoc = (int)(bd.bits & 0xff), bfrq = (int)((bd.bits >> 8) & 0xff);
             int4 dl;
+            const uint32_t enc = bd.bits >> 24;
             if (seg.version > 0 && bdoc > 0 && bfrq > 0) {  // the common case: both parts SIMD128-packed
                 dl = unpack4_simd128(part, bdoc, lane);
                 freqs = unpack4_simd128(part + ((bd.bits >> 16) & 0xff), bfrq, lane);
-            } else {
+                docs = deltas_to_docs(dl, base);
+            } else if (enc == 0) {
                 dl = unpack4(part, bdoc, lane, seg.version, seg.sb_mask);
                 freqs = unpack4(part + ((bd.bits >> 16) & 0xff), bfrq, lane, seg.version, seg.sb_mask);
+                docs = deltas_to_docs(dl, base);
+            } else {  // EF / BITSET doc part: docids, not deltas; the stream cache is free scratch here
+                decode_other_docs(part, enc, b == 0 ? -1 : base, cd, lane);
+                docs = reinterpret_cast<const int4*>(cd)[lane];
+                freqs = unpack4(part + ((bd.bits >> 16) & 0xff), bfrq, lane, seg.version, seg.sb_mask);
+                __syncwarp();
             }
-            docs = deltas_to_docs(dl, base);
         } else {  // vint tail / singleton (posting_reader.rs:308-333, :545-547): lane 0 decodes
             const TermDev td = seg.terms[tc.term_id];
             n_in = td.tail_n;
@@ -770,8 +777,9 @@ struct AndShared {
 // item always covers the whole leaf and one thread replays the chain per step, in docid order.
 constexpr uint32_t kOptScoreThreshold = 100;
 
-template <bool REQOPT>
-__global__ void __launch_bounds__(kEvalThreads)
+// OTHER: some leaf carries EF / BITSET doc blocks (their decoder is compiled out otherwise)
+template <bool REQOPT, bool OTHER>
+__global__ void __launch_bounds__(kEvalThreads, OTHER ? (REQOPT ? 4 : 5) : 1)  // the decoder call must not cost occupancy
 k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     AndShared& sh = *reinterpret_cast<AndShared*>(smem_raw);
@@ -831,8 +839,15 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
             if (prev_last < hi - 1) {
                 const BlockDesc bd = lead.blk_desc[b];
                 const uint4* part = seg.arena + bd.off16;
-                const int4 dl = unpack4(part, (int)(bd.bits & 0xff), lane, seg.version, seg.sb_mask);
-                const int4 dd = deltas_to_docs(dl, b == 0 ? 0 : prev_last);
+                int4 dd;
+                if (!OTHER || (bd.bits >> 24) == 0) {
+                    const int4 dl = unpack4(part, (int)(bd.bits & 0xff), lane, seg.version, seg.sb_mask);
+                    dd = deltas_to_docs(dl, b == 0 ? 0 : prev_last);
+                } else {  // EF / BITSET doc part (this warp's ldoc slice is rewritten below)
+                    decode_other_docs_call(part, bd.bits >> 24, b == 0 ? -1 : prev_last, sh.ldoc + warp * kBlock, lane);
+                    dd = reinterpret_cast<const int4*>(sh.ldoc + warp * kBlock)[lane];
+                    __syncwarp();
+                }
                 const int4 fr = unpack4(part + ((bd.bits >> 16) & 0xff), (int)((bd.bits >> 8) & 0xff), lane,
                                         seg.version, seg.sb_mask);
                 const int docs[4] = {dd.x, dd.y, dd.z, dd.w};
@@ -916,9 +931,13 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
                         bd = tc.blk_desc[cb];
                         const int base = cb == 0 ? 0 : __ldg(tc.blk_last + cb - 1);
                         const uint4* part = seg.arena + bd.off16;
-                        const int4 dl = unpack4(part, (int)(bd.bits & 0xff), lane, seg.version, seg.sb_mask);
-                        const int4 dd = deltas_to_docs(dl, base);
-                        reinterpret_cast<int4*>(sh.slab_docs[warp])[lane] = dd;
+                        if (!OTHER || (bd.bits >> 24) == 0) {
+                            const int4 dl = unpack4(part, (int)(bd.bits & 0xff), lane, seg.version, seg.sb_mask);
+                            const int4 dd = deltas_to_docs(dl, base);
+                            reinterpret_cast<int4*>(sh.slab_docs[warp])[lane] = dd;
+                        } else {
+                            decode_other_docs_call(part, bd.bits >> 24, cb == 0 ? -1 : base, sh.slab_docs[warp], lane);
+                        }
                     } else if (lane == 0) {
                         decode_tail(seg, seg.terms[sh.term_id[t]], sh.slab_docs[warp], sh.slab_freqs[warp]);
                     }
@@ -1213,16 +1232,23 @@ void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_i
     else if (has_not) launch_eval_or_t<false, true, false>(st, p, item_ids, n, wb, kcap);
     else launch_eval_or_t<false, false, false>(st, p, item_ids, n, wb, kcap);
 }
-void launch_eval_and(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, bool req_opt) {
-    if (!n) return;
+template <bool REQOPT, bool OTHER>
+static void launch_eval_and_t(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_eval_and<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AndShared));
-        cudaFuncSetAttribute(k_eval_and<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AndShared));
+        cudaFuncSetAttribute(k_eval_and<REQOPT, OTHER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(AndShared));
         attr_set = true;
     }
-    if (req_opt) k_eval_and<true><<<n, kEvalThreads, sizeof(AndShared), st>>>(p, item_ids);
-    else k_eval_and<false><<<n, kEvalThreads, sizeof(AndShared), st>>>(p, item_ids);
+    k_eval_and<REQOPT, OTHER><<<n, kEvalThreads, sizeof(AndShared), st>>>(p, item_ids);
+}
+void launch_eval_and(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, bool req_opt,
+                     bool has_other_enc) {
+    if (!n) return;
+    if (req_opt && has_other_enc) launch_eval_and_t<true, true>(st, p, item_ids, n);
+    else if (req_opt) launch_eval_and_t<true, false>(st, p, item_ids, n);
+    else if (has_other_enc) launch_eval_and_t<false, true>(st, p, item_ids, n);
+    else launch_eval_and_t<false, false>(st, p, item_ids, n);
 }
 void launch_heap_replay(cudaStream_t st, const ReplayParams& p) {
     if (!p.n_groups) return;

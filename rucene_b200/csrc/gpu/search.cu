@@ -402,13 +402,16 @@ int rg_batch_run(rg_engine* e, rg_batch* b) {
     ep.item_theta = b->item_theta.p;
     ep.error_flag = reinterpret_cast<uint32_t*>(b->arena_next.p + 1);
     RG_CUDA_CHECK(cudaEventRecord(e->ev2, st));
-    bool has_live = false;
-    for (const Segment& sg : e->segs) has_live = has_live || sg.live.p != nullptr;
+    bool has_live = false, has_other = false;
+    for (const Segment& sg : e->segs) {
+        has_live = has_live || sg.live.p != nullptr;
+        has_other = has_other || sg.has_other_enc;
+    }
     launch_eval_or(st, ep, b->or_ids.p, b->n_or, b->max_or_terms, has_live, b->or_has_not, b->or_has_msm);
     RG_CUDA_CHECK(cudaGetLastError());
-    launch_eval_and(st, ep, b->and_ids.p, b->n_and, false);
+    launch_eval_and(st, ep, b->and_ids.p, b->n_and, false, has_other);
     RG_CUDA_CHECK(cudaGetLastError());
-    launch_eval_and(st, ep, b->ro_ids.p, b->n_ro, true);
+    launch_eval_and(st, ep, b->ro_ids.p, b->n_ro, true, has_other);
     RG_CUDA_CHECK(cudaGetLastError());
     RG_CUDA_CHECK(cudaEventRecord(e->ev3, st));
     ReplayParams rp{};

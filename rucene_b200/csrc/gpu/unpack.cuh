@@ -127,6 +127,71 @@ __device__ __forceinline__ int4 deltas_to_docs(int4 d, int base) {
     return p;
 }
 
+// ---- the reference's other doc-block encodings --------------------------------------------
+// EncodeType::EF (Elias-Fano) and EncodeType::BITSET doc blocks (codec/postings/for_util.rs:337-372,
+// read side posting_reader.rs:624-633): a block is its 128 docids, not 128 deltas.  Staged layout
+// (engine.cu): one 16-byte header, then the raw little-endian longs of the file.
+//   BITSET header {min_doc, num_words}: docid = min_doc + position of each set bit (bit_set.rs:351-376)
+//   EF     header {num_low_bits L, n_upper, n_lower}: the i-th set bit of the upper array sits at
+//          position high_i + i; docid_i = ef_base_doc + 1 + ((high_i << L) | low_i), low_i = the
+//          i-th L-bit field of the lower array (elias_fano_decoder.rs:79-108,122-160)
+// Warp-cooperative select: 32-bit words, one per lane per round; popcounts are prefix-summed across
+// the warp so every set bit knows its rank and scatters its docid to out[rank] (shared memory).
+__device__ __forceinline__ void decode_other_docs(const uint4* __restrict__ part, uint32_t enc, int ef_base_doc,
+                                                  int32_t* out, int lane) {
+    const uint4 hdr = ldg16(part);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(part + 1);
+    const bool ef = enc == 1u;
+    const uint32_t n32 = 2u * hdr.y;           // upper array (EF) / bitmap (BITSET), in 32-bit words
+    const uint32_t L = ef ? hdr.x : 0u;
+    const uint32_t* lower = w + n32;
+    const uint32_t n_lower32 = ef ? 2u * hdr.z : 0u;
+    const uint32_t lmask = L ? ((1u << L) - 1u) : 0u;
+    uint32_t rank0 = 0;
+    for (uint32_t base = 0; base < n32 && rank0 < (uint32_t)kBlock; base += 32) {
+        const uint32_t wi = base + lane;
+        uint32_t x = wi < n32 ? __ldg(w + wi) : 0u;
+        const uint32_t c = __popc(x);
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        uint32_t r = rank0 + incl - c;
+        while (x) {
+            const uint32_t bit = __ffs(x) - 1;
+            x &= x - 1;
+            if (r < (uint32_t)kBlock) {
+                const uint32_t pos = wi * 32u + bit;
+                int doc;
+                if (ef) {
+                    uint32_t low = 0;
+                    if (L) {
+                        const uint32_t bp = r * L, j = bp >> 5, sh = bp & 31u;
+                        const uint32_t lo = __ldg(lower + j);
+                        const uint32_t hi = j + 1 < n_lower32 ? __ldg(lower + j + 1) : 0u;
+                        low = __funnelshift_r(lo, hi, sh) & lmask;
+                    }
+                    doc = ef_base_doc + 1 + (int)(((pos - r) << L) | low);
+                } else {
+                    doc = (int)hdr.x + (int)pos;
+                }
+                out[r] = doc;
+            }
+            r++;
+        }
+        rank0 += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
+}
+
+// out-of-line copy for k_eval_and, whose register budget (occupancy) the inlined body would raise
+static __device__ __noinline__ void decode_other_docs_call(const uint4* __restrict__ part, uint32_t enc,
+                                                           int ef_base_doc, int32_t* out, int lane) {
+    decode_other_docs(part, enc, ef_base_doc, out, lane);
+}
+
 // vint / vlong readers over a byte pointer (store/io/data_input.rs:78-111)
 __device__ __forceinline__ int read_vint(const uint8_t* __restrict__ p, uint32_t& pos) {
     uint32_t b = p[pos++];

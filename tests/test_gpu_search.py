@@ -225,6 +225,35 @@ def test_min_should_match_greater_than_one():
             helpers.assert_same_topdocs(got, want, "msm k=%d rp=%d mode=%d" % (k, rp, mode))
 
 
+@pytest.mark.parametrize("version,with_pf", [(1, True), (1, False), (0, False)])
+def test_ef_and_bitset_doc_blocks(version, with_pf):
+    """EncodeType::EF / EncodeType::BITSET doc blocks (codec/postings/for_util.rs:337-372,417-468; read
+    side posting_reader.rs:501-561,612-647,733-779): written where the reference's (dormant) writer rule
+    picks them, decoded on the device by rank/select over the block's bitmaps.  Every query shape, both
+    collector modes, docid ranges, live docs, two leaves."""
+    rng = np.random.default_rng(123 + version)
+    dfs = [0, 1, 127, 128, 129, 300, 1000, 5000, 20000, 33000, 47000]
+    segs, n_other = [], 0
+    for s, lf in enumerate((None, 0.8)):
+        cnt = []
+        seg, _ = helpers.build_segment(rng, 52000 + 300 * s, dfs, doc_version=version, live_fraction=lf,
+                                       dense_terms=(7,), use_ef=True, with_pf=with_pf, counts=cnt)
+        segs.append(seg)
+        n_other += cnt[0][1] + cnt[0][2]
+        assert cnt[0][1] > 0 and cnt[0][2] > 0      # both encodings occur
+    specs = [("term", t) for t in range(len(dfs))]
+    specs += _mixed_specs(rng, len(dfs), 60, kinds=("and", "or"))
+    specs += [("bool", [(ob.MUST, 10), (ob.SHOULD, 9), (ob.SHOULD, 6)], 0),
+              ("bool", [(ob.MUST, 9), (ob.MUST, 10), (ob.MUST_NOT, 8)], 0),
+              ("bool", [(ob.SHOULD, 10), (ob.SHOULD, 8), (ob.SHOULD, 5), (ob.MUST_NOT, 9)], 0),
+              ("bool", [(ob.SHOULD, 10), (ob.SHOULD, 9), (ob.SHOULD, 8)], 2),
+              ("bool", [(ob.MUST, 4), (ob.MUST, 10)], 0), ("bool", [(ob.MUST, 5), (ob.MUST, 6), (ob.MUST, 9)], 0)]
+    for k, rp in ((10, 0), (100, 3000)):
+        for mode in (0, 1):
+            got, want = _run_both(segs, specs, k, mode=mode, range_postings=rp)
+            helpers.assert_same_topdocs(got, want, "ef v%d pf%d k=%d rp=%d mode=%d" % (version, with_pf, k, rp, mode))
+
+
 def test_reference_style_api():
     """Reads like examples/example.rs:111-117."""
     rng = np.random.default_rng(5)
