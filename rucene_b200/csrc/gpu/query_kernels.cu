@@ -779,7 +779,7 @@ constexpr uint32_t kOptScoreThreshold = 100;
 
 // OTHER: some leaf carries EF / BITSET doc blocks (their decoder is compiled out otherwise)
 template <bool REQOPT, bool OTHER>
-__global__ void __launch_bounds__(kEvalThreads, OTHER ? (REQOPT ? 4 : 5) : 1)  // the decoder call must not cost occupancy
+__global__ void __launch_bounds__(kEvalThreads, OTHER ? (REQOPT ? 4 : 5) : 0)  // the decoder call must not cost occupancy
 k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     AndShared& sh = *reinterpret_cast<AndShared*>(smem_raw);
@@ -1208,11 +1208,8 @@ template <bool LIVE, bool NOT, bool MSM>
 static void launch_eval_or_t(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, size_t wb,
                              uint32_t kcap) {
     const size_t smem = wb * kOrWarps;
-    static size_t attr = 0;
-    if (smem > attr) {
-        cudaFuncSetAttribute(k_eval_or<LIVE, NOT, MSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = smem;
-    }
+    // per launch, not cached: the attribute is per device and engines may live on several
+    cudaFuncSetAttribute(k_eval_or<LIVE, NOT, MSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const uint32_t ctas = (n + kOrWarps - 1) / kOrWarps;
     k_eval_or<LIVE, NOT, MSM><<<ctas, kOrThreads, smem, st>>>(p, item_ids, n, (uint32_t)wb, kcap);
 }
@@ -1234,12 +1231,8 @@ void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_i
 }
 template <bool REQOPT, bool OTHER>
 static void launch_eval_and_t(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_eval_and<REQOPT, OTHER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(AndShared));
-        attr_set = true;
-    }
+    cudaFuncSetAttribute(k_eval_and<REQOPT, OTHER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(AndShared));
     k_eval_and<REQOPT, OTHER><<<n, kEvalThreads, sizeof(AndShared), st>>>(p, item_ids);
 }
 void launch_eval_and(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, bool req_opt,
@@ -1253,11 +1246,8 @@ void launch_eval_and(cudaStream_t st, const EvalParams& p, const uint32_t* item_
 void launch_heap_replay(cudaStream_t st, const ReplayParams& p) {
     if (!p.n_groups) return;
     const size_t smem = (size_t)kReplayWarps * p.k * sizeof(rg_hit);
-    static size_t attr = 0;
-    if (smem > attr) {
-        cudaFuncSetAttribute(k_heap_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = smem;
-    }
+    // per launch, not cached: the attribute is per device and engines may live on several
+    cudaFuncSetAttribute(k_heap_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_heap_replay<<<(p.n_groups + kReplayWarps - 1) / kReplayWarps, kReplayWarps * 32, smem, st>>>(p);
 }
 void launch_merge_leaf_records(cudaStream_t st, const uint8_t* records, uint32_t n_leaves,
@@ -1265,11 +1255,8 @@ void launch_merge_leaf_records(cudaStream_t st, const uint8_t* records, uint32_t
                                uint32_t* out_counts, unsigned long long* out_total) {
     if (!n_queries) return;
     const size_t smem = (size_t)kReplayWarps * k * sizeof(rg_hit);
-    static size_t attr = 0;
-    if (smem > attr) {
-        cudaFuncSetAttribute(k_merge_leaf_records, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = smem;
-    }
+    // per launch, not cached: the attribute is per device and engines may live on several
+    cudaFuncSetAttribute(k_merge_leaf_records, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_merge_leaf_records<<<(n_queries + kReplayWarps - 1) / kReplayWarps, kReplayWarps * 32, smem, st>>>(
         records, n_leaves, n_queries, k, out_hits, out_counts, out_total);
 }

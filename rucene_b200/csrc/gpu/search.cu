@@ -382,6 +382,7 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
 int rg_batch_run(rg_engine* e, rg_batch* b) {
     RG_TRY
     if (!e || !b) throw ArgError("null argument");
+    RG_CUDA_CHECK(cudaSetDevice(e->device));
     cudaStream_t st = e->stream;
     RG_CUDA_CHECK(cudaEventRecord(e->ev0, st));
     RG_CUDA_CHECK(cudaMemsetAsync(b->item_head.p, 0xff, b->item_head.bytes(), st));
@@ -445,6 +446,7 @@ int rg_batch_fetch(rg_engine* e, rg_batch* b, rg_hit* out_hits, uint32_t* out_co
     RG_TRY
     if (!e || !b || !out_hits || !out_counts || !out_total_hits) throw ArgError("null argument");
     if (!b->ran) throw ArgError("rg_batch_fetch before rg_batch_run");
+    RG_CUDA_CHECK(cudaSetDevice(e->device));
     cudaStream_t st = e->stream;
     unsigned long long flags[2] = {0, 0};
     RG_CUDA_CHECK(cudaMemcpyAsync(out_hits, b->out_hits.p, (size_t)b->n_queries * b->k * sizeof(rg_hit), cudaMemcpyDeviceToHost, st));
@@ -516,6 +518,7 @@ int rg_merge_leaf_records(rg_engine* e, const void* dev_records_all, uint32_t n_
     RG_TRY
     if (!e || !dev_records_all || !out_hits || !out_counts || !out_total_hits) throw ArgError("null argument");
     if (k == 0 || k > 1024) throw ArgError("k out of range");
+    RG_CUDA_CHECK(cudaSetDevice(e->device));
     cudaStream_t st = e->stream;
     // grow-only engine scratch: no cudaMalloc/cudaFree on the per-batch path
     const size_t nq = std::max<uint32_t>(1, n_queries);
