@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("RUCENE_BENCH_CPU_SAMPLE", 256)))
     ap.add_argument("--range-postings", type=int, default=0)
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-columns", action="store_true",
+                    help="RG_CFG_NO_COLUMNS: evaluate every clause from its block stream (A/B runs)")
     ap.add_argument("--workload", default="c4", choices=["c4", "c3"],
                     help="c4 (headline): 5-term SHOULD top-100 batch 4096 on 100M docs; c3: 2-term MUST "
                          "(ConjunctionScorer) top-10 batch 1024 on 10M docs")
@@ -240,7 +242,8 @@ def main():
     seg_docs = args.docs // world
     seg = codec.synth_segment(SEED_INDEX + rank, seg_docs, args.terms, doc_version=1)
     t_gen = time.perf_counter() - t_gen0
-    eng = engine.Engine(device=local_rank, range_postings=args.range_postings)
+    eng = engine.Engine(device=local_rank, range_postings=args.range_postings,
+                        flags=engine.CFG_NO_COLUMNS if args.no_columns else 0)
     # a dedicated (non-default) torch stream: the engine launches on it and torch.cuda.Event
     # timing sees exactly those launches
     stream = torch.cuda.Stream(device=dev)

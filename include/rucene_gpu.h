@@ -29,6 +29,12 @@ extern "C" {
 
 #define RG_NO_MORE_DOCS 0x7fffffff /* search/mod.rs:59 */
 
+/* rg_config.flags.  Score columns: the BM25 contributions of a dense clause that several
+ * disjunctions of a batch share are materialised once per rg_batch_run into a docid-indexed f32
+ * column (same f32 values the per-query path computes) and read from there. */
+#define RG_CFG_NO_COLUMNS 1u    /* never materialise score columns */
+#define RG_CFG_EAGER_COLUMNS 2u /* a column for every disjunction clause with df >= max_doc/64 (tests) */
+
 typedef struct rg_engine rg_engine;
 typedef struct rg_batch rg_batch;
 typedef struct rg_blockset rg_blockset;
@@ -37,7 +43,7 @@ typedef struct {
     int32_t device;            /* CUDA ordinal; -1 = current device */
     uint64_t cand_arena_bytes; /* candidate arena for exact top-k replay; 0 = default */
     uint32_t range_postings;   /* target postings per (query, docid-range) work item; 0 = default */
-    uint32_t flags;            /* reserved */
+    uint32_t flags;            /* RG_CFG_* */
 } rg_config;
 
 /* Per-term, per-segment handle == BlockTermState

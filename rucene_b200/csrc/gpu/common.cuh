@@ -56,6 +56,8 @@ struct ItemClause {
     float weight;      // idf * boost
     uint32_t cache_id;
     uint32_t flags;    // bit0: MUST_NOT clause (ReqNotScorer: excludes, never scores)
+                       // bit1: SHOULD clause beside a MUST (ReqOptScorer's optional side)
+                       // bit2: score column — term_id is an index into EvalParams::col_ptrs
 };
 
 struct WorkItem {

@@ -530,6 +530,7 @@ void build_segment(rg_engine* e, Segment& seg, int32_t doc_base, int32_t max_doc
     RG_CUDA_CHECK(cudaStreamSynchronize(st));
     for (const Chunk& ch : chunks)
         for (const BlockSrc& b : ch.blocks) seg.has_other_enc = seg.has_other_enc || b.enc != 0;
+    e->col_budget_floats = 0;
     seg.doc_base = doc_base;
     seg.max_doc = max_doc;
     seg.dev.arena = seg.arena.p;

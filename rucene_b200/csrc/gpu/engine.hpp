@@ -98,6 +98,8 @@ struct EvalParams {
     const WorkItem* items;
     const ItemClause* clauses;
     const float* caches;       // n_caches * 256
+    const float* col_base;     // score columns of this batch (see k_build_columns): column c, leaf-local
+    const uint64_t* col_off;   //   docid d lives at col_base[col_off[c] + d]
     uint32_t n_items;
     uint32_t k;
     float k1;
@@ -110,6 +112,16 @@ struct EvalParams {
     uint32_t* item_theta;      // ordered-uint running k-th best, chained item -> item+1
     uint32_t* error_flag;      // bit0: arena exhausted
 };
+// one score column to materialise: the BM25 contributions of (leaf, term, weight, norm cache)
+struct ColumnJob {
+    uint32_t seg, term_id, cache_id;
+    float weight;         // idf * boost, as in the clause
+    uint64_t col_off;     // offset (floats) of the column inside the engine's column arena
+    uint32_t unit_begin;  // first work unit (block / tail) of this job in the launch
+    uint32_t pad;
+};
+void launch_build_columns(cudaStream_t st, const SegDev* segs, const ColumnJob* jobs, uint32_t n_jobs,
+                          uint32_t n_units, const float* caches, float k1, float* col_base);
 void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n,
                     uint32_t max_terms, bool has_live, bool has_not, bool has_msm);
 void launch_eval_and(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, bool req_opt,
@@ -155,6 +167,8 @@ struct rg_engine {
     std::vector<float> h_caches;
     bool caches_dirty = true;
     rg::DevBuf<rg_hit> cand_arena;
+    rg::DevBuf<float> col_arena;        // score columns of the batch being run (grow-only)
+    uint64_t col_budget_floats = 0;     // cap on col_arena; 0 = not computed yet (reset by rg_segment_upload)
     rg::DevBuf<uint8_t> merge_scratch;  // rg_merge_leaf_records outputs (grow-only)
     rg::DevBuf<uint8_t> spare_slab;  // device slab of the last destroyed rg_batch, reused by the next
     uint64_t launches = 0;

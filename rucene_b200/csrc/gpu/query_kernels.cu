@@ -299,7 +299,7 @@ struct WTerm {
     uint32_t term_id;
     float w1;           // weight * (k1 + 1)
     uint32_t is_not;    // MUST_NOT clause: its postings exclude docs (search/scorer/req_not_scorer.rs)
-    uint32_t pad;
+    uint32_t is_col;    // score column: blk_last is really a const float* indexed by docid (see k_build_columns)
 };
 
 // One posting of a clause lands on window slot idx.  SHOULD clause: clause-order f32 add, first
@@ -582,10 +582,27 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
     if (MSM) {
         for (int i = lane; i < kWw / 4; i += 32) reinterpret_cast<uint32_t*>(mc.cnt)[i] = 0u;
     }
-    if (lane < T) {
+    if (lane < T && (p.clauses[it.clause_begin + lane].flags & 4u)) {
+        // score column (a hot, dense clause whose BM25 contributions were materialised once for the
+        // whole batch): no stream; the column is read window by window
+        const ItemClause c = p.clauses[it.clause_begin + lane];
+        WTerm& tc = sh.term[lane];
+        tc.blk_last = reinterpret_cast<const int32_t*>(p.col_base + p.col_off[c.term_id]);
+        tc.blk_desc = nullptr;
+        tc.cache = nullptr;
+        tc.nb = 0;
+        tc.cur = 1;  // > nb: exhausted as a stream
+        tc.n = 0;
+        tc.pos = 0;
+        tc.term_id = c.term_id;
+        tc.w1 = 0.0f;
+        tc.is_not = 0;
+        tc.is_col = 1;
+    } else if (lane < T) {
         const ItemClause c = p.clauses[it.clause_begin + lane];
         const TermDev td = seg.terms[c.term_id];
         WTerm& tc = sh.term[lane];
+        tc.is_col = 0;
         tc.blk_last = seg.blk_last + td.blk_begin;
         tc.blk_desc = seg.blk_desc + td.blk_begin;
         tc.cache = p.caches + (size_t)c.cache_id * 256;
@@ -607,6 +624,9 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
             if (lane == t) nd = first;
         }
     }
+    // a column clause has a (potential) posting at every docid: windows become contiguous and
+    // 4-aligned (16-byte column loads) from the start of the range
+    if (lane < T && sh.term[lane].is_col && lo < hi) nd = lo & ~3;
     long long w0 = __reduce_min_sync(0xffffffffu, nd);
 
     WEmit em;
@@ -645,6 +665,54 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
             const int t = __ffs(active) - 1;
             active &= active - 1;
             WTerm& tc = sh.term[t];
+            if (tc.is_col) {
+                const float* col = reinterpret_cast<const float*>(tc.blk_last);
+                const int wlen = win1 - win0;
+                // the next window's slice of the column (kWw * 4 bytes = 24 lines) towards L1/L2 now:
+                // columns are far larger than L2, and the loads below would otherwise serialise
+                if (lane < kWw / 32 && win1 + lane * 32 < hi)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(col + win1 + lane * 32));
+                const int first_in = lo - win0;  // > 0 only in the first window of a range
+#pragma unroll 2
+                for (int i = lane * 4; i < wlen; i += 128) {
+                    const int d0 = win0 + i;
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(col + d0));
+                    const float sv[4] = {v.x, v.y, v.z, v.w};
+                    if (MSM) {  // per-doc clause counters: the scalar path
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int d = d0 + q;
+                            if (__float_as_uint(sv[q]) != 0xffffffffu && d >= lo && d < win1)
+                                accumulate_posting<NOT, MSM>(sh.acc, i + q, sv[q], false,
+                                                             LIVE ? is_live(seg, d) : true, te, hot, my_matches, mc);
+                        }
+                        continue;
+                    }
+                    // four adjacent docids per lane: one 16-byte read-modify-write of the accumulator window
+                    // (no MUST_NOT marker can be present yet: those clauses are drained last)
+                    uint4 o4 = *reinterpret_cast<const uint4*>(sh.acc + i);
+                    uint32_t o[4] = {o4.x, o4.y, o4.z, o4.w};
+                    uint32_t live4 = 0xfu;
+                    if (LIVE && seg.live) live4 = (uint32_t)(seg.live[d0 >> 6] >> (d0 & 63)) & 0xfu;  // d0 % 4 == 0
+                    bool any_hot = false;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const bool present = __float_as_uint(sv[q]) != 0xffffffffu && i + q >= first_in && i + q < wlen;
+                        const bool fresh = o[q] == kSent;
+                        const float sum = __fadd_rn(fresh ? 0.0f : __uint_as_float(o[q]), sv[q]);
+                        if (present) {
+                            o[q] = __float_as_uint(sum);
+                            if (fresh && ((live4 >> q) & 1u)) my_matches++;
+                            any_hot |= sum > te;
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(sh.acc + i) = make_uint4(o[0], o[1], o[2], o[3]);
+                    if (any_hot) hot |= 1u << (i >> 5);
+                }
+                if (lane == t) nd = win1 < hi ? win1 : kNoMoreDocs;
+                __syncwarp();
+                continue;
+            }
             const int32_t* cd = cdocs + t * kBlock;
             const float* cs = cscores + t * kBlock;
             uint32_t pos = tc.pos, n = tc.n;
@@ -1202,8 +1270,72 @@ k_merge_leaf_records(const uint8_t* __restrict__ records, uint32_t n_leaves, uin
 }
 
 // ------------------------------------------------------------------------------------------
+// k_build_columns — batch-level common subexpression: the BM25 contributions of a hot, dense
+// (term, weight, norm cache) are the same f32 values for every query of the batch that carries
+// the clause, so they are decoded / gathered / divided ONCE into a docid-indexed f32 column
+// (0xffffffff = no posting) that k_eval_or then reads with 16-byte loads.  One warp per
+// 128-posting block (or vint tail) of a job's term.
+// ------------------------------------------------------------------------------------------
+constexpr int kColWarps = 4;
+__global__ void __launch_bounds__(kColWarps * 32)
+k_build_columns(const SegDev* __restrict__ segs, const ColumnJob* __restrict__ jobs, uint32_t n_jobs,
+                uint32_t n_units, const float* __restrict__ caches, float k1, float* __restrict__ col_base) {
+    __shared__ __align__(16) int32_t s_docs[kColWarps][kBlock];
+    __shared__ __align__(16) int32_t s_freqs[kColWarps][kBlock];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t unit = blockIdx.x * kColWarps + warp;
+    if (unit >= n_units) return;
+    uint32_t j = 0;
+    while (j + 1 < n_jobs && jobs[j + 1].unit_begin <= unit) j++;
+    const ColumnJob job = jobs[j];
+    const SegDev seg = segs[job.seg];
+    const TermDev td = seg.terms[job.term_id];
+    const uint32_t b = unit - job.unit_begin;
+    const float* cache = caches + (size_t)job.cache_id * 256;
+    float* col = col_base + job.col_off;
+    const float w1 = __fmul_rn(job.weight, __fadd_rn(k1, 1.0f));  // as k_eval_or computes it
+    int4 docs, freqs;
+    if (b < td.n_blocks) {
+        const BlockDesc bd = seg.blk_desc[td.blk_begin + b];
+        const int base = b == 0 ? 0 : __ldg(seg.blk_last + td.blk_begin + b - 1);
+        const uint4* part = seg.arena + bd.off16;
+        const uint32_t enc = bd.bits >> 24;
+        if (enc == 0) {
+            docs = deltas_to_docs(unpack4(part, (int)(bd.bits & 0xff), lane, seg.version, seg.sb_mask), base);
+        } else {
+            decode_other_docs(part, enc, b == 0 ? -1 : base, s_docs[warp], lane);
+            docs = reinterpret_cast<const int4*>(s_docs[warp])[lane];
+        }
+        freqs = unpack4(part + ((bd.bits >> 16) & 0xff), (int)((bd.bits >> 8) & 0xff), lane, seg.version, seg.sb_mask);
+    } else {
+        const int n_in = (int)td.tail_n;
+        if (lane == 0) decode_tail(seg, td, s_docs[warp], s_freqs[warp]);
+        __syncwarp();
+        const int i0 = 4 * lane;
+        docs = make_int4(i0 < n_in ? s_docs[warp][i0] : -1, i0 + 1 < n_in ? s_docs[warp][i0 + 1] : -1,
+                         i0 + 2 < n_in ? s_docs[warp][i0 + 2] : -1, i0 + 3 < n_in ? s_docs[warp][i0 + 3] : -1);
+        freqs = make_int4(i0 < n_in ? s_freqs[warp][i0] : 1, i0 + 1 < n_in ? s_freqs[warp][i0 + 1] : 1,
+                          i0 + 2 < n_in ? s_freqs[warp][i0 + 2] : 1, i0 + 3 < n_in ? s_freqs[warp][i0 + 3] : 1);
+    }
+    const int d[4] = {docs.x, docs.y, docs.z, docs.w};
+    const int f[4] = {freqs.x, freqs.y, freqs.z, freqs.w};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (d[q] < 0 || d[q] >= seg.max_doc) continue;
+        const float nrm = seg.norms ? __ldg(cache + __ldg(seg.norms + d[q])) : k1;
+        col[d[q]] = bm25_score(w1, (float)f[q], nrm);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+void launch_build_columns(cudaStream_t st, const SegDev* segs, const ColumnJob* jobs, uint32_t n_jobs,
+                          uint32_t n_units, const float* caches, float k1, float* col_base) {
+    if (!n_jobs || !n_units) return;
+    k_build_columns<<<(n_units + kColWarps - 1) / kColWarps, kColWarps * 32, 0, st>>>(segs, jobs, n_jobs, n_units,
+                                                                                      caches, k1, col_base);
+}
 template <bool LIVE, bool NOT, bool MSM>
 static void launch_eval_or_t(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, size_t wb,
                              uint32_t kcap) {

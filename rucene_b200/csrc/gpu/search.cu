@@ -8,7 +8,9 @@
 // the caller can fall through to DefaultIndexSearcher, exactly like an unsupported Query would.
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <tuple>
 #include <type_traits>
 
 #include "engine.hpp"
@@ -35,6 +37,10 @@ struct rg_batch {
     Span<ItemClause> clauses;
     Span<uint32_t> or_ids, and_ids;  // launch order (range-major) of the OR / AND work items
     Span<uint32_t> ro_ids;           // MUST+SHOULD (ReqOptScorer) work items: one per (query, leaf)
+    Span<ColumnJob> col_jobs;        // score columns to materialise before k_eval_or
+    Span<uint64_t> col_off;
+    uint32_t n_col_jobs = 0, n_col_units = 0;
+    uint64_t col_floats = 0;
     Span<uint32_t> group_item_begin, group_out;
     Span<uint32_t> item_head, item_matches, item_theta;
     Span<unsigned long long> arena_next;  // [0] bump pointer, [1] error flag (as u32 view)
@@ -56,6 +62,10 @@ struct HostPlan {
     std::vector<WorkItem> items;
     std::vector<ItemClause> clauses;
     std::vector<uint32_t> or_ids, and_ids, ro_ids;
+    std::vector<ColumnJob> col_jobs;
+    std::vector<uint64_t> col_off;
+    uint32_t n_col_units = 0;
+    uint64_t col_floats = 0;
     std::vector<uint32_t> or_rank, and_rank;  // range index of each id (launch-order key)
     std::vector<uint32_t> group_item_begin, group_out;
     uint64_t postings = 0, algo_bytes = 0;
@@ -123,17 +133,88 @@ QShape classify(const rg_query& q, const rg_clause* clauses, uint32_t n_clauses_
     return s;
 }
 
+// Score columns: which (leaf, term, weight, norm cache) clauses of the batch's disjunctions are
+// worth materialising once for every query that carries them (k_build_columns).  A column costs
+// one pass over the term plus max_doc * 4 bytes; reading it costs ~0.35 warp instructions per
+// DOCID against ~2.3 per POSTING for the block stream, so it pays for dense terms (df >= max_doc/5)
+// that several queries share.  RG_CFG_NO_COLUMNS turns the feature off, RG_CFG_EAGER_COLUMNS makes
+// every clause with df >= max_doc/64 a column (tests).
+using ColKey = std::tuple<uint32_t, uint32_t, uint32_t, uint32_t>;  // leaf, term, weight bits, cache
+std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape>& shapes, const rg_clause* clauses,
+                                          HostPlan& hp) {
+    std::map<ColKey, uint32_t> chosen;
+    if (e->cfg.flags & RG_CFG_NO_COLUMNS) return chosen;
+    const bool eager = (e->cfg.flags & RG_CFG_EAGER_COLUMNS) != 0;
+    const uint32_t min_uses = eager ? 1u : 4u;
+    const uint64_t density_den = eager ? 64u : 5u;
+    std::map<ColKey, uint32_t> uses;
+    for (const QShape& sh : shapes) {
+        if (sh.type != kTypeOr) continue;
+        for (uint32_t si = 0; si < e->segs.size(); si++) {
+            const Segment& seg = e->segs[si];
+            for (uint32_t ci : sh.clause_idx) {
+                const rg_clause& c = clauses[ci];
+                if (c.term_id >= seg.host_terms.size()) continue;
+                const uint64_t df = (uint64_t)seg.host_terms[c.term_id].doc_freq;
+                if (df == 0 || df * density_den < (uint64_t)seg.max_doc) continue;
+                uint32_t wbits;
+                memcpy(&wbits, &c.weight, 4);
+                uses[ColKey(si, c.term_id, wbits, c.cache_id)]++;
+            }
+        }
+    }
+    std::vector<std::pair<uint64_t, ColKey>> ranked;
+    for (const auto& kv : uses) {
+        if (kv.second < min_uses) continue;
+        const Segment& seg = e->segs[std::get<0>(kv.first)];
+        ranked.emplace_back((uint64_t)kv.second * (uint64_t)seg.host_terms[std::get<1>(kv.first)].doc_freq, kv.first);
+    }
+    std::sort(ranked.begin(), ranked.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+    if (e->col_budget_floats == 0) {  // once per index state (cudaMemGetInfo costs milliseconds)
+        size_t free_b = 0, total_b = 0;
+        RG_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+        e->col_budget_floats = std::max<uint64_t>(1, ((uint64_t)free_b + e->col_arena.bytes()) / 3 / sizeof(float));
+    }
+    const uint64_t budget_floats = e->col_budget_floats;
+    for (const auto& r : ranked) {
+        if (hp.col_jobs.size() >= 32) break;
+        const Segment& seg = e->segs[std::get<0>(r.second)];
+        const uint64_t len = ((uint64_t)seg.max_doc + 1024 + 3) & ~3ull;  // windows read past max_doc
+        if (hp.col_floats + len > budget_floats) break;
+        const TermHost& th = seg.host_terms[std::get<1>(r.second)];
+        ColumnJob job{};
+        job.seg = std::get<0>(r.second);
+        job.term_id = std::get<1>(r.second);
+        const uint32_t wbits = std::get<2>(r.second);
+        memcpy(&job.weight, &wbits, 4);
+        job.cache_id = std::get<3>(r.second);
+        job.col_off = hp.col_floats;
+        job.unit_begin = hp.n_col_units;
+        chosen[r.second] = (uint32_t)hp.col_jobs.size();
+        hp.col_jobs.push_back(job);
+        hp.col_off.push_back(job.col_off);
+        hp.col_floats += len;
+        hp.n_col_units += th.n_blocks + (th.tail_n ? 1u : 0u);
+    }
+    return chosen;
+}
+
 void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const rg_clause* clauses,
                 uint32_t n_clauses, uint32_t mode, HostPlan& hp) {
     const uint32_t n_caches = (uint32_t)(e->h_caches.size() / 256);
     const uint64_t range_postings = e->cfg.range_postings;
     const uint32_t n_segs = (uint32_t)e->segs.size();
+    std::vector<QShape> shapes(n_queries);
     for (uint32_t qi = 0; qi < n_queries; qi++) {
-        const QShape shape = classify(queries[qi], clauses, n_clauses);
-        for (uint32_t ci : shape.clause_idx)
+        shapes[qi] = classify(queries[qi], clauses, n_clauses);
+        for (uint32_t ci : shapes[qi].clause_idx)
             if (clauses[ci].cache_id >= n_caches) throw ArgError("clause refers to an unset norm cache");
-        for (uint32_t ci : shape.opt_idx)
+        for (uint32_t ci : shapes[qi].opt_idx)
             if (clauses[ci].cache_id >= n_caches) throw ArgError("clause refers to an unset norm cache");
+    }
+    const std::map<ColKey, uint32_t> columns = choose_columns(e, shapes, clauses, hp);
+    for (uint32_t qi = 0; qi < n_queries; qi++) {
+        const QShape& shape = shapes[qi];
         bool group_open = false;
         uint32_t chain_pos = 0;
         for (uint32_t si = 0; si < n_segs; si++) {
@@ -194,8 +275,19 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
             hp.postings += total_df;
             hp.algo_bytes += bytes;
             const uint32_t clause_begin = (uint32_t)hp.clauses.size();
-            for (uint32_t ci : present)
-                hp.clauses.push_back(ItemClause{clauses[ci].term_id, clauses[ci].weight, clauses[ci].cache_id, 0});
+            for (uint32_t ci : present) {
+                const rg_clause& c = clauses[ci];
+                if (shape.type == kTypeOr && !columns.empty()) {
+                    uint32_t wbits;
+                    memcpy(&wbits, &c.weight, 4);
+                    const auto it = columns.find(ColKey(si, c.term_id, wbits, c.cache_id));
+                    if (it != columns.end()) {  // read the batch's score column instead of the block stream
+                        hp.clauses.push_back(ItemClause{it->second, c.weight, c.cache_id, 4u});
+                        continue;
+                    }
+                }
+                hp.clauses.push_back(ItemClause{c.term_id, c.weight, c.cache_id, 0});
+            }
             for (uint32_t ci : nots) {
                 hp.clauses.push_back(ItemClause{clauses[ci].term_id, 0.0f, clauses[ci].cache_id, 1u});
                 bytes += seg.host_terms[clauses[ci].term_id].enc_bytes;
@@ -334,6 +426,8 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     carve(b->or_ids, hp.or_ids.size());
     carve(b->and_ids, hp.and_ids.size());
     carve(b->ro_ids, hp.ro_ids.size());
+    carve(b->col_jobs, hp.col_jobs.size());
+    carve(b->col_off, hp.col_off.size());
     carve(b->group_item_begin, hp.group_item_begin.size());
     carve(b->group_out, hp.group_out.size());
     carve(b->item_head, b->n_items);
@@ -355,7 +449,7 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
         using T = std::remove_reference_t<decltype(*span.p)>;
         span.p = reinterpret_cast<T*>(b->slab.p + reinterpret_cast<size_t>(span.p));
     };
-    rebase(b->items); rebase(b->clauses); rebase(b->or_ids); rebase(b->and_ids); rebase(b->ro_ids);
+    rebase(b->items); rebase(b->clauses); rebase(b->or_ids); rebase(b->and_ids); rebase(b->ro_ids); rebase(b->col_jobs); rebase(b->col_off);
     rebase(b->group_item_begin); rebase(b->group_out); rebase(b->item_head); rebase(b->item_matches);
     rebase(b->item_theta); rebase(b->arena_next); rebase(b->out_hits); rebase(b->out_counts);
     rebase(b->out_total);
@@ -367,11 +461,16 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     up(b->or_ids, hp.or_ids, st);
     up(b->and_ids, hp.and_ids, st);
     up(b->ro_ids, hp.ro_ids, st);
+    up(b->col_jobs, hp.col_jobs, st);
+    up(b->col_off, hp.col_off, st);
+    b->n_col_jobs = (uint32_t)hp.col_jobs.size();
+    b->n_col_units = hp.n_col_units;
+    b->col_floats = hp.col_floats;
     up(b->group_item_begin, hp.group_item_begin, st);
     up(b->group_out, hp.group_out, st);
     b->h2d_bytes = (hp.items.size() * sizeof(WorkItem)) + hp.clauses.size() * sizeof(ItemClause) +
                    4 * (hp.or_ids.size() + hp.and_ids.size() + hp.ro_ids.size() + hp.group_item_begin.size() + hp.group_out.size());
-    b->kernels_per_run = (b->n_or ? 1 : 0) + (b->n_and ? 1 : 0) + (b->n_ro ? 1 : 0) + (b->n_groups ? 1 : 0) +
+    b->kernels_per_run = (b->n_col_jobs ? 1 : 0) + (b->n_or ? 1 : 0) + (b->n_and ? 1 : 0) + (b->n_ro ? 1 : 0) + (b->n_groups ? 1 : 0) +
                          (p->mode == RG_MODE_SEARCH_PARALLEL ? 1 : 0);
     RG_CUDA_CHECK(cudaStreamSynchronize(st));
     *out = b.release();
@@ -403,6 +502,15 @@ int rg_batch_run(rg_engine* e, rg_batch* b) {
     ep.item_theta = b->item_theta.p;
     ep.error_flag = reinterpret_cast<uint32_t*>(b->arena_next.p + 1);
     RG_CUDA_CHECK(cudaEventRecord(e->ev2, st));
+    if (b->n_col_jobs) {  // materialise this batch's score columns (inside the timed region)
+        if (e->col_arena.n < b->col_floats) e->col_arena.alloc((size_t)b->col_floats);
+        RG_CUDA_CHECK(cudaMemsetAsync(e->col_arena.p, 0xff, (size_t)b->col_floats * sizeof(float), st));
+        launch_build_columns(st, e->d_segs.p, b->col_jobs.p, b->n_col_jobs, b->n_col_units, e->d_caches.p, b->k1,
+                             e->col_arena.p);
+        RG_CUDA_CHECK(cudaGetLastError());
+    }
+    ep.col_base = e->col_arena.p;
+    ep.col_off = b->col_off.p;
     bool has_live = false, has_other = false;
     for (const Segment& sg : e->segs) {
         has_live = has_live || sg.live.p != nullptr;

@@ -14,6 +14,7 @@ RG_OK, RG_EINVAL, RG_ENODEVICE, RG_ECUDA, RG_EUNSUPPORTED, RG_ENOMEM = 0, -1, -2
 MUST, SHOULD, MUST_NOT = 0, 1, 2
 Q_BOOLEAN = 1
 MODE_SEARCH, MODE_SEARCH_PARALLEL = 0, 1
+CFG_NO_COLUMNS, CFG_EAGER_COLUMNS = 1, 2   # rg_config.flags (include/rucene_gpu.h)
 NO_MORE_DOCS = 0x7FFFFFFF
 
 TERM_STATE_DTYPE = np.dtype([("doc_freq", "<i4"), ("singleton_doc_id", "<i4"),
@@ -177,9 +178,9 @@ class BlockSet:
 class Engine:
     """rg_engine handle: one per process / GPU."""
 
-    def __init__(self, device=-1, cand_arena_bytes=0, range_postings=0):
+    def __init__(self, device=-1, cand_arena_bytes=0, range_postings=0, flags=0):
         self.h = None
-        cfg = Config(device, cand_arena_bytes, range_postings, 0)
+        cfg = Config(device, cand_arena_bytes, range_postings, flags)
         h = C.c_void_p()
         _check(lib().rg_engine_create(C.byref(cfg), C.byref(h)))
         self.h = h.value

@@ -154,11 +154,11 @@ class GpuIndexSearcher:
 
     def __init__(self, reader: IndexReader, similarity: Optional[BM25Similarity] = None,
                  device=-1, eng: Optional[engine.Engine] = None, range_postings=0,
-                 cand_arena_bytes=0):
+                 cand_arena_bytes=0, flags=0):
         self.reader = reader
         self.similarity = similarity or BM25Similarity()
         self.engine = eng or engine.Engine(device=device, range_postings=range_postings,
-                                           cand_arena_bytes=cand_arena_bytes)
+                                           cand_arena_bytes=cand_arena_bytes, flags=flags)
         if not eng:
             for seg in reader.segments:
                 self.engine.upload_segment(seg)

@@ -31,11 +31,17 @@ def _run_both(segs, specs, k, mode=0, range_postings=0, threads=4):
     ix = helpers.oracle_index(segs)
     q, c = ob.make_queries(specs)
     want = ix.search_batch(q, c, k, parallel_mode=mode, n_threads=threads)
-    s = search.GpuIndexSearcher(search.IndexReader(segs), range_postings=range_postings)
-    try:
-        got = s.search_batch(helpers.to_queries(specs), k, mode=mode)
-    finally:
-        s.engine.close()
+    # twice: with the planner's own score-column choice (dense clauses shared by >= 4 disjunctions)
+    # and with a column for every clause of df >= max_doc/64 — both must equal the oracle
+    got = None
+    for flags in (engine.CFG_EAGER_COLUMNS, 0):
+        s = search.GpuIndexSearcher(search.IndexReader(segs), range_postings=range_postings, flags=flags)
+        try:
+            got = s.search_batch(helpers.to_queries(specs), k, mode=mode)
+        finally:
+            s.engine.close()
+        if flags:
+            helpers.assert_same_topdocs(got, want, "eager score columns")
     return got, want
 
 
