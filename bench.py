@@ -325,6 +325,7 @@ def main():
     eval_ms = eng.last_kernel_ms("eval")
     replay_ms = eng.last_kernel_ms("replay")
     bstats = batch.stats()
+    n_cols, col_bytes = batch.columns()
     value = args.batch / (ms_step / 1e3)
 
     # ---- e2e: host arrays in, host TopDocs out ---------------------------------------------
@@ -397,7 +398,10 @@ def main():
                         "DRAM traffic is far below the algorithmic bytes because hot posting blocks hit in L2",
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": eval_ms, "replay_ms": replay_ms,
                 "postings_per_launch": bstats["postings"], "work_items": bstats["items"],
-                "candidate_slots": bstats["candidate_slots"]}
+                "candidate_slots": bstats["candidate_slots"],
+                "score_columns": {"n": n_cols, "bytes": col_bytes,
+                                  "note": "dense clauses shared by >= 4 disjunctions of the batch are scored once per "
+                                          "step (k_build_columns, inside the timed region) and read as f32 columns"}}
 
     # ---- ForUtil decode microbench (BASELINE config 2) --------------------------------------
     decode = None

@@ -151,6 +151,8 @@ void rg_batch_destroy(rg_engine* e, rg_batch* b);
  * clauses), [2]=algorithmic bytes the evaluation must read (encoded blocks + tails + tables
  * touched + norms), [3]=candidates emitted by the last run, [4]=kernels per run. */
 int rg_batch_stats(rg_engine* e, rg_batch* b, uint64_t out[8]);
+/* Score columns the planner chose for this batch (see RG_CFG_*): how many, and their bytes in HBM. */
+int rg_batch_columns(rg_engine* e, rg_batch* b, uint32_t* n_columns, uint64_t* bytes);
 
 /* Sharded mode (one segment per GPU).  After rg_batch_run with RG_MODE_SEARCH_PARALLEL the
  * per-query leaf record {uint32 n; uint32 pad; uint64 total_hits; rg_hit heap[k]} (heap-array

@@ -7,6 +7,7 @@
 // TopDocsCollector replay.  Plan shapes outside the accelerated path return RG_EUNSUPPORTED so
 // the caller can fall through to DefaultIndexSearcher, exactly like an unsupported Query would.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -136,7 +137,7 @@ QShape classify(const rg_query& q, const rg_clause* clauses, uint32_t n_clauses_
 // Score columns: which (leaf, term, weight, norm cache) clauses of the batch's disjunctions are
 // worth materialising once for every query that carries them (k_build_columns).  A column costs
 // one pass over the term plus max_doc * 4 bytes; reading it costs ~0.35 warp instructions per
-// DOCID against ~2.3 per POSTING for the block stream, so it pays for dense terms (df >= max_doc/5)
+// DOCID against ~2.3 per POSTING for the block stream, so it pays for dense terms (df >= max_doc/8)
 // that several queries share.  RG_CFG_NO_COLUMNS turns the feature off, RG_CFG_EAGER_COLUMNS makes
 // every clause with df >= max_doc/64 a column (tests).
 using ColKey = std::tuple<uint32_t, uint32_t, uint32_t, uint32_t>;  // leaf, term, weight bits, cache
@@ -146,7 +147,8 @@ std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape
     if (e->cfg.flags & RG_CFG_NO_COLUMNS) return chosen;
     const bool eager = (e->cfg.flags & RG_CFG_EAGER_COLUMNS) != 0;
     const uint32_t min_uses = eager ? 1u : 4u;
-    const uint64_t density_den = eager ? 64u : 5u;
+    uint64_t density_den = eager ? 64u : 8u;  // measured on C4: 5 -> 625 ms, 8 -> 597, 12 -> 610, 20 -> 647
+    if (const char* ev = getenv("RUCENE_B200_COL_DEN")) density_den = std::max(1, atoi(ev));  // tuning runs
     std::map<ColKey, uint32_t> uses;
     for (const QShape& sh : shapes) {
         if (sh.type != kTypeOr) continue;
@@ -608,6 +610,15 @@ int rg_search_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     if (rc == RG_OK) rc = rg_batch_fetch(e, b, out_hits, out_counts, out_total_hits);
     rg_batch_destroy(e, b);
     return rc;
+}
+
+int rg_batch_columns(rg_engine* e, rg_batch* b, uint32_t* n_columns, uint64_t* bytes) {
+    RG_TRY
+    if (!e || !b || !n_columns || !bytes) throw ArgError("null argument");
+    *n_columns = b->n_col_jobs;
+    *bytes = b->col_floats * sizeof(float);
+    return RG_OK;
+    RG_CATCH
 }
 
 int rg_batch_leaf_records(rg_engine* e, rg_batch* b, void** dev_ptr, size_t* record_bytes) {

@@ -82,6 +82,7 @@ def lib():
     L.rg_batch_destroy.argtypes = [vp, vp]
     L.rg_batch_destroy.restype = None
     L.rg_batch_stats.argtypes = [vp, vp, vp]
+    L.rg_batch_columns.argtypes = [vp, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
     L.rg_batch_leaf_records.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.rg_merge_leaf_records.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp]
     L.rg_forutil_decode.argtypes = [vp, vp, C.c_size_t, vp, C.c_uint32, C.c_int, vp, vp]
@@ -126,6 +127,12 @@ class Batch:
         return {"items": int(out[0]), "postings": int(out[1]), "algorithmic_bytes": int(out[2]),
                 "candidate_slots": int(out[3]), "kernels_per_run": int(out[4]),
                 "h2d_bytes": int(out[5]), "or_items": int(out[6]), "and_items": int(out[7])}
+
+    def columns(self):
+        """(number of score columns chosen for this batch, their bytes in HBM)"""
+        n, nbytes = C.c_uint32(), C.c_uint64()
+        _check(lib().rg_batch_columns(self.engine.h, self.h, C.byref(n), C.byref(nbytes)), self.engine.h)
+        return n.value, nbytes.value
 
     def leaf_records(self):
         ptr, nbytes = C.c_void_p(), C.c_size_t()
