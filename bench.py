@@ -394,8 +394,9 @@ def main():
         pass
     roofline = {"bound": "hbm", "kernel": "k_eval_and" if must else "k_eval_or", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "note": "instruction-bound, not HBM-bound: ~4.5 warp instructions per posting (profiles/README.md); "
-                        "DRAM traffic is far below the algorithmic bytes because hot posting blocks hit in L2",
+                "note": "instruction/latency-bound, not HBM-bound: ~3.6 warp instructions per posting "
+                        "(profiles/README.md); DRAM traffic is far below the algorithmic bytes because hot posting "
+                        "blocks and the batch's score columns hit in L2; kernel_ms includes k_build_columns",
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": eval_ms, "replay_ms": replay_ms,
                 "postings_per_launch": bstats["postings"], "work_items": bstats["items"],
                 "candidate_slots": bstats["candidate_slots"],
