@@ -1722,7 +1722,7 @@ int orc_advance_seq(orc_index* ix, uint32_t seg_i, uint32_t term_id, const int32
     BlockDocIterator it(Input(seg.file, seg.file_len), &seg.for_util, seg.use_simd, true,
                         seg.terms[term_id], true);
     for (uint32_t i = 0; i < n; i++) {
-        out_docs[i] = it.advance(targets[i]);
+        out_docs[i] = targets[i] < 0 ? it.next() : it.advance(targets[i]);  // target -1: next()
         out_freqs[i] = out_docs[i] == NO_MORE_DOCS ? 0 : it.freq;
     }
     return 0;

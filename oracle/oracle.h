@@ -91,6 +91,7 @@ int orc_term_weight(orc_index*, uint32_t term_id, float boost, float* out_weight
 int64_t orc_postings(orc_index*, uint32_t seg, uint32_t term_id, int32_t* docs,
                      int32_t* freqs, int64_t cap);
 /* Drive BlockDocIterator::advance(target) for each target in order; out[i]=doc, freq. */
+/* one DocIterator over the term: advance(targets[i]) per entry, or next() where targets[i] == -1 */
 int orc_advance_seq(orc_index*, uint32_t seg, uint32_t term_id, const int32_t* targets,
                     uint32_t n, int32_t* out_docs, int32_t* out_freqs);
 

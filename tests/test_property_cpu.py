@@ -41,6 +41,46 @@ def test_random_list_round_trip_and_advance(seed, version, df, density, ef):
         cur = int(dd)
 
 
+@settings(max_examples=30, deadline=None)
+@given(seed=st.integers(0, 2**31 - 1), version=st.sampled_from([0, 1]), ef=st.sampled_from([0, 1, 2]),
+       df=st.sampled_from([130, 257, 1000, 1024, 4097, 9000]), density=st.sampled_from([0.95, 0.4, 0.02]))
+def test_interleaved_next_and_advance(seed, version, ef, df, density):
+    """What ConjunctionScorer does to a list: next() and advance(target > doc) in any interleaving, over PF,
+    EF and BITSET blocks (EliasFanoDecoder::advance_to_value then next_value, FixedBitSet advance then
+    next_set_bit, skip data in between) — against a plain sorted-array model."""
+    rng = np.random.default_rng(seed)
+    max_doc = max(int(df / density) + 10, df + 10)
+    docs = np.sort(rng.choice(max_doc, size=df, replace=False)).astype(np.int32)
+    freqs = np.minimum(rng.geometric(0.4, size=df), 10**6).astype(np.int32)
+    w = codec.PostingsWriter(doc_version=version, max_doc=max_doc, use_ef=ef > 0, with_pf=ef != 2)
+    w.add_term(docs, freqs)
+    seg = w.finish(norms=np.full(max_doc, 100, np.uint8))
+    ix = helpers.oracle_index([seg])
+    ops, want_d, want_f = [], [], []
+    pos, cur = -1, -1            # index of the current posting, current docid
+    for _ in range(int(rng.integers(5, 120))):
+        if pos >= df:
+            break
+        if rng.random() < 0.5:
+            ops.append(-1)
+            pos += 1
+        else:
+            jump = int(rng.choice([1, 2, 5, 40, 200, 3000]))
+            tgt = cur + 1 + int(rng.integers(0, jump))
+            ops.append(tgt)
+            pos = max(pos + 1, int(np.searchsorted(docs, tgt)))
+        if pos >= df:
+            want_d.append(ob.NO_MORE_DOCS)
+            want_f.append(0)
+        else:
+            cur = int(docs[pos])
+            want_d.append(cur)
+            want_f.append(int(freqs[pos]))
+    got_d, got_f = ix.advance_seq(0, 0, np.array(ops, np.int32))
+    assert list(got_d) == want_d
+    assert [int(f) for d, f in zip(got_d, got_f) if d != ob.NO_MORE_DOCS] == [f for d, f in zip(want_d, want_f) if d != ob.NO_MORE_DOCS]
+
+
 def _heap_model(stream, k):
     """Direct transcription of SURVEY Appendix B (independent of the oracle's C++)."""
     data = []
