@@ -75,10 +75,15 @@ typedef struct {
 /* flags */
 #define RG_Q_BOOLEAN 1u /* built by BooleanQuery::build (boolean_query.rs:40-87); without it
                            the query is a bare TermQuery and n_clauses must be 1 */
+#define RG_Q_DISMAX 2u  /* built by DisjunctionMaxQuery::build over TermQuerys
+                           (search/query/disjunction_max_query.rs:51-68): the clauses are the disjuncts
+                           (occur is ignored), min_should_match carries the BITS of the f32
+                           tie_breaker_multiplier; score = max + (sum - max) * tie_breaker
+                           (search/scorer/disjunction_scorer.rs:241-263) */
 typedef struct {
     uint32_t clause_begin; /* index into the clause array */
     uint32_t n_clauses;
-    int32_t min_should_match; /* as passed to BooleanQuery::build */
+    int32_t min_should_match; /* as passed to BooleanQuery::build (RG_Q_DISMAX: f32 bits, see above) */
     uint32_t flags;
 } rg_query;
 

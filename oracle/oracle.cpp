@@ -1279,6 +1279,54 @@ struct DisjunctionSumScorer : Scorer {
     }
 };
 
+// search/scorer/disjunction_scorer.rs:106-186,241-263 — DisjunctionMaxScorer, SimpleQueue variant
+// (<10 children): the union like DisjunctionSumScorer without min_should_match; score =
+// max + (sum - max) * tie_breaker_multiplier, sum in child order from 0.0f, max from -inf.
+struct DisjunctionMaxScorer : Scorer {
+    std::vector<ScorerPtr> scorers;
+    int32_t curr_doc;
+    float tie_breaker_multiplier;
+    size_t cost_;
+    DisjunctionMaxScorer(std::vector<ScorerPtr> children, float tie) : scorers(std::move(children)), tie_breaker_multiplier(tie) {
+        if (scorers.size() >= 10) throw Error(">=10 disjuncts use DisiPriorityQueue: out of scope (SURVEY 8f-4)");
+        cost_ = 0;
+        curr_doc = NO_MORE_DOCS;
+        for (auto& s : scorers) {
+            cost_ += s->cost();
+            curr_doc = std::min(curr_doc, s->doc_id());
+        }
+    }
+    int32_t doc_id() const override { return curr_doc; }
+    int32_t next() override {  // approximate_next(None) :295-333 with DEFAULT_MIN_SHOULD_MATCH
+        if (curr_doc == NO_MORE_DOCS) return curr_doc;
+        int32_t cd = curr_doc, min_doc = NO_MORE_DOCS;
+        for (auto& s : scorers) {
+            if (s->doc_id() == cd) s->next();
+            min_doc = std::min(min_doc, s->doc_id());
+        }
+        return curr_doc = min_doc;
+    }
+    int32_t advance(int32_t target) override {  // :350-363
+        int32_t min_doc = NO_MORE_DOCS;
+        for (auto& s : scorers) {
+            if (s->doc_id() < target) s->advance(target);
+            min_doc = std::min(min_doc, s->doc_id());
+        }
+        return curr_doc = min_doc;
+    }
+    size_t cost() const override { return cost_; }
+    float score() override {  // score_max :241-263
+        float score_sum = 0.0f, score_max = -INFINITY;
+        for (auto& s : scorers)
+            if (s->doc_id() == curr_doc) {
+                float sub = s->score();
+                score_sum += sub;
+                score_max = std::fmax(score_max, sub);
+            }
+        return score_max + (score_sum - score_max) * tie_breaker_multiplier;
+    }
+};
+
 // search/scorer/req_opt_scorer.rs:19-105
 struct ReqOptScorer : Scorer {
     ScorerPtr req, opt;
@@ -1476,6 +1524,22 @@ static ScorerPtr create_scorer(const orc_index& ix, const SegmentData& seg, cons
         return ScorerPtr(new TermScorer(seg, seg.terms[c.term_id], &plan.weights[ci]));
     };
     if (!q.is_boolean) return term_scorer(0);
+    if (q.is_boolean == 2) {
+        // DisjunctionMaxQuery::build (search/query/disjunction_max_query.rs:51-68): one disjunct is the
+        // disjunct itself; DisjunctionMaxWeight::create_scorer (:135-155): 0 scorers -> None, 1 -> it
+        if (q.n_clauses == 0) throw Error("DisjunctionMaxQuery: sub query should not be empty!");
+        if (q.n_clauses == 1) return term_scorer(0);
+        float tie;
+        std::memcpy(&tie, &q.min_should_match, 4);
+        std::vector<ScorerPtr> v;
+        for (uint32_t i = 0; i < q.n_clauses; i++) {
+            ScorerPtr sc = term_scorer(i);
+            if (sc) v.push_back(std::move(sc));
+        }
+        if (v.empty()) return nullptr;
+        if (v.size() == 1) return std::move(v[0]);
+        return ScorerPtr(new DisjunctionMaxScorer(std::move(v), tie));
+    }
 
     // BooleanQuery::build (:40-87)
     int32_t msm = q.min_should_match;

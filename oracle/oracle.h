@@ -44,8 +44,10 @@ typedef struct {
 typedef struct {
     uint32_t clause_begin;
     uint32_t n_clauses;
-    int32_t min_should_match; /* as passed to BooleanQuery::build */
-    int32_t is_boolean;       /* 0: bare TermQuery (n_clauses==1), 1: BooleanQuery::build */
+    int32_t min_should_match; /* as passed to BooleanQuery::build; kind 2: the bits of the f32
+                                 tie_breaker_multiplier instead */
+    int32_t is_boolean;       /* 0: bare TermQuery (n_clauses==1), 1: BooleanQuery::build,
+                                 2: DisjunctionMaxQuery::build over the clauses' TermQuerys */
 } orc_query;
 
 typedef struct {

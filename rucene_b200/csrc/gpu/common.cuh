@@ -57,7 +57,8 @@ struct ItemClause {
     uint32_t cache_id;
     uint32_t flags;    // bit0: MUST_NOT clause (ReqNotScorer: excludes, never scores)
                        // bit1: SHOULD clause beside a MUST (ReqOptScorer's optional side)
-                       // bit2: score column — term_id is an index into EvalParams::col_ptrs
+                       // bit2: score column — term_id is an index into EvalParams::col_off
+                       // bit3: meta entry after a DisjunctionMaxScorer item's clauses: weight = tie breaker
 };
 
 struct WorkItem {

@@ -123,7 +123,7 @@ struct ColumnJob {
 void launch_build_columns(cudaStream_t st, const SegDev* segs, const ColumnJob* jobs, uint32_t n_jobs,
                           uint32_t n_units, const float* caches, float k1, float* col_base);
 void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n,
-                    uint32_t max_terms, bool has_live, bool has_not, bool has_msm);
+                    uint32_t max_terms, bool has_live, bool has_not, bool has_msm, bool has_dmax);
 void launch_eval_and(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, bool req_opt,
                      bool has_other_enc);
 

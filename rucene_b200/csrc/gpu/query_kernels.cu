@@ -307,11 +307,14 @@ struct WTerm {
 // that is present becomes kExcl and its match is taken back.
 // MSM (min_should_match > 1, disjunction_scorer.rs:317-329): a per-doc clause counter next to the
 // sums; a doc becomes a match when its counter reaches msm.
+// DMAX (DisjunctionMaxScorer, disjunction_scorer.rs:241-263): the running maximum of the clause scores
+// next to their sum; the final score max + (sum - max) * tie_breaker is formed in the window epilogue.
 struct MsmCtx {
     uint8_t* cnt;  // [kWw] clause counters of the window (MSM variants only)
     uint32_t msm;
+    float* mx;     // [kWw] per-doc maximum clause score (DMAX variant only)
 };
-template <bool NOT, bool MSM>
+template <bool NOT, bool MSM, bool DMAX>
 __device__ __forceinline__ void accumulate_posting(uint32_t* acc, int idx, float s, bool is_not, bool live,
                                                    float te, uint32_t& hot, uint32_t& my_matches,
                                                    const MsmCtx& mc) {
@@ -319,6 +322,7 @@ __device__ __forceinline__ void accumulate_posting(uint32_t* acc, int idx, float
     if (!NOT || !is_not) {
         const float sum = __fadd_rn(old == kSent ? 0.0f : __uint_as_float(old), s);
         acc[idx] = __float_as_uint(sum);
+        if (DMAX) mc.mx[idx] = old == kSent ? s : fmaxf(mc.mx[idx], s);
         if (MSM) {
             const uint32_t c = (uint32_t)mc.cnt[idx] + 1u;
             mc.cnt[idx] = (uint8_t)c;
@@ -326,7 +330,8 @@ __device__ __forceinline__ void accumulate_posting(uint32_t* acc, int idx, float
         } else if (old == kSent && live) {
             my_matches++;
         }
-        if (sum > te) hot |= 1u << (idx >> 5);
+        // DMAX: the final score is not the sum, so every touched step is scanned
+        if (DMAX || sum > te) hot |= 1u << (idx >> 5);
     } else if (old != kSent && old != kExcl) {
         acc[idx] = kExcl;
         if (live && (!MSM || mc.cnt[idx] >= mc.msm)) my_matches--;
@@ -409,7 +414,7 @@ __device__ __forceinline__ void wtheta_update(WEmit& em, uint32_t k, uint32_t kc
 // list is exhausted.  Warp-cooperative; all lanes must call it.
 // When called while clause t is being drained into the window [win0, win1) the new block's
 // postings below win1 are accumulated straight from registers (no round trip through the cache).
-template <bool LIVE, bool NOT, bool MSM>
+template <bool LIVE, bool NOT, bool MSM, bool DMAX>
 __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParams& p, WTerm& tc, int32_t* cd,
                                            float* cs, int lo, int hi, int lane, int win0, int win1,
                                            uint32_t* acc, uint32_t& hot, uint32_t& my_matches, float te,
@@ -513,8 +518,8 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
         if (all_direct) {  // the common case for dense clauses: nothing to cache, no cursor arithmetic
 #pragma unroll
             for (int q = 0; q < 4; q++)
-                accumulate_posting<NOT, MSM>(acc, d[q] - win0, sc[q], neg, LIVE ? is_live(seg, d[q]) : true, te,
-                                             hot, my_matches, mc);
+                accumulate_posting<NOT, MSM, DMAX>(acc, d[q] - win0, sc[q], neg, LIVE ? is_live(seg, d[q]) : true,
+                                                   te, hot, my_matches, mc);
             __syncwarp();  // every lane has read tc.cur / tc.nb above
             if (lane == 0) {
                 tc.pos = tc.n = 0;
@@ -526,8 +531,8 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             if (ok[q] && d[q] < win1) {  // still inside the window being drained: accumulate now
-                accumulate_posting<NOT, MSM>(acc, d[q] - win0, sc[q], neg, LIVE ? is_live(seg, d[q]) : true, te,
-                                             hot, my_matches, mc);
+                accumulate_posting<NOT, MSM, DMAX>(acc, d[q] - win0, sc[q], neg, LIVE ? is_live(seg, d[q]) : true,
+                                                   te, hot, my_matches, mc);
                 direct++;
             }
         }
@@ -556,7 +561,7 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
     }
 }
 
-template <bool LIVE, bool NOT, bool MSM>
+template <bool LIVE, bool NOT, bool MSM, bool DMAX>
 __global__ void __launch_bounds__(kOrThreads, 6)
 k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, uint32_t warp_bytes,
           uint32_t kcap) {
@@ -579,6 +584,10 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
     MsmCtx mc;
     mc.cnt = reinterpret_cast<uint8_t*>(cscores + T * kBlock);  // MSM variants reserve kWw more bytes
     mc.msm = max(1u, (uint32_t)it.type >> 4);  // items without min_should_match in an MSM launch: 1
+    mc.mx = reinterpret_cast<float*>(mc.cnt + kWw);  // DMAX variant reserves 4 * kWw more bytes
+    // DisjunctionMaxScorer item: the tie breaker rides in a meta clause after the item's clauses
+    const bool dmax_item = DMAX && (it.type & 4u) != 0;
+    const float tie = dmax_item ? p.clauses[it.clause_begin + T].weight : 0.0f;
     if (MSM) {
         for (int i = lane; i < kWw / 4; i += 32) reinterpret_cast<uint32_t*>(mc.cnt)[i] = 0u;
     }
@@ -618,8 +627,8 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
     uint32_t hot = 0, my_matches = 0;
     int nd = kNoMoreDocs;  // lane t: next cached docid of clause t (kNoMoreDocs = exhausted)
     for (int t = 0; t < T; t++) {
-        if (stream_refill<LIVE, NOT, MSM>(seg, p, sh.term[t], cdocs + t * kBlock, cscores + t * kBlock, lo, hi, lane,
-                                          0, -2147483647 - 1, sh.acc, hot, my_matches, INFINITY, mc)) {
+        if (stream_refill<LIVE, NOT, MSM, DMAX>(seg, p, sh.term[t], cdocs + t * kBlock, cscores + t * kBlock, lo, hi,
+                                                lane, 0, -2147483647 - 1, sh.acc, hot, my_matches, INFINITY, mc)) {
             const int first = cdocs[t * kBlock + sh.term[t].pos];
             if (lane == t) nd = first;
         }
@@ -678,13 +687,13 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                     const int d0 = win0 + i;
                     const float4 v = __ldg(reinterpret_cast<const float4*>(col + d0));
                     const float sv[4] = {v.x, v.y, v.z, v.w};
-                    if (MSM) {  // per-doc clause counters: the scalar path
+                    if (MSM || DMAX) {  // per-doc clause counters / maxima: the scalar path
 #pragma unroll
                         for (int q = 0; q < 4; q++) {
                             const int d = d0 + q;
                             if (__float_as_uint(sv[q]) != 0xffffffffu && d >= lo && d < win1)
-                                accumulate_posting<NOT, MSM>(sh.acc, i + q, sv[q], false,
-                                                             LIVE ? is_live(seg, d) : true, te, hot, my_matches, mc);
+                                accumulate_posting<NOT, MSM, DMAX>(sh.acc, i + q, sv[q], false,
+                                                                   LIVE ? is_live(seg, d) : true, te, hot, my_matches, mc);
                         }
                         continue;
                     }
@@ -722,8 +731,8 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                     __syncwarp();  // every lane has read tc.pos / tc.n / tc.cur
                     if (lane == 0) tc.pos = pos;
                     __syncwarp();
-                    if (!stream_refill<LIVE, NOT, MSM>(seg, p, tc, cdocs + t * kBlock, cscores + t * kBlock, lo, hi,
-                                                       lane, win0, win1, sh.acc, hot, my_matches, te, mc)) {
+                    if (!stream_refill<LIVE, NOT, MSM, DMAX>(seg, p, tc, cdocs + t * kBlock, cscores + t * kBlock, lo, hi,
+                                                             lane, win0, win1, sh.acc, hot, my_matches, te, mc)) {
                         pos = n = 0;
                         break;
                     }
@@ -735,8 +744,8 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                 const bool in_win = d < win1;
                 const uint32_t c = __popc(__ballot_sync(0xffffffffu, in_win));  // sorted: a prefix
                 if (in_win)
-                    accumulate_posting<NOT, MSM>(sh.acc, d - win0, cs[i], NOT && tc.is_not != 0,
-                                                 LIVE ? is_live(seg, d) : true, te, hot, my_matches, mc);
+                    accumulate_posting<NOT, MSM, DMAX>(sh.acc, d - win0, cs[i], NOT && tc.is_not != 0,
+                                                       LIVE ? is_live(seg, d) : true, te, hot, my_matches, mc);
                 pos += c;
                 if (c < 32 && pos < n) break;  // next cached doc is beyond this window
             }
@@ -761,7 +770,11 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                 hot &= hot - 1;
                 const int idx = s * 32 + lane;
                 const uint32_t v = sh.acc[idx];
-                const float sc = __uint_as_float(v);
+                float sc = __uint_as_float(v);
+                if (DMAX && dmax_item) {  // score_max: max + (sum - max) * tie_breaker_multiplier
+                    const float m = mc.mx[idx];
+                    sc = __fadd_rn(m, __fmul_rn(__fsub_rn(sc, m), tie));
+                }
                 const bool cand = v != kSent && (!NOT || v != kExcl) && (open || sc > te) &&
                                   (!MSM || mc.cnt[idx] >= mc.msm) && (LIVE ? is_live(seg, win0 + idx) : true);
                 const uint32_t cm = __ballot_sync(0xffffffffu, cand);
@@ -1336,30 +1349,34 @@ void launch_build_columns(cudaStream_t st, const SegDev* segs, const ColumnJob* 
     k_build_columns<<<(n_units + kColWarps - 1) / kColWarps, kColWarps * 32, 0, st>>>(segs, jobs, n_jobs, n_units,
                                                                                       caches, k1, col_base);
 }
-template <bool LIVE, bool NOT, bool MSM>
+template <bool LIVE, bool NOT, bool MSM, bool DMAX>
 static void launch_eval_or_t(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, size_t wb,
                              uint32_t kcap) {
     const size_t smem = wb * kOrWarps;
     // per launch, not cached: the attribute is per device and engines may live on several
-    cudaFuncSetAttribute(k_eval_or<LIVE, NOT, MSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_eval_or<LIVE, NOT, MSM, DMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const uint32_t ctas = (n + kOrWarps - 1) / kOrWarps;
-    k_eval_or<LIVE, NOT, MSM><<<ctas, kOrThreads, smem, st>>>(p, item_ids, n, (uint32_t)wb, kcap);
+    k_eval_or<LIVE, NOT, MSM, DMAX><<<ctas, kOrThreads, smem, st>>>(p, item_ids, n, (uint32_t)wb, kcap);
 }
 // has_live: some leaf has deleted docs; has_not: some item of the launch carries a MUST_NOT clause
 void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n,
-                    uint32_t max_terms, bool has_live, bool has_not, bool has_msm) {
+                    uint32_t max_terms, bool has_live, bool has_not, bool has_msm, bool has_dmax) {
     if (!n) return;
     const uint32_t kcap = (std::min<uint32_t>(p.k, kMaxK) + 31u) & ~31u;
     size_t wb = sizeof(WarpShared) + (size_t)kcap * sizeof(float) + (size_t)max_terms * kBlock * 8;
     wb = (wb + 15) & ~size_t(15);
-    if (has_msm) {  // min_should_match > 1 somewhere in the batch: the one general variant
+    if (has_dmax) {  // a DisjunctionMaxQuery in the batch: per-doc counters + per-doc maxima
+        wb += kWw + kWw * sizeof(float);
+        wb = (wb + 15) & ~size_t(15);
+        launch_eval_or_t<true, true, true, true>(st, p, item_ids, n, wb, kcap);
+    } else if (has_msm) {  // min_should_match > 1 somewhere in the batch: the general sum variant
         wb += kWw;  // per-doc clause counters
         wb = (wb + 15) & ~size_t(15);
-        launch_eval_or_t<true, true, true>(st, p, item_ids, n, wb, kcap);
-    } else if (has_live && has_not) launch_eval_or_t<true, true, false>(st, p, item_ids, n, wb, kcap);
-    else if (has_live) launch_eval_or_t<true, false, false>(st, p, item_ids, n, wb, kcap);
-    else if (has_not) launch_eval_or_t<false, true, false>(st, p, item_ids, n, wb, kcap);
-    else launch_eval_or_t<false, false, false>(st, p, item_ids, n, wb, kcap);
+        launch_eval_or_t<true, true, true, false>(st, p, item_ids, n, wb, kcap);
+    } else if (has_live && has_not) launch_eval_or_t<true, true, false, false>(st, p, item_ids, n, wb, kcap);
+    else if (has_live) launch_eval_or_t<true, false, false, false>(st, p, item_ids, n, wb, kcap);
+    else if (has_not) launch_eval_or_t<false, true, false, false>(st, p, item_ids, n, wb, kcap);
+    else launch_eval_or_t<false, false, false, false>(st, p, item_ids, n, wb, kcap);
 }
 template <bool REQOPT, bool OTHER>
 static void launch_eval_and_t(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n) {

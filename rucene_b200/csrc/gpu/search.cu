@@ -53,7 +53,7 @@ struct rg_batch {
     size_t zero_bytes = 0;
     uint64_t postings = 0, algo_bytes = 0, h2d_bytes = 0;
     uint32_t kernels_per_run = 0;
-    bool or_has_not = false, or_has_msm = false;
+    bool or_has_not = false, or_has_msm = false, or_has_dmax = false;
     bool ran = false;
 };
 
@@ -71,7 +71,7 @@ struct HostPlan {
     std::vector<uint32_t> group_item_begin, group_out;
     uint64_t postings = 0, algo_bytes = 0;
     uint32_t max_or_terms = 1;
-    bool or_has_not = false, or_has_msm = false;
+    bool or_has_not = false, or_has_msm = false, or_has_dmax = false;
 };
 
 struct QShape {
@@ -79,6 +79,8 @@ struct QShape {
     std::vector<uint32_t> clause_idx;  // scoring clauses (indices into the caller's array), evaluation order
     std::vector<uint32_t> not_idx;     // MUST_NOT clauses (ReqNotScorer)
     uint32_t msm = 0;                  // min_should_match when > 1 on a pure-SHOULD shape, else 0
+    bool dismax = false;               // DisjunctionMaxQuery: score = max + (sum - max) * tie
+    float tie = 0.0f;
     std::vector<uint32_t> opt_idx;     // SHOULD clauses beside a MUST (ReqOptScorer's optional side), clause order
 };
 
@@ -86,6 +88,19 @@ struct QShape {
 QShape classify(const rg_query& q, const rg_clause* clauses, uint32_t n_clauses_total) {
     if ((uint64_t)q.clause_begin + q.n_clauses > n_clauses_total) throw ArgError("query clause range out of bounds");
     QShape s;
+    if (q.flags & RG_Q_DISMAX) {
+        // DisjunctionMaxQuery::build (search/query/disjunction_max_query.rs:51-68) over TermQuerys;
+        // DisjunctionMaxScorer::new (disjunction_scorer.rs:118-139): SimpleQueue below 10 disjuncts
+        if (q.n_clauses == 0) throw ArgError("DisjunctionMaxQuery: sub query should not be empty!");
+        if (q.n_clauses > (uint32_t)kMaxTerms) throw Unsupported(">= 10 disjuncts use DisiPriorityQueue");
+        s.type = kTypeOr;
+        for (uint32_t i = 0; i < q.n_clauses; i++) s.clause_idx.push_back(q.clause_begin + i);
+        if (q.n_clauses > 1) {  // a single disjunct is the disjunct itself
+            s.dismax = true;
+            memcpy(&s.tie, &q.min_should_match, 4);
+        }
+        return s;
+    }
     if (!(q.flags & RG_Q_BOOLEAN)) {
         if (q.n_clauses != 1) throw ArgError("a bare TermQuery has exactly one clause");
         s.type = kTypeOr;  // TermScorer == one-clause disjunction: 0.0f + s == s
@@ -297,6 +312,10 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
             for (uint32_t ci : opts)
                 hp.clauses.push_back(ItemClause{clauses[ci].term_id, clauses[ci].weight, clauses[ci].cache_id, 2u});
             const uint32_t n_item_terms = (uint32_t)(present.size() + nots.size() + opts.size());
+            // DisjunctionMaxWeight::create_scorer (disjunction_max_query.rs:135-155): one scorer in this
+            // leaf is that scorer; otherwise the tie breaker rides in a meta clause after the item's
+            const bool leaf_dismax = shape.dismax && present.size() > 1;
+            if (leaf_dismax) hp.clauses.push_back(ItemClause{0u, shape.tie, 0u, 8u});
             // ranges of ~range_postings postings, at most 256 per (query, leaf): long lists get
             // longer ranges (a range is one warp's sequential job; there are thousands of warps)
             uint64_t R = (cost + range_postings - 1) / range_postings;
@@ -312,7 +331,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 WorkItem it{};
                 it.query = qi;
                 it.seg = (uint16_t)si;
-                it.type = (uint8_t)(leaf_type | (shape.type == kTypeOr ? shape.msm << 4 : 0u));
+                it.type = (uint8_t)(leaf_type | (shape.type == kTypeOr ? shape.msm << 4 : 0u) | (leaf_dismax ? 4u : 0u));
                 it.n_terms = (uint8_t)n_item_terms;
                 it.lo = (int32_t)((uint64_t)seg.max_doc * r / R);
                 it.hi = (int32_t)((uint64_t)seg.max_doc * (r + 1) / R);
@@ -332,6 +351,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                     hp.max_or_terms = std::max<uint32_t>(hp.max_or_terms, n_item_terms);
                     if (!nots.empty()) hp.or_has_not = true;
                     if (shape.msm) hp.or_has_msm = true;
+                    if (leaf_dismax) hp.or_has_dmax = true;
                 }
             }
         }
@@ -411,6 +431,7 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     b->max_or_terms = hp.max_or_terms;
     b->or_has_not = hp.or_has_not;
     b->or_has_msm = hp.or_has_msm;
+    b->or_has_dmax = hp.or_has_dmax;
     b->n_leaves = (uint32_t)e->segs.size();
     b->postings = hp.postings;
     b->algo_bytes = hp.algo_bytes + (uint64_t)n_queries * p->k * sizeof(rg_hit);
@@ -518,7 +539,7 @@ int rg_batch_run(rg_engine* e, rg_batch* b) {
         has_live = has_live || sg.live.p != nullptr;
         has_other = has_other || sg.has_other_enc;
     }
-    launch_eval_or(st, ep, b->or_ids.p, b->n_or, b->max_or_terms, has_live, b->or_has_not, b->or_has_msm);
+    launch_eval_or(st, ep, b->or_ids.p, b->n_or, b->max_or_terms, has_live, b->or_has_not, b->or_has_msm, b->or_has_dmax);
     RG_CUDA_CHECK(cudaGetLastError());
     launch_eval_and(st, ep, b->and_ids.p, b->n_and, false, has_other);
     RG_CUDA_CHECK(cudaGetLastError());

@@ -13,6 +13,7 @@ from . import _build
 RG_OK, RG_EINVAL, RG_ENODEVICE, RG_ECUDA, RG_EUNSUPPORTED, RG_ENOMEM = 0, -1, -2, -3, -4, -5
 MUST, SHOULD, MUST_NOT = 0, 1, 2
 Q_BOOLEAN = 1
+Q_DISMAX = 2    # rg_query.flags: DisjunctionMaxQuery; min_should_match = bits of the f32 tie breaker
 MODE_SEARCH, MODE_SEARCH_PARALLEL = 0, 1
 CFG_NO_COLUMNS, CFG_EAGER_COLUMNS = 1, 2   # rg_config.flags (include/rucene_gpu.h)
 NO_MORE_DOCS = 0x7FFFFFFF

@@ -80,6 +80,22 @@ class BooleanQuery(Query):
 
 
 @dataclass
+class DisjunctionMaxQuery(Query):
+    disjuncts: List[Query]
+    tie_breaker_multiplier: float
+
+    @staticmethod
+    def build(disjuncts, tie_breaker_multiplier):
+        """search/query/disjunction_max_query.rs:51-68 — one disjunct is the disjunct itself."""
+        disjuncts = list(disjuncts)
+        if not disjuncts:
+            raise IllegalArgument("DisjunctionMaxQuery: sub query should not be empty!")
+        if len(disjuncts) == 1:
+            return disjuncts[0]
+        return DisjunctionMaxQuery(disjuncts, float(tie_breaker_multiplier))
+
+
+@dataclass
 class BM25Similarity:
     k1: float = DEFAULT_BM25_K1
     b: float = DEFAULT_BM25_B
@@ -207,6 +223,11 @@ class GpuIndexSearcher:
             for q in query.must_not_queries:
                 add(q, engine.MUST_NOT)
             return (begin, len(clauses) - begin, query.min_should_match, engine.Q_BOOLEAN)
+        if isinstance(query, DisjunctionMaxQuery):
+            for q in query.disjuncts:
+                add(q, engine.SHOULD)
+            tie_bits = int(np.array([query.tie_breaker_multiplier], np.float32).view(np.int32)[0])
+            return (begin, len(clauses) - begin, tie_bits, engine.Q_DISMAX)
         raise engine.Unsupported(engine.RG_EUNSUPPORTED, "query type is not accelerated")
 
     def compile_batch(self, queries):

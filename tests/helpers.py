@@ -90,6 +90,9 @@ def to_queries(specs):
     for s in specs:
         if s[0] == "term":
             out.append(S.TermQuery.new(S.Term.new("body", s[1]), s[2] if len(s) > 2 else 1.0, None))
+        elif s[0] == "dismax":
+            out.append(S.DisjunctionMaxQuery.build(
+                [S.TermQuery.new(S.Term.new("body", cl[0]), cl[1] if len(cl) > 1 else 1.0, None) for cl in s[1]], s[2]))
         else:
             musts, shoulds, nots = [], [], []
             for cl in s[1]:

@@ -182,7 +182,8 @@ class Index:
 
 
 def make_queries(specs):
-    """specs: list of ("term", term_id[, boost]) or ("bool", [(occur, term_id[, boost])...], msm).
+    """specs: list of ("term", term_id[, boost]), ("bool", [(occur, term_id[, boost])...], msm) or
+    ("dismax", [(term_id[, boost])...], tie_breaker_multiplier).
     Returns (queries, clauses) structured arrays for Index.search_batch."""
     qs, cs = [], []
     for s in specs:
@@ -190,6 +191,12 @@ def make_queries(specs):
             boost = s[2] if len(s) > 2 else 1.0
             qs.append((len(cs), 1, 0, 0))
             cs.append((SHOULD, s[1], boost))
+        elif s[0] == "dismax":  # ("dismax", [(term_id[, boost])...], tie_breaker_multiplier)
+            begin = len(cs)
+            for cl in s[1]:
+                cs.append((SHOULD, cl[0], cl[1] if len(cl) > 1 else 1.0))
+            tie_bits = int(np.array([s[2]], np.float32).view(np.int32)[0])
+            qs.append((begin, len(s[1]), tie_bits, 2))
         else:
             begin = len(cs)
             for cl in s[1]:

@@ -141,7 +141,10 @@ def _brute_force(seg_list, postings_list, ix, spec, k, stats=None):
     doc_base = 0
     for seg, postings in zip(seg_list, postings_list):
         kind = spec[0]
-        clauses = [(ob.SHOULD, spec[1], 1.0)] if kind == "term" else spec[1]
+        if kind == "dismax":
+            clauses = [(ob.SHOULD,) + tuple(cl) for cl in spec[1]]
+        else:
+            clauses = [(ob.SHOULD, spec[1], 1.0)] if kind == "term" else spec[1]
         per = []
         for occ, t, *rest in clauses:
             boost = rest[0] if rest else 1.0
@@ -181,6 +184,13 @@ def _brute_force(seg_list, postings_list, ix, spec, k, stats=None):
             msm = spec[2] if kind == "bool" and len(per) > 1 else 0
             if msm > 1:  # disjunction_scorer.rs:317-329
                 docs, score = docs[count >= msm], score[count >= msm]
+            if kind == "dismax" and len(shoulds) > 1:  # score_max, disjunction_scorer.rs:241-263
+                mx = np.full(len(docs), -np.inf, np.float32)
+                for _occ, d, sc in shoulds:
+                    pos = np.searchsorted(docs, d)
+                    mx[pos] = np.maximum(mx[pos], sc)
+                tie = np.float32(spec[2])
+                score = (mx + ((score - mx).astype(np.float32) * tie).astype(np.float32)).astype(np.float32)
         if seg.live_docs is not None:
             live = (seg.live_docs[docs >> 6] >> (docs & 63).astype(np.uint64)) & np.uint64(1)
             docs, score = docs[live == 1], score[live == 1]
@@ -335,3 +345,30 @@ def test_elias_fano_encoder_reference_vectors():
     out = np.zeros(64, np.int64)
     assert L.rc_ef_encode(vals.ctypes.data, 128, 510901, out.ctypes.data, 64, geom.ctypes.data) == 0
     assert list(geom) == [11, 6, 22, 0]       # 510901/128 = 3991 -> 11 low bits; (249 + 128) bits -> 6 longs
+
+
+def test_oracle_disjunction_max_matches_brute_force():
+    """DisjunctionMaxQuery over TermQuerys (query/disjunction_max_query.rs:51-155, scorer
+    disjunction_scorer.rs:106-186,241-263): max + (sum - max) * tie_breaker."""
+    rng = np.random.default_rng(430)
+    dfs = [0, 2, 90, 700, 5000, 14000, 26000]
+    segs, posts = [], []
+    for s in range(2):
+        d = list(dfs)
+        if s == 1:
+            d[5] = 0
+        seg, p = helpers.build_segment(rng, 30000 + 500 * s, d, live_fraction=0.9 if s else None)
+        segs.append(seg)
+        posts.append(p)
+    ix = helpers.oracle_index(segs)
+    specs = [("dismax", [(6,), (5,)], 0.0), ("dismax", [(6,), (5,), (4, 2.0), (3,)], 0.3),
+             ("dismax", [(4,), (0,), (6,)], 1.0), ("dismax", [(3,)], 0.5), ("dismax", [(5,), (2,)], 0.1)]
+    q, c = ob.make_queries(specs)
+    hits, counts, total = ix.search_batch(q, c, 20)
+    for i, spec in enumerate(specs):
+        d, s = _brute_force(segs, posts, ix, spec, 20)
+        want, _ = ob.topk_stream(d, s, 20)
+        assert total[i] == len(d), spec
+        got = hits[i][:counts[i]]
+        assert np.array_equal(got["doc"], want["doc"]), spec
+        assert np.array_equal(got["score"].view(np.uint32), want["score"].view(np.uint32)), spec

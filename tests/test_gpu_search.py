@@ -1,6 +1,8 @@
 """GPU parity: IndexSearcher::search through the C ABI vs the oracle — TopDocs identical
 (docids bit-exact, BM25 scores bit-exact f32 — tighter than the 1e-5 relative the north star
 allows —, same order under ties, same total_hits)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -27,7 +29,7 @@ def _mixed_specs(rng, n_terms, n, kinds=("term", "and", "or")):
     return specs
 
 
-def _run_both(segs, specs, k, mode=0, range_postings=0, threads=4):
+def _run_both(segs, specs, k, mode=0, range_postings=0, threads=4, extra_flags=0):
     ix = helpers.oracle_index(segs)
     q, c = ob.make_queries(specs)
     want = ix.search_batch(q, c, k, parallel_mode=mode, n_threads=threads)
@@ -35,7 +37,8 @@ def _run_both(segs, specs, k, mode=0, range_postings=0, threads=4):
     # and with a column for every clause of df >= max_doc/64 — both must equal the oracle
     got = None
     for flags in (engine.CFG_EAGER_COLUMNS, 0):
-        s = search.GpuIndexSearcher(search.IndexReader(segs), range_postings=range_postings, flags=flags)
+        s = search.GpuIndexSearcher(search.IndexReader(segs), range_postings=range_postings,
+                                    flags=flags | extra_flags)
         try:
             got = s.search_batch(helpers.to_queries(specs), k, mode=mode)
         finally:
@@ -258,6 +261,40 @@ def test_ef_and_bitset_doc_blocks(version, with_pf):
         for mode in (0, 1):
             got, want = _run_both(segs, specs, k, mode=mode, range_postings=rp)
             helpers.assert_same_topdocs(got, want, "ef v%d pf%d k=%d rp=%d mode=%d" % (version, with_pf, k, rp, mode))
+
+
+def test_disjunction_max_query():
+    """DisjunctionMaxQuery over TermQuerys (search/query/disjunction_max_query.rs:51-155;
+    DisjunctionMaxScorer, search/scorer/disjunction_scorer.rs:106-186,241-263): the union of the disjuncts,
+    score = max + (sum - max) * tie_breaker_multiplier.  One disjunct (in the query, or present in a leaf)
+    is that TermScorer.  Mixed into a batch with the other shapes; both collector modes; ranges; live docs."""
+    rng = np.random.default_rng(97)
+    dfs = [0, 1, 130, 900, 5000, 14000, 26000, 33000, 36000]
+    segs = []
+    for s, lf in enumerate((None, 0.85)):
+        d = list(dfs)
+        if s == 1:
+            d[5] = 0
+        segs.append(helpers.build_segment(rng, 38000 + 900 * s, d, live_fraction=lf)[0])
+    specs = [("dismax", [(8,), (7,)], 0.0),
+             ("dismax", [(8,), (7,), (6, 2.0), (5,), (4,)], 0.3),
+             ("dismax", [(4,), (5,), (0,)], 1.0),
+             ("dismax", [(3,)], 0.5),                                 # one disjunct: the TermQuery itself
+             ("dismax", [(5,), (2,)], 0.1),                           # one of them missing from the second leaf
+             ("dismax", [(8,), (7,), (6,), (5,), (4,), (3,), (2,), (1,), (0,)], 0.25),
+             ("dismax", [(6,), (6,)], 0.5)]
+    for i in range(24):
+        t = int(rng.integers(2, 6))
+        terms = [int(x) for x in rng.choice(len(dfs), size=t, replace=False)]
+        specs.append(("dismax", [(x, float(rng.choice([1.0, 0.5, 3.0]))) for x in terms],
+                      float(rng.choice([0.0, 0.1, 0.5, 1.0]))))
+    specs += _mixed_specs(rng, len(dfs), 12, kinds=("term", "and", "or"))
+    specs += [("bool", [(ob.SHOULD, 8), (ob.SHOULD, 7), (ob.SHOULD, 6)], 2),
+              ("bool", [(ob.SHOULD, 8), (ob.SHOULD, 6), (ob.MUST_NOT, 7)], 0)]
+    for k, rp in ((10, 0), (100, 2500)):
+        for mode in (0, 1):
+            got, want = _run_both(segs, specs, k, mode=mode, range_postings=rp)
+            helpers.assert_same_topdocs(got, want, "dismax k=%d rp=%d mode=%d" % (k, rp, mode))
 
 
 def test_reference_style_api():
