@@ -1,14 +1,19 @@
 // query_kernels.cu — the fused query-evaluation kernels (sm_100a, integer/HBM-bound work).
 //
-//   k_eval_or   : TermQuery / pure-SHOULD BooleanQuery (+ MUST_NOT).  One WARP per (query, segment,
-//                 docid range).  Every clause is a cached block stream: a posting block is unpacked,
-//                 prefix-summed (warp scan) and BM25-scored exactly once into shared memory; clauses
-//                 are drained in clause order into a warp-private window of 1024 docids — the f32
+//   k_build_columns: batch-level common subexpression — the BM25 contributions of a dense clause that
+//                 several disjunctions of the batch share, computed once into a docid-indexed f32 column.
+//   k_eval_or   : TermQuery / pure-SHOULD BooleanQuery (+ MUST_NOT, min_should_match) / DisjunctionMaxQuery.
+//                 One WARP per (query, segment, docid range).  Every clause is a cached block stream: a
+//                 posting block is unpacked (PF, or EF / BITSET by rank-select), prefix-summed (warp scan)
+//                 and BM25-scored exactly once — straight into the window when it falls inside it, else
+//                 into shared memory — or it is a score column read with 16-byte loads; clauses are
+//                 drained in clause order into a warp-private window of 768 docids — the f32
 //                 summation order of DisjunctionSumScorer::score_sum
 //                 (search/scorer/disjunction_scorer.rs:211-225).  Matches are counted when a doc is
 //                 first touched (total_hits); only docs whose sum can still beat the top-k heap root
 //                 are scanned and appended, in docid order, to the query's candidate list.
-//   k_eval_and  : pure-MUST BooleanQuery (+ MUST_NOT) (ConjunctionScorer, search/scorer/conjunction_scorer.rs).
+//   k_eval_and  : pure-MUST BooleanQuery (+ MUST_NOT) (ConjunctionScorer, search/scorer/conjunction_scorer.rs)
+//                 and MUST+SHOULD (ReqOptScorer: optional clauses + the sequential running-mean chain).
 //                 The cheapest list leads (stable sort by cost, :30); 8 lead blocks per step are
 //                 decoded, every lead doc locates its block in each other list via the level-0
 //                 skip table (galloping binary search), that block is decoded once per warp into
