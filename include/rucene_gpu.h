@@ -29,11 +29,15 @@ extern "C" {
 
 #define RG_NO_MORE_DOCS 0x7fffffff /* search/mod.rs:59 */
 
-/* rg_config.flags.  Score columns: the BM25 contributions of a dense clause that several
- * disjunctions of a batch share are materialised once per rg_batch_run into a docid-indexed f32
- * column (same f32 values the per-query path computes) and read from there. */
+/* rg_config.flags.  Presence bitmaps: every term with df >= max_doc/64 (largest first, within a byte
+ * budget) gets a bitmap over the leaf's docids at upload.  Score columns: the BM25 contributions of
+ * such a term for one (weight, norm cache, k1) are materialised into a docid-indexed f32 column (the
+ * same f32 values the per-query path computes) the first time two clauses of a batch share them, kept
+ * across batches (LRU within 1/3 of the free HBM) and read from there. */
 #define RG_CFG_NO_COLUMNS 1u    /* never materialise score columns */
 #define RG_CFG_EAGER_COLUMNS 2u /* a column for every disjunction clause with df >= max_doc/64 (tests) */
+#define RG_CFG_NO_BITMAPS 4u    /* no presence bitmaps at upload (and therefore no score columns) */
+#define RG_CFG_NO_MAXSCORE 8u   /* evaluate every disjunction with the exhaustive kernel (A/B runs, tests) */
 
 typedef struct rg_engine rg_engine;
 typedef struct rg_batch rg_batch;
@@ -111,6 +115,12 @@ void rg_engine_destroy(rg_engine* e);
 const char* rg_last_error(rg_engine* e);
 /* Launch on this cudaStream_t (e.g. torch's current stream); NULL = the engine's own stream. */
 int rg_engine_set_stream(rg_engine* e, void* cuda_stream);
+/* Change rg_config.flags of a live engine (planning-time flags take effect with the next
+ * rg_batch_prepare; RG_CFG_NO_BITMAPS only affects later uploads). */
+int rg_engine_set_flags(rg_engine* e, uint32_t flags);
+/* Persistent score columns: [0]=columns cached, [1]=their bytes in HBM, [2]=columns built so far,
+ * [3]=cache hits so far. */
+int rg_engine_column_stats(rg_engine* e, uint64_t out[4]);
 /* Number of this library's kernels launched so far (bench.py's gpu_launches). */
 uint64_t rg_engine_launch_count(rg_engine* e);
 /* Device-side timing of the last rg_batch_run / rg_blockset_decode, CUDA events on the launch
@@ -179,6 +189,13 @@ int rg_merge_leaf_records(rg_engine* e, const void* dev_records_all, uint32_t n_
 int rg_forutil_decode(rg_engine* e, const uint8_t* stream, size_t len, const uint64_t* offsets,
                       uint32_t n_blocks, int doc_version, const int32_t forutil_table[32],
                       int32_t* out);
+/* The same over an uploaded segment: block pairs [first_block, first_block + n_blocks) of its index image
+ * in file order, each decoded to 128 doc deltas + 128 freqs (BASELINE config 2, "realistic" blocks).
+ * out (host, n_blocks*256 int32) may be NULL: the decode then only runs and is timed
+ * (rg_engine_last_kernel_ms("decode")).  stats: [0]=encoded bytes read (pro rata of the segment's
+ * 1+payload per part), [1]=bytes written, [2]=blocks decoded, [3]=blocks in the segment. */
+int rg_segment_decode(rg_engine* e, uint32_t seg_ord, uint64_t first_block, uint64_t n_blocks, int32_t* out,
+                      uint64_t stats[4]);
 /* Staged variant: blocks are parsed once, their payload bytes copied unchanged into 16-byte
  * aligned slots in HBM; decode then runs with everything resident. */
 int rg_blockset_stage(rg_engine* e, const uint8_t* stream, size_t len, const uint64_t* offsets,

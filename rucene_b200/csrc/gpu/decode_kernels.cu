@@ -35,6 +35,36 @@ k_decode_staged(const uint4* __restrict__ arena, const BlockDesc* __restrict__ d
         if (first + u < n_blocks) stg16_streaming(out + (size_t)(first + u) * 32 + lane, v[u]);
 }
 
+// Every block pair [doc-delta block][freq block] of an uploaded segment, in file order (BASELINE config 2,
+// "realistic" value set): what ForUtil::read_block + read_block returns per pair (for_util.rs:187-243;
+// the doc part stays deltas).  out: n_blocks x (128 deltas, 128 freqs).  EF / BITSET doc parts are skipped
+// (they are not ForUtil-packed); their 128 output slots are left untouched.
+__global__ void __launch_bounds__(kDecodeThreads)
+k_decode_segment(const uint4* __restrict__ arena, const BlockDesc* __restrict__ desc, uint32_t first,
+                 uint32_t n_blocks, int4* __restrict__ out, int version, uint32_t sb_mask) {
+    const int lane = lane_id();
+    const uint32_t warp = (blockIdx.x * kDecodeThreads + threadIdx.x) >> 5;
+    const uint32_t b0 = warp * 2;
+    if (b0 >= n_blocks) return;
+    BlockDesc d[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) d[u] = desc[first + min(b0 + u, n_blocks - 1)];
+    int4 dv[2], fv[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        const uint4* part = arena + d[u].off16;
+        dv[u] = (d[u].bits >> 24) ? make_int4(0, 0, 0, 0) : unpack4(part, (int)(d[u].bits & 0xff), lane, version, sb_mask);
+        fv[u] = unpack4(part + ((d[u].bits >> 16) & 0xff), (int)((d[u].bits >> 8) & 0xff), lane, version, sb_mask);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        if (b0 + u >= n_blocks) break;
+        int4* o = out + (size_t)(b0 + u) * 64 + lane;
+        if (!(d[u].bits >> 24)) stg16_streaming(o, dv[u]);
+        stg16_streaming(o + 32, fv[u]);
+    }
+}
+
 // ---- in-place decode of the raw stream ----------------------------------------------------
 // 32-bit little-endian word at an arbitrary byte address, from two aligned loads.
 __device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t* __restrict__ p) {
@@ -123,6 +153,15 @@ void launch_decode_staged(cudaStream_t st, const uint4* arena, const BlockDesc* 
     const uint32_t ctas = (warps + (kDecodeThreads / 32) - 1) / (kDecodeThreads / 32);
     k_decode_staged<<<ctas, kDecodeThreads, 0, st>>>(arena, desc, n_blocks,
                                                      reinterpret_cast<int4*>(out), version, sb_mask);
+}
+
+void launch_decode_segment(cudaStream_t st, const uint4* arena, const BlockDesc* desc, uint32_t first,
+                           uint32_t n_blocks, int32_t* out, int version, uint32_t sb_mask) {
+    if (n_blocks == 0) return;
+    const uint32_t warps = (n_blocks + 1) / 2;
+    const uint32_t ctas = (warps + (kDecodeThreads / 32) - 1) / (kDecodeThreads / 32);
+    k_decode_segment<<<ctas, kDecodeThreads, 0, st>>>(arena, desc, first, n_blocks, reinterpret_cast<int4*>(out),
+                                                      version, sb_mask);
 }
 
 void launch_decode_raw(cudaStream_t st, const uint8_t* stream, const uint64_t* offsets,

@@ -246,6 +246,44 @@ int32_t other_block_last_doc(const BlockSrc& b, int32_t ef_base_doc) {
     return (int32_t)((((pos - (kBlock - 1)) << L) | low) + 1 + ef_base_doc);
 }
 
+// all docids of an EF / BITSET block (host side, upload-time validation); returns how many were found (<= 128)
+int other_block_docs(const BlockSrc& b, int32_t ef_base_doc, int32_t* out) {
+    int n = 0;
+    if (b.enc == 2) {
+        for (int w = 0; w < b.hdr[1]; w++) {
+            uint64_t x = le64(b.doc_src + 8 * (size_t)w);
+            while (x) {
+                if (n == kBlock) return kBlock + 1;
+                out[n++] = b.hdr[0] + 64 * w + __builtin_ctzll(x);
+                x &= x - 1;
+            }
+        }
+        return n;
+    }
+    const int L = b.hdr[0];
+    const uint8_t* lo = b.doc_src + 8 * (size_t)b.hdr[1];
+    for (int w = 0; w < b.hdr[1] && n < kBlock; w++) {
+        uint64_t x = le64(b.doc_src + 8 * (size_t)w);
+        while (x && n < kBlock) {
+            const int64_t pos = 64 * (int64_t)w + __builtin_ctzll(x);
+            x &= x - 1;
+            int64_t low = 0;
+            if (L) {
+                const int64_t bitpos = (int64_t)L * n;
+                const size_t wi = (size_t)(bitpos >> 6);
+                const int at = (int)(bitpos & 63);
+                uint64_t v = le64(lo + 8 * wi) >> at;
+                if (at + L > 64) v |= le64(lo + 8 * (wi + 1)) << (64 - at);
+                low = (int64_t)(v & ((1ull << L) - 1));
+            }
+            const int64_t doc = (((pos - n) << L) | low) + 1 + ef_base_doc;
+            if (doc < 0 || doc > 0x7ffffffe) return -1;
+            out[n++] = (int32_t)doc;
+        }
+    }
+    return n;
+}
+
 struct TermParse {
     uint32_t n_blocks = 0;
     const uint8_t* tail_src = nullptr;
@@ -258,12 +296,13 @@ inline uint32_t part_units(int sz) { return sz == 0 ? 1u : (uint32_t)((sz + 15) 
 
 // Walk one term's region (posting_writer.rs:334-351,491-502 layout; skip level 0 per
 // skip_writer.rs:209-226,241-259).
-void parse_term(const uint8_t* file, size_t len, const DocHeader& h, const rg_term_state& ts,
+void parse_term(const uint8_t* file, size_t len, const DocHeader& h, const rg_term_state& ts, int32_t max_doc,
                 std::vector<BlockSrc>& blocks, TermParse& tp) {
     const int df = ts.doc_freq;
     tp = TermParse();
     if (df <= 0) return;
     if (df == 1) {
+        if (ts.singleton_doc_id < 0 || ts.singleton_doc_id >= max_doc) throw ArgError("singleton_doc_id outside [0, max_doc)");
         tp.tail_n = 1;
         return;
     }
@@ -318,8 +357,10 @@ void parse_term(const uint8_t* file, size_t len, const DocHeader& h, const rg_te
     tp.tail_n = (uint32_t)(df % kBlock);
     tp.tail_src = file + in.pos;
     size_t tail_start = in.pos;
+    int64_t tail_delta_sum = 0;
     for (uint32_t i = 0; i < tp.tail_n; i++) {
         uint32_t code = (uint32_t)in.vint();
+        tail_delta_sum += code >> 1;
         if (!(code & 1)) in.vint();
     }
     tp.tail_bytes = (uint32_t)(in.pos - tail_start);
@@ -365,6 +406,27 @@ void parse_term(const uint8_t* file, size_t len, const DocHeader& h, const rg_te
         blocks[first + i].last_doc = last;
     }
     tp.tail_base = nb ? last : 0;
+    // The kernels index norms / live docs / windows with these docids: a corrupt file must fail here
+    // (RG_EINVAL), not as an out-of-bounds device access.
+    int32_t prev = -1;
+    for (uint32_t i = 0; i < nb; i++) {
+        const BlockSrc& b = blocks[first + i];
+        if (b.last_doc <= prev || b.last_doc >= max_doc || (int64_t)b.last_doc - prev < kBlock)
+            throw ArgError("corrupt postings: block last docids must increase by >= 128 and stay below max_doc");
+        if (b.enc) {  // EF / BITSET: every docid of the block, decoded here once, must be increasing in (prev, last_doc]
+            int32_t docs[kBlock];
+            if (other_block_docs(b, prev, docs) != kBlock) throw ArgError("corrupt EF/BITSET doc block: not 128 docids");
+            int32_t q = prev;
+            for (int k = 0; k < kBlock; k++) {
+                if (docs[k] <= q) throw ArgError("corrupt EF/BITSET doc block: docids not increasing");
+                q = docs[k];
+            }
+            if (q != b.last_doc) throw ArgError("corrupt EF/BITSET doc block: disagrees with the skip data");
+        }
+        prev = b.last_doc;
+    }
+    if (tp.tail_n && (int64_t)tp.tail_base + tail_delta_sum >= (int64_t)max_doc)
+        throw ArgError("corrupt postings: vint tail runs past max_doc");
 }
 
 int hw_threads() {
@@ -448,7 +510,7 @@ void build_segment(rg_engine* e, Segment& seg, int32_t doc_base, int32_t max_doc
         Chunk& ch = chunks[ci];
         ch.tp.resize(ch.t1 - ch.t0);
         for (uint32_t t = ch.t0; t < ch.t1; t++) {
-            parse_term(file, len, h, terms[t], ch.blocks, ch.tp[t - ch.t0]);
+            parse_term(file, len, h, terms[t], max_doc, ch.blocks, ch.tp[t - ch.t0]);
         }
         for (const BlockSrc& b : ch.blocks) ch.units += part_units(b.doc_sz) + part_units(b.freq_sz);
         for (const TermParse& tp : ch.tp) ch.tail_bytes += tp.tail_bytes;
@@ -529,7 +591,11 @@ void build_segment(rg_engine* e, Segment& seg, int32_t doc_base, int32_t max_doc
     if (live) upload(seg.live, live, ((size_t)max_doc + 63) / 64, st);
     RG_CUDA_CHECK(cudaStreamSynchronize(st));
     for (const Chunk& ch : chunks)
-        for (const BlockSrc& b : ch.blocks) seg.has_other_enc = seg.has_other_enc || b.enc != 0;
+        for (const BlockSrc& b : ch.blocks) {
+            seg.has_other_enc = seg.has_other_enc || b.enc != 0;
+            seg.block_enc_bytes += 2ull + (b.doc_sz ? b.doc_sz : 1u) + (b.freq_sz ? b.freq_sz : 1u);
+        }
+    seg.n_blocks_total = n_blocks;
     e->col_budget_floats = 0;
     seg.doc_base = doc_base;
     seg.max_doc = max_doc;
@@ -545,8 +611,43 @@ void build_segment(rg_engine* e, Segment& seg, int32_t doc_base, int32_t max_doc
     seg.dev.n_terms = n_terms;
     seg.dev.version = h.version;
     seg.dev.sb_mask = h.sb_mask;
-    seg.device_bytes = seg.arena.bytes() + seg.blk_last.bytes() + seg.blk_desc.bytes() +
-                       seg.tails.bytes() + seg.terms.bytes() + seg.norms.bytes() + seg.live.bytes();
+    // ---- presence bitmaps of the dense terms (device-side: one warp per block sets 128 bits)
+    seg.bitmap_slot.assign(n_terms, -1);
+    if (!(e->cfg.flags & RG_CFG_NO_BITMAPS)) {
+        std::vector<uint32_t> dense;
+        for (uint32_t t = 0; t < n_terms; t++)
+            if ((uint64_t)std::max(terms[t].doc_freq, 0) * kBitmapDen >= (uint64_t)max_doc && terms[t].doc_freq >= 2)
+                dense.push_back(t);
+        std::sort(dense.begin(), dense.end(), [&](uint32_t a, uint32_t b) {
+            return terms[a].doc_freq != terms[b].doc_freq ? terms[a].doc_freq > terms[b].doc_freq : a < b;
+        });
+        seg.bitmap_words = (((uint64_t)max_doc + 31) / 32 + 64 + 3) & ~3ull;
+        const uint64_t budget = std::max<uint64_t>(64ull << 20, seg.arena.bytes());  // bytes
+        const size_t n_bm = (size_t)std::min<uint64_t>(dense.size(), budget / (seg.bitmap_words * 4));
+        if (n_bm) {
+            dense.resize(n_bm);
+            seg.bitmaps.alloc(n_bm * seg.bitmap_words);
+            RG_CUDA_CHECK(cudaMemsetAsync(seg.bitmaps.p, 0, seg.bitmaps.bytes(), st));
+            std::vector<ColumnJob> jobs(n_bm);
+            uint32_t units = 0;
+            for (size_t i = 0; i < n_bm; i++) {
+                const uint32_t t = dense[i];
+                seg.bitmap_slot[t] = (int32_t)i;
+                jobs[i] = ColumnJob{0u, t, 0u, 0.0f, seg.bitmaps.p + i * seg.bitmap_words, units, 0u};
+                units += seg.host_terms[t].n_blocks + (seg.host_terms[t].tail_n ? 1u : 0u);
+            }
+            DevBuf<SegDev> d_seg;
+            DevBuf<ColumnJob> d_jobs;
+            upload(d_seg, &seg.dev, 1, st);
+            upload(d_jobs, jobs.data(), jobs.size(), st);
+            launch_build_bitmaps(st, d_seg.p, d_jobs.p, (uint32_t)n_bm, units);
+            RG_CUDA_CHECK(cudaGetLastError());
+            e->launches++;
+            RG_CUDA_CHECK(cudaStreamSynchronize(st));
+        }
+    }
+    seg.device_bytes = seg.arena.bytes() + seg.blk_last.bytes() + seg.blk_desc.bytes() + seg.tails.bytes() +
+                       seg.terms.bytes() + seg.norms.bytes() + seg.live.bytes() + seg.bitmaps.bytes();
 }
 
 }  // namespace rg
@@ -646,6 +747,26 @@ int rg_engine_set_stream(rg_engine* e, void* s) {
 
 uint64_t rg_engine_launch_count(rg_engine* e) { return e ? e->launches : 0; }
 
+int rg_engine_set_flags(rg_engine* e, uint32_t flags) {
+    RG_TRY
+    if (!e) throw ArgError("engine is null");
+    // RG_CFG_NO_BITMAPS acts at upload time: it cannot be cleared once a segment went up without bitmaps
+    e->cfg.flags = flags;
+    return RG_OK;
+    RG_CATCH
+}
+
+int rg_engine_column_stats(rg_engine* e, uint64_t out[4]) {
+    RG_TRY
+    if (!e || !out) throw ArgError("null argument");
+    out[0] = e->col_cache.size();
+    out[1] = e->col_floats * sizeof(float);
+    out[2] = e->col_builds;
+    out[3] = e->col_hits;
+    return RG_OK;
+    RG_CATCH
+}
+
 float rg_engine_last_kernel_ms(rg_engine* e, const char* which) {
     if (!e || !which) return -1.f;
     std::string w(which);
@@ -676,6 +797,7 @@ int rg_segment_upload(rg_engine* e, uint32_t seg_ord, int32_t doc_base, int32_t 
     build_segment(e, seg, doc_base, max_doc, doc_file, doc_len, norms, live_docs, terms, n_terms);
     e->segs.push_back(std::move(seg));
     e->segs_dirty = true;
+    e->generation++;  // batches prepared before this upload are stale (rg_batch_run checks)
     return RG_OK;
     RG_CATCH
 }
@@ -687,11 +809,56 @@ int rg_norm_cache_set(rg_engine* e, uint32_t cache_id, const float cache[256]) {
     if (e->h_caches.size() < (size_t)(cache_id + 1) * 256) e->h_caches.resize((size_t)(cache_id + 1) * 256, 0.f);
     memcpy(&e->h_caches[(size_t)cache_id * 256], cache, 256 * sizeof(float));
     e->caches_dirty = true;
+    e->generation++;
+    if (e->cache_nonneg.size() <= cache_id) e->cache_nonneg.resize(cache_id + 1, 0);
+    bool nonneg = true;
+    for (int i = 0; i < 256; i++) nonneg = nonneg && cache[i] >= 0.0f;  // false for NaN as well
+    e->cache_nonneg[cache_id] = nonneg ? 1 : 0;
+    // score columns computed with the previous contents of this cache are no longer valid
+    for (auto it = e->col_cache.begin(); it != e->col_cache.end();) {
+        if (std::get<3>(it->first) == cache_id) {
+            e->col_floats -= it->second->len;
+            it = e->col_cache.erase(it);
+        } else {
+            ++it;
+        }
+    }
     return RG_OK;
     RG_CATCH
 }
 
 // ---------------------------------------------------------------- block codec entry points
+int rg_segment_decode(rg_engine* e, uint32_t seg_ord, uint64_t first_block, uint64_t n_blocks, int32_t* out,
+                      uint64_t stats[4]) {
+    RG_TRY
+    if (!e || !stats) throw ArgError("null argument");
+    if (seg_ord >= e->segs.size()) throw ArgError("no such segment");
+    const Segment& seg = e->segs[seg_ord];
+    if (first_block > seg.n_blocks_total) throw ArgError("first_block out of range");
+    n_blocks = std::min<uint64_t>(n_blocks, seg.n_blocks_total - first_block);
+    RG_CUDA_CHECK(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    DevBuf<int32_t> d_out;
+    d_out.alloc(std::max<uint64_t>(1, n_blocks) * 2 * kBlock);
+    if (out) RG_CUDA_CHECK(cudaMemsetAsync(d_out.p, 0, d_out.bytes(), st));
+    RG_CUDA_CHECK(cudaEventRecord(e->ev0, st));
+    launch_decode_segment(st, seg.arena.p, seg.blk_desc.p, (uint32_t)first_block, (uint32_t)n_blocks, d_out.p,
+                          seg.dev.version, seg.dev.sb_mask);
+    RG_CUDA_CHECK(cudaGetLastError());
+    if (n_blocks) e->launches++;
+    RG_CUDA_CHECK(cudaEventRecord(e->ev1, st));
+    if (out) RG_CUDA_CHECK(cudaMemcpyAsync(out, d_out.p, n_blocks * 2 * kBlock * 4, cudaMemcpyDeviceToHost, st));
+    RG_CUDA_CHECK(cudaStreamSynchronize(st));
+    RG_CUDA_CHECK(cudaEventElapsedTime(&e->last_decode_ms, e->ev0, e->ev1));
+    stats[0] = seg.n_blocks_total ? seg.block_enc_bytes * n_blocks / seg.n_blocks_total : 0;  // pro rata
+    stats[1] = n_blocks * 2 * kBlock * 4;
+    stats[2] = n_blocks;
+    stats[3] = seg.n_blocks_total;
+    return RG_OK;
+    RG_CATCH
+}
+
+
 static void table_to_header(int doc_version, const int32_t forutil_table[32], DocHeader& h) {
     if (!forutil_table) throw ArgError("forutil_table is null");
     if (doc_version < 0 || doc_version > 1) throw ArgError("doc_version must be 0 or 1");

@@ -3,8 +3,11 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <map>
+#include <memory>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "common.cuh"
@@ -62,6 +65,28 @@ struct DevBuf {
     size_t bytes() const { return n * sizeof(T); }
 };
 
+// A score column as the kernels see it: f32 BM25 contribution per leaf-local docid (0xffffffff = no
+// posting) + the term's presence bitmap (null when the term has none).
+struct ColRef {
+    const float* col;
+    const uint32_t* bits;
+};
+
+// Persistent score column (engine-owned, LRU): the contributions of one (leaf, term, weight, norm
+// cache, k1) are the same f32 values for every query that carries the clause, in this batch and in
+// later ones, so they are materialised once and kept while HBM allows.
+using ColKey = std::tuple<uint32_t, uint32_t, uint32_t, uint32_t, uint32_t>;  // leaf, term, weight bits, cache, k1 bits
+struct ColEntry {
+    ColKey key;
+    float* col = nullptr;  // cudaMalloc'ed, len floats
+    const uint32_t* bits = nullptr;
+    uint64_t len = 0;
+    uint64_t last_use = 0;
+    ~ColEntry() {
+        if (col) cudaFree(col);
+    }
+};
+
 // host-side view of a term (for planning and byte accounting)
 struct TermHost {
     int32_t doc_freq = 0;
@@ -81,6 +106,16 @@ struct Segment {
     DevBuf<uint8_t> norms;
     DevBuf<uint64_t> live;
     bool has_other_enc = false;  // some doc block is EF / BITSET encoded
+    uint64_t n_blocks_total = 0;
+    uint64_t block_enc_bytes = 0;  // sum over block pairs of (1 + payload) per part, as the codec wrote them
+    // Presence bitmaps of the dense terms (df >= max_doc / kBitmapDen, largest first, within a byte
+    // budget): bit d of a term's bitmap = "the term has a posting on docid d".  Built once at upload
+    // (k_build_bitmaps); total_hits of a disjunction is then a popcount over ORed words and the
+    // non-essential clauses of k_eval_or_ms never have to be decoded.  bitmap_words = words per term
+    // (max_doc/32 rounded up + 64 zero words so a 1024-doc window may read past max_doc).
+    DevBuf<uint32_t> bitmaps;
+    uint64_t bitmap_words = 0;
+    std::vector<int32_t> bitmap_slot;  // per term: index of its bitmap, -1 = none
     std::vector<TermHost> host_terms;
     int32_t doc_base = 0, max_doc = 0;
     uint64_t device_bytes = 0;
@@ -89,6 +124,8 @@ struct Segment {
 // kernel launchers (decode_kernels.cu)
 void launch_decode_staged(cudaStream_t st, const uint4* arena, const BlockDesc* desc,
                           uint32_t n_blocks, int32_t* out, int version, uint32_t sb_mask);
+void launch_decode_segment(cudaStream_t st, const uint4* arena, const BlockDesc* desc, uint32_t first,
+                           uint32_t n_blocks, int32_t* out, int version, uint32_t sb_mask);
 void launch_decode_raw(cudaStream_t st, const uint8_t* stream, const uint64_t* offsets,
                        uint32_t n_blocks, int32_t* out, int version, uint32_t sb_mask);
 
@@ -98,8 +135,7 @@ struct EvalParams {
     const WorkItem* items;
     const ItemClause* clauses;
     const float* caches;       // n_caches * 256
-    const float* col_base;     // score columns of this batch (see k_build_columns): column c, leaf-local
-    const uint64_t* col_off;   //   docid d lives at col_base[col_off[c] + d]
+    const ColRef* cols;        // score columns referenced by this batch (see k_build_columns)
     uint32_t n_items;
     uint32_t k;
     float k1;
@@ -112,18 +148,24 @@ struct EvalParams {
     uint32_t* item_theta;      // ordered-uint running k-th best, chained item -> item+1
     uint32_t* error_flag;      // bit0: arena exhausted
 };
-// one score column to materialise: the BM25 contributions of (leaf, term, weight, norm cache)
+// one score column to materialise: the BM25 contributions of (leaf, term, weight, norm cache, k1);
+// a bitmap job (weight unused) sets presence bits instead
 struct ColumnJob {
     uint32_t seg, term_id, cache_id;
     float weight;         // idf * boost, as in the clause
-    uint64_t col_off;     // offset (floats) of the column inside the engine's column arena
+    void* dst;            // float* column (leaf-local docid index) or uint32_t* bitmap
     uint32_t unit_begin;  // first work unit (block / tail) of this job in the launch
     uint32_t pad;
 };
 void launch_build_columns(cudaStream_t st, const SegDev* segs, const ColumnJob* jobs, uint32_t n_jobs,
-                          uint32_t n_units, const float* caches, float k1, float* col_base);
+                          uint32_t n_units, const float* caches, float k1);
+void launch_build_bitmaps(cudaStream_t st, const SegDev* seg, const ColumnJob* jobs, uint32_t n_jobs,
+                          uint32_t n_units);
 void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n,
                     uint32_t max_terms, bool has_live, bool has_not, bool has_msm, bool has_dmax);
+// eval_or_ms.cu: pure-SHOULD sum disjunctions whose dense clauses all have a score column + bitmap
+void launch_eval_or_ms(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n,
+                       uint32_t max_streams, bool has_live);
 void launch_eval_and(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, bool req_opt,
                      bool has_other_enc);
 
@@ -167,8 +209,15 @@ struct rg_engine {
     std::vector<float> h_caches;
     bool caches_dirty = true;
     rg::DevBuf<rg_hit> cand_arena;
-    rg::DevBuf<float> col_arena;        // score columns of the batch being run (grow-only)
-    uint64_t col_budget_floats = 0;     // cap on col_arena; 0 = not computed yet (reset by rg_segment_upload)
+    // persistent score columns: map-resident entries count against col_budget_floats (1/3 of the free
+    // HBM when first needed); batches hold shared_ptrs, so an evicted / invalidated column lives until
+    // the last batch that references it is destroyed
+    std::map<rg::ColKey, std::shared_ptr<rg::ColEntry>> col_cache;
+    uint64_t col_floats = 0;            // floats held by map-resident entries
+    uint64_t col_budget_floats = 0;     // 0 = not computed yet (reset by rg_segment_upload)
+    uint64_t col_tick = 0, col_builds = 0, col_hits = 0;
+    uint64_t generation = 1;            // bumped by rg_segment_upload / rg_norm_cache_set (stale-batch check)
+    std::vector<uint8_t> cache_nonneg;  // per norm cache: every entry >= 0 (MaxScore bound needs it)
     rg::DevBuf<uint8_t> merge_scratch;  // rg_merge_leaf_records outputs (grow-only)
     rg::DevBuf<uint8_t> spare_slab;  // device slab of the last destroyed rg_batch, reused by the next
     uint64_t launches = 0;

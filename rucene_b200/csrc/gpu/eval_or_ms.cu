@@ -1,0 +1,378 @@
+// eval_or_ms.cu — k_eval_or_ms: pure-SHOULD sum disjunctions (DisjunctionSumScorer, TermScorer) over
+// presence bitmaps + score columns, with MaxScore-style non-essential clauses.  sm_100a, integer/HBM work.
+//
+// What the reference computes (search/scorer/disjunction_scorer.rs:187-244, bulk_scorer.rs:89-122,
+// collector/top_docs.rs:67-95) is, per (query, leaf): total_hits = |union of the clauses' live docs| and the
+// TopDocsCollector heap fed with every union doc in docid order, score = clause-order f32 sum.  A doc changes
+// the heap only if root.score < score.  With theta = a proven lower bound of the heap root at that point
+// (eval_shared.cuh) the evaluation splits into
+//   * counting   — needs presence only.  Dense terms carry a presence bitmap built at upload, so a
+//                  clause that is a score column costs one 32-bit word per 32 docids: popc(OR of words);
+//   * candidates — only docs whose score can exceed theta.  Column clauses are ordered by their score
+//                  bound ub = nextafter(weight*(k1+1)) (BM25's tf-norm factor is < 1 for norm >= 0); the
+//                  longest prefix whose rounded-up sum S stays <= theta is NON-ESSENTIAL: a doc that
+//                  matches only such clauses scores <= S <= theta <= root and can never be collected into
+//                  the heap.  Every doc that matches an essential clause (block-stream clauses always are)
+//                  gets its exact score: clauses are visited in clause order and add into a per-window
+//                  accumulator, block streams by scatter, columns by gathering col[d] for the docs of the
+//                  window's essential set E that carry the clause's bit.
+// Because the low-idf (dense) clauses are the ones that become non-essential once k better docs were seen,
+// most of a long disjunction's postings are never decoded or scored, only counted — and the result is still
+// bit-identical to the reference, ties included, because the heap replay sees every doc that could enter.
+//
+// Work item = (query, leaf, docid range), one WARP each.  The warp walks windows of up to 1024 docids
+// (lane l owns presence word l); a window starts at the next posting of an essential clause and ends where
+// a stream's cached block ends (so every stream posting of the window is in shared memory before the
+// clause-ordered pass starts); the docids between windows hold non-essential postings only and are
+// counted in bulk from the bitmaps.
+#include "eval_shared.cuh"
+
+namespace rg {
+
+constexpr int kMsWarps = 4;
+constexpr int kMsThreads = kMsWarps * 32;
+constexpr int kMsW = 1024;  // docids per window = 32 lanes x one 32-bit presence word
+
+struct MsCol {
+    const float* col;      // leaf-local docid -> BM25 contribution (valid where the bitmap has a bit)
+    const uint32_t* bits;  // presence bitmap of the term
+};
+
+struct alignas(16) MsWarpShared {  // followed by topk[kcap] floats, then cdocs[S][128], cscores[S][128]
+    float acc[kMsW];               // 0.0f = untouched; touched docs are exactly the bits of E
+    uint32_t ubits[32];            // presence words of the block-stream clauses in this window
+    WTerm term[kMaxTerms];         // block-stream clauses (same cursor as k_eval_or)
+    MsCol colv[kMaxTerms];
+    float newc[kNewcW];
+};
+
+// docs of [a, b) present in any column clause (and live): bulk popcount over the bitmaps; per-lane partial sum
+template <bool LIVE>
+__device__ __forceinline__ uint32_t ms_count_range(const MsWarpShared& sh, uint32_t col_mask, const SegDev& seg,
+                                                   int a, int b, int lane) {
+    uint32_t cnt = 0;
+    const int w_end = (b + 31) >> 5;
+    for (int w = (a >> 5) + lane; w < w_end; w += 32) {
+        const int d0 = w << 5;
+        uint32_t m = 0xffffffffu;
+        if (d0 < a) m &= ~((1u << (a - d0)) - 1u);
+        if (d0 + 32 > b) m &= (1u << (b - d0)) - 1u;
+        uint32_t u = 0;
+        for (uint32_t cm = col_mask; cm; cm &= cm - 1) u |= __ldg(sh.colv[__ffs(cm) - 1].bits + w);
+        u &= m;
+        if (LIVE && seg.live) u &= reinterpret_cast<const uint32_t*>(seg.live)[w];
+        cnt += __popc(u);
+    }
+    return cnt;
+}
+
+template <bool LIVE>
+__global__ void __launch_bounds__(kMsThreads, 5)
+k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, uint32_t warp_bytes,
+             uint32_t kcap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t wid = blockIdx.x * kMsWarps + warp;
+    if (wid >= n_ids) return;
+    unsigned char* sbase = smem_raw + (size_t)warp * warp_bytes;
+    MsWarpShared& sh = *reinterpret_cast<MsWarpShared*>(sbase);
+    float* topk = reinterpret_cast<float*>(sbase + sizeof(MsWarpShared));
+    int32_t* cdocs = reinterpret_cast<int32_t*>(topk + kcap);
+    const uint32_t item_idx = item_ids[wid];
+    const WorkItem it = p.items[item_idx];
+    const SegDev seg = p.segs[it.seg];
+    const int T = it.n_terms;
+    const int lo = it.lo, hi = it.hi;
+
+    // ---- clauses: lane t < T owns clause t
+    bool is_col = false;
+    float ub = 0.0f;  // score bound of a column clause (INF: never non-essential)
+    ItemClause c{};
+    if (lane < T) {
+        c = p.clauses[it.clause_begin + lane];
+        is_col = (c.flags & 4u) != 0;
+    }
+    const uint32_t col_mask = __ballot_sync(0xffffffffu, is_col);
+    const uint32_t stream_mask = __ballot_sync(0xffffffffu, lane < T && !is_col);
+    const int n_streams = __popc(stream_mask);
+    float* cscores = reinterpret_cast<float*>(cdocs + n_streams * kBlock);
+    const int my_slot = __popc(stream_mask & ((1u << lane) - 1u));  // stream cache slot of clause `lane`
+    if (is_col) {
+        const ColRef r = p.cols[c.term_id];
+        sh.colv[lane] = MsCol{r.col, r.bits};
+        const float w1 = __fmul_rn(c.weight, __fadd_rn(p.k1, 1.0f));
+        // score = rn(rn(w1*f) / rn(f + norm)) with f >= 1, norm >= 0  =>  score <= nextafter(w1)
+        ub = (c.flags & 16u) || !(w1 >= 0.0f) || !(w1 < INFINITY) ? INFINITY : __uint_as_float(__float_as_uint(w1) + 1u);
+    } else if (lane < T) {
+        const TermDev td = seg.terms[c.term_id];
+        WTerm& tc = sh.term[lane];
+        tc.is_col = 0;
+        tc.blk_last = seg.blk_last + td.blk_begin;
+        tc.blk_desc = seg.blk_desc + td.blk_begin;
+        tc.cache = p.caches + (size_t)c.cache_id * 256;
+        tc.nb = td.n_blocks;
+        tc.cur = lower_bound_i32(tc.blk_last, 0, td.n_blocks, lo);
+        tc.n = 0;
+        tc.pos = 0;
+        tc.term_id = c.term_id;
+        tc.w1 = __fmul_rn(c.weight, __fadd_rn(p.k1, 1.0f));
+        tc.is_not = 0;
+    }
+    // non-essential test: clause t is non-essential while S_t <= theta, S_t = rounded-up sum of the bounds of the
+    // column clauses ordered before-or-at t by (ub, clause index), inflated by 2^-20 so it also covers the
+    // rounding of the reference's round-to-nearest clause-order sum of up to 9 scores
+    float ne_bound = INFINITY;
+    {
+        float S = 0.0f;
+        for (int j = 0; j < T; j++) {
+            const float ubj = __shfl_sync(0xffffffffu, ub, j);
+            if (((col_mask >> j) & 1u) && (ubj < ub || (ubj == ub && j <= lane))) S = __fadd_ru(S, ubj);
+        }
+        if (is_col && ub < INFINITY) ne_bound = __fmul_ru(S, 1.00000095367431640625f);
+    }
+    for (int i = lane; i < kMsW / 4; i += 32) reinterpret_cast<float4*>(sh.acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+
+    MsmCtx mc_unused{nullptr, 1u, nullptr};
+    uint32_t hot_unused = 0, mm_unused = 0;
+    int nd = kNoMoreDocs;  // stream lane t: next cached docid of clause t (kNoMoreDocs = exhausted)
+    for (uint32_t m = stream_mask; m; m &= m - 1) {
+        const int t = __ffs(m) - 1;
+        const int slot = __popc(stream_mask & ((1u << t) - 1u));
+        if (stream_refill<false, false, false, false>(seg, p, sh.term[t], cdocs + slot * kBlock, cscores + slot * kBlock, lo,
+                                                      hi, lane, 0, -2147483647 - 1, reinterpret_cast<uint32_t*>(sh.acc), hot_unused, mm_unused,
+                                                      INFINITY, mc_unused)) {
+            const int first = cdocs[slot * kBlock + sh.term[t].pos];
+            if (lane == t) nd = first;
+        }
+    }
+
+    WEmit em;
+    em.topk = topk;
+    em.topk_n = 0;
+    em.theta_local = -INFINITY;
+    em.theta_in = 0;
+    em.run_slot = kNone;
+    em.run_cap = 0;
+    em.run_cnt = 0;
+    em.matches = 0;
+    em.overflow = false;
+    const bool lb_ok = (uint32_t)lane < it.chain_pos;
+    const uint32_t* theta_lb = p.item_theta + item_idx - 1 - (lb_ok ? lane : 0);
+    uint32_t win_no = 0;
+    uint32_t my_matches = 0;
+    int pos = lo;  // every docid < pos is counted and, where needed, scored
+
+    for (;;) {
+        uint32_t inherited = 0;
+        if ((win_no++ & 7u) == 0 && it.chain_pos) {
+            inherited = lb_ok ? ld_volatile_u32(theta_lb) : 0u;
+            inherited = __reduce_max_sync(0xffffffffu, inherited);
+        }
+        em.theta_in = max(em.theta_in, inherited);
+        float te = em.theta_local;
+        if (em.theta_in > kOrderedNegInf) te = fmaxf(te, ordered_to_float(em.theta_in));
+        const bool open = te == -INFINITY;
+        const uint32_t ne_mask = open ? 0u : __ballot_sync(0xffffffffu, is_col && ne_bound <= te);
+        const uint32_t ess_cols = col_mask & ~ne_mask;
+        // ---- next window: the next posting of an essential clause (an essential column has one anywhere)
+        int w0 = __reduce_min_sync(0xffffffffu, is_col ? kNoMoreDocs : nd);
+        if (ess_cols) w0 = pos;
+        if (w0 >= hi) {  // nothing essential left: the rest of the range is only counted
+            if (col_mask && pos < hi) my_matches += ms_count_range<LIVE>(sh, col_mask, seg, pos, hi, lane);
+            break;
+        }
+        if (col_mask && w0 > pos) my_matches += ms_count_range<LIVE>(sh, col_mask, seg, pos, w0, lane);
+        const int win0 = w0;
+        const int base = win0 & ~31;
+        int win1 = min(hi, base + kMsW);
+        {   // a stream whose cached block ends inside the window (and that has more blocks) ends the window there
+            int trunc = 0x7fffffff;
+            if (!is_col && lane < T) {
+                const WTerm& tc = sh.term[lane];
+                if (tc.pos < tc.n && tc.cur <= tc.nb) trunc = cdocs[my_slot * kBlock + tc.n - 1] + 1;
+            }
+            win1 = min(win1, __reduce_min_sync(0xffffffffu, trunc));
+        }
+        // docs of [win0, win1) inside this lane's word
+        uint32_t lmask;
+        {
+            const int wlo = max(win0 - (base + 32 * lane), 0), whi = min(win1 - (base + 32 * lane), 32);
+            lmask = whi <= wlo ? 0u : ((whi >= 32 ? 0xffffffffu : ((1u << whi) - 1u)) & ~((1u << wlo) - 1u));
+        }
+        // ---- 1. presence of the block-stream clauses (their postings of this window are all cached)
+        sh.ubits[lane] = 0u;
+        __syncwarp();
+        const uint32_t act = __ballot_sync(0xffffffffu, !is_col && nd < win1);
+        for (uint32_t m = act; m; m &= m - 1) {
+            const int t = __ffs(m) - 1;
+            const int slot = __popc(stream_mask & ((1u << t) - 1u));
+            const WTerm& tc = sh.term[t];
+            const int32_t* cd = cdocs + slot * kBlock;
+            const uint32_t n = tc.n;
+            for (uint32_t i = tc.pos + lane;; i += 32) {
+                const int d = i < n ? cd[i] : kNoMoreDocs;
+                const bool in_win = d < win1;
+                if (in_win) atomicOr(&sh.ubits[(d - base) >> 5], 1u << ((d - base) & 31));
+                if (!__all_sync(0xffffffffu, in_win)) break;
+            }
+        }
+        __syncwarp();
+        // ---- 2. presence words: E = docs that need an exact score, U = docs that count
+        uint32_t E = sh.ubits[lane];
+        uint32_t U = E;
+        const int wi = (base >> 5) + lane;
+        if (lmask) {
+            for (uint32_t m = col_mask; m; m &= m - 1) {
+                const int t = __ffs(m) - 1;
+                const uint32_t w = __ldg(sh.colv[t].bits + wi) & lmask;
+                U |= w;
+                if ((ess_cols >> t) & 1u) E |= w;
+            }
+        }
+        uint32_t lw = 0xffffffffu;
+        if (LIVE && seg.live) lw = lmask ? reinterpret_cast<const uint32_t*>(seg.live)[wi] : 0u;
+        my_matches += __popc(U & lw);
+        // ---- 3. exact scores of the docs in E: clauses in clause order (DisjunctionSumScorer::score_sum)
+        uint32_t hot = 0;
+        for (int t = 0; t < T; t++) {
+            if ((stream_mask >> t) & 1u) {
+                if (!((act >> t) & 1u)) continue;
+                const int slot = __popc(stream_mask & ((1u << t) - 1u));
+                WTerm& tc = sh.term[t];
+                const int32_t* cd = cdocs + slot * kBlock;
+                const float* cs = cscores + slot * kBlock;
+                uint32_t cpos = tc.pos;
+                const uint32_t n = tc.n;
+                for (;;) {
+                    const uint32_t i = cpos + lane;
+                    const int d = i < n ? cd[i] : kNoMoreDocs;
+                    const bool in_win = d < win1;
+                    const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, in_win));  // sorted: a prefix
+                    if (in_win) {
+                        const int idx = d - base;
+                        const float sum = __fadd_rn(sh.acc[idx], cs[i]);
+                        sh.acc[idx] = sum;
+                        if (sum > te) hot |= 1u << (idx >> 5);
+                    }
+                    cpos += cnt;
+                    if (cnt < 32) break;
+                }
+                __syncwarp();  // every lane has read this clause's cursor
+                if (lane == 0) tc.pos = cpos;
+                if (lane == t) nd = cpos < n ? cd[cpos] : kNoMoreDocs;  // an emptied cache is refilled below
+                __syncwarp();
+            } else {
+                uint32_t w = lmask ? (__ldg(sh.colv[t].bits + wi) & E & lmask) : 0u;
+                if (!__any_sync(0xffffffffu, w != 0u)) continue;
+                const float* col = sh.colv[t].col + base + 32 * lane;
+                float* a = sh.acc + 32 * lane;
+                while (w) {
+                    const int b = __ffs(w) - 1;
+                    w &= w - 1;
+                    const float sum = __fadd_rn(a[b], __ldg(col + b));
+                    a[b] = sum;
+                    if (sum > te) hot |= 1u << lane;
+                }
+                __syncwarp();
+            }
+        }
+        hot = __reduce_or_sync(0xffffffffu, hot);
+        // ---- 4. candidates: touched docs (bits of E) whose score beats theta, in docid order
+        {
+            uint32_t newc_n = 0;
+            while (hot) {
+                const int s = __ffs(hot) - 1;
+                hot &= hot - 1;
+                const int idx = s * 32 + lane;
+                const float sc = sh.acc[idx];
+                const uint32_t Es = __shfl_sync(0xffffffffu, E, s);
+                const uint32_t ls = __shfl_sync(0xffffffffu, lw, s);
+                const bool cand = ((Es & ls) >> lane) & 1u && (open || sc > te);
+                const uint32_t cm = __ballot_sync(0xffffffffu, cand);
+                if (!cm || em.overflow) continue;
+                const uint32_t cn = __popc(cm);
+                CandRun* hdr = reinterpret_cast<CandRun*>(p.cand_arena);
+                if (em.run_slot == kNone || em.run_cnt + cn > em.run_cap) {
+                    uint32_t slot = 0;
+                    const uint32_t cap = em.run_slot == kNone ? kRunFirst : kRunMin;
+                    if (lane == 0) {
+                        const unsigned long long s64 = atomicAdd(p.arena_next, (unsigned long long)cap + 1ull);
+                        slot = (s64 + cap + 1ull > (unsigned long long)p.arena_slots) ? kNone : (uint32_t)s64;
+                        if (slot == kNone) atomicOr(p.error_flag, 1u);
+                        else if (em.run_slot == kNone) p.item_head[item_idx] = slot;
+                        else hdr[em.run_slot] = CandRun{slot, em.run_cnt};
+                    }
+                    slot = __shfl_sync(0xffffffffu, slot, 0);
+                    if (slot == kNone) {
+                        em.overflow = true;
+                        continue;
+                    }
+                    em.run_slot = slot;
+                    em.run_cap = cap;
+                    em.run_cnt = 0;
+                }
+                if (cand) {
+                    const uint32_t r = __popc(cm & ((1u << lane) - 1u));
+                    p.cand_arena[em.run_slot + 1 + em.run_cnt + r] = rg_hit{base + idx + seg.doc_base, sc};
+                    if (newc_n + r < (uint32_t)kNewcW) sh.newc[newc_n + r] = sc;
+                }
+                em.run_cnt += cn;
+                newc_n += cn;
+                if (lane == 0) hdr[em.run_slot] = CandRun{kNone, em.run_cnt};
+            }
+            __syncwarp();
+            // re-arm the accumulator words that were touched (E bits live in the owning lane's word)
+            if (E) {
+#pragma unroll
+                for (int g = 0; g < 8; g++) reinterpret_cast<float4*>(sh.acc + 32 * lane)[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            wtheta_update(em, p.k, kcap, lane, sh.newc, newc_n, p.item_theta + item_idx);
+            __syncwarp();
+        }
+        pos = win1;
+        // ---- 5. refill the streams whose cached block is used up
+        {
+            bool need = false;
+            if (!is_col && lane < T && nd == kNoMoreDocs) {
+                const WTerm& tc = sh.term[lane];
+                need = tc.pos >= tc.n && tc.cur <= tc.nb;
+            }
+            for (uint32_t m = __ballot_sync(0xffffffffu, need); m; m &= m - 1) {
+                const int t = __ffs(m) - 1;
+                const int slot = __popc(stream_mask & ((1u << t) - 1u));
+                int first = kNoMoreDocs;
+                if (stream_refill<false, false, false, false>(seg, p, sh.term[t], cdocs + slot * kBlock, cscores + slot * kBlock,
+                                                              lo, hi, lane, 0, -2147483647 - 1, reinterpret_cast<uint32_t*>(sh.acc), hot_unused,
+                                                              mm_unused, INFINITY, mc_unused))
+                    first = cdocs[slot * kBlock + sh.term[t].pos];
+                if (lane == t) nd = first;
+            }
+        }
+        if (pos >= hi) break;
+    }
+    my_matches = __reduce_add_sync(0xffffffffu, my_matches);
+    if (lane == 0) p.item_matches[item_idx] = my_matches;
+}
+
+template <bool LIVE>
+static void launch_eval_or_ms_t(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, size_t wb,
+                                uint32_t kcap) {
+    const size_t smem = wb * kMsWarps;
+    // per launch, not cached: the attribute is per device and engines may live on several
+    cudaFuncSetAttribute(k_eval_or_ms<LIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const uint32_t ctas = (n + kMsWarps - 1) / kMsWarps;
+    k_eval_or_ms<LIVE><<<ctas, kMsThreads, smem, st>>>(p, item_ids, n, (uint32_t)wb, kcap);
+}
+
+void launch_eval_or_ms(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n,
+                       uint32_t max_streams, bool has_live) {
+    if (!n) return;
+    const uint32_t kcap = (std::min<uint32_t>(p.k, kMaxK) + 31u) & ~31u;
+    size_t wb = sizeof(MsWarpShared) + (size_t)kcap * sizeof(float) + (size_t)max_streams * kBlock * 8;
+    wb = (wb + 15) & ~size_t(15);
+    if (has_live) launch_eval_or_ms_t<true>(st, p, item_ids, n, wb, kcap);
+    else launch_eval_or_ms_t<false>(st, p, item_ids, n, wb, kcap);
+}
+
+}  // namespace rg

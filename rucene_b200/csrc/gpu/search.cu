@@ -29,7 +29,9 @@ struct Span {
 struct rg_batch {
     uint32_t n_queries = 0, k = 0, mode = 0;
     float k1 = 1.2f;
-    uint32_t n_items = 0, n_or = 0, n_and = 0, n_ro = 0, n_groups = 0, n_leaves = 0, max_or_terms = 1;
+    uint32_t n_items = 0, n_or = 0, n_ms = 0, n_and = 0, n_ro = 0, n_groups = 0, n_leaves = 0, max_or_terms = 1,
+             max_ms_streams = 0;
+    uint64_t generation = 0;  // engine->generation at prepare time
     // One device allocation per batch (cudaMalloc/cudaFree cost milliseconds each next to a
     // multi-GB index image; the engine keeps the last slab for the next batch).  Layout:
     // [plan arrays copied from the host][item_head: 0xff per run][everything zeroed per run].
@@ -37,10 +39,11 @@ struct rg_batch {
     Span<WorkItem> items;
     Span<ItemClause> clauses;
     Span<uint32_t> or_ids, and_ids;  // launch order (range-major) of the OR / AND work items
+    Span<uint32_t> ms_ids;           // OR work items evaluated by k_eval_or_ms (bitmaps + non-essential clauses)
     Span<uint32_t> ro_ids;           // MUST+SHOULD (ReqOptScorer) work items: one per (query, leaf)
-    Span<ColumnJob> col_jobs;        // score columns to materialise before k_eval_or
-    Span<uint64_t> col_off;
-    uint32_t n_col_jobs = 0, n_col_units = 0;
+    Span<ColRef> col_refs;           // score columns this batch reads (ItemClause.term_id indexes it)
+    std::vector<std::shared_ptr<ColEntry>> cols;  // keeps them alive (the engine's LRU may drop them meanwhile)
+    uint32_t n_cols_built = 0;       // columns materialised by this rg_batch_prepare (the others were cached)
     uint64_t col_floats = 0;
     Span<uint32_t> group_item_begin, group_out;
     Span<uint32_t> item_head, item_matches, item_theta;
@@ -62,12 +65,12 @@ namespace {
 struct HostPlan {
     std::vector<WorkItem> items;
     std::vector<ItemClause> clauses;
-    std::vector<uint32_t> or_ids, and_ids, ro_ids;
-    std::vector<ColumnJob> col_jobs;
-    std::vector<uint64_t> col_off;
-    uint32_t n_col_units = 0;
+    std::vector<uint32_t> or_ids, ms_ids, and_ids, ro_ids;
+    std::vector<ColRef> col_refs;
+    std::vector<std::shared_ptr<ColEntry>> cols;
+    uint32_t n_cols_built = 0, max_ms_streams = 0;
     uint64_t col_floats = 0;
-    std::vector<uint32_t> or_rank, and_rank;  // range index of each id (launch-order key)
+    std::vector<uint32_t> or_rank, ms_rank, and_rank;  // range index of each id (launch-order key)
     std::vector<uint32_t> group_item_begin, group_out;
     uint64_t postings = 0, algo_bytes = 0;
     uint32_t max_or_terms = 1;
@@ -149,21 +152,20 @@ QShape classify(const rg_query& q, const rg_clause* clauses, uint32_t n_clauses_
     return s;
 }
 
-// Score columns: which (leaf, term, weight, norm cache) clauses of the batch's disjunctions are
-// worth materialising once for every query that carries them (k_build_columns).  A column costs
-// one pass over the term plus max_doc * 4 bytes; reading it costs ~0.35 warp instructions per
-// DOCID against ~2.3 per POSTING for the block stream, so it pays for dense terms (df >= max_doc/8)
-// that several queries share.  RG_CFG_NO_COLUMNS turns the feature off, RG_CFG_EAGER_COLUMNS makes
-// every clause with df >= max_doc/64 a column (tests).
-using ColKey = std::tuple<uint32_t, uint32_t, uint32_t, uint32_t>;  // leaf, term, weight bits, cache
+// Score columns: which (leaf, term, weight, norm cache, k1) clauses of the batch's disjunctions are read
+// from a materialised f32 column (k_build_columns) instead of their block stream.  Only terms with a
+// presence bitmap (df >= max_doc/64, chosen at upload) qualify.  Columns are persistent: a key that is
+// already in the engine's cache is used as is; a new one is built when at least two clauses of the
+// batch share it (RG_CFG_EAGER_COLUMNS: one), most valuable (uses x df) first, evicting least recently
+// used columns no batch references while over the HBM budget.  RG_CFG_NO_COLUMNS turns the feature off.
 std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape>& shapes, const rg_clause* clauses,
-                                          HostPlan& hp) {
+                                          float k1, HostPlan& hp) {
     std::map<ColKey, uint32_t> chosen;
-    if (e->cfg.flags & RG_CFG_NO_COLUMNS) return chosen;
+    if (e->cfg.flags & (RG_CFG_NO_COLUMNS | RG_CFG_NO_BITMAPS)) return chosen;
     const bool eager = (e->cfg.flags & RG_CFG_EAGER_COLUMNS) != 0;
-    const uint32_t min_uses = eager ? 1u : 4u;
-    uint64_t density_den = eager ? 64u : 8u;  // measured on C4: 5 -> 625 ms, 8 -> 597, 12 -> 610, 20 -> 647
-    if (const char* ev = getenv("RUCENE_B200_COL_DEN")) density_den = std::max(1, atoi(ev));  // tuning runs
+    const uint32_t min_uses = eager ? 1u : 2u;
+    uint32_t k1bits;
+    memcpy(&k1bits, &k1, 4);
     std::map<ColKey, uint32_t> uses;
     for (const QShape& sh : shapes) {
         if (sh.type != kTypeOr) continue;
@@ -171,53 +173,96 @@ std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape
             const Segment& seg = e->segs[si];
             for (uint32_t ci : sh.clause_idx) {
                 const rg_clause& c = clauses[ci];
-                if (c.term_id >= seg.host_terms.size()) continue;
-                const uint64_t df = (uint64_t)seg.host_terms[c.term_id].doc_freq;
-                if (df == 0 || df * density_den < (uint64_t)seg.max_doc) continue;
+                if (c.term_id >= seg.host_terms.size() || seg.bitmap_slot[c.term_id] < 0) continue;
                 uint32_t wbits;
                 memcpy(&wbits, &c.weight, 4);
-                uses[ColKey(si, c.term_id, wbits, c.cache_id)]++;
+                uses[ColKey(si, c.term_id, wbits, c.cache_id, k1bits)]++;
             }
         }
     }
-    std::vector<std::pair<uint64_t, ColKey>> ranked;
-    for (const auto& kv : uses) {
-        if (kv.second < min_uses) continue;
-        const Segment& seg = e->segs[std::get<0>(kv.first)];
-        ranked.emplace_back((uint64_t)kv.second * (uint64_t)seg.host_terms[std::get<1>(kv.first)].doc_freq, kv.first);
-    }
-    std::sort(ranked.begin(), ranked.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+    if (uses.empty()) return chosen;
     if (e->col_budget_floats == 0) {  // once per index state (cudaMemGetInfo costs milliseconds)
         size_t free_b = 0, total_b = 0;
         RG_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-        e->col_budget_floats = std::max<uint64_t>(1, ((uint64_t)free_b + e->col_arena.bytes()) / 3 / sizeof(float));
+        e->col_budget_floats = std::max<uint64_t>(1, ((uint64_t)free_b / sizeof(float) + e->col_floats) / 3);
     }
-    const uint64_t budget_floats = e->col_budget_floats;
-    for (const auto& r : ranked) {
-        if (hp.col_jobs.size() >= 32) break;
+    auto add_ref = [&](const ColKey& key, const std::shared_ptr<ColEntry>& ent) {
+        ent->last_use = ++e->col_tick;
+        chosen[key] = (uint32_t)hp.col_refs.size();
+        hp.col_refs.push_back(ColRef{ent->col, ent->bits});
+        hp.cols.push_back(ent);
+        hp.col_floats += ent->len;
+    };
+    std::vector<std::pair<uint64_t, ColKey>> to_build;
+    for (const auto& kv : uses) {
+        const auto it = e->col_cache.find(kv.first);
+        if (it != e->col_cache.end()) {
+            e->col_hits++;
+            add_ref(kv.first, it->second);
+        } else if (kv.second >= min_uses) {
+            const Segment& seg = e->segs[std::get<0>(kv.first)];
+            to_build.emplace_back((uint64_t)kv.second * (uint64_t)seg.host_terms[std::get<1>(kv.first)].doc_freq, kv.first);
+        }
+    }
+    std::sort(to_build.begin(), to_build.end(), [](const auto& x, const auto& y) { return x.first > y.first; });
+    std::vector<ColumnJob> jobs;
+    uint32_t n_units = 0;
+    cudaStream_t st = e->stream;
+    for (const auto& r : to_build) {
+        if (hp.col_refs.size() >= 4096) break;
         const Segment& seg = e->segs[std::get<0>(r.second)];
         const uint64_t len = ((uint64_t)seg.max_doc + 1024 + 3) & ~3ull;  // windows read past max_doc
-        if (hp.col_floats + len > budget_floats) break;
+        while (e->col_floats + len > e->col_budget_floats) {  // evict the least recently used unreferenced column
+            auto victim = e->col_cache.end();
+            for (auto it = e->col_cache.begin(); it != e->col_cache.end(); ++it)
+                if (it->second.use_count() == 1 && (victim == e->col_cache.end() || it->second->last_use < victim->second->last_use))
+                    victim = it;
+            if (victim == e->col_cache.end()) break;
+            e->col_floats -= victim->second->len;
+            e->col_cache.erase(victim);  // cudaFree: synchronises, which also orders it after running kernels
+        }
+        if (e->col_floats + len > e->col_budget_floats) break;
+        auto ent = std::make_shared<ColEntry>();
+        ent->key = r.second;
+        ent->len = len;
+        if (cudaMalloc(reinterpret_cast<void**>(&ent->col), len * sizeof(float)) != cudaSuccess) {
+            cudaGetLastError();
+            ent->col = nullptr;
+            break;
+        }
         const TermHost& th = seg.host_terms[std::get<1>(r.second)];
+        ent->bits = seg.bitmaps.p + (size_t)seg.bitmap_slot[std::get<1>(r.second)] * seg.bitmap_words;
+        RG_CUDA_CHECK(cudaMemsetAsync(ent->col, 0xff, len * sizeof(float), st));
         ColumnJob job{};
         job.seg = std::get<0>(r.second);
         job.term_id = std::get<1>(r.second);
         const uint32_t wbits = std::get<2>(r.second);
         memcpy(&job.weight, &wbits, 4);
         job.cache_id = std::get<3>(r.second);
-        job.col_off = hp.col_floats;
-        job.unit_begin = hp.n_col_units;
-        chosen[r.second] = (uint32_t)hp.col_jobs.size();
-        hp.col_jobs.push_back(job);
-        hp.col_off.push_back(job.col_off);
-        hp.col_floats += len;
-        hp.n_col_units += th.n_blocks + (th.tail_n ? 1u : 0u);
+        job.dst = ent->col;
+        job.unit_begin = n_units;
+        n_units += th.n_blocks + (th.tail_n ? 1u : 0u);
+        jobs.push_back(job);
+        e->col_cache[r.second] = ent;
+        e->col_floats += len;
+        e->col_builds++;
+        add_ref(r.second, ent);
+    }
+    if (!jobs.empty()) {
+        DevBuf<ColumnJob> d_jobs;
+        d_jobs.alloc(jobs.size());
+        RG_CUDA_CHECK(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(ColumnJob), cudaMemcpyHostToDevice, st));
+        launch_build_columns(st, e->d_segs.p, d_jobs.p, (uint32_t)jobs.size(), n_units, e->d_caches.p, k1);
+        RG_CUDA_CHECK(cudaGetLastError());
+        RG_CUDA_CHECK(cudaStreamSynchronize(st));  // d_jobs goes out of scope
+        e->launches++;
+        hp.n_cols_built = (uint32_t)jobs.size();
     }
     return chosen;
 }
 
 void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const rg_clause* clauses,
-                uint32_t n_clauses, uint32_t mode, HostPlan& hp) {
+                uint32_t n_clauses, uint32_t mode, float k1, HostPlan& hp) {
     const uint32_t n_caches = (uint32_t)(e->h_caches.size() / 256);
     const uint64_t range_postings = e->cfg.range_postings;
     const uint32_t n_segs = (uint32_t)e->segs.size();
@@ -228,8 +273,14 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
             if (clauses[ci].cache_id >= n_caches) throw ArgError("clause refers to an unset norm cache");
         for (uint32_t ci : shapes[qi].opt_idx)
             if (clauses[ci].cache_id >= n_caches) throw ArgError("clause refers to an unset norm cache");
+        // MUST_NOT clauses never score, but the kernels still form cache pointers from the id
+        for (uint32_t ci : shapes[qi].not_idx)
+            if (clauses[ci].cache_id >= n_caches) throw ArgError("clause refers to an unset norm cache");
     }
-    const std::map<ColKey, uint32_t> columns = choose_columns(e, shapes, clauses, hp);
+    const std::map<ColKey, uint32_t> columns = choose_columns(e, shapes, clauses, k1, hp);
+    uint32_t k1bits;
+    memcpy(&k1bits, &k1, 4);
+    const bool no_ms = (e->cfg.flags & RG_CFG_NO_MAXSCORE) != 0;
     for (uint32_t qi = 0; qi < n_queries; qi++) {
         const QShape& shape = shapes[qi];
         bool group_open = false;
@@ -292,17 +343,40 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
             hp.postings += total_df;
             hp.algo_bytes += bytes;
             const uint32_t clause_begin = (uint32_t)hp.clauses.size();
+            // A disjunction goes to k_eval_or_ms (presence bitmaps, non-essential clauses are only counted)
+            // when it is a plain sum of SHOULD clauses, reads at least one score column, and none of its
+            // other clauses is dense (a dense block stream would cut its windows to a few docids).
+            bool use_ms = false;
+            if (shape.type == kTypeOr && !columns.empty()) {
+                uint32_t n_col = 0;
+                bool dense_stream = false;
+                for (uint32_t ci : present) {
+                    const rg_clause& c = clauses[ci];
+                    uint32_t wbits;
+                    memcpy(&wbits, &c.weight, 4);
+                    if (columns.count(ColKey(si, c.term_id, wbits, c.cache_id, k1bits))) n_col++;
+                    else if ((uint64_t)seg.host_terms[c.term_id].doc_freq * 32u >= (uint64_t)seg.max_doc) dense_stream = true;
+                }
+                use_ms = !no_ms && n_col > 0 && !dense_stream && nots.empty() && !shape.msm && !(shape.dismax && present.size() > 1);
+            }
+            uint32_t n_streams = 0;
             for (uint32_t ci : present) {
                 const rg_clause& c = clauses[ci];
                 if (shape.type == kTypeOr && !columns.empty()) {
                     uint32_t wbits;
                     memcpy(&wbits, &c.weight, 4);
-                    const auto it = columns.find(ColKey(si, c.term_id, wbits, c.cache_id));
-                    if (it != columns.end()) {  // read the batch's score column instead of the block stream
-                        hp.clauses.push_back(ItemClause{it->second, c.weight, c.cache_id, 4u});
+                    const auto it = columns.find(ColKey(si, c.term_id, wbits, c.cache_id, k1bits));
+                    // the exhaustive kernel scans a column docid by docid: that only pays for df >= max_doc/8
+                    if (it != columns.end() &&
+                        (use_ms || (uint64_t)seg.host_terms[c.term_id].doc_freq * 8u >= (uint64_t)seg.max_doc)) {
+                        // bit4: the MaxScore bound w*(k1+1) needs weight >= 0 and cache entries >= 0
+                        const bool boundable = c.weight >= 0.0f && c.weight < INFINITY && k1 >= 0.0f &&
+                                               c.cache_id < e->cache_nonneg.size() && e->cache_nonneg[c.cache_id];
+                        hp.clauses.push_back(ItemClause{it->second, c.weight, c.cache_id, 4u | (boundable ? 0u : 16u)});
                         continue;
                     }
                 }
+                n_streams++;
                 hp.clauses.push_back(ItemClause{c.term_id, c.weight, c.cache_id, 0});
             }
             for (uint32_t ci : nots) {
@@ -345,6 +419,10 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 } else if (leaf_type == (int)kTypeAnd) {
                     hp.and_ids.push_back(idx);
                     hp.and_rank.push_back((uint32_t)r);
+                } else if (use_ms) {
+                    hp.ms_ids.push_back(idx);
+                    hp.ms_rank.push_back((uint32_t)r);
+                    hp.max_ms_streams = std::max<uint32_t>(hp.max_ms_streams, n_streams);
                 } else {
                     hp.or_ids.push_back(idx);
                     hp.or_rank.push_back((uint32_t)r);
@@ -371,6 +449,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
         ids.swap(out);
     };
     by_rank(hp.or_ids, hp.or_rank);
+    by_rank(hp.ms_ids, hp.ms_rank);
     by_rank(hp.and_ids, hp.and_rank);
     // heap groups = contiguous item runs starting at chain-start items
     for (uint32_t i = 0; i < hp.items.size(); i++)
@@ -417,8 +496,14 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     e->sync_tables();
     ensure_arena(e);
     HostPlan hp;
-    plan_batch(e, queries, n_queries, clauses, n_clauses, p->mode, hp);
+    plan_batch(e, queries, n_queries, clauses, n_clauses, p->mode, p->k1, hp);
     std::unique_ptr<rg_batch> b(new rg_batch());
+    b->generation = e->generation;
+    b->cols = std::move(hp.cols);
+    b->n_cols_built = hp.n_cols_built;
+    b->col_floats = hp.col_floats;
+    b->n_ms = (uint32_t)hp.ms_ids.size();
+    b->max_ms_streams = hp.max_ms_streams;
     b->n_queries = n_queries;
     b->k = p->k;
     b->mode = p->mode;
@@ -448,9 +533,9 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     carve(b->clauses, hp.clauses.size());
     carve(b->or_ids, hp.or_ids.size());
     carve(b->and_ids, hp.and_ids.size());
+    carve(b->ms_ids, hp.ms_ids.size());
     carve(b->ro_ids, hp.ro_ids.size());
-    carve(b->col_jobs, hp.col_jobs.size());
-    carve(b->col_off, hp.col_off.size());
+    carve(b->col_refs, hp.col_refs.size());
     carve(b->group_item_begin, hp.group_item_begin.size());
     carve(b->group_out, hp.group_out.size());
     carve(b->item_head, b->n_items);
@@ -472,7 +557,7 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
         using T = std::remove_reference_t<decltype(*span.p)>;
         span.p = reinterpret_cast<T*>(b->slab.p + reinterpret_cast<size_t>(span.p));
     };
-    rebase(b->items); rebase(b->clauses); rebase(b->or_ids); rebase(b->and_ids); rebase(b->ro_ids); rebase(b->col_jobs); rebase(b->col_off);
+    rebase(b->items); rebase(b->clauses); rebase(b->or_ids); rebase(b->and_ids); rebase(b->ms_ids); rebase(b->ro_ids); rebase(b->col_refs);
     rebase(b->group_item_begin); rebase(b->group_out); rebase(b->item_head); rebase(b->item_matches);
     rebase(b->item_theta); rebase(b->arena_next); rebase(b->out_hits); rebase(b->out_counts);
     rebase(b->out_total);
@@ -483,17 +568,15 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     up(b->clauses, hp.clauses, st);
     up(b->or_ids, hp.or_ids, st);
     up(b->and_ids, hp.and_ids, st);
+    up(b->ms_ids, hp.ms_ids, st);
     up(b->ro_ids, hp.ro_ids, st);
-    up(b->col_jobs, hp.col_jobs, st);
-    up(b->col_off, hp.col_off, st);
-    b->n_col_jobs = (uint32_t)hp.col_jobs.size();
-    b->n_col_units = hp.n_col_units;
-    b->col_floats = hp.col_floats;
+    up(b->col_refs, hp.col_refs, st);
     up(b->group_item_begin, hp.group_item_begin, st);
     up(b->group_out, hp.group_out, st);
     b->h2d_bytes = (hp.items.size() * sizeof(WorkItem)) + hp.clauses.size() * sizeof(ItemClause) +
-                   4 * (hp.or_ids.size() + hp.and_ids.size() + hp.ro_ids.size() + hp.group_item_begin.size() + hp.group_out.size());
-    b->kernels_per_run = (b->n_col_jobs ? 1 : 0) + (b->n_or ? 1 : 0) + (b->n_and ? 1 : 0) + (b->n_ro ? 1 : 0) + (b->n_groups ? 1 : 0) +
+                   4 * (hp.or_ids.size() + hp.ms_ids.size() + hp.and_ids.size() + hp.ro_ids.size() + hp.group_item_begin.size() + hp.group_out.size()) +
+                   hp.col_refs.size() * sizeof(ColRef);
+    b->kernels_per_run = (b->n_ms ? 1 : 0) + (b->n_or ? 1 : 0) + (b->n_and ? 1 : 0) + (b->n_ro ? 1 : 0) + (b->n_groups ? 1 : 0) +
                          (p->mode == RG_MODE_SEARCH_PARALLEL ? 1 : 0);
     RG_CUDA_CHECK(cudaStreamSynchronize(st));
     *out = b.release();
@@ -504,6 +587,8 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
 int rg_batch_run(rg_engine* e, rg_batch* b) {
     RG_TRY
     if (!e || !b) throw ArgError("null argument");
+    if (b->generation != e->generation)
+        throw ArgError("stale batch: a segment was uploaded or a norm cache changed after rg_batch_prepare");
     RG_CUDA_CHECK(cudaSetDevice(e->device));
     cudaStream_t st = e->stream;
     RG_CUDA_CHECK(cudaEventRecord(e->ev0, st));
@@ -525,20 +610,14 @@ int rg_batch_run(rg_engine* e, rg_batch* b) {
     ep.item_theta = b->item_theta.p;
     ep.error_flag = reinterpret_cast<uint32_t*>(b->arena_next.p + 1);
     RG_CUDA_CHECK(cudaEventRecord(e->ev2, st));
-    if (b->n_col_jobs) {  // materialise this batch's score columns (inside the timed region)
-        if (e->col_arena.n < b->col_floats) e->col_arena.alloc((size_t)b->col_floats);
-        RG_CUDA_CHECK(cudaMemsetAsync(e->col_arena.p, 0xff, (size_t)b->col_floats * sizeof(float), st));
-        launch_build_columns(st, e->d_segs.p, b->col_jobs.p, b->n_col_jobs, b->n_col_units, e->d_caches.p, b->k1,
-                             e->col_arena.p);
-        RG_CUDA_CHECK(cudaGetLastError());
-    }
-    ep.col_base = e->col_arena.p;
-    ep.col_off = b->col_off.p;
+    ep.cols = b->col_refs.p;
     bool has_live = false, has_other = false;
     for (const Segment& sg : e->segs) {
         has_live = has_live || sg.live.p != nullptr;
         has_other = has_other || sg.has_other_enc;
     }
+    launch_eval_or_ms(st, ep, b->ms_ids.p, b->n_ms, b->max_ms_streams, has_live);
+    RG_CUDA_CHECK(cudaGetLastError());
     launch_eval_or(st, ep, b->or_ids.p, b->n_or, b->max_or_terms, has_live, b->or_has_not, b->or_has_msm, b->or_has_dmax);
     RG_CUDA_CHECK(cudaGetLastError());
     launch_eval_and(st, ep, b->and_ids.p, b->n_and, false, has_other);
@@ -615,7 +694,7 @@ int rg_batch_stats(rg_engine* e, rg_batch* b, uint64_t out[8]) {
     out[3] = used;
     out[4] = b->kernels_per_run;
     out[5] = b->h2d_bytes;
-    out[6] = b->n_or;
+    out[6] = b->n_or + b->n_ms;
     out[7] = b->n_and + b->n_ro;
     return RG_OK;
     RG_CATCH
@@ -636,7 +715,7 @@ int rg_search_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries,
 int rg_batch_columns(rg_engine* e, rg_batch* b, uint32_t* n_columns, uint64_t* bytes) {
     RG_TRY
     if (!e || !b || !n_columns || !bytes) throw ArgError("null argument");
-    *n_columns = b->n_col_jobs;
+    *n_columns = (uint32_t)b->cols.size();
     *bytes = b->col_floats * sizeof(float);
     return RG_OK;
     RG_CATCH

@@ -15,7 +15,7 @@ MUST, SHOULD, MUST_NOT = 0, 1, 2
 Q_BOOLEAN = 1
 Q_DISMAX = 2    # rg_query.flags: DisjunctionMaxQuery; min_should_match = bits of the f32 tie breaker
 MODE_SEARCH, MODE_SEARCH_PARALLEL = 0, 1
-CFG_NO_COLUMNS, CFG_EAGER_COLUMNS = 1, 2   # rg_config.flags (include/rucene_gpu.h)
+CFG_NO_COLUMNS, CFG_EAGER_COLUMNS, CFG_NO_BITMAPS, CFG_NO_MAXSCORE = 1, 2, 4, 8   # rg_config.flags (include/rucene_gpu.h)
 NO_MORE_DOCS = 0x7FFFFFFF
 
 TERM_STATE_DTYPE = np.dtype([("doc_freq", "<i4"), ("singleton_doc_id", "<i4"),
@@ -65,6 +65,8 @@ def lib():
     L.rg_engine_destroy.argtypes = [vp]
     L.rg_engine_destroy.restype = None
     L.rg_engine_set_stream.argtypes = [vp, vp]
+    L.rg_engine_set_flags.argtypes = [vp, C.c_uint32]
+    L.rg_engine_column_stats.argtypes = [vp, vp]
     L.rg_engine_launch_count.restype = C.c_uint64
     L.rg_engine_launch_count.argtypes = [vp]
     L.rg_engine_last_kernel_ms.restype = C.c_float
@@ -86,6 +88,7 @@ def lib():
     L.rg_batch_columns.argtypes = [vp, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
     L.rg_batch_leaf_records.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.rg_merge_leaf_records.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp]
+    L.rg_segment_decode.argtypes = [vp, C.c_uint32, C.c_uint64, C.c_uint64, vp, vp]
     L.rg_forutil_decode.argtypes = [vp, vp, C.c_size_t, vp, C.c_uint32, C.c_int, vp, vp]
     L.rg_blockset_stage.argtypes = [vp, vp, C.c_size_t, vp, C.c_uint32, C.c_int, vp, C.POINTER(vp)]
     L.rg_blockset_decode.argtypes = [vp, vp]
@@ -208,6 +211,14 @@ class Engine:
     def set_stream(self, cuda_stream):
         _check(lib().rg_engine_set_stream(self.h, cuda_stream), self.h)
 
+    def set_flags(self, flags):
+        _check(lib().rg_engine_set_flags(self.h, flags), self.h)
+
+    def column_stats(self):
+        out = np.zeros(4, np.uint64)
+        _check(lib().rg_engine_column_stats(self.h, _p(out)), self.h)
+        return {"cached": int(out[0]), "bytes": int(out[1]), "built": int(out[2]), "hits": int(out[3])}
+
     def launch_count(self):
         return int(lib().rg_engine_launch_count(self.h))
 
@@ -270,6 +281,19 @@ class Engine:
         return hits, counts, total
 
     # ---- block codec ----
+    def segment_decode(self, seg_ord, first_block=0, n_blocks=1 << 62, fetch=False):
+        """Decode block pairs of an uploaded segment (doc deltas + freqs).  -> (stats, out or None)"""
+        stats = np.zeros(4, np.uint64)
+        out = None
+        if fetch:
+            probe = np.zeros(4, np.uint64)
+            _check(lib().rg_segment_decode(self.h, seg_ord, first_block, 0, None, _p(probe)), self.h)
+            n = int(min(n_blocks, int(probe[3]) - first_block))
+            out = np.zeros((n, 2, 128), np.int32)
+        _check(lib().rg_segment_decode(self.h, seg_ord, first_block, n_blocks, _p(out), _p(stats)), self.h)
+        return {"encoded_bytes": int(stats[0]), "decoded_bytes": int(stats[1]), "blocks": int(stats[2]),
+                "segment_blocks": int(stats[3])}, out
+
     def forutil_decode(self, stream, offsets, doc_version, table):
         stream = np.ascontiguousarray(stream, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)

@@ -1,7 +1,8 @@
-"""One index segment per GPU: search_parallel semantics across ranks.
+"""One index segment (or a contiguous run of segments) per GPU: search_parallel semantics
+across ranks.
 
-Every rank holds ONE leaf (docid range [doc_base, doc_base+max_doc)), evaluates the whole query
-batch against it with a per-leaf TopDocs heap (search/collector/top_docs.rs:145-155), then ONE
+Every rank holds its leaves (docid ranges [doc_base, doc_base+max_doc)), evaluates the whole query
+batch against them with a per-leaf TopDocs heap (search/collector/top_docs.rs:145-155), then ONE
 all-gather moves the fixed-size leaf records {u32 n; u32 pad; u64 total_hits; (doc,score)[k] in
 heap-array order} and every rank replays finish_parallel (top_docs.rs:157-172) in leaf order.
 Weights are computed once from the statistics of the largest leaf — rank 0's when all leaves are
@@ -41,7 +42,7 @@ def broadcast_stats(doc_freq, doc_count, sum_total_term_freq, src=0, device=None
 
 
 def gather_leaf_records(local_records, group=None):
-    """local_records: uint8 tensor [n_queries * record_bytes] (CPU/gloo or CUDA/nccl).
+    """local_records: uint8 tensor [n_local_leaves * n_queries * record_bytes] (CPU/gloo or CUDA/nccl).
     Returns a uint8 tensor laid out [leaf][query][record] in rank (= leaf) order."""
     world = dist.get_world_size(group)
     out = torch.empty(world * local_records.numel(), dtype=torch.uint8, device=local_records.device)
@@ -55,23 +56,36 @@ def gather_leaf_records(local_records, group=None):
 
 
 class ShardedSearcher:
-    """GPU searcher over one local leaf + NCCL all-gather of per-leaf top-k."""
+    """GPU searcher over the local leaves + one all-gather of per-leaf top-k.
 
-    def __init__(self, engine, n_queries_hint=0, group=None):
+    The engine launches on torch's current stream (set in every search_batch), so the evaluation
+    kernels, the NCCL all-gather and the merge kernel are ordered on ONE stream without events.
+    With a gloo process group (several ranks sharing one GPU, CPU-only transports) the records are
+    staged through host memory instead."""
+
+    def __init__(self, engine, group=None):
         self.engine = engine
         self.group = group
         self.world = dist.get_world_size(group)
         self.device = torch.device("cuda", torch.cuda.current_device())
+        self.on_device = dist.get_backend(group) == "nccl"
 
     def search_batch(self, queries, clauses, k, k1=1.2):
         from . import engine as E
+        stream = torch.cuda.current_stream(self.device)
+        self.engine.set_stream(stream.cuda_stream)
         batch = self.engine.prepare(queries, clauses, k, k1=k1, mode=E.MODE_SEARCH_PARALLEL)
         try:
             batch.run()
             ptr, rb = batch.leaf_records()
             n = len(queries)
-            local = device_bytes_tensor(ptr, rb * n, self.device)
-            allrec = gather_leaf_records(local, self.group)
-            return self.engine.merge_leaf_records(allrec.data_ptr(), self.world, n, k)
+            n_local = self.engine.n_segments
+            local = device_bytes_tensor(ptr, n_local * rb * n, self.device)
+            if self.on_device:
+                allrec = gather_leaf_records(local, self.group)
+            else:
+                stream.synchronize()
+                allrec = gather_leaf_records(local.cpu(), self.group).to(self.device)
+            return self.engine.merge_leaf_records(allrec.data_ptr(), self.world * n_local, n, k)
         finally:
             batch.close()

@@ -19,19 +19,27 @@ from rucene_b200 import codec, engine, sharded  # noqa: E402
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    # SHARDED_SAME_DEVICE=1: every rank uses cuda:0 (NCCL refuses two ranks on one device, so the records
+    # travel over gloo through host memory) — the N>1 path on a one-GPU box
+    same_device = os.environ.get("SHARDED_SAME_DEVICE") == "1"
+    if same_device:
+        local_rank = 0
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    dist.init_process_group("nccl", device_id=dev)
+    if same_device:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=dev)
     max_doc, n_terms, k = 120000, 3000, 100
     segs = [codec.synth_segment(0x5EED0005 + r, max_doc, n_terms, doc_version=1) for r in range(world)]
     local = segs[rank]
     eng = engine.Engine(device=local_rank, range_postings=20000)
     stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    eng.set_stream(stream.cuda_stream)
+    torch.cuda.set_stream(stream)   # ShardedSearcher points the engine at torch's current stream itself
     eng.upload_segment(local, doc_base=rank * max_doc)
     df0, doc_count, sum_ttf = sharded.broadcast_stats(local.terms["doc_freq"], local.doc_count,
-                                                      local.sum_total_term_freq, src=0, device=dev)
+                                                      local.sum_total_term_freq, src=0,
+                                                      device=None if same_device else dev)
     avgdl = codec.bm25_avg_field_length(sum_ttf, doc_count, max_doc * world)
     eng.set_norm_cache(0, codec.bm25_norm_cache(1.2, 0.75, avgdl))
     rng = np.random.default_rng(0x5EED0005)

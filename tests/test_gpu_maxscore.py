@@ -1,0 +1,159 @@
+"""GPU parity of the presence-bitmap / score-column / non-essential-clause route (k_eval_or_ms) and of
+what surrounds it: persistent columns across batches, invalidation, stale batches, the segment-wide
+block decode (BASELINE config 2, realistic blocks)."""
+import numpy as np
+import pytest
+
+import helpers
+import oracle_binding as ob
+from rucene_b200 import codec, engine, search
+
+pytestmark = pytest.mark.gpu
+
+
+def _or_specs(rng, n_terms, n, t_min=1, t_max=7, boosts=False):
+    specs = []
+    for ts in helpers.distinct_query_terms(rng, n_terms, n, t_min, t_max):
+        if boosts:
+            specs.append(("bool", [(ob.SHOULD, t, float(rng.choice([0.25, 1.0, 1.0, 3.0, 10.0]))) for t in ts], 0))
+        else:
+            specs.append(("bool", [(ob.SHOULD, t) for t in ts], 0))
+    return specs
+
+
+def _check(searcher, ix, specs, k, label, mode=0):
+    q, c = ob.make_queries(specs)
+    want = ix.search_batch(q, c, k, parallel_mode=mode, n_threads=4)
+    got = searcher.search_batch(helpers.to_queries(specs), k, mode=mode)
+    helpers.assert_same_topdocs(got, want, label)
+
+
+@pytest.mark.parametrize("k", [1, 10, 100])
+def test_zipf_disjunctions_all_routes(k):
+    """Log-uniform term ranks over a Zipfian segment: dense clauses become score columns (non-essential once
+    theta has risen), sparse ones stay block streams; many docid ranges per query, theta chaining."""
+    seg = codec.synth_segment(0x5EED0001, 400000, 4000, doc_version=1)
+    ix = helpers.oracle_index([seg])
+    rng = np.random.default_rng(20 + k)
+    specs = _or_specs(rng, 4000, 70) + [("term", 0), ("term", 7), ("term", 300)]
+    for flags in (engine.CFG_EAGER_COLUMNS, 0):
+        for rp in (0, 6000):
+            s = search.GpuIndexSearcher(search.IndexReader([seg]), range_postings=rp, flags=flags)
+            try:
+                _check(s, ix, specs, k, "zipf k=%d flags=%d rp=%d" % (k, flags, rp))
+                if flags:
+                    assert s.engine.column_stats()["cached"] > 0
+            finally:
+                s.engine.close()
+
+
+def test_boosts_change_the_essential_order_and_negative_boost_is_never_pruned():
+    seg = codec.synth_segment(0x5EED0011, 250000, 2500, doc_version=1)
+    ix = helpers.oracle_index([seg])
+    rng = np.random.default_rng(5)
+    specs = _or_specs(rng, 2500, 60, 2, 6, boosts=True)
+    specs += [("bool", [(ob.SHOULD, 0, -1.0), (ob.SHOULD, 3), (ob.SHOULD, 40)], 0),
+              ("bool", [(ob.SHOULD, 1, 0.0), (ob.SHOULD, 2), (ob.SHOULD, 900)], 0),
+              ("bool", [(ob.SHOULD, 0), (ob.SHOULD, 1), (ob.SHOULD, 2), (ob.SHOULD, 3), (ob.SHOULD, 4)], 0)]
+    s = search.GpuIndexSearcher(search.IndexReader([seg]), range_postings=8000, flags=engine.CFG_EAGER_COLUMNS)
+    try:
+        for k in (5, 50):
+            _check(s, ix, specs, k, "boosts k=%d" % k)
+    finally:
+        s.engine.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_leaves_live_docs_and_clustered_streams(mode):
+    """Several leaves with deleted docs; sparse terms whose postings are clustered (consecutive docids) so a
+    stream's cached block ends inside a window and cuts it; massive score ties (constant freq / norm)."""
+    rng = np.random.default_rng(77 + mode)
+    segs = []
+    for s_i, md in enumerate((90000, 70000, 81000)):
+        w = codec.PostingsWriter(doc_version=1, max_doc=md)
+        dfs = [60000, 30000, 9000, 3000, 700, 300, 129, 5, 1]
+        for t, df in enumerate(dfs):
+            if t in (3, 4):  # clustered: runs of consecutive docids
+                starts = np.sort(rng.choice(md - 600, size=df // 100, replace=False))
+                docs = np.unique(np.concatenate([np.arange(a, a + 100) for a in starts]))[:df].astype(np.int32)
+            else:
+                docs = np.sort(rng.choice(md, size=df, replace=False)).astype(np.int32)
+            freqs = np.ones(len(docs), np.int32) if t in (0, 4) else (1 + rng.geometric(0.5, size=len(docs)) - 1).clip(1, 255).astype(np.int32)
+            w.add_term(docs, freqs)
+        norms = np.full(md, 120, np.uint8) if s_i == 1 else rng.integers(100, 140, md).astype(np.uint8)
+        live = None
+        if s_i != 0:
+            bits = rng.random(md) < 0.8
+            words = np.zeros((md + 63) // 64, np.uint64)
+            idx = np.nonzero(bits)[0]
+            np.bitwise_or.at(words, idx >> 6, np.uint64(1) << (idx & 63).astype(np.uint64))
+            live = words
+        segs.append(w.finish(norms=norms, live_docs=live))
+    ix = helpers.oracle_index(segs)
+    specs = [("term", t) for t in range(9)]
+    for i in range(60):
+        t = int(rng.integers(2, 7))
+        specs.append(("bool", [(ob.SHOULD, int(x)) for x in rng.choice(9, size=t, replace=False)], 0))
+    for flags in (engine.CFG_EAGER_COLUMNS, 0):
+        s = search.GpuIndexSearcher(search.IndexReader(segs), range_postings=4000, flags=flags)
+        try:
+            for k in (3, 100):
+                _check(s, ix, specs, k, "leaves mode=%d flags=%d k=%d" % (mode, flags, k), mode=mode)
+        finally:
+            s.engine.close()
+
+
+def test_columns_persist_across_batches_and_follow_the_norm_cache():
+    seg = codec.synth_segment(0x5EED0021, 300000, 3000, doc_version=1)
+    rng = np.random.default_rng(9)
+    s = search.GpuIndexSearcher(search.IndexReader([seg]))
+    try:
+        ix = helpers.oracle_index([seg])
+        a = _or_specs(rng, 3000, 40, 2, 5)
+        _check(s, ix, a, 10, "first batch")
+        st1 = s.engine.column_stats()
+        assert st1["built"] > 0 and st1["cached"] == st1["built"]
+        b = a[:20] + _or_specs(rng, 3000, 30, 2, 5)
+        _check(s, ix, b, 10, "second batch")
+        st2 = s.engine.column_stats()
+        assert st2["hits"] > st1["hits"]          # columns of the first batch were reused
+        # a batch prepared before the cache changes must not run afterwards
+        q, c = s.compile_batch(helpers.to_queries(a))
+        stale = s.engine.prepare(q, c, 10)
+        # new similarity parameters: same cache id, new contents -> cached columns are dropped
+        cache2 = codec.bm25_norm_cache(1.2, 0.3, s._avgdl)
+        s.engine.set_norm_cache(0, cache2)
+        with pytest.raises(engine.EngineError):
+            stale.run()
+        stale.close()
+        assert s.engine.column_stats()["cached"] == 0
+        ix2 = helpers.oracle_index([seg], b=0.3)
+        _check(s, ix2, b, 10, "after the norm cache changed")
+    finally:
+        s.engine.close()
+
+
+def test_segment_decode_matches_the_oracle_reader():
+    """rg_segment_decode: every block pair of the uploaded segment -> 128 doc deltas + 128 freqs."""
+    seg = codec.synth_segment(0x5EED0031, 120000, 600, doc_version=1)
+    ix = helpers.oracle_index([seg])
+    eng = engine.Engine()
+    try:
+        eng.upload_segment(seg)
+        stats, out = eng.segment_decode(0, fetch=True)
+        assert stats["blocks"] == stats["segment_blocks"] == out.shape[0] > 100
+        blk = 0
+        for t in range(600):
+            df = int(seg.terms["doc_freq"][t])
+            nb = df // 128
+            if nb == 0:
+                continue
+            docs, freqs = ix.postings(0, t, df + 1)
+            d = docs[:nb * 128].astype(np.int64)
+            deltas = np.diff(np.concatenate([[0], d])).reshape(nb, 128)
+            assert np.array_equal(out[blk:blk + nb, 0, :], deltas), t
+            assert np.array_equal(out[blk:blk + nb, 1, :], freqs[:nb * 128].reshape(nb, 128)), t
+            blk += nb
+        assert blk == out.shape[0]
+    finally:
+        eng.close()

@@ -33,10 +33,12 @@ def _run_both(segs, specs, k, mode=0, range_postings=0, threads=4, extra_flags=0
     ix = helpers.oracle_index(segs)
     q, c = ob.make_queries(specs)
     want = ix.search_batch(q, c, k, parallel_mode=mode, n_threads=threads)
-    # twice: with the planner's own score-column choice (dense clauses shared by >= 4 disjunctions)
-    # and with a column for every clause of df >= max_doc/64 — both must equal the oracle
+    # every evaluation route must equal the oracle: a score column for every clause of df >= max_doc/64
+    # (k_eval_or_ms: presence bitmaps + non-essential clauses), the same columns read by the exhaustive kernel,
+    # no bitmaps / columns at all (block streams only), and the planner's own choice
     got = None
-    for flags in (engine.CFG_EAGER_COLUMNS, 0):
+    for flags in (engine.CFG_EAGER_COLUMNS, engine.CFG_EAGER_COLUMNS | engine.CFG_NO_MAXSCORE,
+                  engine.CFG_NO_BITMAPS, 0):
         s = search.GpuIndexSearcher(search.IndexReader(segs), range_postings=range_postings,
                                     flags=flags | extra_flags)
         try:
@@ -44,7 +46,7 @@ def _run_both(segs, specs, k, mode=0, range_postings=0, threads=4, extra_flags=0
         finally:
             s.engine.close()
         if flags:
-            helpers.assert_same_topdocs(got, want, "eager score columns")
+            helpers.assert_same_topdocs(got, want, "engine flags %d" % flags)
     return got, want
 
 

@@ -1,4 +1,5 @@
-"""Sharded mode on real GPUs (needs >= 2 devices; skipped otherwise): BASELINE config 5 in small —
+"""Sharded mode on real GPUs (one test needs >= 2 devices and is skipped otherwise; the other runs the
+same path with two ranks on ONE device): BASELINE config 5 in small —
 one segment per GPU, mixed AND/OR batch, NCCL all-gather of per-segment top-k + device merge,
 TopDocs identical to the oracle's leaf-ordered search_parallel."""
 import os
@@ -20,4 +21,16 @@ def test_one_segment_per_gpu_matches_oracle():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(here, "sharded_gpu_worker.py")]
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert p.returncode == 0 and "SHARDED_OK" in p.stdout, p.stdout[-3000:]
+
+
+def test_two_ranks_share_one_gpu_matches_oracle():
+    """The N>1 path on a one-GPU box: two processes, each with its own engine and leaf on cuda:0; leaf records
+    come from rg_batch_leaf_records, cross ranks in one all-gather (gloo, staged through host memory because
+    NCCL refuses two ranks on one device) and are merged by rg_merge_leaf_records in leaf order."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, SHARDED_SAME_DEVICE="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29519", os.path.join(here, "sharded_gpu_worker.py")]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
     assert p.returncode == 0 and "SHARDED_OK" in p.stdout, p.stdout[-3000:]
