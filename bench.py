@@ -72,6 +72,7 @@ def parse_args():
     ap.add_argument("--no-extra", action="store_true", help="skip the C3 / C5 legs and the A/B legs of the default run")
     ap.add_argument("--no-columns", action="store_true",
                     help="RG_CFG_NO_COLUMNS: evaluate every clause from its block stream (A/B runs)")
+    ap.add_argument("--stats", action="store_true", help="RG_CFG_STATS: event counters of k_eval_or_ms in the line")
     ap.add_argument("--no-maxscore", action="store_true",
                     help="RG_CFG_NO_MAXSCORE: exhaustive disjunction kernel only (A/B runs)")
     a = ap.parse_args()
@@ -435,6 +436,7 @@ def run_workload(ctx, name, w, args, steps, warmup, cpu_queries, cpu_seconds, fl
     replay_ms = eng.last_kernel_ms("replay")
     bstats = batch.stats()
     n_cols, col_bytes = batch.columns()
+    dbg = batch.debug() if (flags & engine.CFG_STATS) else None
     out = {"value": nq / (ms_step / 1e3), "ms_per_step": ms_step, "config": workload_config(name, w, world)}
     per_rank_eval = [eval_ms]
     if world > 1:
@@ -492,7 +494,7 @@ def run_workload(ctx, name, w, args, steps, warmup, cpu_queries, cpu_seconds, fl
                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "split": e2e_split,
                         "same_result_as_resident_path": consistent},
                 "gpu_launches": int(launches), "clocks": clocks,
-                "first_batch_ms": first_batch_ms,
+                "first_batch_ms": first_batch_ms, "kernel_events": dbg,
                 "per_rank_eval_ms": per_rank_eval,
                 "setup": {"index_gen_s": t_gen, "upload_s": t_up, "index_image_bytes": eng.index_bytes(),
                           "doc_file_bytes": int(sum(s.doc_file.size for s in segs)),
@@ -656,7 +658,8 @@ def main():
     tr = load_traffic()
     ctx.traffic = {} if args.scaled else {n: tr.get(n) for n in WORKLOADS}
 
-    flags = (engine.CFG_NO_COLUMNS if args.no_columns else 0) | (engine.CFG_NO_MAXSCORE if args.no_maxscore else 0)
+    flags = ((engine.CFG_NO_COLUMNS if args.no_columns else 0) | (engine.CFG_NO_MAXSCORE if args.no_maxscore else 0) |
+             (engine.CFG_STATS if args.stats else 0))
     name, w = args.workload, args.w
     main_res = run_workload(ctx, name, w, args, args.steps, args.warmup, args.cpu_sample, args.cpu_seconds, flags=flags)
     eng, batch = ctx.last_engine, ctx.last_batch
@@ -667,7 +670,7 @@ def main():
     eng.close()
     extra = {}
     ab = {}
-    if not args.no_extra and not args.scaled and name == "c4" and flags == 0:
+    if not args.no_extra and not args.scaled and name == "c4" and (flags & ~engine.CFG_STATS) == 0:
         # A/B legs on the same workload: what the other evaluation routes deliver (2 steps each)
         for label, fl in (("block_streams_only", engine.CFG_NO_COLUMNS | engine.CFG_NO_MAXSCORE),
                           ("columns_exhaustive_kernel", engine.CFG_NO_MAXSCORE)):
@@ -688,6 +691,7 @@ def main():
                 "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"],
                 "roofline": main_res.get("roofline"), "cpu_baseline": main_res.get("cpu_baseline"),
                 "first_batch_ms": main_res["first_batch_ms"], "per_rank_eval_ms": main_res["per_rank_eval_ms"],
+                "kernel_events": main_res.get("kernel_events"),
                 "forutil_decode": decode, "ab": ab or None, "workloads": extra or None, "setup": main_res["setup"]}
         print(json.dumps(line))
     if ctx.world > 1:

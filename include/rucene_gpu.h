@@ -38,6 +38,7 @@ extern "C" {
 #define RG_CFG_EAGER_COLUMNS 2u /* a column for every disjunction clause with df >= max_doc/64 (tests) */
 #define RG_CFG_NO_BITMAPS 4u    /* no presence bitmaps at upload (and therefore no score columns) */
 #define RG_CFG_NO_MAXSCORE 8u   /* evaluate every disjunction with the exhaustive kernel (A/B runs, tests) */
+#define RG_CFG_STATS 16u        /* count events inside k_eval_or_ms (rg_batch_debug); costs a few atomics per work item */
 
 typedef struct rg_engine rg_engine;
 typedef struct rg_batch rg_batch;
@@ -62,8 +63,12 @@ typedef struct {
     int64_t skip_offset;      /* relative to doc_start_fp; -1 when doc_freq<=128 */
 } rg_term_state;
 
-/* BooleanClause occur (search/query/boolean_query.rs:30-36: must/should/must_not lists). */
-enum { RG_MUST = 0, RG_SHOULD = 1, RG_MUST_NOT = 2 };
+/* BooleanClause occur (search/query/boolean_query.rs:30-36: must/should/filter/must_not lists).
+ * RG_FILTER: a required clause that does not score — its weight is built with needs_scores = false
+ * (boolean_query.rs:108-110), i.e. NonScoringSimilarity, score 0f32 (searcher.rs:158-197); the clause's
+ * `weight` is ignored.  A query whose only clause is a FILTER is the reference's
+ * ConstantScoreQuery::with_boost(filter, 0) (boolean_query.rs:66-75): the term's docs with score 0. */
+enum { RG_MUST = 0, RG_SHOULD = 1, RG_MUST_NOT = 2, RG_FILTER = 3 };
 
 /* One TermQuery leaf of the plan, with what TermWeight carries after
  * BM25Similarity::compute_weight (search/similarity/bm25_similarity.rs:151-177):
@@ -166,6 +171,11 @@ void rg_batch_destroy(rg_engine* e, rg_batch* b);
  * clauses), [2]=algorithmic bytes the evaluation must read (encoded blocks + tails + tables
  * touched + norms), [3]=candidates emitted by the last run, [4]=kernels per run. */
 int rg_batch_stats(rg_engine* e, rg_batch* b, uint64_t out[8]);
+/* RG_CFG_STATS event counters of the last run: [0]=work items of k_eval_or_ms, [1]=windows, [2]=windows with an
+ * essential column, [3]=windows before any theta, [4]=docids only counted (between windows), [5]=stream postings
+ * accumulated, [6]=column gathers, [7]=block refills, [8]=candidates, [9]=32-doc steps scanned for candidates,
+ * [10]=windows cut by a stream's cache end, [11]=column clauses non-essential (summed over windows). */
+int rg_batch_debug(rg_engine* e, rg_batch* b, uint64_t out[16]);
 /* Score columns the planner chose for this batch (see RG_CFG_*): how many, and their bytes in HBM. */
 int rg_batch_columns(rg_engine* e, rg_batch* b, uint32_t* n_columns, uint64_t* bytes);
 

@@ -1156,6 +1156,33 @@ struct TermScorer : Scorer {
     }
 };
 
+// A FILTER clause: BooleanQuery::create_weight builds its weight with needs_scores = false
+// (query/boolean_query.rs:108-110), so TermQuery::create_weight picks NonScoringSimilarity
+// (searcher.rs:724-730) whose scorer returns 0f32 (:192-197) and the postings are opened with
+// PostingIteratorFlags::NONE (term_query.rs:145-150): same docids, the freq blocks are skipped.
+struct FilterTermScorer : Scorer {
+    BlockDocIterator it;
+    FilterTermScorer(const SegmentData& seg, const orc_term_state& ts)
+        : it(Input(seg.file, seg.file_len), &seg.for_util, seg.use_simd, true, ts, false) {}
+    int32_t doc_id() const override { return it.doc; }
+    int32_t next() override { return it.next(); }
+    int32_t advance(int32_t t) override { return it.advance(t); }
+    size_t cost() const override { return it.cost(); }
+    float score() override { return 0.0f; }
+};
+
+// MatchAllDocsQuery (query/match_all_query.rs:28-116): ConstantScoreScorer { score: weight = 0f32 (the
+// default; normalisation is commented out, searcher.rs:709-722), iterator: AllDocsIterator (:118-158) }
+struct AllDocsScorer : Scorer {
+    int32_t doc = -1, max_doc;
+    explicit AllDocsScorer(int32_t md) : max_doc(md) {}
+    int32_t doc_id() const override { return doc; }
+    int32_t next() override { return advance(doc + 1); }
+    int32_t advance(int32_t target) override { return doc = target >= max_doc ? NO_MORE_DOCS : target; }
+    size_t cost() const override { return (size_t)std::max(1, max_doc); }
+    float score() override { return 0.0f; }
+};
+
 // search/mod.rs:209-367 — MockDocIterator / MockSimpleScorer (score = doc id)
 struct MockScorer : Scorer {
     std::vector<int32_t> docs;
@@ -1521,6 +1548,7 @@ static ScorerPtr create_scorer(const orc_index& ix, const SegmentData& seg, cons
     auto term_scorer = [&](uint32_t ci) -> ScorerPtr {
         const orc_clause& c = clauses[q.clause_begin + ci];
         if (c.term_id >= seg.terms.size() || seg.terms[c.term_id].doc_freq <= 0) return nullptr;
+        if (c.occur == ORC_FILTER) return ScorerPtr(new FilterTermScorer(seg, seg.terms[c.term_id]));
         return ScorerPtr(new TermScorer(seg, seg.terms[c.term_id], &plan.weights[ci]));
     };
     if (!q.is_boolean) return term_scorer(0);
@@ -1543,19 +1571,24 @@ static ScorerPtr create_scorer(const orc_index& ix, const SegmentData& seg, cons
 
     // BooleanQuery::build (:40-87)
     int32_t msm = q.min_should_match;
-    std::vector<uint32_t> musts, shoulds, must_nots;
+    std::vector<uint32_t> musts, shoulds, filters, must_nots;
     for (uint32_t i = 0; i < q.n_clauses; i++) {
         int occ = clauses[q.clause_begin + i].occur;
-        (occ == ORC_MUST ? musts : occ == ORC_SHOULD ? shoulds : must_nots).push_back(i);
+        (occ == ORC_MUST ? musts : occ == ORC_SHOULD ? shoulds : occ == ORC_FILTER ? filters : must_nots).push_back(i);
     }
     if (msm <= 0) msm = musts.empty() ? 1 : 0;
-    if (musts.size() + shoulds.size() + must_nots.size() == 0) throw Error("boolean query should at least contain one inner query!");
-    if (must_nots.empty() && musts.size() + shoulds.size() == 1)
-        return term_scorer(musts.size() == 1 ? musts[0] : shoulds[0]);
-    if (musts.size() + shoulds.size() == 0)
-        throw Error("pure MUST_NOT (MatchAllDocsQuery) is out of scope");
+    if (musts.size() + shoulds.size() + filters.size() + must_nots.size() == 0)
+        throw Error("boolean query should at least contain one inner query!");
+    // one positive clause and nothing else: the clause itself — a lone filter becomes
+    // ConstantScoreQuery::with_boost(filter, 0f32) (:66-75), i.e. its docs with score 0
+    if (must_nots.empty() && musts.size() + shoulds.size() + filters.size() == 1)
+        return term_scorer(musts.size() == 1 ? musts[0] : shoulds.size() == 1 ? shoulds[0] : filters[0]);
+    const bool match_all = musts.size() + shoulds.size() + filters.size() == 0;  // :76-79 musts.push(MatchAllDocsQuery)
+    // create_weight (:96-125): must_weights = musts, then filters (needs_scores = false)
+    musts.insert(musts.end(), filters.begin(), filters.end());
 
     ScorerPtr must_scorer, should_scorer, must_not_scorer;
+    if (match_all) must_scorer.reset(new AllDocsScorer(seg.max_doc));
     if (!musts.empty()) {
         std::vector<ScorerPtr> v;
         for (uint32_t ci : musts) {

@@ -33,7 +33,7 @@ typedef struct {
     int64_t skip_offset;     /* relative to doc_start_fp, -1 if doc_freq<=128 */
 } orc_term_state;
 
-enum { ORC_MUST = 0, ORC_SHOULD = 1, ORC_MUST_NOT = 2 };
+enum { ORC_MUST = 0, ORC_SHOULD = 1, ORC_MUST_NOT = 2, ORC_FILTER = 3 };
 
 typedef struct {
     int32_t occur;

@@ -147,6 +147,7 @@ struct EvalParams {
     uint32_t* item_matches;    // matches per item (total_hits contribution)
     uint32_t* item_theta;      // ordered-uint running k-th best, chained item -> item+1
     uint32_t* error_flag;      // bit0: arena exhausted
+    unsigned long long* dbg;   // optional event counters of k_eval_or_ms (RG_CFG_STATS), else null
 };
 // one score column to materialise: the BM25 contributions of (leaf, term, weight, norm cache, k1);
 // a bitmap job (weight unused) sets presence bits instead

@@ -162,6 +162,9 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
     uint32_t win_no = 0;
     uint32_t my_matches = 0;
     int pos = lo;  // every docid < pos is counted and, where needed, scored
+    // RG_CFG_STATS event counters (warp-uniform unless noted)
+    uint32_t st_win = 0, st_ess = 0, st_open = 0, st_gap = 0, st_post = 0, st_gather = 0 /* per lane */, st_refill = 0,
+             st_cand = 0, st_steps = 0, st_cut = 0, st_ne = 0;
 
     for (;;) {
         uint32_t inherited = 0;
@@ -169,7 +172,12 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
             inherited = lb_ok ? ld_volatile_u32(theta_lb) : 0u;
             inherited = __reduce_max_sync(0xffffffffu, inherited);
         }
-        em.theta_in = max(em.theta_in, inherited);
+        if (inherited > em.theta_in) {
+            // hand an inherited bound on at once: an item that finds no candidate of its own never reaches
+            // wtheta_update, and its successors look back over 32 items only
+            em.theta_in = inherited;
+            if (lane == 0) atomicMax(p.item_theta + item_idx, inherited);
+        }
         float te = em.theta_local;
         if (em.theta_in > kOrderedNegInf) te = fmaxf(te, ordered_to_float(em.theta_in));
         const bool open = te == -INFINITY;
@@ -183,6 +191,11 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
             break;
         }
         if (col_mask && w0 > pos) my_matches += ms_count_range<LIVE>(sh, col_mask, seg, pos, w0, lane);
+        st_gap += (uint32_t)(w0 - pos);
+        st_win++;
+        st_ess += ess_cols != 0;
+        st_open += open;
+        st_ne += __popc(ne_mask);
         const int win0 = w0;
         const int base = win0 & ~31;
         int win1 = min(hi, base + kMsW);
@@ -192,7 +205,9 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                 const WTerm& tc = sh.term[lane];
                 if (tc.pos < tc.n && tc.cur <= tc.nb) trunc = cdocs[my_slot * kBlock + tc.n - 1] + 1;
             }
-            win1 = min(win1, __reduce_min_sync(0xffffffffu, trunc));
+            const int t_all = __reduce_min_sync(0xffffffffu, trunc);
+            st_cut += t_all < win1;
+            win1 = min(win1, t_all);
         }
         // docs of [win0, win1) inside this lane's word
         uint32_t lmask;
@@ -256,6 +271,7 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                         if (sum > te) hot |= 1u << (idx >> 5);
                     }
                     cpos += cnt;
+                    st_post += cnt;
                     if (cnt < 32) break;
                 }
                 __syncwarp();  // every lane has read this clause's cursor
@@ -272,6 +288,7 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                     w &= w - 1;
                     const float sum = __fadd_rn(a[b], __ldg(col + b));
                     a[b] = sum;
+                    st_gather++;
                     if (sum > te) hot |= 1u << lane;
                 }
                 __syncwarp();
@@ -285,6 +302,7 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                 const int s = __ffs(hot) - 1;
                 hot &= hot - 1;
                 const int idx = s * 32 + lane;
+                st_steps++;
                 const float sc = sh.acc[idx];
                 const uint32_t Es = __shfl_sync(0xffffffffu, E, s);
                 const uint32_t ls = __shfl_sync(0xffffffffu, lw, s);
@@ -319,6 +337,7 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                 }
                 em.run_cnt += cn;
                 newc_n += cn;
+                st_cand += cn;
                 if (lane == 0) hdr[em.run_slot] = CandRun{kNone, em.run_cnt};
             }
             __syncwarp();
@@ -342,6 +361,7 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                 const int t = __ffs(m) - 1;
                 const int slot = __popc(stream_mask & ((1u << t) - 1u));
                 int first = kNoMoreDocs;
+                st_refill++;
                 if (stream_refill<false, false, false, false>(seg, p, sh.term[t], cdocs + slot * kBlock, cscores + slot * kBlock,
                                                               lo, hi, lane, 0, -2147483647 - 1, reinterpret_cast<uint32_t*>(sh.acc), hot_unused,
                                                               mm_unused, INFINITY, mc_unused))
@@ -353,6 +373,14 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
     }
     my_matches = __reduce_add_sync(0xffffffffu, my_matches);
     if (lane == 0) p.item_matches[item_idx] = my_matches;
+    if (p.dbg) {
+        st_gather = __reduce_add_sync(0xffffffffu, st_gather);
+        if (lane == 0) {
+            const uint32_t v[12] = {1u, st_win, st_ess, st_open, st_gap, st_post, st_gather, st_refill, st_cand, st_steps, st_cut, st_ne};
+#pragma unroll
+            for (int i = 0; i < 12; i++) atomicAdd(p.dbg + i, (unsigned long long)v[i]);
+        }
+    }
 }
 
 template <bool LIVE>

@@ -138,7 +138,12 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
             inherited = __reduce_max_sync(0xffffffffu, inherited);
         }
         hot = 0;
-        em.theta_in = max(em.theta_in, inherited);
+        if (inherited > em.theta_in) {
+            // hand an inherited bound on at once: an item that finds no candidate of its own never reaches
+            // wtheta_update, and its successors look back over 32 items only
+            em.theta_in = inherited;
+            if (lane == 0) atomicMax(p.item_theta + item_idx, inherited);
+        }
         float te = em.theta_local;
         if (em.theta_in > kOrderedNegInf) te = fmaxf(te, ordered_to_float(em.theta_in));
         const bool open = te == -INFINITY;
@@ -316,6 +321,7 @@ struct AndShared {
     uint32_t term_id[kMaxTerms];
     uint32_t is_not[kMaxTerms];            // MUST_NOT clauses: a hit kills the lead doc, a miss keeps it
     uint32_t is_opt[kMaxTerms];            // SHOULD clauses next to a MUST (ReqOptScorer's optional side)
+    const float* colp[kMaxTerms];          // non-lead clause read from its score column (one gather per lead doc)
     uint32_t hint[kEvalWarps][kMaxTerms];  // per-warp galloping hints into the skip tables
     // ReqOptScorer (search/scorer/req_opt_scorer.rs:19-65): optional-side sums per lead slot, the
     // per-step match masks in docid order, and the scorer's sequential state (thread 0 owns it)
@@ -349,11 +355,13 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
     emit_init(sh.emit);
     if ((int)threadIdx.x < T) {
         const ItemClause c = p.clauses[it.clause_begin + threadIdx.x];
-        const TermDev td = seg.terms[c.term_id];
+        const bool is_col = (c.flags & 4u) != 0;  // term_id indexes p.cols then (never the lead clause)
+        const TermDev td = is_col ? TermDev{} : seg.terms[c.term_id];
         TermCtx& tc = sh.term[threadIdx.x];
         sh.term_id[threadIdx.x] = c.term_id;
         sh.is_not[threadIdx.x] = c.flags & 1u;
         sh.is_opt[threadIdx.x] = (c.flags >> 1) & 1u;
+        sh.colp[threadIdx.x] = is_col ? p.cols[c.term_id].col : nullptr;
         tc.blk_last = seg.blk_last + td.blk_begin;
         tc.blk_desc = seg.blk_desc + td.blk_begin;
         tc.cache = p.caches + (size_t)c.cache_id * 256;
@@ -458,6 +466,31 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
             const float w1 = tc.w1;
             const bool neg = sh.is_not[t] != 0;
             const bool opt = REQOPT && sh.is_opt[t] != 0;
+            if (const float* col = sh.colp[t]) {
+                // the clause's BM25 contributions sit in a docid-indexed column (0xffffffff = no posting): no skip
+                // search, no block decode — the same f32 value the stream path would compute
+#pragma unroll
+                for (int r = 0; r < kAndSteps; r++) {
+                    const int slot = warp * kBlock + r * 32 + lane;
+                    const int d = sh.ldoc[slot];
+                    if (d == kNoMoreDocs) continue;
+                    const float v = __ldg(col + d);
+                    if (__float_as_uint(v) != 0xffffffffu) {
+                        if (neg) {
+                            sh.ldoc[slot] = kNoMoreDocs;  // ReqNotScorer: excluded
+                        } else if (opt) {
+                            const float o = sh.oscore[slot];
+                            sh.oscore[slot] = __fadd_rn(__float_as_uint(o) == kSent ? 0.0f : o, v);
+                        } else {
+                            sh.lscore[slot] = __fadd_rn(sh.lscore[slot], v);
+                        }
+                    } else if (!neg && !opt) {
+                        sh.ldoc[slot] = kNoMoreDocs;
+                    }
+                }
+                __syncwarp();
+                continue;
+            }
             for (int r = 0; r < kAndSteps; r++) {
                 const int slot = warp * kBlock + r * 32 + lane;
                 int d = sh.ldoc[slot];

@@ -48,6 +48,7 @@ struct rg_batch {
     Span<uint32_t> group_item_begin, group_out;
     Span<uint32_t> item_head, item_matches, item_theta;
     Span<unsigned long long> arena_next;  // [0] bump pointer, [1] error flag (as u32 view)
+    Span<unsigned long long> dbg;         // RG_CFG_STATS counters (zeroed per run)
     Span<rg_hit> out_hits;
     Span<uint32_t> out_counts;
     Span<unsigned long long> out_total;
@@ -85,7 +86,12 @@ struct QShape {
     bool dismax = false;               // DisjunctionMaxQuery: score = max + (sum - max) * tie
     float tie = 0.0f;
     std::vector<uint32_t> opt_idx;     // SHOULD clauses beside a MUST (ReqOptScorer's optional side), clause order
+    bool match_all = false;            // only MUST_NOT clauses: BooleanQuery::build adds MatchAllDocsQuery (score 0)
 };
+
+// what a clause scores with: a FILTER clause is a required clause with NonScoringSimilarity, i.e. exactly 0f32
+// (= BM25 with weight +0: 0 * (k1+1) * f / (f + norm) = +0 for any finite norm)
+inline float clause_weight(const rg_clause& c) { return c.occur == RG_FILTER ? 0.0f : c.weight; }
 
 // BooleanQuery::build + BooleanWeight::create_scorer wiring for the accelerated shapes.
 QShape classify(const rg_query& q, const rg_clause* clauses, uint32_t n_clauses_total) {
@@ -110,21 +116,30 @@ QShape classify(const rg_query& q, const rg_clause* clauses, uint32_t n_clauses_
         s.clause_idx.push_back(q.clause_begin);
         return s;
     }
-    std::vector<uint32_t> musts, shoulds, must_nots;
+    std::vector<uint32_t> musts, shoulds, filters, must_nots;
     for (uint32_t i = 0; i < q.n_clauses; i++) {
         const rg_clause& c = clauses[q.clause_begin + i];
         if (c.occur == RG_MUST) musts.push_back(q.clause_begin + i);
         else if (c.occur == RG_SHOULD) shoulds.push_back(q.clause_begin + i);
         else if (c.occur == RG_MUST_NOT) must_nots.push_back(q.clause_begin + i);
+        else if (c.occur == RG_FILTER) filters.push_back(q.clause_begin + i);
         else throw ArgError("unknown occur");
     }
     int32_t msm = q.min_should_match > 0 ? q.min_should_match : (musts.empty() ? 1 : 0);
-    if (musts.size() + shoulds.size() + must_nots.size() == 0)
+    if (musts.size() + shoulds.size() + filters.size() + must_nots.size() == 0)
         throw ArgError("boolean query should at least contain one inner query!");
-    if (musts.empty() && shoulds.empty())
-        throw Unsupported("pure MUST_NOT (MatchAllDocsQuery) is not accelerated");
-    if (musts.size() + shoulds.size() + must_nots.size() > (size_t)kMaxTerms)
+    if (musts.size() + shoulds.size() + filters.size() + must_nots.size() > (size_t)kMaxTerms)
         throw Unsupported("more than 9 clauses");
+    // BooleanQuery::create_weight (:96-125): must_weights = the MUST clauses, then the FILTER clauses
+    // (needs_scores = false); BooleanWeight::create_scorer treats them alike from there on
+    musts.insert(musts.end(), filters.begin(), filters.end());
+    if (musts.empty() && shoulds.empty()) {
+        // only MUST_NOT clauses (:76-79): musts.push(MatchAllDocsQuery) -> ReqNotScorer(all docs with score 0, ...)
+        s.type = kTypeOr;
+        s.match_all = true;
+        s.not_idx = must_nots;
+        return s;
+    }
     // BooleanWeight::create_scorer (:253-278): ReqNotScorer(must | should, must_not); the excluded
     // set is the union of the MUST_NOT clauses (DisjunctionSumScorer with needs_scores = false)
     s.not_idx = must_nots;
@@ -158,29 +173,38 @@ QShape classify(const rg_query& q, const rg_clause* clauses, uint32_t n_clauses_
 // already in the engine's cache is used as is; a new one is built when at least two clauses of the
 // batch share it (RG_CFG_EAGER_COLUMNS: one), most valuable (uses x df) first, evicting least recently
 // used columns no batch references while over the HBM budget.  RG_CFG_NO_COLUMNS turns the feature off.
+constexpr uint32_t kMatchAllTerm = 0xffffffffu;  // ColKey term of a leaf's MatchAllDocsQuery column
+
 std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape>& shapes, const rg_clause* clauses,
                                           float k1, HostPlan& hp) {
     std::map<ColKey, uint32_t> chosen;
-    if (e->cfg.flags & (RG_CFG_NO_COLUMNS | RG_CFG_NO_BITMAPS)) return chosen;
+    const bool cols_off = (e->cfg.flags & (RG_CFG_NO_COLUMNS | RG_CFG_NO_BITMAPS)) != 0;  // (a match-all column is not optional)
     const bool eager = (e->cfg.flags & RG_CFG_EAGER_COLUMNS) != 0;
     const uint32_t min_uses = eager ? 1u : 2u;
     uint32_t k1bits;
     memcpy(&k1bits, &k1, 4);
     std::map<ColKey, uint32_t> uses;
+    bool any_match_all = false;
     for (const QShape& sh : shapes) {
-        if (sh.type != kTypeOr) continue;
+        any_match_all = any_match_all || sh.match_all;
+        if (cols_off) continue;
         for (uint32_t si = 0; si < e->segs.size(); si++) {
             const Segment& seg = e->segs[si];
-            for (uint32_t ci : sh.clause_idx) {
+            auto count = [&](uint32_t ci) {
                 const rg_clause& c = clauses[ci];
-                if (c.term_id >= seg.host_terms.size() || seg.bitmap_slot[c.term_id] < 0) continue;
+                if (c.term_id >= seg.host_terms.size() || seg.bitmap_slot[c.term_id] < 0) return;
+                const float w = clause_weight(c);
                 uint32_t wbits;
-                memcpy(&wbits, &c.weight, 4);
+                memcpy(&wbits, &w, 4);
                 uses[ColKey(si, c.term_id, wbits, c.cache_id, k1bits)]++;
-            }
+            };
+            for (uint32_t ci : sh.clause_idx) count(ci);
+            // conjunctions probe the columns of their non-lead clauses (which clause leads depends on the leaf;
+            // the lead's use is counted too and simply stays unused)
+            for (uint32_t ci : sh.opt_idx) count(ci);
         }
     }
-    if (uses.empty()) return chosen;
+    if (uses.empty() && !any_match_all) return chosen;
     if (e->col_budget_floats == 0) {  // once per index state (cudaMemGetInfo costs milliseconds)
         size_t free_b = 0, total_b = 0;
         RG_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
@@ -208,6 +232,27 @@ std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape
     std::vector<ColumnJob> jobs;
     uint32_t n_units = 0;
     cudaStream_t st = e->stream;
+    if (any_match_all) {
+        // MatchAllDocsQuery (query/match_all_query.rs:28-116) as a column: every docid of the leaf, score 0f32
+        for (uint32_t si = 0; si < e->segs.size(); si++) {
+            const ColKey key(si, kMatchAllTerm, 0u, 0u, 0u);
+            auto it = e->col_cache.find(key);
+            if (it == e->col_cache.end()) {
+                auto ent = std::make_shared<ColEntry>();
+                ent->key = key;
+                ent->len = ((uint64_t)e->segs[si].max_doc + 1024 + 3) & ~3ull;
+                if (cudaMalloc(reinterpret_cast<void**>(&ent->col), ent->len * sizeof(float)) != cudaSuccess) {
+                    cudaGetLastError();
+                    ent->col = nullptr;
+                    continue;
+                }
+                RG_CUDA_CHECK(cudaMemsetAsync(ent->col, 0, ent->len * sizeof(float), st));
+                e->col_floats += ent->len;
+                it = e->col_cache.emplace(key, ent).first;
+            }
+            add_ref(key, it->second);
+        }
+    }
     for (const auto& r : to_build) {
         if (hp.col_refs.size() >= 4096) break;
         const Segment& seg = e->segs[std::get<0>(r.second)];
@@ -297,7 +342,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 else if (shape.type != kTypeOr) dead = true;  // create_scorer -> None (:201-206)
             }
             const bool new_group = mode == RG_MODE_SEARCH_PARALLEL || !group_open;
-            if (dead || present.empty()) continue;
+            if (dead || (present.empty() && !shape.match_all)) continue;
             if (shape.type == kTypeOr && shape.msm > present.size()) continue;  // nothing can reach msm here
             std::vector<uint32_t> nots;  // MUST_NOT clauses present in this leaf (:236-251)
             for (uint32_t ci : shape.not_idx) {
@@ -312,7 +357,9 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
             // no SHOULD scorer in this leaf -> the MUST side alone, no ReqOptScorer (:259-266)
             const int leaf_type = shape.type == kTypeReqOpt && opts.empty() ? (int)kTypeAnd : shape.type;
             uint64_t cost = 0, bytes = 0, total_df = 0;
-            if (shape.type != kTypeOr) {
+            if (shape.match_all) {
+                cost = total_df = (uint64_t)seg.max_doc;  // AllDocsIterator: every docid of the leaf
+            } else if (shape.type != kTypeOr) {
                 // ConjunctionScorer::new: stable sort by cost() = doc_freq (:30)
                 std::stable_sort(present.begin(), present.end(), [&](uint32_t a, uint32_t b) {
                     return seg.host_terms[clauses[a].term_id].doc_freq < seg.host_terms[clauses[b].term_id].doc_freq;
@@ -340,52 +387,75 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 bytes += cost;  // one norm byte per scored posting
                 total_df = cost;
             }
+            for (uint32_t ci : nots) bytes += seg.host_terms[clauses[ci].term_id].enc_bytes;
             hp.postings += total_df;
             hp.algo_bytes += bytes;
             const uint32_t clause_begin = (uint32_t)hp.clauses.size();
-            // A disjunction goes to k_eval_or_ms (presence bitmaps, non-essential clauses are only counted)
-            // when it is a plain sum of SHOULD clauses, reads at least one score column, and none of its
-            // other clauses is dense (a dense block stream would cut its windows to a few docids).
+            // score column of a clause in this leaf (-1: none)
+            auto col_of = [&](uint32_t ci) -> int64_t {
+                if (columns.empty()) return -1;
+                const rg_clause& c = clauses[ci];
+                const float w = clause_weight(c);
+                uint32_t wbits;
+                memcpy(&wbits, &w, 4);
+                const auto it = columns.find(ColKey(si, c.term_id, wbits, c.cache_id, k1bits));
+                return it == columns.end() ? -1 : (int64_t)it->second;
+            };
+            auto df_of = [&](uint32_t ci) { return (uint64_t)seg.host_terms[clauses[ci].term_id].doc_freq; };
             bool use_ms = false;
-            if (shape.type == kTypeOr && !columns.empty()) {
+            uint32_t n_streams = 0;
+            if (shape.match_all) {
+                // the leaf's match-all column (every docid present, score 0) + the MUST_NOT streams: k_eval_or<NOT>
+                const auto it = columns.find(ColKey(si, kMatchAllTerm, 0u, 0u, 0u));
+                if (it == columns.end()) throw Unsupported("no memory for the MatchAllDocsQuery column");
+                hp.clauses.push_back(ItemClause{it->second, 0.0f, 0u, 4u | 16u});
+            } else if (shape.type == kTypeOr) {
+                // A disjunction goes to k_eval_or_ms (presence bitmaps, non-essential clauses are only counted)
+                // when it is a plain sum of SHOULD clauses, reads at least one score column, and none of its
+                // other clauses is dense (a dense block stream would cut its windows to a few docids).
                 uint32_t n_col = 0;
                 bool dense_stream = false;
                 for (uint32_t ci : present) {
-                    const rg_clause& c = clauses[ci];
-                    uint32_t wbits;
-                    memcpy(&wbits, &c.weight, 4);
-                    if (columns.count(ColKey(si, c.term_id, wbits, c.cache_id, k1bits))) n_col++;
-                    else if ((uint64_t)seg.host_terms[c.term_id].doc_freq * 32u >= (uint64_t)seg.max_doc) dense_stream = true;
+                    if (col_of(ci) >= 0) n_col++;
+                    else if (df_of(ci) * 32u >= (uint64_t)seg.max_doc) dense_stream = true;
                 }
                 use_ms = !no_ms && n_col > 0 && !dense_stream && nots.empty() && !shape.msm && !(shape.dismax && present.size() > 1);
-            }
-            uint32_t n_streams = 0;
-            for (uint32_t ci : present) {
-                const rg_clause& c = clauses[ci];
-                if (shape.type == kTypeOr && !columns.empty()) {
-                    uint32_t wbits;
-                    memcpy(&wbits, &c.weight, 4);
-                    const auto it = columns.find(ColKey(si, c.term_id, wbits, c.cache_id, k1bits));
+                for (uint32_t ci : present) {
+                    const rg_clause& c = clauses[ci];
+                    const int64_t col = col_of(ci);
                     // the exhaustive kernel scans a column docid by docid: that only pays for df >= max_doc/8
-                    if (it != columns.end() &&
-                        (use_ms || (uint64_t)seg.host_terms[c.term_id].doc_freq * 8u >= (uint64_t)seg.max_doc)) {
+                    if (col >= 0 && (use_ms || df_of(ci) * 8u >= (uint64_t)seg.max_doc)) {
                         // bit4: the MaxScore bound w*(k1+1) needs weight >= 0 and cache entries >= 0
-                        const bool boundable = c.weight >= 0.0f && c.weight < INFINITY && k1 >= 0.0f &&
+                        const float w = clause_weight(c);
+                        const bool boundable = w >= 0.0f && w < INFINITY && k1 >= 0.0f &&
                                                c.cache_id < e->cache_nonneg.size() && e->cache_nonneg[c.cache_id];
-                        hp.clauses.push_back(ItemClause{it->second, c.weight, c.cache_id, 4u | (boundable ? 0u : 16u)});
+                        hp.clauses.push_back(ItemClause{(uint32_t)col, w, c.cache_id, 4u | (boundable ? 0u : 16u)});
                         continue;
                     }
+                    n_streams++;
+                    hp.clauses.push_back(ItemClause{c.term_id, clause_weight(c), c.cache_id, 0});
                 }
-                n_streams++;
-                hp.clauses.push_back(ItemClause{c.term_id, c.weight, c.cache_id, 0});
+            } else {
+                // conjunction: the lead (cheapest) clause is a block stream; every other clause that has a score
+                // column is probed by one gather per lead doc instead of skip search + block decode
+                for (size_t i = 0; i < present.size(); i++) {
+                    const rg_clause& c = clauses[present[i]];
+                    const int64_t col = i == 0 ? -1 : col_of(present[i]);
+                    if (col >= 0) hp.clauses.push_back(ItemClause{(uint32_t)col, clause_weight(c), c.cache_id, 4u});
+                    else hp.clauses.push_back(ItemClause{c.term_id, clause_weight(c), c.cache_id, 0});
+                }
             }
             for (uint32_t ci : nots) {
-                hp.clauses.push_back(ItemClause{clauses[ci].term_id, 0.0f, clauses[ci].cache_id, 1u});
-                bytes += seg.host_terms[clauses[ci].term_id].enc_bytes;
+                const int64_t col = shape.type == kTypeOr ? -1 : col_of(ci);  // conjunctions: any column of the term will do
+                if (col >= 0) hp.clauses.push_back(ItemClause{(uint32_t)col, 0.0f, clauses[ci].cache_id, 1u | 4u});
+                else hp.clauses.push_back(ItemClause{clauses[ci].term_id, 0.0f, clauses[ci].cache_id, 1u});
             }
-            for (uint32_t ci : opts)
-                hp.clauses.push_back(ItemClause{clauses[ci].term_id, clauses[ci].weight, clauses[ci].cache_id, 2u});
-            const uint32_t n_item_terms = (uint32_t)(present.size() + nots.size() + opts.size());
+            for (uint32_t ci : opts) {
+                const int64_t col = col_of(ci);
+                if (col >= 0) hp.clauses.push_back(ItemClause{(uint32_t)col, clauses[ci].weight, clauses[ci].cache_id, 2u | 4u});
+                else hp.clauses.push_back(ItemClause{clauses[ci].term_id, clauses[ci].weight, clauses[ci].cache_id, 2u});
+            }
+            const uint32_t n_item_terms = (uint32_t)(present.size() + (shape.match_all ? 1 : 0) + nots.size() + opts.size());
             // DisjunctionMaxWeight::create_scorer (disjunction_max_query.rs:135-155): one scorer in this
             // leaf is that scorer; otherwise the tie breaker rides in a meta clause after the item's
             const bool leaf_dismax = shape.dismax && present.size() > 1;
@@ -543,6 +613,7 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     carve(b->item_matches, b->n_items);
     carve(b->item_theta, b->n_items);
     carve(b->arena_next, 2);
+    carve(b->dbg, 16);
     carve(b->out_hits, (size_t)std::max<uint32_t>(1, n_queries) * p->k);
     carve(b->out_counts, n_queries);
     carve(b->out_total, n_queries);
@@ -559,7 +630,7 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     };
     rebase(b->items); rebase(b->clauses); rebase(b->or_ids); rebase(b->and_ids); rebase(b->ms_ids); rebase(b->ro_ids); rebase(b->col_refs);
     rebase(b->group_item_begin); rebase(b->group_out); rebase(b->item_head); rebase(b->item_matches);
-    rebase(b->item_theta); rebase(b->arena_next); rebase(b->out_hits); rebase(b->out_counts);
+    rebase(b->item_theta); rebase(b->arena_next); rebase(b->dbg); rebase(b->out_hits); rebase(b->out_counts);
     rebase(b->out_total);
     if (p->mode == RG_MODE_SEARCH_PARALLEL) rebase(b->leaf_records);
     b->zero_begin = b->slab.p + zero_off;
@@ -609,6 +680,7 @@ int rg_batch_run(rg_engine* e, rg_batch* b) {
     ep.item_matches = b->item_matches.p;
     ep.item_theta = b->item_theta.p;
     ep.error_flag = reinterpret_cast<uint32_t*>(b->arena_next.p + 1);
+    ep.dbg = (e->cfg.flags & RG_CFG_STATS) ? b->dbg.p : nullptr;
     RG_CUDA_CHECK(cudaEventRecord(e->ev2, st));
     ep.cols = b->col_refs.p;
     bool has_live = false, has_other = false;
@@ -710,6 +782,18 @@ int rg_search_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     if (rc == RG_OK) rc = rg_batch_fetch(e, b, out_hits, out_counts, out_total_hits);
     rg_batch_destroy(e, b);
     return rc;
+}
+
+int rg_batch_debug(rg_engine* e, rg_batch* b, uint64_t out[16]) {
+    RG_TRY
+    if (!e || !b || !out) throw ArgError("null argument");
+    memset(out, 0, 16 * sizeof(uint64_t));
+    if (b->ran) {
+        RG_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        RG_CUDA_CHECK(cudaMemcpy(out, b->dbg.p, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    }
+    return RG_OK;
+    RG_CATCH
 }
 
 int rg_batch_columns(rg_engine* e, rg_batch* b, uint32_t* n_columns, uint64_t* bytes) {

@@ -15,7 +15,7 @@ MUST, SHOULD, MUST_NOT = 0, 1, 2
 Q_BOOLEAN = 1
 Q_DISMAX = 2    # rg_query.flags: DisjunctionMaxQuery; min_should_match = bits of the f32 tie breaker
 MODE_SEARCH, MODE_SEARCH_PARALLEL = 0, 1
-CFG_NO_COLUMNS, CFG_EAGER_COLUMNS, CFG_NO_BITMAPS, CFG_NO_MAXSCORE = 1, 2, 4, 8   # rg_config.flags (include/rucene_gpu.h)
+CFG_NO_COLUMNS, CFG_EAGER_COLUMNS, CFG_NO_BITMAPS, CFG_NO_MAXSCORE, CFG_STATS = 1, 2, 4, 8, 16   # rg_config.flags (include/rucene_gpu.h)
 NO_MORE_DOCS = 0x7FFFFFFF
 
 TERM_STATE_DTYPE = np.dtype([("doc_freq", "<i4"), ("singleton_doc_id", "<i4"),
@@ -85,6 +85,7 @@ def lib():
     L.rg_batch_destroy.argtypes = [vp, vp]
     L.rg_batch_destroy.restype = None
     L.rg_batch_stats.argtypes = [vp, vp, vp]
+    L.rg_batch_debug.argtypes = [vp, vp, vp]
     L.rg_batch_columns.argtypes = [vp, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
     L.rg_batch_leaf_records.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.rg_merge_leaf_records.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp]
@@ -131,6 +132,15 @@ class Batch:
         return {"items": int(out[0]), "postings": int(out[1]), "algorithmic_bytes": int(out[2]),
                 "candidate_slots": int(out[3]), "kernels_per_run": int(out[4]),
                 "h2d_bytes": int(out[5]), "or_items": int(out[6]), "and_items": int(out[7])}
+
+    def debug(self):
+        """RG_CFG_STATS event counters of the last run (include/rucene_gpu.h: rg_batch_debug)"""
+        out = np.zeros(16, np.uint64)
+        _check(lib().rg_batch_debug(self.engine.h, self.h, _p(out)), self.engine.h)
+        names = ["items", "windows", "windows_with_essential_column", "windows_before_theta", "docids_only_counted",
+                 "stream_postings", "column_gathers", "refills", "candidates", "steps_scanned", "windows_cut",
+                 "nonessential_clause_windows"]
+        return {n: int(out[i]) for i, n in enumerate(names)}
 
     def columns(self):
         """(number of score columns chosen for this batch, their bytes in HBM)"""
