@@ -10,7 +10,8 @@ namespace rg {
 constexpr int kBlock = 128;           // codec/postings/posting_format.rs BLOCK_SIZE
 constexpr int kMaxTerms = 9;          // DisjunctionSumScorer SimpleQueue regime (< 10 children)
 constexpr int kNoMoreDocs = 0x7fffffff;
-constexpr int kBitmapDen = 64;        // terms with df >= max_doc / 64 get a presence bitmap at upload
+constexpr int kBitmapDen = 1024;      // terms with df >= max_doc / 1024 get a presence bitmap at upload (within a budget)
+constexpr int kColumnDen = 64;        // terms with df >= max_doc / 64 may also get a score column (per weight, on demand)
 
 // ------------------------------------------------------------------ index image in HBM
 // Every full 128-posting block pair of a term owns one 16-byte aligned slot in `arena`:
@@ -59,7 +60,8 @@ struct ItemClause {
     uint32_t flags;    // bit0: MUST_NOT clause (ReqNotScorer: excludes, never scores)
                        // bit1: SHOULD clause beside a MUST (ReqOptScorer's optional side)
                        // bit2: score column — term_id is an index into EvalParams::cols
-                       // bit4: (with bit2) never treat as non-essential: weight < 0 / NaN or a norm cache with negative entries
+                       // bit4: no usable score bound: weight < 0 / NaN or a norm cache with negative entries
+                       // bit5: block stream of a term that has a presence bitmap: bits [16, 32) index EvalParams::cols (.bits)
                        // bit3: meta entry after a DisjunctionMaxScorer item's clauses: weight = tie breaker
 };
 

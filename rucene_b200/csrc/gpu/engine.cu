@@ -622,7 +622,9 @@ void build_segment(rg_engine* e, Segment& seg, int32_t doc_base, int32_t max_doc
             return terms[a].doc_freq != terms[b].doc_freq ? terms[a].doc_freq > terms[b].doc_freq : a < b;
         });
         seg.bitmap_words = (((uint64_t)max_doc + 31) / 32 + 64 + 3) & ~3ull;
-        const uint64_t budget = std::max<uint64_t>(64ull << 20, seg.arena.bytes());  // bytes
+        size_t free_b = 0, total_b = 0;
+        RG_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+        const uint64_t budget = std::max<uint64_t>(64ull << 20, (uint64_t)free_b / 5);  // bytes: a fifth of the free HBM
         const size_t n_bm = (size_t)std::min<uint64_t>(dense.size(), budget / (seg.bitmap_words * 4));
         if (n_bm) {
             dense.resize(n_bm);

@@ -1,54 +1,56 @@
 // eval_or_ms.cu — k_eval_or_ms: pure-SHOULD sum disjunctions (DisjunctionSumScorer, TermScorer) over
-// presence bitmaps + score columns, with MaxScore-style non-essential clauses.  sm_100a, integer/HBM work.
+// presence bitmaps, score columns and a bit-sliced per-document score bound.  sm_100a, integer/HBM work.
 //
 // What the reference computes (search/scorer/disjunction_scorer.rs:187-244, bulk_scorer.rs:89-122,
 // collector/top_docs.rs:67-95) is, per (query, leaf): total_hits = |union of the clauses' live docs| and the
 // TopDocsCollector heap fed with every union doc in docid order, score = clause-order f32 sum.  A doc changes
 // the heap only if root.score < score.  With theta = a proven lower bound of the heap root at that point
 // (eval_shared.cuh) the evaluation splits into
-//   * counting   — needs presence only.  Dense terms carry a presence bitmap built at upload, so a
-//                  clause that is a score column costs one 32-bit word per 32 docids: popc(OR of words);
-//   * candidates — only docs whose score can exceed theta.  Column clauses are ordered by their score
-//                  bound ub = nextafter(weight*(k1+1)) (BM25's tf-norm factor is < 1 for norm >= 0); the
-//                  longest prefix whose rounded-up sum S stays <= theta is NON-ESSENTIAL: a doc that
-//                  matches only such clauses scores <= S <= theta <= root and can never be collected into
-//                  the heap.  Every doc that matches an essential clause (block-stream clauses always are)
-//                  gets its exact score: clauses are visited in clause order and add into a per-window
-//                  accumulator, block streams by scatter, columns by gathering col[d] for the docs of the
-//                  window's essential set E that carry the clause's bit.
-// Because the low-idf (dense) clauses are the ones that become non-essential once k better docs were seen,
-// most of a long disjunction's postings are never decoded or scored, only counted — and the result is still
-// bit-identical to the reference, ties included, because the heap replay sees every doc that could enter.
+//   * counting   — needs presence only.  Every term with df >= max_doc/1024 carries a presence bitmap built at
+//                  upload, so such a clause costs one 32-bit word per 32 docids: popc(OR of the words);
+//   * candidates — only docs whose score can exceed theta.  A clause's contribution is bounded by
+//                  ub = nextafter(weight*(k1+1)) (BM25's tf-norm factor is < 1 for norm >= 0).  The bounds are
+//                  quantised to q = ceil(ub * 63 / theta) and summed PER DOCUMENT for 32 docids at a time with a
+//                  bit-sliced adder over the clauses' bitmap words (6 planes + a sticky carry): a doc whose carry
+//                  stays clear has sum(ub of its clauses) <= theta, scores <= theta <= root and can never be
+//                  collected into the heap.  The docs with a carry, plus every doc of a clause without a bitmap
+//                  (sparse block streams), form the window's set E and get their exact score: clauses are visited
+//                  in clause order and add into a per-window accumulator — sparse streams by scatter, score columns
+//                  by gathering col[d], block streams that have a bitmap by seeking to the window and scattering
+//                  the postings that fall on E.
+// Most postings of a long disjunction are therefore never decoded or scored, only counted, and the result is
+// still bit-identical to the reference, ties included, because the heap replay sees every doc that could enter.
 //
-// Work item = (query, leaf, docid range), one WARP each.  The warp walks windows of up to 1024 docids
-// (lane l owns presence word l); a window starts at the next posting of an essential clause and ends where
-// a stream's cached block ends (so every stream posting of the window is in shared memory before the
-// clause-ordered pass starts); the docids between windows hold non-essential postings only and are
-// counted in bulk from the bitmaps.
+// Work item = (query, leaf, docid range), one WARP each.  The warp walks windows of up to 1024 docids (lane l owns
+// presence word l).  While some combination of bitmap clauses can still beat theta the windows are contiguous
+// (each costs the word loads + the adder unless E is non-empty); once no combination can, windows exist only at
+// the postings of the sparse streams and everything between them is counted in bulk from the bitmaps.  A window
+// ends where a sparse stream's cached block ends, so all its sparse postings are in shared memory when E is formed.
 #include "eval_shared.cuh"
 
 namespace rg {
 
 constexpr int kMsWarps = 4;
 constexpr int kMsThreads = kMsWarps * 32;
-constexpr int kMsW = 1024;  // docids per window = 32 lanes x one 32-bit presence word
+constexpr int kMsW = 1024;     // docids per window = 32 lanes x one 32-bit presence word
+constexpr int kMsPlanes = 6;   // bit-sliced bound: theta <-> 2^6 - 1
+constexpr uint32_t kMsSat = 1u << kMsPlanes;
 
-struct MsCol {
-    const float* col;      // leaf-local docid -> BM25 contribution (valid where the bitmap has a bit)
-    const uint32_t* bits;  // presence bitmap of the term
-};
+enum : int { kKindNone = 0, kKindCol = 1, kKindBStream = 2, kKindSparse = 3 };
 
 struct alignas(16) MsWarpShared {  // followed by topk[kcap] floats, then cdocs[S][128], cscores[S][128]
     float acc[kMsW];               // 0.0f = untouched; touched docs are exactly the bits of E
-    uint32_t ubits[32];            // presence words of the block-stream clauses in this window
+    uint32_t ubits[32];            // presence words of the sparse streams in this window
+    uint32_t ebits[32];            // E: the docs of this window that get an exact score
     WTerm term[kMaxTerms];         // block-stream clauses (same cursor as k_eval_or)
-    MsCol colv[kMaxTerms];
+    const float* col[kMaxTerms];   // score column (leaf-local docid -> BM25 contribution), column clauses
+    const uint32_t* bits[kMaxTerms];  // presence bitmap, column clauses and block streams of dense-enough terms
     float newc[kNewcW];
 };
 
-// docs of [a, b) present in any column clause (and live): bulk popcount over the bitmaps; per-lane partial sum
+// docs of [a, b) present in any bitmap clause (and live): bulk popcount; per-lane partial sum
 template <bool LIVE>
-__device__ __forceinline__ uint32_t ms_count_range(const MsWarpShared& sh, uint32_t col_mask, const SegDev& seg,
+__device__ __forceinline__ uint32_t ms_count_range(const MsWarpShared& sh, uint32_t bmask, const SegDev& seg,
                                                    int a, int b, int lane) {
     uint32_t cnt = 0;
     const int w_end = (b + 31) >> 5;
@@ -58,7 +60,7 @@ __device__ __forceinline__ uint32_t ms_count_range(const MsWarpShared& sh, uint3
         if (d0 < a) m &= ~((1u << (a - d0)) - 1u);
         if (d0 + 32 > b) m &= (1u << (b - d0)) - 1u;
         uint32_t u = 0;
-        for (uint32_t cm = col_mask; cm; cm &= cm - 1) u |= __ldg(sh.colv[__ffs(cm) - 1].bits + w);
+        for (uint32_t cm = bmask; cm; cm &= cm - 1) u |= __ldg(sh.bits[__ffs(cm) - 1] + w);
         u &= m;
         if (LIVE && seg.live) u &= reinterpret_cast<const uint32_t*>(seg.live)[w];
         cnt += __popc(u);
@@ -85,25 +87,25 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
     const int lo = it.lo, hi = it.hi;
 
     // ---- clauses: lane t < T owns clause t
-    bool is_col = false;
-    float ub = 0.0f;  // score bound of a column clause (INF: never non-essential)
+    int kind = kKindNone;
+    float ub = 0.0f;  // score bound of a bitmap clause (INF: no usable bound)
     ItemClause c{};
     if (lane < T) {
         c = p.clauses[it.clause_begin + lane];
-        is_col = (c.flags & 4u) != 0;
+        kind = (c.flags & 4u) ? kKindCol : (c.flags & 32u) ? kKindBStream : kKindSparse;
     }
-    const uint32_t col_mask = __ballot_sync(0xffffffffu, is_col);
-    const uint32_t stream_mask = __ballot_sync(0xffffffffu, lane < T && !is_col);
-    const int n_streams = __popc(stream_mask);
-    float* cscores = reinterpret_cast<float*>(cdocs + n_streams * kBlock);
+    const uint32_t col_mask = __ballot_sync(0xffffffffu, kind == kKindCol);
+    const uint32_t bstream_mask = __ballot_sync(0xffffffffu, kind == kKindBStream);
+    const uint32_t sparse_mask = __ballot_sync(0xffffffffu, kind == kKindSparse);
+    const uint32_t stream_mask = bstream_mask | sparse_mask;
+    const uint32_t bmask = col_mask | bstream_mask;  // clauses with a presence bitmap
+    float* cscores = reinterpret_cast<float*>(cdocs + __popc(stream_mask) * kBlock);
     const int my_slot = __popc(stream_mask & ((1u << lane) - 1u));  // stream cache slot of clause `lane`
-    if (is_col) {
+    if (kind == kKindCol) {
         const ColRef r = p.cols[c.term_id];
-        sh.colv[lane] = MsCol{r.col, r.bits};
-        const float w1 = __fmul_rn(c.weight, __fadd_rn(p.k1, 1.0f));
-        // score = rn(rn(w1*f) / rn(f + norm)) with f >= 1, norm >= 0  =>  score <= nextafter(w1)
-        ub = (c.flags & 16u) || !(w1 >= 0.0f) || !(w1 < INFINITY) ? INFINITY : __uint_as_float(__float_as_uint(w1) + 1u);
-    } else if (lane < T) {
+        sh.col[lane] = r.col;
+        sh.bits[lane] = r.bits;
+    } else if (kind != kKindNone) {
         const TermDev td = seg.terms[c.term_id];
         WTerm& tc = sh.term[lane];
         tc.is_col = 0;
@@ -117,31 +119,26 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
         tc.term_id = c.term_id;
         tc.w1 = __fmul_rn(c.weight, __fadd_rn(p.k1, 1.0f));
         tc.is_not = 0;
+        sh.col[lane] = nullptr;
+        sh.bits[lane] = kind == kKindBStream ? p.cols[c.flags >> 16].bits : nullptr;
     }
-    // non-essential test: clause t is non-essential while S_t <= theta, S_t = rounded-up sum of the bounds of the
-    // column clauses ordered before-or-at t by (ub, clause index), inflated by 2^-20 so it also covers the
-    // rounding of the reference's round-to-nearest clause-order sum of up to 9 scores
-    float ne_bound = INFINITY;
-    {
-        float S = 0.0f;
-        for (int j = 0; j < T; j++) {
-            const float ubj = __shfl_sync(0xffffffffu, ub, j);
-            if (((col_mask >> j) & 1u) && (ubj < ub || (ubj == ub && j <= lane))) S = __fadd_ru(S, ubj);
-        }
-        if (is_col && ub < INFINITY) ne_bound = __fmul_ru(S, 1.00000095367431640625f);
+    if ((bmask >> lane) & 1u) {
+        const float w1 = __fmul_rn(c.weight, __fadd_rn(p.k1, 1.0f));
+        // score = rn(rn(w1*f) / rn(f + norm)) with f >= 1, norm >= 0  =>  score <= nextafter(w1)
+        ub = (c.flags & 16u) || !(w1 >= 0.0f) || !(w1 < INFINITY) ? INFINITY : __uint_as_float(__float_as_uint(w1) + 1u);
     }
     for (int i = lane; i < kMsW / 4; i += 32) reinterpret_cast<float4*>(sh.acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
 
     MsmCtx mc_unused{nullptr, 1u, nullptr};
     uint32_t hot_unused = 0, mm_unused = 0;
-    int nd = kNoMoreDocs;  // stream lane t: next cached docid of clause t (kNoMoreDocs = exhausted)
-    for (uint32_t m = stream_mask; m; m &= m - 1) {
+    int nd = kNoMoreDocs;  // sparse stream lane t: next cached docid of clause t (kNoMoreDocs = exhausted)
+    for (uint32_t m = sparse_mask; m; m &= m - 1) {  // (streams that have a bitmap are decoded on demand)
         const int t = __ffs(m) - 1;
         const int slot = __popc(stream_mask & ((1u << t) - 1u));
         if (stream_refill<false, false, false, false>(seg, p, sh.term[t], cdocs + slot * kBlock, cscores + slot * kBlock, lo,
-                                                      hi, lane, 0, -2147483647 - 1, reinterpret_cast<uint32_t*>(sh.acc), hot_unused, mm_unused,
-                                                      INFINITY, mc_unused)) {
+                                                      hi, lane, 0, -2147483647 - 1, reinterpret_cast<uint32_t*>(sh.acc),
+                                                      hot_unused, mm_unused, INFINITY, mc_unused)) {
             const int first = cdocs[slot * kBlock + sh.term[t].pos];
             if (lane == t) nd = first;
         }
@@ -162,9 +159,14 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
     uint32_t win_no = 0;
     uint32_t my_matches = 0;
     int pos = lo;  // every docid < pos is counted and, where needed, scored
+    // quantised bounds, valid for theta == q_te
+    float q_te = NAN;
+    uint32_t q = 0;          // lane t: q of clause t (kMsSat: any doc of the clause must be scored)
+    bool prune = false;      // a usable theta exists: docs without a carry are dropped
+    bool need_scan = bmask != 0;  // some combination of bitmap clauses can still beat theta
     // RG_CFG_STATS event counters (warp-uniform unless noted)
-    uint32_t st_win = 0, st_ess = 0, st_open = 0, st_gap = 0, st_post = 0, st_gather = 0 /* per lane */, st_refill = 0,
-             st_cand = 0, st_steps = 0, st_cut = 0, st_ne = 0;
+    uint32_t st_win = 0, st_scan = 0, st_open = 0, st_gap = 0, st_post = 0, st_gather = 0 /* per lane */, st_refill = 0,
+             st_cand = 0, st_steps = 0, st_cut = 0, st_scored = 0, st_edocs = 0 /* per lane */;
 
     for (;;) {
         uint32_t inherited = 0;
@@ -181,27 +183,40 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
         float te = em.theta_local;
         if (em.theta_in > kOrderedNegInf) te = fmaxf(te, ordered_to_float(em.theta_in));
         const bool open = te == -INFINITY;
-        const uint32_t ne_mask = open ? 0u : __ballot_sync(0xffffffffu, is_col && ne_bound <= te);
-        const uint32_t ess_cols = col_mask & ~ne_mask;
-        // ---- next window: the next posting of an essential clause (an essential column has one anywhere)
-        int w0 = __reduce_min_sync(0xffffffffu, is_col ? kNoMoreDocs : nd);
-        if (ess_cols) w0 = pos;
-        if (w0 >= hi) {  // nothing essential left: the rest of the range is only counted
-            if (col_mask && pos < hi) my_matches += ms_count_range<LIVE>(sh, col_mask, seg, pos, hi, lane);
+        if (!(te == q_te)) {  // theta moved: requantise the clause bounds
+            q_te = te;
+            prune = !open && te > 0.0f;
+            if (prune) {
+                // sum(ub) <= theta * (1 - 2^-20) also covers the rounding of the reference's round-to-nearest
+                // clause-order sum of up to 9 scores; everything rounds towards "keep the doc"
+                const float scale = __fdiv_ru((float)(kMsSat - 1u), __fmul_rd(te, 0.99999904632568359375f));
+                const float x = __fmul_ru(ub, scale);
+                q = ((bmask >> lane) & 1u) ? (x < (float)kMsSat ? (uint32_t)ceilf(x) : kMsSat) : 0u;  // NaN -> kMsSat
+                if (((bmask >> lane) & 1u) && q == 0u) q = 1u;
+                need_scan = __reduce_add_sync(0xffffffffu, q) >= kMsSat;
+            } else {
+                q = ((bmask >> lane) & 1u) ? kMsSat : 0u;
+                need_scan = bmask != 0;
+            }
+        }
+        // ---- next window: here if bitmap clauses can still matter, else at the next sparse posting
+        int w0 = need_scan ? pos : __reduce_min_sync(0xffffffffu, kind == kKindSparse ? nd : kNoMoreDocs);
+        if (w0 >= hi) {  // nothing left that could be scored: the rest of the range is only counted
+            if (bmask && pos < hi) my_matches += ms_count_range<LIVE>(sh, bmask, seg, pos, hi, lane);
+            st_gap += (uint32_t)(hi - pos);
             break;
         }
-        if (col_mask && w0 > pos) my_matches += ms_count_range<LIVE>(sh, col_mask, seg, pos, w0, lane);
+        if (bmask && w0 > pos) my_matches += ms_count_range<LIVE>(sh, bmask, seg, pos, w0, lane);
         st_gap += (uint32_t)(w0 - pos);
         st_win++;
-        st_ess += ess_cols != 0;
+        st_scan += need_scan;
         st_open += open;
-        st_ne += __popc(ne_mask);
         const int win0 = w0;
         const int base = win0 & ~31;
         int win1 = min(hi, base + kMsW);
-        {   // a stream whose cached block ends inside the window (and that has more blocks) ends the window there
+        {   // a sparse stream whose cached block ends inside the window (and that has more blocks) ends the window there
             int trunc = 0x7fffffff;
-            if (!is_col && lane < T) {
+            if (kind == kKindSparse) {
                 const WTerm& tc = sh.term[lane];
                 if (tc.pos < tc.n && tc.cur <= tc.nb) trunc = cdocs[my_slot * kBlock + tc.n - 1] + 1;
             }
@@ -215,86 +230,161 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
             const int wlo = max(win0 - (base + 32 * lane), 0), whi = min(win1 - (base + 32 * lane), 32);
             lmask = whi <= wlo ? 0u : ((whi >= 32 ? 0xffffffffu : ((1u << whi) - 1u)) & ~((1u << wlo) - 1u));
         }
-        // ---- 1. presence of the block-stream clauses (their postings of this window are all cached)
-        sh.ubits[lane] = 0u;
-        __syncwarp();
-        const uint32_t act = __ballot_sync(0xffffffffu, !is_col && nd < win1);
-        for (uint32_t m = act; m; m &= m - 1) {
-            const int t = __ffs(m) - 1;
-            const int slot = __popc(stream_mask & ((1u << t) - 1u));
-            const WTerm& tc = sh.term[t];
-            const int32_t* cd = cdocs + slot * kBlock;
-            const uint32_t n = tc.n;
-            for (uint32_t i = tc.pos + lane;; i += 32) {
-                const int d = i < n ? cd[i] : kNoMoreDocs;
-                const bool in_win = d < win1;
-                if (in_win) atomicOr(&sh.ubits[(d - base) >> 5], 1u << ((d - base) & 31));
-                if (!__all_sync(0xffffffffu, in_win)) break;
+        // ---- 1. presence of the sparse streams (their postings of this window are all cached)
+        const uint32_t act = __ballot_sync(0xffffffffu, kind == kKindSparse && nd < win1);
+        uint32_t E = 0;
+        if (act) {
+            sh.ubits[lane] = 0u;
+            __syncwarp();
+            for (uint32_t m = act; m; m &= m - 1) {
+                const int t = __ffs(m) - 1;
+                const int slot = __popc(stream_mask & ((1u << t) - 1u));
+                const WTerm& tc = sh.term[t];
+                const int32_t* cd = cdocs + slot * kBlock;
+                const uint32_t n = tc.n;
+                for (uint32_t i = tc.pos + lane;; i += 32) {
+                    const int d = i < n ? cd[i] : kNoMoreDocs;
+                    const bool in_win = d < win1;
+                    if (in_win) atomicOr(&sh.ubits[(d - base) >> 5], 1u << ((d - base) & 31));
+                    if (!__all_sync(0xffffffffu, in_win)) break;
+                }
             }
+            __syncwarp();
+            E = sh.ubits[lane];
         }
-        __syncwarp();
-        // ---- 2. presence words: E = docs that need an exact score, U = docs that count
-        uint32_t E = sh.ubits[lane];
+        // ---- 2. bitmap words: U = docs that count; bit-sliced sum of the quantised bounds -> carry = may beat theta
         uint32_t U = E;
         const int wi = (base >> 5) + lane;
-        if (lmask) {
-            for (uint32_t m = col_mask; m; m &= m - 1) {
+        {
+            uint32_t S[kMsPlanes];
+#pragma unroll
+            for (int i = 0; i < kMsPlanes; i++) S[i] = 0u;
+            uint32_t over = 0u;
+            for (uint32_t m = bmask; m; m &= m - 1) {
                 const int t = __ffs(m) - 1;
-                const uint32_t w = __ldg(sh.colv[t].bits + wi) & lmask;
+                const uint32_t w = lmask ? (__ldg(sh.bits[t] + wi) & lmask) : 0u;
                 U |= w;
-                if ((ess_cols >> t) & 1u) E |= w;
+                const uint32_t qt = __shfl_sync(0xffffffffu, q, t);
+                if (qt >= kMsSat) {  // no usable bound (or no theta yet): every doc of the clause
+                    over |= w;
+                } else if (need_scan) {
+                    uint32_t carry = 0u;
+#pragma unroll
+                    for (int i = 0; i < kMsPlanes; i++) {
+                        if ((qt >> i) & 1u) {  // warp-uniform
+                            const uint32_t x = S[i] ^ w;
+                            const uint32_t c2 = (S[i] & w) | (x & carry);
+                            S[i] = x ^ carry;
+                            carry = c2;
+                        } else {
+                            const uint32_t c2 = S[i] & carry;
+                            S[i] ^= carry;
+                            carry = c2;
+                        }
+                    }
+                    over |= carry;
+                }
             }
+            E |= over;
         }
         uint32_t lw = 0xffffffffu;
         if (LIVE && seg.live) lw = lmask ? reinterpret_cast<const uint32_t*>(seg.live)[wi] : 0u;
         my_matches += __popc(U & lw);
-        // ---- 3. exact scores of the docs in E: clauses in clause order (DisjunctionSumScorer::score_sum)
         uint32_t hot = 0;
-        for (int t = 0; t < T; t++) {
-            if ((stream_mask >> t) & 1u) {
-                if (!((act >> t) & 1u)) continue;
-                const int slot = __popc(stream_mask & ((1u << t) - 1u));
-                WTerm& tc = sh.term[t];
-                const int32_t* cd = cdocs + slot * kBlock;
-                const float* cs = cscores + slot * kBlock;
-                uint32_t cpos = tc.pos;
-                const uint32_t n = tc.n;
-                for (;;) {
-                    const uint32_t i = cpos + lane;
-                    const int d = i < n ? cd[i] : kNoMoreDocs;
-                    const bool in_win = d < win1;
-                    const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, in_win));  // sorted: a prefix
-                    if (in_win) {
-                        const int idx = d - base;
-                        const float sum = __fadd_rn(sh.acc[idx], cs[i]);
-                        sh.acc[idx] = sum;
-                        if (sum > te) hot |= 1u << (idx >> 5);
+        if (__any_sync(0xffffffffu, E != 0u)) {
+            st_scored++;
+            st_edocs += __popc(E);
+            sh.ebits[lane] = E;
+            __syncwarp();
+            // ---- 3. exact scores of the docs in E: clauses in clause order (DisjunctionSumScorer::score_sum)
+            for (int t = 0; t < T; t++) {
+                const int kt = __shfl_sync(0xffffffffu, kind, t);
+                if (kt == kKindSparse) {
+                    if (!((act >> t) & 1u)) continue;
+                    const int slot = __popc(stream_mask & ((1u << t) - 1u));
+                    WTerm& tc = sh.term[t];
+                    const int32_t* cd = cdocs + slot * kBlock;
+                    const float* cs = cscores + slot * kBlock;
+                    uint32_t cpos = tc.pos;
+                    const uint32_t n = tc.n;
+                    for (;;) {
+                        const uint32_t i = cpos + lane;
+                        const int d = i < n ? cd[i] : kNoMoreDocs;
+                        const bool in_win = d < win1;
+                        const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, in_win));  // sorted: a prefix
+                        if (in_win) {
+                            const int idx = d - base;
+                            const float sum = __fadd_rn(sh.acc[idx], cs[i]);
+                            sh.acc[idx] = sum;
+                            if (sum > te) hot |= 1u << (idx >> 5);
+                        }
+                        cpos += cnt;
+                        st_post += cnt;
+                        if (cnt < 32) break;
                     }
-                    cpos += cnt;
-                    st_post += cnt;
-                    if (cnt < 32) break;
+                    __syncwarp();  // every lane has read this clause's cursor
+                    if (lane == 0) tc.pos = cpos;
+                    if (lane == t) nd = cpos < n ? cd[cpos] : kNoMoreDocs;  // an emptied cache is refilled below
+                    __syncwarp();
+                } else if (kt == kKindCol) {
+                    uint32_t w = lmask ? (__ldg(sh.bits[t] + wi) & E) : 0u;
+                    if (!__any_sync(0xffffffffu, w != 0u)) continue;
+                    const float* col = sh.col[t] + base + 32 * lane;
+                    float* a = sh.acc + 32 * lane;
+                    while (w) {
+                        const int b = __ffs(w) - 1;
+                        w &= w - 1;
+                        const float sum = __fadd_rn(a[b], __ldg(col + b));
+                        a[b] = sum;
+                        st_gather++;
+                        if (sum > te) hot |= 1u << lane;
+                    }
+                    __syncwarp();
+                } else if (kt == kKindBStream) {
+                    // a block stream that does not drive windows: seek to this window, add the postings that fall on E
+                    if (!__any_sync(0xffffffffu, lmask && (__ldg(sh.bits[t] + wi) & E) != 0u)) continue;
+                    const int slot = __popc(stream_mask & ((1u << t) - 1u));
+                    WTerm& tc = sh.term[t];
+                    int32_t* cd = cdocs + slot * kBlock;
+                    float* cs = cscores + slot * kBlock;
+                    for (;;) {
+                        uint32_t cpos = tc.pos;
+                        const uint32_t n = tc.n;
+                        if (cpos >= n || cd[n - 1] < win0) {  // nothing cached for this window
+                            if (tc.cur > tc.nb) break;        // exhausted
+                            __syncwarp();                     // every lane has read the cursor
+                            if (lane == 0) tc.cur = lower_bound_gallop(tc.blk_last, min(tc.cur, tc.nb), tc.nb, win0);
+                            __syncwarp();
+                            st_refill++;
+                            if (!stream_refill<false, false, false, false>(seg, p, tc, cd, cs, lo, hi, lane, 0, -2147483647 - 1,
+                                                                          reinterpret_cast<uint32_t*>(sh.acc), hot_unused,
+                                                                          mm_unused, INFINITY, mc_unused))
+                                break;
+                            continue;
+                        }
+                        const uint32_t i = cpos + lane;
+                        const int d = i < n ? cd[i] : kNoMoreDocs;
+                        const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, d < win1));  // sorted: a prefix
+                        if (d >= win0 && d < win1) {
+                            const int idx = d - base;
+                            if ((sh.ebits[idx >> 5] >> (idx & 31)) & 1u) {
+                                const float sum = __fadd_rn(sh.acc[idx], cs[i]);
+                                sh.acc[idx] = sum;
+                                if (sum > te) hot |= 1u << (idx >> 5);
+                            }
+                        }
+                        st_post += cnt;
+                        __syncwarp();  // every lane has read the cursor
+                        if (lane == 0) tc.pos = cpos + cnt;
+                        __syncwarp();
+                        if (cnt < 32 && cpos + cnt < n) break;  // the next cached posting lies beyond the window
+                        // else: 32 more may follow, or the cache is used up and the next block may reach into the window
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();  // every lane has read this clause's cursor
-                if (lane == 0) tc.pos = cpos;
-                if (lane == t) nd = cpos < n ? cd[cpos] : kNoMoreDocs;  // an emptied cache is refilled below
-                __syncwarp();
-            } else {
-                uint32_t w = lmask ? (__ldg(sh.colv[t].bits + wi) & E & lmask) : 0u;
-                if (!__any_sync(0xffffffffu, w != 0u)) continue;
-                const float* col = sh.colv[t].col + base + 32 * lane;
-                float* a = sh.acc + 32 * lane;
-                while (w) {
-                    const int b = __ffs(w) - 1;
-                    w &= w - 1;
-                    const float sum = __fadd_rn(a[b], __ldg(col + b));
-                    a[b] = sum;
-                    st_gather++;
-                    if (sum > te) hot |= 1u << lane;
-                }
-                __syncwarp();
             }
+            hot = __reduce_or_sync(0xffffffffu, hot);
         }
-        hot = __reduce_or_sync(0xffffffffu, hot);
         // ---- 4. candidates: touched docs (bits of E) whose score beats theta, in docid order
         {
             uint32_t newc_n = 0;
@@ -350,10 +440,10 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
             __syncwarp();
         }
         pos = win1;
-        // ---- 5. refill the streams whose cached block is used up
+        // ---- 5. refill the sparse streams whose cached block is used up
         {
             bool need = false;
-            if (!is_col && lane < T && nd == kNoMoreDocs) {
+            if (kind == kKindSparse && nd == kNoMoreDocs) {
                 const WTerm& tc = sh.term[lane];
                 need = tc.pos >= tc.n && tc.cur <= tc.nb;
             }
@@ -363,8 +453,9 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                 int first = kNoMoreDocs;
                 st_refill++;
                 if (stream_refill<false, false, false, false>(seg, p, sh.term[t], cdocs + slot * kBlock, cscores + slot * kBlock,
-                                                              lo, hi, lane, 0, -2147483647 - 1, reinterpret_cast<uint32_t*>(sh.acc), hot_unused,
-                                                              mm_unused, INFINITY, mc_unused))
+                                                              lo, hi, lane, 0, -2147483647 - 1,
+                                                              reinterpret_cast<uint32_t*>(sh.acc), hot_unused, mm_unused,
+                                                              INFINITY, mc_unused))
                     first = cdocs[slot * kBlock + sh.term[t].pos];
                 if (lane == t) nd = first;
             }
@@ -375,10 +466,12 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
     if (lane == 0) p.item_matches[item_idx] = my_matches;
     if (p.dbg) {
         st_gather = __reduce_add_sync(0xffffffffu, st_gather);
+        st_edocs = __reduce_add_sync(0xffffffffu, st_edocs);
         if (lane == 0) {
-            const uint32_t v[12] = {1u, st_win, st_ess, st_open, st_gap, st_post, st_gather, st_refill, st_cand, st_steps, st_cut, st_ne};
+            const uint32_t v[13] = {1u, st_win, st_scan, st_open, st_gap, st_post, st_gather, st_refill, st_cand, st_steps,
+                                    st_cut, st_scored, st_edocs};
 #pragma unroll
-            for (int i = 0; i < 12; i++) atomicAdd(p.dbg + i, (unsigned long long)v[i]);
+            for (int i = 0; i < 13; i++) atomicAdd(p.dbg + i, (unsigned long long)v[i]);
         }
     }
 }

@@ -68,6 +68,7 @@ struct HostPlan {
     std::vector<ItemClause> clauses;
     std::vector<uint32_t> or_ids, ms_ids, and_ids, ro_ids;
     std::vector<ColRef> col_refs;
+    std::map<std::pair<uint32_t, uint32_t>, uint32_t> bitmap_refs;  // (leaf, term) -> col_refs entry {null, bits}
     std::vector<std::shared_ptr<ColEntry>> cols;
     uint32_t n_cols_built = 0, max_ms_streams = 0;
     uint64_t col_floats = 0;
@@ -193,6 +194,7 @@ std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape
             auto count = [&](uint32_t ci) {
                 const rg_clause& c = clauses[ci];
                 if (c.term_id >= seg.host_terms.size() || seg.bitmap_slot[c.term_id] < 0) return;
+                if ((uint64_t)seg.host_terms[c.term_id].doc_freq * kColumnDen < (uint64_t)seg.max_doc) return;
                 const float w = clause_weight(c);
                 uint32_t wbits;
                 memcpy(&wbits, &w, 4);
@@ -413,27 +415,37 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 // A disjunction goes to k_eval_or_ms (presence bitmaps, non-essential clauses are only counted)
                 // when it is a plain sum of SHOULD clauses, reads at least one score column, and none of its
                 // other clauses is dense (a dense block stream would cut its windows to a few docids).
-                uint32_t n_col = 0;
+                uint32_t n_bitmap = 0;
                 bool dense_stream = false;
                 for (uint32_t ci : present) {
-                    if (col_of(ci) >= 0) n_col++;
-                    else if (df_of(ci) * 32u >= (uint64_t)seg.max_doc) dense_stream = true;
+                    if (seg.bitmap_slot[clauses[ci].term_id] >= 0) n_bitmap++;
+                    else if (df_of(ci) * 32u >= (uint64_t)seg.max_doc) dense_stream = true;  // (bitmap budget ran out)
                 }
-                use_ms = !no_ms && n_col > 0 && !dense_stream && nots.empty() && !shape.msm && !(shape.dismax && present.size() > 1);
+                use_ms = !no_ms && n_bitmap > 0 && !dense_stream && nots.empty() && !shape.msm && !(shape.dismax && present.size() > 1);
                 for (uint32_t ci : present) {
                     const rg_clause& c = clauses[ci];
                     const int64_t col = col_of(ci);
+                    const float w = clause_weight(c);
+                    // bit4: the score bound w*(k1+1) needs weight >= 0 and cache entries >= 0
+                    const bool boundable = w >= 0.0f && w < INFINITY && k1 >= 0.0f &&
+                                           c.cache_id < e->cache_nonneg.size() && e->cache_nonneg[c.cache_id];
                     // the exhaustive kernel scans a column docid by docid: that only pays for df >= max_doc/8
                     if (col >= 0 && (use_ms || df_of(ci) * 8u >= (uint64_t)seg.max_doc)) {
-                        // bit4: the MaxScore bound w*(k1+1) needs weight >= 0 and cache entries >= 0
-                        const float w = clause_weight(c);
-                        const bool boundable = w >= 0.0f && w < INFINITY && k1 >= 0.0f &&
-                                               c.cache_id < e->cache_nonneg.size() && e->cache_nonneg[c.cache_id];
                         hp.clauses.push_back(ItemClause{(uint32_t)col, w, c.cache_id, 4u | (boundable ? 0u : 16u)});
                         continue;
                     }
                     n_streams++;
-                    hp.clauses.push_back(ItemClause{c.term_id, clause_weight(c), c.cache_id, 0});
+                    uint32_t flags = 0;
+                    if (use_ms && seg.bitmap_slot[c.term_id] >= 0) {  // a block stream whose presence comes from its bitmap
+                        const auto key = std::make_pair(si, c.term_id);
+                        auto it = hp.bitmap_refs.find(key);
+                        if (it == hp.bitmap_refs.end()) {
+                            it = hp.bitmap_refs.emplace(key, (uint32_t)hp.col_refs.size()).first;
+                            hp.col_refs.push_back(ColRef{nullptr, seg.bitmaps.p + (size_t)seg.bitmap_slot[c.term_id] * seg.bitmap_words});
+                        }
+                        if (it->second < 65536u) flags = 32u | (boundable ? 0u : 16u) | (it->second << 16);
+                    }
+                    hp.clauses.push_back(ItemClause{c.term_id, w, c.cache_id, flags});
                 }
             } else {
                 // conjunction: the lead (cheapest) clause is a block stream; every other clause that has a score

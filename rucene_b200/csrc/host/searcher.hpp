@@ -51,6 +51,16 @@ struct TermQuery : Query {
     static QueryPtr create(Term t, float boost = 1.0f) { return std::make_shared<TermQuery>(std::move(t), boost); }
 };
 
+// MatchAllDocsQuery (search/query/match_all_query.rs:28-116): every docid, score 0f32
+struct MatchAllDocsQuery : Query {};
+// ConstantScoreQuery::with_boost(query, boost) (match_all_query.rs:162-205)
+struct ConstantScoreQuery : Query {
+    QueryPtr query;
+    float boost;
+    ConstantScoreQuery(QueryPtr q, float b) : query(std::move(q)), boost(b) {}
+    static QueryPtr with_boost(QueryPtr q, float b) { return std::make_shared<ConstantScoreQuery>(std::move(q), b); }
+};
+
 struct BooleanQuery : Query {
     std::vector<QueryPtr> must_queries, should_queries, filter_queries, must_not_queries;
     int32_t min_should_match = 0;
@@ -64,8 +74,10 @@ struct BooleanQuery : Query {
         if (must_nots.empty() && musts.size() + shoulds.size() + filters.size() == 1) {
             if (musts.size() == 1) return musts[0];
             if (shoulds.size() == 1) return shoulds[0];
-            throw UnsupportedQuery("ConstantScoreQuery(filter) is not accelerated");
+            return ConstantScoreQuery::with_boost(filters[0], 0.0f);
         }
+        if (musts.size() + shoulds.size() + filters.size() == 0)  // only must_not exists (:76-79)
+            musts.push_back(std::make_shared<MatchAllDocsQuery>());
         auto q = std::make_shared<BooleanQuery>();
         q->must_queries = std::move(musts);
         q->should_queries = std::move(shoulds);
@@ -209,9 +221,20 @@ private:
             q.n_clauses = 1;
             return q;
         }
+        if (auto cq = dynamic_cast<const ConstantScoreQuery*>(&query)) {  // the lone FILTER clause of build()
+            auto tq = dynamic_cast<const TermQuery*>(cq->query.get());
+            if (!tq || cq->boost != 0.0f) throw UnsupportedQuery("only ConstantScoreQuery(TermQuery, 0) is accelerated");
+            clauses.push_back(clause_of(*tq, RG_FILTER));
+            q.n_clauses = 1;
+            q.flags = RG_Q_BOOLEAN;
+            return q;
+        }
         auto bq = dynamic_cast<const BooleanQuery*>(&query);
         if (!bq) throw UnsupportedQuery("query type is not accelerated");
-        if (!bq->filter_queries.empty()) throw UnsupportedQuery("FILTER clauses are not accelerated");
+        std::vector<QueryPtr> musts = bq->must_queries;
+        if (musts.size() == 1 && dynamic_cast<const MatchAllDocsQuery*>(musts[0].get()) && bq->should_queries.empty() &&
+            bq->filter_queries.empty() && !bq->must_not_queries.empty())
+            musts.clear();  // the engine reads "only MUST_NOT clauses" as MatchAllDocsQuery minus those terms
         auto add = [&](const std::vector<QueryPtr>& v, int32_t occur) {
             for (const QueryPtr& c : v) {
                 auto tq = dynamic_cast<const TermQuery*>(c.get());
@@ -219,7 +242,8 @@ private:
                 clauses.push_back(clause_of(*tq, occur));
             }
         };
-        add(bq->must_queries, RG_MUST);
+        add(musts, RG_MUST);
+        add(bq->filter_queries, RG_FILTER);
         add(bq->should_queries, RG_SHOULD);
         add(bq->must_not_queries, RG_MUST_NOT);
         q.n_clauses = (uint32_t)clauses.size() - q.clause_begin;

@@ -11,7 +11,7 @@ import numpy as np
 from . import _build
 
 RG_OK, RG_EINVAL, RG_ENODEVICE, RG_ECUDA, RG_EUNSUPPORTED, RG_ENOMEM = 0, -1, -2, -3, -4, -5
-MUST, SHOULD, MUST_NOT = 0, 1, 2
+MUST, SHOULD, MUST_NOT, FILTER = 0, 1, 2, 3
 Q_BOOLEAN = 1
 Q_DISMAX = 2    # rg_query.flags: DisjunctionMaxQuery; min_should_match = bits of the f32 tie breaker
 MODE_SEARCH, MODE_SEARCH_PARALLEL = 0, 1
@@ -137,9 +137,9 @@ class Batch:
         """RG_CFG_STATS event counters of the last run (include/rucene_gpu.h: rg_batch_debug)"""
         out = np.zeros(16, np.uint64)
         _check(lib().rg_batch_debug(self.engine.h, self.h, _p(out)), self.engine.h)
-        names = ["items", "windows", "windows_with_essential_column", "windows_before_theta", "docids_only_counted",
+        names = ["items", "windows", "windows_scanned_with_bound", "windows_before_theta", "docids_only_counted",
                  "stream_postings", "column_gathers", "refills", "candidates", "steps_scanned", "windows_cut",
-                 "nonessential_clause_windows"]
+                 "windows_scored", "docs_scored"]
         return {n: int(out[i]) for i, n in enumerate(names)}
 
     def columns(self):

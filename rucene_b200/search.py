@@ -6,6 +6,8 @@ Same names and argument meaning as the Rust reference (paths relative to
     Term                 index/mod.rs Term::new(field, bytes)
     TermQuery            search/query/term_query.rs:46-49    TermQuery::new(term, boost, ctx)
     BooleanQuery.build   search/query/boolean_query.rs:40-87 build(musts, shoulds, filters, must_nots, msm)
+    ConstantScoreQuery   search/query/match_all_query.rs:162-205 (what a lone FILTER clause becomes, boost 0)
+    MatchAllDocsQuery    search/query/match_all_query.rs:28-116  (what build() adds to a pure MUST_NOT query)
     BM25Similarity       search/similarity/bm25_similarity.rs:45-46 (k1=1.2, b=0.75)
     TopDocsCollector     search/collector/top_docs.rs:107-124 TopDocsCollector::new(k) / top_docs()
     TopDocs / ScoreDoc   search/sort_field/collapse_top_docs.rs:22-68,288-326
@@ -56,6 +58,23 @@ class IllegalArgument(ValueError):
 
 
 @dataclass
+class MatchAllDocsQuery(Query):
+    """Every docid of every leaf, score 0f32 (the weight's default; normalisation is commented out in
+    searcher.rs:709-722)."""
+
+
+@dataclass
+class ConstantScoreQuery(Query):
+    """ConstantScoreQuery::with_boost(query, boost): the docs of `query` (evaluated without scores), score = boost."""
+    query: Query
+    boost: float = 0.0
+
+    @staticmethod
+    def with_boost(query, boost):
+        return ConstantScoreQuery(query, float(boost))
+
+
+@dataclass
 class BooleanQuery(Query):
     must_queries: List[Query]
     should_queries: List[Query]
@@ -75,7 +94,9 @@ class BooleanQuery(Query):
                 return musts[0]
             if shoulds:
                 return shoulds[0]
-            raise engine.Unsupported(engine.RG_EUNSUPPORTED, "ConstantScoreQuery(filter) is not accelerated")
+            return ConstantScoreQuery.with_boost(filters[0], 0.0)
+        if not (musts or shoulds or filters):
+            musts.append(MatchAllDocsQuery())  # only must_not exists (:76-79)
         return BooleanQuery(musts, shoulds, filters, must_nots, msm)
 
 
@@ -213,11 +234,23 @@ class GpuIndexSearcher:
         if isinstance(query, TermQuery):
             add(query, engine.SHOULD)
             return (begin, 1, 0, 0)
+        if isinstance(query, ConstantScoreQuery):
+            if query.boost != 0.0:
+                raise engine.Unsupported(engine.RG_EUNSUPPORTED, "ConstantScoreQuery with a non-zero boost is not accelerated")
+            add(query.query, engine.FILTER)   # the lone FILTER clause of BooleanQuery::build (:66-75)
+            return (begin, 1, 0, engine.Q_BOOLEAN)
         if isinstance(query, BooleanQuery):
-            if query.filter_queries:
-                raise engine.Unsupported(engine.RG_EUNSUPPORTED, "FILTER clauses are not accelerated")
-            for q in query.must_queries:
+            musts = list(query.must_queries)
+            if any(isinstance(q, MatchAllDocsQuery) for q in musts):
+                # only as build() writes it: the single MUST of a query that has nothing but MUST_NOT clauses —
+                # the engine reads "only MUST_NOT clauses" as exactly that
+                if len(musts) != 1 or query.should_queries or query.filter_queries or not query.must_not_queries:
+                    raise engine.Unsupported(engine.RG_EUNSUPPORTED, "MatchAllDocsQuery beside other positive clauses")
+                musts = []
+            for q in musts:
                 add(q, engine.MUST)
+            for q in query.filter_queries:
+                add(q, engine.FILTER)
             for q in query.should_queries:
                 add(q, engine.SHOULD)
             for q in query.must_not_queries:

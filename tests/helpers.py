@@ -94,11 +94,12 @@ def to_queries(specs):
             out.append(S.DisjunctionMaxQuery.build(
                 [S.TermQuery.new(S.Term.new("body", cl[0]), cl[1] if len(cl) > 1 else 1.0, None) for cl in s[1]], s[2]))
         else:
-            musts, shoulds, nots = [], [], []
+            musts, shoulds, filters, nots = [], [], [], []
             for cl in s[1]:
                 q = S.TermQuery.new(S.Term.new("body", cl[1]), cl[2] if len(cl) > 2 else 1.0, None)
-                (musts if cl[0] == ob.MUST else shoulds if cl[0] == ob.SHOULD else nots).append(q)
-            out.append(S.BooleanQuery.build(musts, shoulds, [], nots, s[2] if len(s) > 2 else 0))
+                (musts if cl[0] == ob.MUST else shoulds if cl[0] == ob.SHOULD else filters if cl[0] == ob.FILTER
+                 else nots).append(q)
+            out.append(S.BooleanQuery.build(musts, shoulds, filters, nots, s[2] if len(s) > 2 else 0))
     return out
 
 

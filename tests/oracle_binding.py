@@ -21,7 +21,7 @@ QUERY_DTYPE = np.dtype([("clause_begin", "<u4"), ("n_clauses", "<u4"),
                         ("min_should_match", "<i4"), ("is_boolean", "<i4")])
 HIT_DTYPE = np.dtype([("doc", "<i4"), ("score", "<f4")])
 
-MUST, SHOULD, MUST_NOT = 0, 1, 2
+MUST, SHOULD, MUST_NOT, FILTER = 0, 1, 2, 3
 NO_MORE_DOCS = 0x7FFFFFFF
 
 _lib = None

@@ -299,6 +299,38 @@ def test_disjunction_max_query():
             helpers.assert_same_topdocs(got, want, "dismax k=%d rp=%d mode=%d" % (k, rp, mode))
 
 
+def test_filter_clauses_and_pure_must_not():
+    """FILTER clauses (required, score 0f32: boolean_query.rs:108-110, searcher.rs:158-197), a lone FILTER
+    (ConstantScoreQuery boost 0) and pure MUST_NOT queries (MatchAllDocsQuery, boolean_query.rs:76-79), mixed into a
+    batch with the other shapes; leaves with live docs; both collector modes."""
+    rng = np.random.default_rng(131)
+    dfs = [0, 1, 60, 129, 900, 4000, 9000, 21000, 30000]
+    segs = [helpers.build_segment(rng, 34000 + 500 * s, dfs, live_fraction=lf)[0] for s, lf in enumerate((None, 0.85))]
+    specs = [("bool", [(ob.FILTER, 7)], 0),
+             ("bool", [(ob.MUST, 8), (ob.FILTER, 7)], 0),
+             ("bool", [(ob.FILTER, 8), (ob.MUST, 5), (ob.MUST, 7)], 0),
+             ("bool", [(ob.FILTER, 8), (ob.FILTER, 7)], 0),
+             ("bool", [(ob.FILTER, 8), (ob.SHOULD, 7), (ob.SHOULD, 4)], 0),
+             ("bool", [(ob.MUST, 6), (ob.FILTER, 8), (ob.SHOULD, 7), (ob.MUST_NOT, 5)], 0),
+             ("bool", [(ob.FILTER, 8), (ob.MUST_NOT, 7)], 0),
+             ("bool", [(ob.MUST, 8), (ob.FILTER, 0)], 0),
+             ("bool", [(ob.MUST_NOT, 8)], 0),
+             ("bool", [(ob.MUST_NOT, 7), (ob.MUST_NOT, 4), (ob.MUST_NOT, 0)], 0),
+             ("bool", [(ob.MUST_NOT, 0)], 0),                   # nothing excluded: every live doc, score 0
+             ("bool", [(ob.SHOULD, 5), (ob.MUST_NOT, 8)], 0)]
+    for i in range(30):
+        n_f, n_m, n_n = int(rng.integers(1, 3)), int(rng.integers(0, 3)), int(rng.integers(0, 2))
+        terms = [int(x) for x in rng.choice(len(dfs), size=n_f + n_m + n_n, replace=False)]
+        cl = [(ob.FILTER, t) for t in terms[:n_f]] + [(ob.MUST, t) for t in terms[n_f:n_f + n_m]]
+        cl += [(ob.MUST_NOT, t) for t in terms[n_f + n_m:]]
+        specs.append(("bool", [cl[j] for j in rng.permutation(len(cl))], 0))
+    specs += _mixed_specs(rng, len(dfs), 12, kinds=("term", "and", "or"))
+    for k, rp in ((10, 0), (100, 2500)):
+        for mode in (0, 1):
+            got, want = _run_both(segs, specs, k, mode=mode, range_postings=rp)
+            helpers.assert_same_topdocs(got, want, "filter k=%d rp=%d mode=%d" % (k, rp, mode))
+
+
 def test_reference_style_api():
     """Reads like examples/example.rs:111-117."""
     rng = np.random.default_rng(5)
@@ -320,8 +352,21 @@ def test_reference_style_api():
         collector = search.TopDocsCollector.new(10)   # MUST + SHOULD: ReqOptScorer
         searcher.search(q, collector)
         assert collector.top_docs().total_hits() == 1666
-        with pytest.raises(engine.Unsupported):   # FILTER clauses are outside the accelerated path
-            searcher.search(search.BooleanQuery.build([query], [], [query], [], 0), search.TopDocsCollector.new(10))
+        collector = search.TopDocsCollector.new(10)   # MUST + FILTER: the filter restricts, only the MUST scores
+        searcher.search(search.BooleanQuery.build([query], [], [search.TermQuery.new(search.Term.new("body", b"world"))], [], 0),
+                        collector)
+        both = np.intersect1d(posts[0][0], posts[1][0])
+        assert collector.top_docs().total_hits() == len(both)
+        lone = search.BooleanQuery.build([], [], [query], [], 0)   # a lone FILTER: ConstantScoreQuery(boost 0)
+        assert isinstance(lone, search.ConstantScoreQuery)
+        collector = search.TopDocsCollector.new(10)
+        searcher.search(lone, collector)
+        assert collector.top_docs().total_hits() == 1666 and all(d.score == 0.0 for d in collector.top_docs().score_docs())
+        only_not = search.BooleanQuery.build([], [], [], [query], 0)   # pure MUST_NOT: MatchAllDocsQuery minus the term
+        assert isinstance(only_not.must_queries[0], search.MatchAllDocsQuery)
+        collector = search.TopDocsCollector.new(10)
+        searcher.search(only_not, collector)
+        assert collector.top_docs().total_hits() == 10000 - 1666
         with pytest.raises(search.IllegalArgument):
             search.BooleanQuery.build([], [], [], [], 0)
     finally:
