@@ -436,7 +436,8 @@ def run_workload(ctx, name, w, args, steps, warmup, cpu_queries, cpu_seconds, fl
     replay_ms = eng.last_kernel_ms("replay")
     bstats = batch.stats()
     n_cols, col_bytes = batch.columns()
-    dbg = batch.debug() if (flags & engine.CFG_STATS) else None
+    dbg_all = batch.debug()
+    dbg = dbg_all if (flags & engine.CFG_STATS) else None
     out = {"value": nq / (ms_step / 1e3), "ms_per_step": ms_step, "config": workload_config(name, w, world)}
     per_rank_eval = [eval_ms]
     if world > 1:
@@ -504,11 +505,17 @@ def run_workload(ctx, name, w, args, steps, warmup, cpu_queries, cpu_seconds, fl
     if rank == 0:
         peak, peak_src = measured_peaks()
         algo_bytes = bstats["algorithmic_bytes"]
+        upper_bytes = None
+        if name == "c3" and dbg_all["and_touched_bytes"] > 0:
+            # conjunctions: SURVEY 8d asks for TOUCHED blocks — counted by the kernel itself (lead list in full +
+            # the blocks / table entries / column cells it probed); the planner's figure is the upper bound
+            upper_bytes, algo_bytes = algo_bytes, dbg_all["and_touched_bytes"] + nq * k * 8
         achieved = algo_bytes / (eval_ms / 1e3) / 1e9 if eval_ms > 0 else 0.0
         out["roofline"] = {
             "bound": "hbm", "kernel": "k_eval_and" if name == "c3" else "k_eval_or_ms (+ k_eval_or for the items it does not take)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ctx.traffic.get(name),
-            "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": eval_ms,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "upper_bound_bytes_all_lists": upper_bytes,
+            "kernel_ms": eval_ms,
             "replay_ms": replay_ms, "postings_per_launch": bstats["postings"], "work_items": bstats["items"],
             "candidate_slots": bstats["candidate_slots"],
             "note": "algorithmic bytes = SURVEY 8d: every clause's encoded blocks + tails + 12 B/block of tables + one "

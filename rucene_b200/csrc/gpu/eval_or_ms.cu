@@ -154,6 +154,7 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
     em.run_cnt = 0;
     em.matches = 0;
     em.overflow = false;
+    wtheta_inherit(em, p, item_idx, it.chain_pos, kcap, lane);
     const bool lb_ok = (uint32_t)lane < it.chain_pos;
     const uint32_t* theta_lb = p.item_theta + item_idx - 1 - (lb_ok ? lane : 0);
     uint32_t win_no = 0;

@@ -323,6 +323,8 @@ struct alignas(16) WarpShared {  // followed by topk[kcap] floats, then cdocs[T]
 // warp-level candidate emitter state (registers, uniform across lanes)
 struct WEmit {
     float* topk;       // shared memory, kcap floats
+    float* gtopk;      // global mirror of topk (EvalParams::item_topk row of this item), null = not kept
+    uint32_t* gcount;  // its published entry count
     uint32_t topk_n;
     float theta_local;
     uint32_t theta_in;
@@ -366,22 +368,75 @@ __device__ __forceinline__ void wtheta_update(WEmit& em, uint32_t k, uint32_t kc
     for (uint32_t i = 0; i < n_new; i++) {
         const float x = newc[i];
         if (n < k) {
-            if (lane == 0) em.topk[n] = x;
+            if (lane == 0) {
+                em.topk[n] = x;
+                if (em.gtopk) em.gtopk[n] = x;
+            }
             n++;
             __syncwarp();
             if (n == k) wtheta_recompute(em, k, lane, theta, argmin);
         } else if (x > theta) {
-            if (lane == 0) em.topk[argmin] = x;
+            if (lane == 0) {
+                em.topk[argmin] = x;
+                if (em.gtopk) em.gtopk[argmin] = x;
+            }
             __syncwarp();
             wtheta_recompute(em, k, lane, theta, argmin);
         }
     }
+    const bool grew = n != em.topk_n;
     em.topk_n = n;
     em.theta_local = n == k ? theta : -INFINITY;
     if (lane == 0) {
+        if (em.gcount && grew) {  // entries first, then the count a successor reads
+            __threadfence();
+            *reinterpret_cast<volatile uint32_t*>(em.gcount) = n;
+        }
         uint32_t ord = em.theta_in;
         if (em.theta_local != -INFINITY) ord = max(ord, float_to_ordered(em.theta_local));
         if (ord > kOrderedNegInf) atomicMax(theta_out, ord);
+    }
+}
+
+// Start of a work item: take over the running top-k of the heap chain.  Every item mirrors its top-k scores
+// (of docs it has passed, plus what it inherited) into EvalParams::item_topk; a later range of the same chain
+// copies the nearest predecessor's array — all of those docs come earlier in collection order, every doc lives
+// in one slot of one array, so the k-th best of the copy is a lower bound of the heap root when this range
+// starts — and keeps inserting its own candidates.  Without it theta would only be the best per-range k-th
+// score, far below the root of a heap that has seen hundreds of ranges.
+__device__ __forceinline__ void wtheta_inherit(WEmit& em, const EvalParams& p, uint32_t item_idx, uint32_t chain_pos,
+                                               uint32_t kcap, int lane) {
+    em.gtopk = nullptr;
+    em.gcount = nullptr;
+    if (!p.item_topk || p.k > kcap) return;
+    em.gtopk = p.item_topk + (size_t)item_idx * kcap;
+    em.gcount = p.item_topk_n + item_idx;
+    if (chain_pos == 0) return;
+    uint32_t cnt = 0;
+    if ((uint32_t)lane < chain_pos) cnt = ld_volatile_u32(p.item_topk_n + item_idx - 1 - lane);
+    const uint32_t have = __ballot_sync(0xffffffffu, cnt > 0u);
+    if (!have) return;
+    const int src_lane = __ffs(have) - 1;  // nearest predecessor that has published something
+    const uint32_t n = min(__shfl_sync(0xffffffffu, cnt, src_lane), p.k);
+    __threadfence();
+    const float* src = p.item_topk + (size_t)(item_idx - 1 - (uint32_t)src_lane) * kcap;
+    for (uint32_t j = lane; j < n; j += 32) {
+        const float v = __uint_as_float(ld_volatile_u32(reinterpret_cast<const uint32_t*>(src + j)));
+        em.topk[j] = v;
+        em.gtopk[j] = v;
+    }
+    __syncwarp();
+    em.topk_n = n;
+    if (n == p.k) {
+        float theta;
+        int argmin;
+        wtheta_recompute(em, p.k, lane, theta, argmin);
+        em.theta_local = theta;
+    }
+    if (lane == 0) {
+        __threadfence();
+        *reinterpret_cast<volatile uint32_t*>(em.gcount) = n;
+        if (em.theta_local != -INFINITY) atomicMax(p.item_theta + item_idx, float_to_ordered(em.theta_local));
     }
 }
 

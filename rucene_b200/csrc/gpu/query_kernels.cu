@@ -123,6 +123,7 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
     em.run_cnt = 0;
     em.matches = 0;
     em.overflow = false;
+    wtheta_inherit(em, p, item_idx, it.chain_pos, kcap, lane);
     // theta look-back: the up-to-32 preceding items of this heap chain (each publishes
     // max(own, inherited)), re-read every 8 windows
     const bool lb_ok = (uint32_t)lane < it.chain_pos;
@@ -384,6 +385,7 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
     __syncwarp();
     float ro_sum = 0.0f;    // ReqOptScorer::scores_sum / scores_num (thread 0)
     uint32_t ro_num = 0;
+    uint32_t touched = 0;   // bytes this thread asked for (block parts are charged to lane 0 of the decoding warp)
 
     for (uint32_t b0 = lead.cur;; b0 += kEvalWarps) {
         // ---- 1. decode this step's lead blocks (one per warp; pseudo-block lead_nb = vint tail)
@@ -403,6 +405,7 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
             if (prev_last < hi - 1) {
                 const BlockDesc bd = lead.blk_desc[b];
                 const uint4* part = seg.arena + bd.off16;
+                if (lane == 0) touched += 12u + 16u * (((bd.bits >> 16) & 0xffu) + max(1u, (bd.bits >> 8) & 0xffu));
                 int4 dd;
                 if (!OTHER || (bd.bits >> 24) == 0) {
                     const int4 dl = unpack4(part, (int)(bd.bits & 0xff), lane, seg.version, seg.sb_mask);
@@ -427,6 +430,7 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
                     if (ok) {
                         const float nrm = seg.norms ? __ldg(lead.cache + __ldg(seg.norms + d)) : p.k1;
                         s = bm25_score(lw1, (float)fq[i], nrm);
+                        touched += 1u;
                     }
                     os[i] = s;
                 }
@@ -475,6 +479,7 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
                     const int d = sh.ldoc[slot];
                     if (d == kNoMoreDocs) continue;
                     const float v = __ldg(col + d);
+                    touched += 4u;
                     if (__float_as_uint(v) != 0xffffffffu) {
                         if (neg) {
                             sh.ldoc[slot] = kNoMoreDocs;  // ReqNotScorer: excluded
@@ -497,6 +502,7 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
                 bool pending = d != kNoMoreDocs;
                 uint32_t bi = 0;
                 if (pending) {
+                    touched += 8u;  // skip-table probe (galloping search)
                     bi = lower_bound_gallop(tc.blk_last, min(sh.hint[warp][t], nb), nb, d);
                     if (bi == nb && !(tc.tail_n > 0 && (nb == 0 || d > tc.tail_base))) {
                         pending = false;  // beyond the last posting of this clause
@@ -518,6 +524,7 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
                     BlockDesc bd{};
                     if (full_block) {
                         bd = tc.blk_desc[cb];
+                        if (lane == 0) touched += 12u + 16u * ((bd.bits >> 16) & 0xffu);
                         const int base = cb == 0 ? 0 : __ldg(tc.blk_last + cb - 1);
                         const uint4* part = seg.arena + bd.off16;
                         if (!OTHER || (bd.bits >> 24) == 0) {
@@ -552,6 +559,7 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
                             }
                             const float nrm = seg.norms ? __ldg(tc.cache + __ldg(seg.norms + d)) : p.k1;
                             const float sc = bm25_score(w1, (float)f, nrm);
+                            touched += 9u;  // freq word(s) + norm byte
                             if (opt) {  // DisjunctionSumScorer::score_sum: clause order, from 0.0f
                                 const float o = sh.oscore[slot];
                                 sh.oscore[slot] = __fadd_rn(__float_as_uint(o) == kSent ? 0.0f : o, sc);
@@ -615,6 +623,8 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
     }
     __syncthreads();
     if (threadIdx.x == 0) p.item_matches[item_idx] = sh.emit.matches;
+    touched = __reduce_add_sync(0xffffffffu, touched);
+    if (lane == 0 && touched) atomicAdd(p.touched, (unsigned long long)touched);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -46,7 +46,9 @@ struct rg_batch {
     uint32_t n_cols_built = 0;       // columns materialised by this rg_batch_prepare (the others were cached)
     uint64_t col_floats = 0;
     Span<uint32_t> group_item_begin, group_out;
-    Span<uint32_t> item_head, item_matches, item_theta;
+    Span<uint32_t> item_head, item_matches, item_theta, item_topk_n;
+    Span<float> item_topk;  // [n_items][kcap] (not zeroed: item_topk_n says what is valid)
+    uint32_t topk_cap = 0;
     Span<unsigned long long> arena_next;  // [0] bump pointer, [1] error flag (as u32 view)
     Span<unsigned long long> dbg;         // RG_CFG_STATS counters (zeroed per run)
     Span<rg_hit> out_hits;
@@ -620,10 +622,17 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     carve(b->col_refs, hp.col_refs.size());
     carve(b->group_item_begin, hp.group_item_begin.size());
     carve(b->group_out, hp.group_out.size());
+    // running top-k scores of every OR work item (theta inheritance along a heap chain); skipped when it would
+    // not fit comfortably (huge batches with k near 1024): theta then falls back to the per-range bound
+    b->topk_cap = (std::min<uint32_t>(p->k, 1024u) + 31u) & ~31u;
+    const size_t topk_floats = (size_t)b->n_items * b->topk_cap;
+    const bool keep_topk = topk_floats * sizeof(float) <= (2ull << 30);
+    carve(b->item_topk, keep_topk ? topk_floats : 1);
     carve(b->item_head, b->n_items);
     const size_t zero_off = off;
     carve(b->item_matches, b->n_items);
     carve(b->item_theta, b->n_items);
+    carve(b->item_topk_n, b->n_items);
     carve(b->arena_next, 2);
     carve(b->dbg, 16);
     carve(b->out_hits, (size_t)std::max<uint32_t>(1, n_queries) * p->k);
@@ -642,7 +651,7 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     };
     rebase(b->items); rebase(b->clauses); rebase(b->or_ids); rebase(b->and_ids); rebase(b->ms_ids); rebase(b->ro_ids); rebase(b->col_refs);
     rebase(b->group_item_begin); rebase(b->group_out); rebase(b->item_head); rebase(b->item_matches);
-    rebase(b->item_theta); rebase(b->arena_next); rebase(b->dbg); rebase(b->out_hits); rebase(b->out_counts);
+    rebase(b->item_theta); rebase(b->item_topk_n); rebase(b->item_topk); rebase(b->arena_next); rebase(b->dbg); rebase(b->out_hits); rebase(b->out_counts);
     rebase(b->out_total);
     if (p->mode == RG_MODE_SEARCH_PARALLEL) rebase(b->leaf_records);
     b->zero_begin = b->slab.p + zero_off;
@@ -691,8 +700,11 @@ int rg_batch_run(rg_engine* e, rg_batch* b) {
     ep.item_head = b->item_head.p;
     ep.item_matches = b->item_matches.p;
     ep.item_theta = b->item_theta.p;
+    ep.item_topk = b->item_topk.n > 1 ? b->item_topk.p : nullptr;
+    ep.item_topk_n = b->item_topk_n.p;
     ep.error_flag = reinterpret_cast<uint32_t*>(b->arena_next.p + 1);
     ep.dbg = (e->cfg.flags & RG_CFG_STATS) ? b->dbg.p : nullptr;
+    ep.touched = b->dbg.p + 15;
     RG_CUDA_CHECK(cudaEventRecord(e->ev2, st));
     ep.cols = b->col_refs.p;
     bool has_live = false, has_other = false;

@@ -140,7 +140,9 @@ class Batch:
         names = ["items", "windows", "windows_scanned_with_bound", "windows_before_theta", "docids_only_counted",
                  "stream_postings", "column_gathers", "refills", "candidates", "steps_scanned", "windows_cut",
                  "windows_scored", "docs_scored"]
-        return {n: int(out[i]) for i, n in enumerate(names)}
+        d = {n: int(out[i]) for i, n in enumerate(names)}
+        d["and_touched_bytes"] = int(out[15])   # always counted by k_eval_and (no RG_CFG_STATS needed)
+        return d
 
     def columns(self):
         """(number of score columns chosen for this batch, their bytes in HBM)"""

@@ -41,11 +41,24 @@ int main() {
             }
             std::printf("\n");
         }
-        bool threw = false;
-        try {  // FILTER clauses are outside the accelerated path
+        {   // MUST + FILTER on the same term: the filter restricts (here: not at all) and scores 0f32
             auto q5 = BooleanQuery::build({q1}, {}, {q1}, {}, 0);
-            TopDocsCollector c(10);
+            TopDocsCollector c(10), c1(10);
             searcher.search(*q5, c);
+            searcher.search(*q1, c1);
+            bool same = c.top_docs().total_hits() == c1.top_docs().total_hits() &&
+                        c.top_docs().score_docs().size() == c1.top_docs().score_docs().size();
+            for (size_t i = 0; same && i < c.top_docs().score_docs().size(); i++)
+                same = c.top_docs().score_docs()[i].doc == c1.top_docs().score_docs()[i].doc &&
+                       c.top_docs().score_docs()[i].score == c1.top_docs().score_docs()[i].score;
+            std::printf("filter_same_as_must:%d\n", (int)same);
+        }
+        bool threw = false;
+        try {  // a nested BooleanQuery clause is outside the accelerated path
+            auto inner = BooleanQuery::build({q1, q1}, {}, {}, {}, 0);
+            auto q6 = BooleanQuery::build({inner, q1}, {}, {}, {}, 0);
+            TopDocsCollector c(10);
+            searcher.search(*q6, c);
         } catch (const UnsupportedQuery&) { threw = true; }
         std::printf("unsupported:%d\n", (int)threw);
     } catch (const Error& e) {
