@@ -192,6 +192,15 @@ int rg_merge_leaf_records(rg_engine* e, const void* dev_records_all, uint32_t n_
                           uint32_t n_queries, uint32_t k, rg_hit* out_hits, uint32_t* out_counts,
                           uint64_t* out_total_hits);
 
+/* The whole sharded step behind one call, for a host that holds an ncclComm_t (no Python / torch needed):
+ * runs the prepared RG_MODE_SEARCH_PARALLEL batch, all-gathers every rank's leaf records with ncclAllGather on the
+ * engine's stream and replays finish_parallel in leaf order (rank r holds leaves [r*L, (r+1)*L), L = segments
+ * uploaded to each engine, the same on every rank).  nccl_comm: the caller's ncclComm_t, n_ranks its size.
+ * libnccl is resolved at run time (symbols already in the process, else dlopen("libnccl.so.2")); without it the
+ * call fails with RG_EUNSUPPORTED.  Host outputs as in rg_search_batch; every rank receives the merged result. */
+int rg_batch_run_sharded(rg_engine* e, rg_batch* b, void* nccl_comm, uint32_t n_ranks, rg_hit* out_hits,
+                         uint32_t* out_counts, uint64_t* out_total_hits);
+
 /* ---------------------------------------------------------------- block codec ----- */
 /* ForUtil::read_block over a raw block stream (codec/postings/for_util.rs:187-243;
  * SIMD128Packer::unpack util/packed/packed_simd.rs:126-252 when doc_version>0, else

@@ -1250,16 +1250,118 @@ struct ConjunctionScorer : Scorer {
 };
 
 // search/scorer/disjunction_scorer.rs:24-104,187-376 — SimpleQueue variant (<10 children)
+// util/disi.rs:135-336 — DisiPriorityQueue: a binary min-heap of the sub-scorers on their current docid
+// (push = up_heap, PeekMut drop = update_top = down_heap from the root) and top_list(): the sub-scorers that sit
+// on the top docid, collected by walking the heap from the root and PREPENDING each hit, so score_sum /
+// score_max (search/scorer/disjunction_scorer.rs:226-240,264-286) add the scores in the reverse of that walk.
+// The heap layout depends on the whole history of next() calls, and with it the f32 summation order.
+struct DisiQueue {
+    struct W {
+        Scorer* s;
+        W* next;
+    };
+    std::vector<W> buffer;
+    std::vector<W*> heap;
+    size_t size = 0;
+    explicit DisiQueue(std::vector<ScorerPtr>& children) {  // :163-181
+        buffer.reserve(children.size());
+        for (auto& c : children) buffer.push_back(W{c.get(), nullptr});
+        heap.assign(children.size(), nullptr);
+        for (W& w : buffer) {  // do_push :239-245
+            heap[size] = &w;
+            up_heap(size);
+            size++;
+        }
+    }
+    W* top() const { return heap[0]; }
+    void up_heap(size_t i) {  // :296-309
+        W* node = heap[i];
+        const int32_t node_doc = node->s->doc_id();
+        while (i > 0) {
+            const size_t j = ((i + 1) >> 1) - 1;
+            if (node_doc >= heap[j]->s->doc_id()) break;
+            heap[i] = heap[j];
+            i = j;
+        }
+        heap[i] = node;
+    }
+    void update_top() {  // down_heap(size) :311-336
+        size_t i = 0;
+        W* node = heap[0];
+        size_t j = ((i + 1) << 1) - 1;
+        if (j < size) {
+            size_t k = j + 1;
+            if (k < size && heap[k]->s->doc_id() < heap[j]->s->doc_id()) j = k;
+            if (heap[j]->s->doc_id() < node->s->doc_id()) {
+                for (;;) {
+                    heap[i] = heap[j];
+                    i = j;
+                    j = ((i + 1) << 1) - 1;
+                    k = j + 1;
+                    if (k < size && heap[k]->s->doc_id() < heap[j]->s->doc_id()) j = k;
+                    if (j >= size || heap[j]->s->doc_id() >= node->s->doc_id()) break;
+                }
+                heap[i] = node;
+            }
+        }
+    }
+    W* top_list_to(W* list, size_t i) {  // :213-231
+        W* w = heap[i];
+        if (w->s->doc_id() == list->s->doc_id()) {
+            w->next = list;
+            list = w;
+            const size_t left = ((i + 1) << 1) - 1, right = left + 1;
+            if (right < size) {
+                list = top_list_to(list, left);
+                list = top_list_to(list, right);
+            } else if (left < size && heap[left]->s->doc_id() == list->s->doc_id()) {
+                heap[left]->next = list;
+                list = heap[left];
+            }
+        }
+        return list;
+    }
+    W* top_list() {  // :190-206
+        W* list = heap[0];
+        list->next = nullptr;
+        if (size >= 3) {
+            list = top_list_to(list, 1);
+            list = top_list_to(list, 2);
+        } else if (size == 2 && heap[1]->s->doc_id() == list->s->doc_id()) {
+            heap[1]->next = list;
+            list = heap[1];
+        }
+        return list;
+    }
+    int32_t next_doc() {  // SubScorers::approximate_next, DPQ arm (disjunction_scorer.rs:334-347)
+        const int32_t doc = top()->s->doc_id();
+        for (;;) {
+            top()->s->next();
+            update_top();
+            if (top()->s->doc_id() != doc) break;
+        }
+        return top()->s->doc_id();
+    }
+    int32_t advance(int32_t target) {  // :364-374
+        for (;;) {
+            top()->s->advance(target);
+            update_top();
+            if (top()->s->doc_id() >= target) break;
+        }
+        return top()->s->doc_id();
+    }
+};
+
 struct DisjunctionSumScorer : Scorer {
     std::vector<ScorerPtr> scorers;
     int32_t curr_doc;
     bool needs_scores;
     int32_t min_should_match;
     size_t cost_;
+    std::unique_ptr<DisiQueue> dpq;  // >= 10 children and min_should_match <= 1 (:41-45)
     DisjunctionSumScorer(std::vector<ScorerPtr> children, bool needs, int32_t msm)
         : scorers(std::move(children)), needs_scores(needs), min_should_match(msm) {
-        if (!(scorers.size() < 10 || msm > 1))
-            throw Error(">=10 SHOULD clauses use DisiPriorityQueue: out of scope (SURVEY 8f-4)");
+        if (!(scorers.size() < 10 || msm > 1)) dpq.reset(new DisiQueue(scorers));
         cost_ = 0;
         curr_doc = NO_MORE_DOCS;
         for (auto& s : scorers) {
@@ -1267,8 +1369,9 @@ struct DisjunctionSumScorer : Scorer {
             curr_doc = std::min(curr_doc, s->doc_id());
         }
     }
-    int32_t doc_id() const override { return curr_doc; }
+    int32_t doc_id() const override { return dpq ? dpq->top()->s->doc_id() : curr_doc; }
     int32_t next() override {  // :295-333
+        if (dpq) return dpq->next_doc();
         int32_t msm = min_should_match > 1 ? min_should_match : 1;
         for (;;) {
             if (curr_doc == NO_MORE_DOCS) return curr_doc;
@@ -1289,6 +1392,7 @@ struct DisjunctionSumScorer : Scorer {
         }
     }
     int32_t advance(int32_t target) override {  // :350-363
+        if (dpq) return dpq->advance(target);
         int32_t min_doc = NO_MORE_DOCS;
         for (auto& s : scorers) {
             if (s->doc_id() < target) s->advance(target);
@@ -1297,9 +1401,13 @@ struct DisjunctionSumScorer : Scorer {
         return curr_doc = min_doc;
     }
     size_t cost() const override { return cost_; }
-    float score() override {  // :57-64,211-225
+    float score() override {  // :57-64,211-240
         if (!needs_scores) return 0.0f;
         float score = 0.0f;
+        if (dpq) {
+            for (DisiQueue::W* w = dpq->top_list(); w; w = w->next) score += w->s->score();
+            return score;
+        }
         for (auto& s : scorers)
             if (s->doc_id() == curr_doc) score += s->score();
         return score;

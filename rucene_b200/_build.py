@@ -78,7 +78,7 @@ def build_gpu(force=False):
         os.makedirs(LIB, exist_ok=True)
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
         _run([nvcc] + NVCC_FLAGS + ["-I" + INC, "-I" + gdir, "-shared", "-o", out] + srcs
-             + ["-lcudart"], "build_gpu.log")
+             + ["-lcudart", "-ldl"], "build_gpu.log")
     return out
 
 

@@ -42,6 +42,7 @@ struct alignas(16) MsWarpShared {  // followed by topk[kcap] floats, then cdocs[
     float acc[kMsW];               // 0.0f = untouched; touched docs are exactly the bits of E
     uint32_t ubits[32];            // presence words of the sparse streams in this window
     uint32_t ebits[32];            // E: the docs of this window that get an exact score
+    uint32_t cw[kMaxTerms][32];    // this window's presence words of the bitmap clauses (lane-owned, masked)
     WTerm term[kMaxTerms];         // block-stream clauses (same cursor as k_eval_or)
     const float* col[kMaxTerms];   // score column (leaf-local docid -> BM25 contribution), column clauses
     const uint32_t* bits[kMaxTerms];  // presence bitmap, column clauses and block streams of dense-enough terms
@@ -257,13 +258,23 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
         uint32_t U = E;
         const int wi = (base >> 5) + lane;
         {
+            // all words first (independent loads in flight together), then the arithmetic
+            uint32_t wv[kMaxTerms];
+#pragma unroll
+            for (int t = 0; t < kMaxTerms; t++)
+                wv[t] = (((bmask >> t) & 1u) && lmask) ? (__ldg(sh.bits[t] + wi) & lmask) : 0u;
+            // the next window's line of every bitmap towards L1 while this one is processed
+            if (((bmask >> lane) & 1u) && base + kMsW < hi)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(sh.bits[lane] + (base >> 5) + 32));
             uint32_t S[kMsPlanes];
 #pragma unroll
             for (int i = 0; i < kMsPlanes; i++) S[i] = 0u;
             uint32_t over = 0u;
-            for (uint32_t m = bmask; m; m &= m - 1) {
-                const int t = __ffs(m) - 1;
-                const uint32_t w = lmask ? (__ldg(sh.bits[t] + wi) & lmask) : 0u;
+#pragma unroll
+            for (int t = 0; t < kMaxTerms; t++) {
+                if (!((bmask >> t) & 1u)) continue;  // warp-uniform
+                const uint32_t w = wv[t];
+                sh.cw[t][lane] = w;
                 U |= w;
                 const uint32_t qt = __shfl_sync(0xffffffffu, q, t);
                 if (qt >= kMsSat) {  // no usable bound (or no theta yet): every doc of the clause
@@ -297,6 +308,18 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
             st_edocs += __popc(E);
             sh.ebits[lane] = E;
             __syncwarp();
+            // the column cells this window will read, towards L1 now: the clause-ordered pass below would otherwise
+            // pay one DRAM round trip per column clause, one after the other
+            for (uint32_t m = col_mask; m; m &= m - 1) {
+                const int t = __ffs(m) - 1;
+                uint32_t w = sh.cw[t][lane] & E;
+                const float* col = sh.col[t] + base + 32 * lane;
+                while (w) {
+                    const int b = __ffs(w) - 1;
+                    w &= w - 1;
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(col + b));
+                }
+            }
             // ---- 3. exact scores of the docs in E: clauses in clause order (DisjunctionSumScorer::score_sum)
             for (int t = 0; t < T; t++) {
                 const int kt = __shfl_sync(0xffffffffu, kind, t);
@@ -328,7 +351,7 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                     if (lane == t) nd = cpos < n ? cd[cpos] : kNoMoreDocs;  // an emptied cache is refilled below
                     __syncwarp();
                 } else if (kt == kKindCol) {
-                    uint32_t w = lmask ? (__ldg(sh.bits[t] + wi) & E) : 0u;
+                    uint32_t w = sh.cw[t][lane] & E;
                     if (!__any_sync(0xffffffffu, w != 0u)) continue;
                     const float* col = sh.col[t] + base + 32 * lane;
                     float* a = sh.acc + 32 * lane;
@@ -343,7 +366,7 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                     __syncwarp();
                 } else if (kt == kKindBStream) {
                     // a block stream that does not drive windows: seek to this window, add the postings that fall on E
-                    if (!__any_sync(0xffffffffu, lmask && (__ldg(sh.bits[t] + wi) & E) != 0u)) continue;
+                    if (!__any_sync(0xffffffffu, (sh.cw[t][lane] & E) != 0u)) continue;
                     const int slot = __popc(stream_mask & ((1u << t) - 1u));
                     WTerm& tc = sh.term[t];
                     int32_t* cd = cdocs + slot * kBlock;

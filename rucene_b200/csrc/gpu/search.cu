@@ -6,6 +6,8 @@
 // (query, segment, docid range) evaluated by k_eval_or / k_eval_and, followed by the exact
 // TopDocsCollector replay.  Plan shapes outside the accelerated path return RG_EUNSUPPORTED so
 // the caller can fall through to DefaultIndexSearcher, exactly like an unsupported Query would.
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -866,6 +868,40 @@ int rg_merge_leaf_records(rg_engine* e, const void* dev_records_all, uint32_t n_
     RG_CUDA_CHECK(cudaMemcpyAsync(out_total_hits, d_total.p, (size_t)n_queries * 8, cudaMemcpyDeviceToHost, st));
     RG_CUDA_CHECK(cudaStreamSynchronize(st));
     return RG_OK;
+    RG_CATCH
+}
+
+// ncclAllGather, resolved at run time so that librucene_gpu.so carries no link-time NCCL dependency (a PyTorch
+// process already holds its own libnccl; a Rust host links whichever it wants)
+using nccl_all_gather_fn = int (*)(const void*, void*, size_t, int /*ncclDataType_t*/, void* /*ncclComm_t*/, cudaStream_t);
+static nccl_all_gather_fn resolve_nccl_all_gather() {
+    static nccl_all_gather_fn fn = [] {
+        void* sym = dlsym(RTLD_DEFAULT, "ncclAllGather");
+        if (!sym) {
+            if (void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL)) sym = dlsym(h, "ncclAllGather");
+        }
+        return reinterpret_cast<nccl_all_gather_fn>(sym);
+    }();
+    return fn;
+}
+
+int rg_batch_run_sharded(rg_engine* e, rg_batch* b, void* nccl_comm, uint32_t n_ranks, rg_hit* out_hits,
+                         uint32_t* out_counts, uint64_t* out_total_hits) {
+    RG_TRY
+    if (!e || !b || !nccl_comm || !out_hits || !out_counts || !out_total_hits) throw ArgError("null argument");
+    if (b->mode != RG_MODE_SEARCH_PARALLEL) throw ArgError("rg_batch_run_sharded needs a RG_MODE_SEARCH_PARALLEL batch");
+    if (n_ranks == 0 || (uint64_t)n_ranks * b->n_leaves > 65535) throw ArgError("bad rank count");
+    const nccl_all_gather_fn all_gather = resolve_nccl_all_gather();
+    if (!all_gather) throw Unsupported("libnccl is not available in this process (ncclAllGather not found)");
+    int rc = rg_batch_run(e, b);
+    if (rc != RG_OK) return rc;
+    RG_CUDA_CHECK(cudaSetDevice(e->device));
+    const size_t local = (size_t)b->n_leaves * std::max<uint32_t>(1, b->n_queries) * leaf_record_bytes(b->k);
+    if (e->gather_scratch.n < local * n_ranks) e->gather_scratch.alloc(local * n_ranks);
+    const int nrc = all_gather(b->leaf_records.p, e->gather_scratch.p, local, 1 /* ncclUint8 */, nccl_comm, e->stream);
+    if (nrc != 0) throw ArgError("ncclAllGather failed with ncclResult_t " + std::to_string(nrc));
+    return rg_merge_leaf_records(e, e->gather_scratch.p, n_ranks * b->n_leaves, b->n_queries, b->k, out_hits, out_counts,
+                                 out_total_hits);
     RG_CATCH
 }
 

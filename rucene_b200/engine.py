@@ -88,6 +88,7 @@ def lib():
     L.rg_batch_debug.argtypes = [vp, vp, vp]
     L.rg_batch_columns.argtypes = [vp, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
     L.rg_batch_leaf_records.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.rg_batch_run_sharded.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, vp]
     L.rg_merge_leaf_records.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp]
     L.rg_segment_decode.argtypes = [vp, C.c_uint32, C.c_uint64, C.c_uint64, vp, vp]
     L.rg_forutil_decode.argtypes = [vp, vp, C.c_size_t, vp, C.c_uint32, C.c_int, vp, vp]
@@ -149,6 +150,16 @@ class Batch:
         n, nbytes = C.c_uint32(), C.c_uint64()
         _check(lib().rg_batch_columns(self.engine.h, self.h, C.byref(n), C.byref(nbytes)), self.engine.h)
         return n.value, nbytes.value
+
+    def run_sharded(self, nccl_comm, n_ranks):
+        """rg_batch_run_sharded: run + ncclAllGather of the leaf records over the caller's ncclComm_t + leaf-order
+        merge, entirely inside the C library."""
+        hits = np.zeros((self.n_queries, self.k), HIT_DTYPE)
+        counts = np.zeros(self.n_queries, np.uint32)
+        total = np.zeros(self.n_queries, np.uint64)
+        _check(lib().rg_batch_run_sharded(self.engine.h, self.h, nccl_comm, n_ranks, _p(hits), _p(counts), _p(total)),
+               self.engine.h)
+        return hits, counts, total
 
     def leaf_records(self):
         ptr, nbytes = C.c_void_p(), C.c_size_t()

@@ -56,6 +56,29 @@ def main():
     s = sharded.ShardedSearcher(eng)
     got = s.search_batch(q, c, k)
     torch.cuda.synchronize()
+    got_c = None
+    if not same_device:
+        # the same step through rg_batch_run_sharded: a raw ncclComm_t (created here with ctypes, as a Rust / C++
+        # host would with its own binding) — run, ncclAllGather and the leaf-order merge happen inside the C library
+        import ctypes
+
+        class UniqueId(ctypes.Structure):
+            _fields_ = [("internal", ctypes.c_byte * 128)]
+        nccl = ctypes.CDLL("libnccl.so.2")
+        uid = UniqueId()
+        if rank == 0:
+            assert nccl.ncclGetUniqueId(ctypes.byref(uid)) == 0
+        t = torch.frombuffer(bytearray(bytes(uid)), dtype=torch.uint8).to(dev)
+        dist.broadcast(t, 0)
+        ctypes.memmove(ctypes.byref(uid), bytes(t.cpu().numpy().tobytes()), 128)
+        comm = ctypes.c_void_p()
+        nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, UniqueId, ctypes.c_int]
+        assert nccl.ncclCommInitRank(ctypes.byref(comm), world, uid, rank) == 0
+        b = eng.prepare(q, c, k, mode=engine.MODE_SEARCH_PARALLEL)
+        got_c = b.run_sharded(comm, world)
+        b.close()
+        nccl.ncclCommDestroy.argtypes = [ctypes.c_void_p]
+        nccl.ncclCommDestroy(comm)
     ok = True
     if rank == 0:
         ix = ob.Index()
@@ -64,6 +87,8 @@ def main():
         want = ix.search_batch(oq, oc, k, parallel_mode=1, n_threads=8)
         try:
             helpers.assert_same_topdocs(got, want, "sharded world=%d" % world)
+            if got_c is not None:
+                helpers.assert_same_topdocs(got_c, want, "rg_batch_run_sharded world=%d" % world)
             print("SHARDED_OK world=%d queries=%d" % (world, len(q)))
         except AssertionError as e:
             ok = False

@@ -49,4 +49,5 @@ def test_cpp_mirror_matches_oracle():
         got = [tuple(int(x) for x in p.split(":")) for p in parts[1:]]
         want = [(int(h["doc"]), int(np.float32(h["score"]).view(np.uint32))) for h in hits[i][:counts[i]]]
         assert got == want
-    assert lines[4] == "unsupported:1"
+    assert lines[4] == "filter_same_as_must:1"
+    assert lines[5] == "unsupported:1"
