@@ -1422,8 +1422,9 @@ struct DisjunctionMaxScorer : Scorer {
     int32_t curr_doc;
     float tie_breaker_multiplier;
     size_t cost_;
+    std::unique_ptr<DisiQueue> dpq;  // >= 10 disjuncts (:118-139)
     DisjunctionMaxScorer(std::vector<ScorerPtr> children, float tie) : scorers(std::move(children)), tie_breaker_multiplier(tie) {
-        if (scorers.size() >= 10) throw Error(">=10 disjuncts use DisiPriorityQueue: out of scope (SURVEY 8f-4)");
+        if (scorers.size() >= 10) dpq.reset(new DisiQueue(scorers));
         cost_ = 0;
         curr_doc = NO_MORE_DOCS;
         for (auto& s : scorers) {
@@ -1431,8 +1432,9 @@ struct DisjunctionMaxScorer : Scorer {
             curr_doc = std::min(curr_doc, s->doc_id());
         }
     }
-    int32_t doc_id() const override { return curr_doc; }
+    int32_t doc_id() const override { return dpq ? dpq->top()->s->doc_id() : curr_doc; }
     int32_t next() override {  // approximate_next(None) :295-333 with DEFAULT_MIN_SHOULD_MATCH
+        if (dpq) return dpq->next_doc();
         if (curr_doc == NO_MORE_DOCS) return curr_doc;
         int32_t cd = curr_doc, min_doc = NO_MORE_DOCS;
         for (auto& s : scorers) {
@@ -1441,7 +1443,8 @@ struct DisjunctionMaxScorer : Scorer {
         }
         return curr_doc = min_doc;
     }
-    int32_t advance(int32_t target) override {  // :350-363
+    int32_t advance(int32_t target) override {  // :350-374
+        if (dpq) return dpq->advance(target);
         int32_t min_doc = NO_MORE_DOCS;
         for (auto& s : scorers) {
             if (s->doc_id() < target) s->advance(target);
@@ -1450,7 +1453,16 @@ struct DisjunctionMaxScorer : Scorer {
         return curr_doc = min_doc;
     }
     size_t cost() const override { return cost_; }
-    float score() override {  // score_max :241-263
+    float score() override {  // score_max :241-286
+        if (dpq) {
+            float score_sum = 0.0f, score_max = -INFINITY;
+            for (DisiQueue::W* w = dpq->top_list(); w; w = w->next) {
+                const float sub = w->s->score();
+                score_sum += sub;
+                if (sub > score_max) score_max = sub;
+            }
+            return score_max + (score_sum - score_max) * tie_breaker_multiplier;
+        }
         float score_sum = 0.0f, score_max = -INFINITY;
         for (auto& s : scorers)
             if (s->doc_id() == curr_doc) {

@@ -9,6 +9,7 @@ namespace rg {
 
 constexpr int kBlock = 128;           // codec/postings/posting_format.rs BLOCK_SIZE
 constexpr int kMaxTerms = 9;          // DisjunctionSumScorer SimpleQueue regime (< 10 children)
+constexpr int kDpqMaxTerms = 32;      // widest disjunction the DisiPriorityQueue kernel takes (>= 10 clauses in a leaf)
 constexpr int kNoMoreDocs = 0x7fffffff;
 constexpr int kBitmapDen = 1024;      // terms with df >= max_doc / 1024 get a presence bitmap at upload (within a budget)
 constexpr int kColumnDen = 64;        // terms with df >= max_doc / 64 may also get a score column (per weight, on demand)
@@ -51,7 +52,7 @@ struct SegDev {
 };
 
 // ------------------------------------------------------------------ plan (device side)
-enum : uint32_t { kTypeOr = 0, kTypeAnd = 1, kTypeReqOpt = 2 };
+enum : uint32_t { kTypeOr = 0, kTypeAnd = 1, kTypeReqOpt = 2, kTypeDpq = 3 };
 
 struct ItemClause {
     uint32_t term_id;

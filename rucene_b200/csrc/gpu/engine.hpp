@@ -167,6 +167,9 @@ void launch_build_bitmaps(cudaStream_t st, const SegDev* seg, const ColumnJob* j
                           uint32_t n_units);
 void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n,
                     uint32_t max_terms, bool has_live, bool has_not, bool has_msm, bool has_dmax);
+// eval_dpq.cu: disjunctions with >= 10 clauses in a leaf (DisiPriorityQueue order), one warp per (query, leaf)
+void launch_eval_dpq(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, uint32_t max_terms,
+                     bool has_live);
 // eval_or_ms.cu: pure-SHOULD sum disjunctions whose dense clauses all have a score column + bitmap
 void launch_eval_or_ms(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n,
                        uint32_t max_streams, bool has_live);

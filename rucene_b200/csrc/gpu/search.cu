@@ -42,6 +42,8 @@ struct rg_batch {
     Span<ItemClause> clauses;
     Span<uint32_t> or_ids, and_ids;  // launch order (range-major) of the OR / AND work items
     Span<uint32_t> ms_ids;           // OR work items evaluated by k_eval_or_ms (bitmaps + non-essential clauses)
+    Span<uint32_t> dpq_ids;          // disjunctions with >= 10 clauses in the leaf (k_eval_dpq), one per (query, leaf)
+    uint32_t n_dpq = 0, max_dpq_terms = 0;
     Span<uint32_t> ro_ids;           // MUST+SHOULD (ReqOptScorer) work items: one per (query, leaf)
     Span<ColRef> col_refs;           // score columns this batch reads (ItemClause.term_id indexes it)
     std::vector<std::shared_ptr<ColEntry>> cols;  // keeps them alive (the engine's LRU may drop them meanwhile)
@@ -70,7 +72,8 @@ namespace {
 struct HostPlan {
     std::vector<WorkItem> items;
     std::vector<ItemClause> clauses;
-    std::vector<uint32_t> or_ids, ms_ids, and_ids, ro_ids;
+    std::vector<uint32_t> or_ids, ms_ids, and_ids, ro_ids, dpq_ids;
+    uint32_t max_dpq_terms = 0;
     std::vector<ColRef> col_refs;
     std::map<std::pair<uint32_t, uint32_t>, uint32_t> bitmap_refs;  // (leaf, term) -> col_refs entry {null, bits}
     std::vector<std::shared_ptr<ColEntry>> cols;
@@ -106,7 +109,7 @@ QShape classify(const rg_query& q, const rg_clause* clauses, uint32_t n_clauses_
         // DisjunctionMaxQuery::build (search/query/disjunction_max_query.rs:51-68) over TermQuerys;
         // DisjunctionMaxScorer::new (disjunction_scorer.rs:118-139): SimpleQueue below 10 disjuncts
         if (q.n_clauses == 0) throw ArgError("DisjunctionMaxQuery: sub query should not be empty!");
-        if (q.n_clauses > (uint32_t)kMaxTerms) throw Unsupported(">= 10 disjuncts use DisiPriorityQueue");
+        if (q.n_clauses > (uint32_t)kDpqMaxTerms) throw Unsupported("more than 32 disjuncts");
         s.type = kTypeOr;
         for (uint32_t i = 0; i < q.n_clauses; i++) s.clause_idx.push_back(q.clause_begin + i);
         if (q.n_clauses > 1) {  // a single disjunct is the disjunct itself
@@ -133,8 +136,13 @@ QShape classify(const rg_query& q, const rg_clause* clauses, uint32_t n_clauses_
     int32_t msm = q.min_should_match > 0 ? q.min_should_match : (musts.empty() ? 1 : 0);
     if (musts.size() + shoulds.size() + filters.size() + must_nots.size() == 0)
         throw ArgError("boolean query should at least contain one inner query!");
-    if (musts.size() + shoulds.size() + filters.size() + must_nots.size() > (size_t)kMaxTerms)
-        throw Unsupported("more than 9 clauses");
+    // up to 9 clauses of any mix; wider queries only as pure SHOULD disjunctions (DisiPriorityQueue kernel)
+    const size_t n_all = musts.size() + shoulds.size() + filters.size() + must_nots.size();
+    if (n_all > (size_t)kMaxTerms) {
+        const bool pure_should = musts.empty() && filters.empty() && must_nots.empty();
+        if (!pure_should || n_all > (size_t)kDpqMaxTerms || msm > 1)
+            throw Unsupported("more than 9 clauses (only pure SHOULD disjunctions of up to 32 clauses with min_should_match <= 1 go wider)");
+    }
     // BooleanQuery::create_weight (:96-125): must_weights = the MUST clauses, then the FILTER clauses
     // (needs_scores = false); BooleanWeight::create_scorer treats them alike from there on
     musts.insert(musts.end(), filters.begin(), filters.end());
@@ -161,7 +169,6 @@ QShape classify(const rg_query& q, const rg_clause* clauses, uint32_t n_clauses_
         s.opt_idx = shoulds;
         return s;
     }
-    if (shoulds.size() >= 10) throw Unsupported(">= 10 SHOULD clauses use DisiPriorityQueue");
     s.type = kTypeOr;
     s.clause_idx = shoulds;
     // min_should_match > 1 only ever filters a disjunction that is iterated with next(): the
@@ -361,7 +368,11 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 if (t < seg.host_terms.size() && seg.host_terms[t].doc_freq > 0) opts.push_back(ci);
             }
             // no SHOULD scorer in this leaf -> the MUST side alone, no ReqOptScorer (:259-266)
-            const int leaf_type = shape.type == kTypeReqOpt && opts.empty() ? (int)kTypeAnd : shape.type;
+            // ten or more sub-scorers in this leaf: DisjunctionSumScorer / DisjunctionMaxScorer switch to the
+            // DisiPriorityQueue (disjunction_scorer.rs:41-45,118-139), whose summation order only k_eval_dpq reproduces
+            const bool leaf_dpq = shape.type == kTypeOr && !shape.match_all && present.size() >= 10;
+            const int leaf_type = leaf_dpq ? (int)kTypeDpq
+                                           : (shape.type == kTypeReqOpt && opts.empty() ? (int)kTypeAnd : shape.type);
             uint64_t cost = 0, bytes = 0, total_df = 0;
             if (shape.match_all) {
                 cost = total_df = (uint64_t)seg.max_doc;  // AllDocsIterator: every docid of the leaf
@@ -415,6 +426,8 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 const auto it = columns.find(ColKey(si, kMatchAllTerm, 0u, 0u, 0u));
                 if (it == columns.end()) throw Unsupported("no memory for the MatchAllDocsQuery column");
                 hp.clauses.push_back(ItemClause{it->second, 0.0f, 0u, 4u | 16u});
+            } else if (leaf_dpq) {
+                for (uint32_t ci : present) hp.clauses.push_back(ItemClause{clauses[ci].term_id, clause_weight(clauses[ci]), clauses[ci].cache_id, 0});
             } else if (shape.type == kTypeOr) {
                 // A disjunction goes to k_eval_or_ms (presence bitmaps, non-essential clauses are only counted)
                 // when it is a plain sum of SHOULD clauses, reads at least one score column, and none of its
@@ -481,7 +494,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
             uint64_t R = (cost + range_postings - 1) / range_postings;
             R = std::min<uint64_t>(R, 256);
             R = std::max<uint64_t>(1, std::min<uint64_t>(R, (uint64_t)(seg.max_doc + kBlock - 1) / kBlock));
-            if (leaf_type == (int)kTypeReqOpt) R = 1;  // sequential scorer state: one item per leaf
+            if (leaf_type == (int)kTypeReqOpt || leaf_dpq) R = 1;  // sequential scorer state: one item per leaf
             if (new_group) {
                 // SEARCH: one heap per query over all its leaves; SEARCH_PARALLEL: one per leaf
                 hp.group_out.push_back(mode == RG_MODE_SEARCH_PARALLEL ? si * n_queries + qi : qi);
@@ -500,7 +513,10 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 chain_pos = it.chain_pos + 1;
                 const uint32_t idx = (uint32_t)hp.items.size();
                 hp.items.push_back(it);
-                if (leaf_type == (int)kTypeReqOpt) {
+                if (leaf_dpq) {
+                    hp.dpq_ids.push_back(idx);
+                    hp.max_dpq_terms = std::max<uint32_t>(hp.max_dpq_terms, n_item_terms);
+                } else if (leaf_type == (int)kTypeReqOpt) {
                     hp.ro_ids.push_back(idx);
                 } else if (leaf_type == (int)kTypeAnd) {
                     hp.and_ids.push_back(idx);
@@ -590,6 +606,8 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     b->col_floats = hp.col_floats;
     b->n_ms = (uint32_t)hp.ms_ids.size();
     b->max_ms_streams = hp.max_ms_streams;
+    b->n_dpq = (uint32_t)hp.dpq_ids.size();
+    b->max_dpq_terms = hp.max_dpq_terms;
     b->n_queries = n_queries;
     b->k = p->k;
     b->mode = p->mode;
@@ -620,6 +638,7 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     carve(b->or_ids, hp.or_ids.size());
     carve(b->and_ids, hp.and_ids.size());
     carve(b->ms_ids, hp.ms_ids.size());
+    carve(b->dpq_ids, hp.dpq_ids.size());
     carve(b->ro_ids, hp.ro_ids.size());
     carve(b->col_refs, hp.col_refs.size());
     carve(b->group_item_begin, hp.group_item_begin.size());
@@ -651,7 +670,7 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
         using T = std::remove_reference_t<decltype(*span.p)>;
         span.p = reinterpret_cast<T*>(b->slab.p + reinterpret_cast<size_t>(span.p));
     };
-    rebase(b->items); rebase(b->clauses); rebase(b->or_ids); rebase(b->and_ids); rebase(b->ms_ids); rebase(b->ro_ids); rebase(b->col_refs);
+    rebase(b->items); rebase(b->clauses); rebase(b->or_ids); rebase(b->and_ids); rebase(b->ms_ids); rebase(b->dpq_ids); rebase(b->ro_ids); rebase(b->col_refs);
     rebase(b->group_item_begin); rebase(b->group_out); rebase(b->item_head); rebase(b->item_matches);
     rebase(b->item_theta); rebase(b->item_topk_n); rebase(b->item_topk); rebase(b->arena_next); rebase(b->dbg); rebase(b->out_hits); rebase(b->out_counts);
     rebase(b->out_total);
@@ -663,14 +682,15 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     up(b->or_ids, hp.or_ids, st);
     up(b->and_ids, hp.and_ids, st);
     up(b->ms_ids, hp.ms_ids, st);
+    up(b->dpq_ids, hp.dpq_ids, st);
     up(b->ro_ids, hp.ro_ids, st);
     up(b->col_refs, hp.col_refs, st);
     up(b->group_item_begin, hp.group_item_begin, st);
     up(b->group_out, hp.group_out, st);
     b->h2d_bytes = (hp.items.size() * sizeof(WorkItem)) + hp.clauses.size() * sizeof(ItemClause) +
-                   4 * (hp.or_ids.size() + hp.ms_ids.size() + hp.and_ids.size() + hp.ro_ids.size() + hp.group_item_begin.size() + hp.group_out.size()) +
+                   4 * (hp.or_ids.size() + hp.ms_ids.size() + hp.dpq_ids.size() + hp.and_ids.size() + hp.ro_ids.size() + hp.group_item_begin.size() + hp.group_out.size()) +
                    hp.col_refs.size() * sizeof(ColRef);
-    b->kernels_per_run = (b->n_ms ? 1 : 0) + (b->n_or ? 1 : 0) + (b->n_and ? 1 : 0) + (b->n_ro ? 1 : 0) + (b->n_groups ? 1 : 0) +
+    b->kernels_per_run = (b->n_ms ? 1 : 0) + (b->n_dpq ? 1 : 0) + (b->n_or ? 1 : 0) + (b->n_and ? 1 : 0) + (b->n_ro ? 1 : 0) + (b->n_groups ? 1 : 0) +
                          (p->mode == RG_MODE_SEARCH_PARALLEL ? 1 : 0);
     RG_CUDA_CHECK(cudaStreamSynchronize(st));
     *out = b.release();
@@ -717,6 +737,8 @@ int rg_batch_run(rg_engine* e, rg_batch* b) {
     launch_eval_or_ms(st, ep, b->ms_ids.p, b->n_ms, b->max_ms_streams, has_live);
     RG_CUDA_CHECK(cudaGetLastError());
     launch_eval_or(st, ep, b->or_ids.p, b->n_or, b->max_or_terms, has_live, b->or_has_not, b->or_has_msm, b->or_has_dmax);
+    RG_CUDA_CHECK(cudaGetLastError());
+    launch_eval_dpq(st, ep, b->dpq_ids.p, b->n_dpq, b->max_dpq_terms, has_live);
     RG_CUDA_CHECK(cudaGetLastError());
     launch_eval_and(st, ep, b->and_ids.p, b->n_and, false, has_other);
     RG_CUDA_CHECK(cudaGetLastError());
@@ -792,7 +814,7 @@ int rg_batch_stats(rg_engine* e, rg_batch* b, uint64_t out[8]) {
     out[3] = used;
     out[4] = b->kernels_per_run;
     out[5] = b->h2d_bytes;
-    out[6] = b->n_or + b->n_ms;
+    out[6] = b->n_or + b->n_ms + b->n_dpq;
     out[7] = b->n_and + b->n_ro;
     return RG_OK;
     RG_CATCH

@@ -331,6 +331,46 @@ def test_filter_clauses_and_pure_must_not():
             helpers.assert_same_topdocs(got, want, "filter k=%d rp=%d mode=%d" % (k, rp, mode))
 
 
+def test_wide_disjunctions_follow_the_disi_priority_queue():
+    """>= 10 sub-scorers in a leaf: DisjunctionSumScorer / DisjunctionMaxScorer keep them in a DisiPriorityQueue
+    (disjunction_scorer.rs:41-45,118-139) and add the scores in the order of its top_list() walk (util/disi.rs:190-231),
+    which k_eval_dpq replays literally.  Leaves where fewer than ten of the terms exist fall back to the SimpleQueue
+    kernels; live docs; both collector modes; mixed into a batch with the other shapes."""
+    rng = np.random.default_rng(171)
+    dfs = [9000, 8000, 7000, 6500, 6000, 5000, 4500, 4000, 3000, 2500, 2000, 1200, 600, 129, 40, 1, 0]
+    segs = []
+    for s, lf in enumerate((None, 0.85, None)):
+        d = list(dfs)
+        if s == 2:
+            for t in (1, 3, 5, 7, 9, 11, 12, 13):   # only 8 of the terms exist in the last leaf: SimpleQueue there
+                d[t] = 0
+        segs.append(helpers.build_segment(rng, 15000 + 400 * s, d, live_fraction=lf)[0])
+    specs = [("bool", [(ob.SHOULD, t) for t in range(10)], 0),
+             ("bool", [(ob.SHOULD, t) for t in range(17)], 0),
+             ("bool", [(ob.SHOULD, t, float(rng.choice([0.5, 1.0, 2.0]))) for t in rng.permutation(16)], 0),
+             ("bool", [(ob.SHOULD, t) for t in (15, 14, 13, 12, 0, 1, 2, 3, 4, 5, 6)], 1),
+             ("dismax", [(t,) for t in range(12)], 0.3),
+             ("dismax", [(int(t), float(rng.choice([1.0, 3.0]))) for t in rng.permutation(14)], 0.0),
+             ("dismax", [(t,) for t in range(10)], 1.0)]
+    for i in range(8):
+        n = int(rng.integers(10, 17))
+        specs.append(("bool", [(ob.SHOULD, int(t)) for t in rng.choice(17, size=n, replace=False)], 0))
+    specs += _mixed_specs(rng, len(dfs), 12, kinds=("term", "and", "or"))
+    for k in (10, 100):
+        for mode in (0, 1):
+            got, want = _run_both(segs, specs, k, mode=mode)
+            helpers.assert_same_topdocs(got, want, "dpq k=%d mode=%d" % (k, mode))
+    s = search.GpuIndexSearcher(search.IndexReader(segs))
+    try:   # wider than the kernel takes, or wide and not a plain disjunction: the caller falls back
+        for bad in (("bool", [(ob.SHOULD, t % 17) for t in range(33)], 0),
+                    ("bool", [(ob.SHOULD, t) for t in range(11)] + [(ob.MUST_NOT, 12)], 0),
+                    ("bool", [(ob.SHOULD, t) for t in range(11)], 2)):
+            with pytest.raises(engine.Unsupported):
+                s.search_batch(helpers.to_queries([bad]), 10)
+    finally:
+        s.engine.close()
+
+
 def test_reference_style_api():
     """Reads like examples/example.rs:111-117."""
     rng = np.random.default_rng(5)
