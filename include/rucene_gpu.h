@@ -144,6 +144,20 @@ float rg_engine_last_kernel_ms(rg_engine* e, const char* which);
 int rg_segment_upload(rg_engine* e, uint32_t seg_ord, int32_t doc_base, int32_t max_doc,
                       const uint8_t* doc_file, size_t doc_len, const uint8_t* norms,
                       const uint64_t* live_docs, const rg_term_state* terms, uint32_t n_terms);
+/* Terms dictionary of an uploaded segment, for exact lookups on the device: replaces the per-query
+ * SegmentTermIterator::seek_exact (codec/postings/blocktree/blocktree_reader.rs:1364, term_iter_frame.rs:436) +
+ * decode_term (posting_reader.rs:264-306) of TermQuery::create_weight / TermWeight::create_scorer.
+ * bytes: the field's terms concatenated in dictionary order (sorted unsigned bytewise, unique — the order the
+ * BlockTree iterates them); offsets[n_terms + 1]; term_ids[i] = engine-wide term id of entry i (its row in the
+ * rg_term_state table of rg_segment_upload), NULL = i. */
+int rg_terms_upload(rg_engine* e, uint32_t seg_ord, const uint8_t* bytes, const uint64_t* offsets,
+                    const uint32_t* term_ids, uint32_t n_terms);
+/* Resolve a batch of query terms (concatenated bytes + offsets[n + 1]) against every segment's dictionary with one
+ * kernel.  out_term_ids[i] = the engine-wide id to put into rg_clause.term_id (0xffffffff: in no segment — such a
+ * clause is simply absent everywhere); out_doc_freq (optional, [n_segments][n]) = its doc_freq per segment, which
+ * is what term_statistics (searcher.rs:732-767) needs for the weight. */
+int rg_terms_lookup(rg_engine* e, const uint8_t* bytes, const uint64_t* offsets, uint32_t n, uint32_t* out_term_ids,
+                    int32_t* out_doc_freq);
 /* BM25SimWeight.cache (bm25_similarity.rs:161-165), one per (field, k1, b, avgdl). */
 int rg_norm_cache_set(rg_engine* e, uint32_t cache_id, const float cache[256]);
 /* Bytes of device memory held by segment images. */

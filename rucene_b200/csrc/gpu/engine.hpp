@@ -117,6 +117,12 @@ struct Segment {
     uint64_t bitmap_words = 0;
     std::vector<int32_t> bitmap_slot;  // per term: index of its bitmap, -1 = none
     std::vector<TermHost> host_terms;
+    // terms dictionary for exact lookups on the device (terms_dict.cu): sorted term bytes + engine-wide ids
+    DevBuf<uint8_t> dict_bytes;
+    DevBuf<uint64_t> dict_off;
+    DevBuf<uint32_t> dict_ids;
+    uint32_t dict_n = 0;
+    bool has_dict = false;
     int32_t doc_base = 0, max_doc = 0;
     uint64_t device_bytes = 0;
 };

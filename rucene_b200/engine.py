@@ -76,6 +76,8 @@ def lib():
     L.rg_segment_upload.argtypes = [vp, C.c_uint32, C.c_int32, C.c_int32, vp, C.c_size_t, vp, vp,
                                     vp, C.c_uint32]
     L.rg_norm_cache_set.argtypes = [vp, C.c_uint32, vp]
+    L.rg_terms_upload.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_uint32]
+    L.rg_terms_lookup.argtypes = [vp, vp, vp, C.c_uint32, vp, vp]
     L.rg_search_batch.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, C.POINTER(SearchParams), vp,
                                   vp, vp]
     L.rg_batch_prepare.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, C.POINTER(SearchParams),
@@ -265,6 +267,29 @@ class Engine:
                self.h)
         self.n_segments += 1
         self._next_base = doc_base + seg.max_doc
+
+    @staticmethod
+    def _pack_terms(terms):
+        blob = b"".join(terms)
+        off = np.zeros(len(terms) + 1, np.uint64)
+        if terms:
+            off[1:] = np.cumsum([len(t) for t in terms])
+        return np.frombuffer(blob, np.uint8) if blob else np.zeros(1, np.uint8), off
+
+    def upload_terms(self, seg_ord, terms, term_ids=None):
+        """terms: list of bytes in dictionary order (sorted, unique); term_ids: engine-wide id per entry."""
+        blob, off = self._pack_terms(list(terms))
+        ids = None if term_ids is None else np.ascontiguousarray(term_ids, dtype=np.uint32)
+        _check(lib().rg_terms_upload(self.h, seg_ord, _p(blob), _p(off), _p(ids), len(terms)), self.h)
+
+    def lookup_terms(self, terms):
+        """-> (engine-wide term ids, doc_freq[n_segments][n]) resolved on the device."""
+        terms = list(terms)
+        blob, off = self._pack_terms(terms)
+        ids = np.zeros(len(terms), np.uint32)
+        df = np.zeros((max(1, self.n_segments), len(terms)), np.int32)
+        _check(lib().rg_terms_lookup(self.h, _p(blob), _p(off), len(terms), _p(ids), _p(df)), self.h)
+        return ids, df
 
     def set_norm_cache(self, cache_id, cache):
         c = np.ascontiguousarray(cache, dtype=np.float32)

@@ -191,8 +191,13 @@ class GpuIndexSearcher:
 
     def __init__(self, reader: IndexReader, similarity: Optional[BM25Similarity] = None,
                  device=-1, eng: Optional[engine.Engine] = None, range_postings=0,
-                 cand_arena_bytes=0, flags=0):
+                 cand_arena_bytes=0, flags=0, device_terms=False):
+        """device_terms: upload every leaf's terms dictionary (rg_terms_upload) and resolve the Term bytes of a batch
+        with one device lookup (rg_terms_lookup) instead of the host-side dict — what replaces the per-query
+        SegmentTermIterator::seek_exact of the reference."""
         self.reader = reader
+        self.device_terms = bool(device_terms)
+        self._resolved = None
         self.similarity = similarity or BM25Similarity()
         self.engine = eng or engine.Engine(device=device, range_postings=range_postings,
                                            cand_arena_bytes=cand_arena_bytes, flags=flags)
@@ -210,6 +215,13 @@ class GpuIndexSearcher:
         self._avgdl = codec.bm25_avg_field_length(self._sum_ttf, self._doc_count, self._max_doc)
         self._cache = codec.bm25_norm_cache(self.similarity.k1, self.similarity.b, self._avgdl)
         self.engine.set_norm_cache(0, self._cache)
+        if self.device_terms:
+            if not reader.term_ids:
+                raise IllegalArgument("device_terms needs IndexReader.term_ids (the dictionary)")
+            entries = sorted((b, tid) for (f, b), tid in reader.term_ids.items() if f == reader.field_name)
+            for ord_, seg in enumerate(segs):   # a leaf's dictionary holds the terms that occur in it
+                mine = [(b, tid) for b, tid in entries if tid < len(seg.terms) and seg.terms["doc_freq"][tid] > 0]
+                self.engine.upload_terms(ord_, [b for b, _ in mine], [tid for _, tid in mine])
 
     # TermQuery::create_weight -> BM25Similarity::compute_weight
     def term_weight(self, term_id, boost):
@@ -226,6 +238,12 @@ class GpuIndexSearcher:
         def add(q, occur):
             if not isinstance(q, TermQuery):
                 raise engine.Unsupported(engine.RG_EUNSUPPORTED, "only TermQuery leaves are accelerated")
+            if self._resolved is not None:   # ids and doc_freq came from the device dictionary
+                tid, df = self._resolved.get((q.term.field, bytes(q.term.bytes)), (None, 0))
+                doc_count = self._max_doc if self._doc_count == -1 else self._doc_count
+                w = np.float32(np.float32(codec.bm25_idf(df, doc_count)) * np.float32(q.boost))
+                clauses.append((occur, 0xFFFFFFFF if tid is None else tid, w, 0))
+                return
             tid = self.reader.term_id(q.term)
             absent = tid is None
             clauses.append((occur, 0xFFFFFFFF if absent else tid,
@@ -263,8 +281,32 @@ class GpuIndexSearcher:
             return (begin, len(clauses) - begin, tie_bits, engine.Q_DISMAX)
         raise engine.Unsupported(engine.RG_EUNSUPPORTED, "query type is not accelerated")
 
+    def _resolve_on_device(self, queries):
+        """One rg_terms_lookup for every Term of the batch -> {(field, bytes): (term id or None, df in the stats leaf)}"""
+        terms = set()
+
+        def walk(q):
+            if isinstance(q, TermQuery):
+                if q.term.field == self.reader.field_name:
+                    terms.add(bytes(q.term.bytes))
+            elif isinstance(q, ConstantScoreQuery):
+                walk(q.query)
+            elif isinstance(q, BooleanQuery):
+                for sub in q.must_queries + q.should_queries + q.filter_queries + q.must_not_queries:
+                    walk(sub)
+            elif isinstance(q, DisjunctionMaxQuery):
+                for sub in q.disjuncts:
+                    walk(sub)
+        for q in queries:
+            walk(q)
+        terms = sorted(terms)
+        ids, df = self.engine.lookup_terms(terms)
+        return {(self.reader.field_name, b): (None if ids[i] == 0xFFFFFFFF else int(ids[i]), int(df[self._stats_seg][i]))
+                for i, b in enumerate(terms)}
+
     def compile_batch(self, queries):
         clauses, qs = [], []
+        self._resolved = self._resolve_on_device(queries) if self.device_terms else None
         for q in queries:
             qs.append(self._compile(q, clauses))
         return (np.array(qs, dtype=engine.QUERY_DTYPE).reshape(-1),

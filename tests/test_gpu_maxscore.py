@@ -157,3 +157,45 @@ def test_segment_decode_matches_the_oracle_reader():
         assert blk == out.shape[0]
     finally:
         eng.close()
+
+
+def test_device_terms_dictionary_resolves_a_batch():
+    """rg_terms_upload / rg_terms_lookup: exact lookups of the batch's Term bytes on the device (the reference's
+    per-query SegmentTermIterator::seek_exact, blocktree_reader.rs:1364) — absent terms, prefixes of present terms,
+    the empty term, long terms, bytes 0x00 / 0xff, terms present in one leaf only — then the same searches as with
+    the host-side dictionary."""
+    rng = np.random.default_rng(99)
+    names = [b"", b"\x00", b"\x00\x00", b"a", b"ab", b"abc", b"abd", b"b" * 300, b"b" * 301, b"\xff", b"\xff\xff",
+             b"zebra", b"zebr\xc3\xa4", b"hello", b"world"]
+    dfs = [int(x) for x in rng.integers(50, 9000, len(names))]
+    segs = []
+    for s in range(2):
+        d = list(dfs)
+        if s == 1:
+            d[3] = 0      # b"a" lives in the first leaf only
+            d[13] = 0
+        segs.append(helpers.build_segment(rng, 20000 + 500 * s, d)[0])
+    term_ids = {("body", n): i for i, n in enumerate(names)}
+    reader = search.IndexReader(segs, term_ids=term_ids)
+    dev = search.GpuIndexSearcher(reader, device_terms=True)
+    host = search.GpuIndexSearcher(reader)
+    try:
+        probes = names + [b"abcd", b"aa", b"\x00\x00\x00", b"b" * 299, b"b" * 302, b"zebr", b"zebrb", b"\xfe", b"nope"]
+        ids, df = dev.engine.lookup_terms(probes)
+        for i, pb in enumerate(probes):
+            want = term_ids.get(("body", pb))
+            assert (None if ids[i] == 0xFFFFFFFF else int(ids[i])) == want, pb
+            for s in range(2):
+                assert df[s][i] == (0 if want is None else int(segs[s].terms["doc_freq"][want])), (pb, s)
+        T = lambda b, boost=1.0: search.TermQuery.new(search.Term.new("body", b), boost, None)   # noqa: E731
+        queries = [T(b"hello"), T(b"nope"), T(b"a"),
+                   search.BooleanQuery.build([T(b"abc"), T(b"abd")], [], [], [], 0),
+                   search.BooleanQuery.build([], [T(b""), T(b"\xff"), T(b"b" * 300), T(b"absent"), T(b"zebra", 2.0)], [], [], 0),
+                   search.BooleanQuery.build([T(b"world")], [T(b"a")], [T(b"ab")], [T(b"\x00")], 0),
+                   search.DisjunctionMaxQuery.build([T(b"hello"), T(b"world"), T(b"zebr\xc3\xa4")], 0.2)]
+        helpers.assert_same_topdocs(dev.search_batch(queries, 10), host.search_batch(queries, 10), "device dictionary")
+        with pytest.raises(engine.EngineError):   # not in dictionary order
+            dev.engine.upload_terms(0, [b"b", b"a"], [0, 1])
+    finally:
+        dev.engine.close()
+        host.engine.close()
