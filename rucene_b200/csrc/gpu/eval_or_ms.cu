@@ -30,18 +30,22 @@
 
 namespace rg {
 
-constexpr int kMsWarps = 4;
+// One warp per CTA: work items differ wildly in length (a range where nothing can beat theta is a bulk popcount,
+// one that must score is thousands of windows), and a CTA keeps its slot until its slowest warp is done.
+constexpr int kMsWarps = 1;
 constexpr int kMsThreads = kMsWarps * 32;
 constexpr int kMsW = 1024;     // docids per window = 32 lanes x one 32-bit presence word
+constexpr int kMsSlots = 64;   // docs of a window that get an exact score (a fuller window is cut short)
 constexpr int kMsPlanes = 6;   // bit-sliced bound: theta <-> 2^6 - 1
 constexpr uint32_t kMsSat = 1u << kMsPlanes;
 
 enum : int { kKindNone = 0, kKindCol = 1, kKindBStream = 2, kKindSparse = 3 };
 
 struct alignas(16) MsWarpShared {  // followed by topk[kcap] floats, then cdocs[S][128], cscores[S][128]
-    float acc[kMsW];               // 0.0f = untouched; touched docs are exactly the bits of E
+    float acc[kMsSlots];           // one accumulator per doc of E, in docid order (slot = rank of the doc's bit in E)
     uint32_t ubits[32];            // presence words of the sparse streams in this window
     uint32_t ebits[32];            // E: the docs of this window that get an exact score
+    uint32_t epre[32];             // number of E bits in the words before word w
     uint32_t cw[kMaxTerms][32];    // this window's presence words of the bitmap clauses (lane-owned, masked)
     WTerm term[kMaxTerms];         // block-stream clauses (same cursor as k_eval_or)
     const float* col[kMaxTerms];   // score column (leaf-local docid -> BM25 contribution), column clauses
@@ -70,7 +74,7 @@ __device__ __forceinline__ uint32_t ms_count_range(const MsWarpShared& sh, uint3
 }
 
 template <bool LIVE>
-__global__ void __launch_bounds__(kMsThreads, 5)
+__global__ void __launch_bounds__(kMsThreads, 24)
 k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, uint32_t warp_bytes,
              uint32_t kcap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -128,7 +132,8 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
         // score = rn(rn(w1*f) / rn(f + norm)) with f >= 1, norm >= 0  =>  score <= nextafter(w1)
         ub = (c.flags & 16u) || !(w1 >= 0.0f) || !(w1 < INFINITY) ? INFINITY : __uint_as_float(__float_as_uint(w1) + 1u);
     }
-    for (int i = lane; i < kMsW / 4; i += 32) reinterpret_cast<float4*>(sh.acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    sh.acc[lane] = 0.0f;
+    sh.acc[lane + 32] = 0.0f;
     __syncwarp();
 
     MsmCtx mc_unused{nullptr, 1u, nullptr};
@@ -138,7 +143,7 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
         const int t = __ffs(m) - 1;
         const int slot = __popc(stream_mask & ((1u << t) - 1u));
         if (stream_refill<false, false, false, false>(seg, p, sh.term[t], cdocs + slot * kBlock, cscores + slot * kBlock, lo,
-                                                      hi, lane, 0, -2147483647 - 1, reinterpret_cast<uint32_t*>(sh.acc),
+                                                      hi, lane, 0, -2147483647 - 1, sh.ubits,
                                                       hot_unused, mm_unused, INFINITY, mc_unused)) {
             const int first = cdocs[slot * kBlock + sh.term[t].pos];
             if (lane == t) nd = first;
@@ -299,14 +304,40 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
             }
             E |= over;
         }
+        // at most kMsSlots docs are scored per window: a fuller window ends at the word where the count is reached
+        uint32_t epre = 0, n_e = 0;
+        const bool any_e = __any_sync(0xffffffffu, E != 0u);
+        if (any_e) {
+            uint32_t incl = __popc(E);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += x;
+            }
+            const uint32_t cutm = __ballot_sync(0xffffffffu, incl > (uint32_t)kMsSlots);
+            if (cutm) {  // lanes >= cut leave the window (cut >= 2: a word holds 32 docs)
+                const int cut = __ffs(cutm) - 1;
+                win1 = base + 32 * cut;
+                if (lane >= cut) {
+                    E = 0u;
+                    U = 0u;
+                    lmask = 0u;
+                    incl = 0u;
+                }
+                st_cut++;
+            }
+            epre = incl - __popc(E);
+            n_e = __reduce_max_sync(0xffffffffu, incl);
+        }
         uint32_t lw = 0xffffffffu;
         if (LIVE && seg.live) lw = lmask ? reinterpret_cast<const uint32_t*>(seg.live)[wi] : 0u;
         my_matches += __popc(U & lw);
         uint32_t hot = 0;
-        if (__any_sync(0xffffffffu, E != 0u)) {
+        if (any_e) {
             st_scored++;
             st_edocs += __popc(E);
             sh.ebits[lane] = E;
+            sh.epre[lane] = epre;
             __syncwarp();
             // the column cells this window will read, towards L1 now: the clause-ordered pass below would otherwise
             // pay one DRAM round trip per column clause, one after the other
@@ -338,8 +369,9 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                         const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, in_win));  // sorted: a prefix
                         if (in_win) {
                             const int idx = d - base;
-                            const float sum = __fadd_rn(sh.acc[idx], cs[i]);
-                            sh.acc[idx] = sum;
+                            const uint32_t slot = sh.epre[idx >> 5] + __popc(sh.ebits[idx >> 5] & ((1u << (idx & 31)) - 1u));
+                            const float sum = __fadd_rn(sh.acc[slot], cs[i]);
+                            sh.acc[slot] = sum;
                             if (sum > te) hot |= 1u << (idx >> 5);
                         }
                         cpos += cnt;
@@ -354,12 +386,12 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                     uint32_t w = sh.cw[t][lane] & E;
                     if (!__any_sync(0xffffffffu, w != 0u)) continue;
                     const float* col = sh.col[t] + base + 32 * lane;
-                    float* a = sh.acc + 32 * lane;
                     while (w) {
                         const int b = __ffs(w) - 1;
                         w &= w - 1;
-                        const float sum = __fadd_rn(a[b], __ldg(col + b));
-                        a[b] = sum;
+                        const uint32_t slot = epre + __popc(E & ((1u << b) - 1u));
+                        const float sum = __fadd_rn(sh.acc[slot], __ldg(col + b));
+                        sh.acc[slot] = sum;
                         st_gather++;
                         if (sum > te) hot |= 1u << lane;
                     }
@@ -381,7 +413,7 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                             __syncwarp();
                             st_refill++;
                             if (!stream_refill<false, false, false, false>(seg, p, tc, cd, cs, lo, hi, lane, 0, -2147483647 - 1,
-                                                                          reinterpret_cast<uint32_t*>(sh.acc), hot_unused,
+                                                                          sh.ubits, hot_unused,
                                                                           mm_unused, INFINITY, mc_unused))
                                 break;
                             continue;
@@ -391,9 +423,11 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                         const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, d < win1));  // sorted: a prefix
                         if (d >= win0 && d < win1) {
                             const int idx = d - base;
-                            if ((sh.ebits[idx >> 5] >> (idx & 31)) & 1u) {
-                                const float sum = __fadd_rn(sh.acc[idx], cs[i]);
-                                sh.acc[idx] = sum;
+                            const uint32_t ew = sh.ebits[idx >> 5];
+                            if ((ew >> (idx & 31)) & 1u) {
+                                const uint32_t slot = sh.epre[idx >> 5] + __popc(ew & ((1u << (idx & 31)) - 1u));
+                                const float sum = __fadd_rn(sh.acc[slot], cs[i]);
+                                sh.acc[slot] = sum;
                                 if (sum > te) hot |= 1u << (idx >> 5);
                             }
                         }
@@ -417,9 +451,10 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                 hot &= hot - 1;
                 const int idx = s * 32 + lane;
                 st_steps++;
-                const float sc = sh.acc[idx];
                 const uint32_t Es = __shfl_sync(0xffffffffu, E, s);
+                const uint32_t ps = __shfl_sync(0xffffffffu, epre, s);
                 const uint32_t ls = __shfl_sync(0xffffffffu, lw, s);
+                const float sc = ((Es >> lane) & 1u) ? sh.acc[ps + __popc(Es & ((1u << lane) - 1u))] : 0.0f;
                 const bool cand = ((Es & ls) >> lane) & 1u && (open || sc > te);
                 const uint32_t cm = __ballot_sync(0xffffffffu, cand);
                 if (!cm || em.overflow) continue;
@@ -456,10 +491,8 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
             }
             __syncwarp();
             // re-arm the accumulator words that were touched (E bits live in the owning lane's word)
-            if (E) {
-#pragma unroll
-                for (int g = 0; g < 8; g++) reinterpret_cast<float4*>(sh.acc + 32 * lane)[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            if ((uint32_t)lane < n_e) sh.acc[lane] = 0.0f;
+            if ((uint32_t)lane + 32u < n_e) sh.acc[lane + 32] = 0.0f;
             wtheta_update(em, p.k, kcap, lane, sh.newc, newc_n, p.item_theta + item_idx);
             __syncwarp();
         }
@@ -478,7 +511,7 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                 st_refill++;
                 if (stream_refill<false, false, false, false>(seg, p, sh.term[t], cdocs + slot * kBlock, cscores + slot * kBlock,
                                                               lo, hi, lane, 0, -2147483647 - 1,
-                                                              reinterpret_cast<uint32_t*>(sh.acc), hot_unused, mm_unused,
+                                                              sh.ubits, hot_unused, mm_unused,
                                                               INFINITY, mc_unused))
                     first = cdocs[slot * kBlock + sh.term[t].pos];
                 if (lane == t) nd = first;
