@@ -259,7 +259,7 @@ __device__ __forceinline__ bool is_live(const SegDev& seg, int doc) {
 //       next block / the vint tail) whenever it runs dry;
 //   scan the touched 32-doc steps in docid order -> total_hits, theta filter, candidates;
 //   next window start = min over clauses of their next cached docid (exact).
-constexpr int kOrWarps = 4;
+constexpr int kOrWarps = 1;  // one warp per CTA: a CTA's slot is held until its slowest warp is done
 constexpr int kOrThreads = kOrWarps * 32;
 constexpr int kWw = 768;            // docids per window
 constexpr int kNewcW = 64;

@@ -37,7 +37,7 @@ namespace rg {
 
 
 template <bool LIVE, bool NOT, bool MSM, bool DMAX>
-__global__ void __launch_bounds__(kOrThreads, 6)
+__global__ void __launch_bounds__(kOrThreads, 24)
 k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, uint32_t warp_bytes,
           uint32_t kcap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
