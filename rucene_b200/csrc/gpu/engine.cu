@@ -635,6 +635,7 @@ void build_segment(rg_engine* e, Segment& seg, int32_t doc_base, int32_t max_doc
             for (size_t i = 0; i < n_bm; i++) {
                 const uint32_t t = dense[i];
                 seg.bitmap_slot[t] = (int32_t)i;
+                seg.bitmap_terms.push_back(t);
                 jobs[i] = ColumnJob{0u, t, 0u, 0.0f, seg.bitmaps.p + i * seg.bitmap_words, units, 0u};
                 units += seg.host_terms[t].n_blocks + (seg.host_terms[t].tail_n ? 1u : 0u);
             }
@@ -816,6 +817,9 @@ int rg_norm_cache_set(rg_engine* e, uint32_t cache_id, const float cache[256]) {
     bool nonneg = true;
     for (int i = 0; i < 256; i++) nonneg = nonneg && cache[i] >= 0.0f;  // false for NaN as well
     e->cache_nonneg[cache_id] = nonneg ? 1 : 0;
+    for (Segment& sg : e->segs)  // and so are the high tf-norm planes of this cache
+        for (auto it = sg.tf_planes.begin(); it != sg.tf_planes.end();)
+            it = it->first.first == cache_id ? sg.tf_planes.erase(it) : std::next(it);
     // score columns computed with the previous contents of this cache are no longer valid
     for (auto it = e->col_cache.begin(); it != e->col_cache.end();) {
         if (std::get<3>(it->first) == cache_id) {

@@ -70,6 +70,17 @@ struct DevBuf {
 struct ColRef {
     const float* col;
     const uint32_t* bits;
+    const uint32_t* hi;   // "high tf-norm" plane of the term for the clause's norm cache (null: none), see TfPlanes
+};
+
+// BM25's tf-norm factor f/(f+norm) of a posting is <= kTfLow for most postings (f = 1 in an average-length doc gives
+// 0.45).  For every bitmap term one more bit per docid says "this posting's factor is above kTfLow" (for one norm
+// cache and k1: the factor depends on them), so the per-document score bound of k_eval_or_ms can use kTfLow*ub for
+// the others.  One buffer per (segment, cache id, k1), built for all bitmap terms of the segment the first time a
+// batch needs it.
+constexpr float kTfLow = 0.55f;
+struct TfPlanes {
+    DevBuf<uint32_t> bits;  // [n bitmap terms][bitmap_words], same slot order as Segment::bitmaps
 };
 
 // Persistent score column (engine-owned, LRU): the contributions of one (leaf, term, weight, norm
@@ -116,6 +127,8 @@ struct Segment {
     DevBuf<uint32_t> bitmaps;
     uint64_t bitmap_words = 0;
     std::vector<int32_t> bitmap_slot;  // per term: index of its bitmap, -1 = none
+    std::vector<uint32_t> bitmap_terms;  // slot -> term id
+    std::map<std::pair<uint32_t, uint32_t>, TfPlanes> tf_planes;  // (cache id, k1 bits) -> high tf-norm planes
     std::vector<TermHost> host_terms;
     // terms dictionary for exact lookups on the device (terms_dict.cu): sorted term bytes + engine-wide ids
     DevBuf<uint8_t> dict_bytes;
@@ -171,6 +184,9 @@ void launch_build_columns(cudaStream_t st, const SegDev* segs, const ColumnJob* 
                           uint32_t n_units, const float* caches, float k1);
 void launch_build_bitmaps(cudaStream_t st, const SegDev* seg, const ColumnJob* jobs, uint32_t n_jobs,
                           uint32_t n_units);
+// jobs carry cache_id; a posting sets its bit when its tf-norm factor (rounded up) exceeds tf_low
+void launch_build_tf_planes(cudaStream_t st, const SegDev* segs, const ColumnJob* jobs, uint32_t n_jobs,
+                            uint32_t n_units, const float* caches, float k1, float tf_low);
 void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n,
                     uint32_t max_terms, bool has_live, bool has_not, bool has_msm, bool has_dmax);
 // eval_dpq.cu: disjunctions with >= 10 clauses in a leaf (DisiPriorityQueue order), one warp per (query, leaf)

@@ -42,13 +42,15 @@ constexpr uint32_t kMsSat = 1u << kMsPlanes;
 enum : int { kKindNone = 0, kKindCol = 1, kKindBStream = 2, kKindSparse = 3 };
 
 struct alignas(16) MsWarpShared {  // followed by topk[kcap] floats, then cdocs[S][128], cscores[S][128]
-    uint16_t edoc[kMsSlots];       // the docs of E (index inside the window), in docid order
+    float acc[kMsSlots];           // one accumulator per doc of E, in docid order (slot = rank of the doc's bit in E)
     uint32_t ubits[32];            // presence words of the sparse streams in this window
-    float cval[kMaxTerms][32];     // column cells of the docs being scored (lane-owned)
+    uint32_t ebits[32];            // E: the docs of this window that get an exact score
+    uint32_t epre[32];             // number of E bits in the words before word w
     uint32_t cw[kMaxTerms][32];    // this window's presence words of the bitmap clauses (lane-owned, masked)
     WTerm term[kMaxTerms];         // block-stream clauses (same cursor as k_eval_or)
     const float* col[kMaxTerms];   // score column (leaf-local docid -> BM25 contribution), column clauses
     const uint32_t* bits[kMaxTerms];  // presence bitmap, column clauses and block streams of dense-enough terms
+    const uint32_t* hi[kMaxTerms];    // "tf-norm factor above kTfLow" plane of the same clauses (null: none)
     float newc[kNewcW];
 };
 
@@ -109,6 +111,7 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
         const ColRef r = p.cols[c.term_id];
         sh.col[lane] = r.col;
         sh.bits[lane] = r.bits;
+        sh.hi[lane] = r.hi;
     } else if (kind != kKindNone) {
         const TermDev td = seg.terms[c.term_id];
         WTerm& tc = sh.term[lane];
@@ -125,12 +128,19 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
         tc.is_not = 0;
         sh.col[lane] = nullptr;
         sh.bits[lane] = kind == kKindBStream ? p.cols[c.flags >> 16].bits : nullptr;
+        sh.hi[lane] = kind == kKindBStream ? p.cols[c.flags >> 16].hi : nullptr;
     }
+    float ub_lo = 0.0f;  // bound for the postings whose high-tf plane bit is clear
     if ((bmask >> lane) & 1u) {
         const float w1 = __fmul_rn(c.weight, __fadd_rn(p.k1, 1.0f));
-        // score = rn(rn(w1*f) / rn(f + norm)) with f >= 1, norm >= 0  =>  score <= nextafter(w1)
+        // score = rn(rn(w1*f) / rn(f + norm)) with f >= 1, norm >= 0  =>  score <= nextafter(w1); with a tf-norm factor
+        // (rounded up at build time) <= kTfLow:  score <= w1 * kTfLow * (1 + 4 * 2^-24)
         ub = (c.flags & 16u) || !(w1 >= 0.0f) || !(w1 < INFINITY) ? INFINITY : __uint_as_float(__float_as_uint(w1) + 1u);
+        ub_lo = sh.hi[lane] && ub < INFINITY ? __fmul_ru(__fmul_ru(w1, kTfLow), 1.000001f) : ub;
     }
+    const uint32_t hmask = __ballot_sync(0xffffffffu, ((bmask >> lane) & 1u) && sh.hi[lane] != nullptr && ub < INFINITY);
+    sh.acc[lane] = 0.0f;
+    sh.acc[lane + 32] = 0.0f;
     __syncwarp();
 
     MsmCtx mc_unused{nullptr, 1u, nullptr};
@@ -166,6 +176,7 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
     // quantised bounds, valid for theta == q_te
     float q_te = NAN;
     uint32_t q = 0;          // lane t: q of clause t (kMsSat: any doc of the clause must be scored)
+    uint32_t q_lo = 0;       // ... of its postings with a low tf-norm factor (== q without a plane)
     bool prune = false;      // a usable theta exists: docs without a carry are dropped
     bool need_scan = bmask != 0;  // some combination of bitmap clauses can still beat theta
     // RG_CFG_STATS event counters (warp-uniform unless noted)
@@ -197,9 +208,12 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                 const float x = __fmul_ru(ub, scale);
                 q = ((bmask >> lane) & 1u) ? (x < (float)kMsSat ? (uint32_t)ceilf(x) : kMsSat) : 0u;  // NaN -> kMsSat
                 if (((bmask >> lane) & 1u) && q == 0u) q = 1u;
+                const float xl = __fmul_ru(ub_lo, scale);
+                q_lo = ((hmask >> lane) & 1u) ? min(q, max(1u, (uint32_t)ceilf(xl))) : q;
                 need_scan = __reduce_add_sync(0xffffffffu, q) >= kMsSat;
             } else {
                 q = ((bmask >> lane) & 1u) ? kMsSat : 0u;
+                q_lo = q;
                 need_scan = bmask != 0;
             }
         }
@@ -261,10 +275,12 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
         const int wi = (base >> 5) + lane;
         {
             // all words first (independent loads in flight together), then the arithmetic
-            uint32_t wv[kMaxTerms];
+            uint32_t wv[kMaxTerms], hv[kMaxTerms];
 #pragma unroll
-            for (int t = 0; t < kMaxTerms; t++)
+            for (int t = 0; t < kMaxTerms; t++) {
                 wv[t] = (((bmask >> t) & 1u) && lmask) ? (__ldg(sh.bits[t] + wi) & lmask) : 0u;
+                hv[t] = (((hmask >> t) & 1u) && lmask && need_scan) ? __ldg(sh.hi[t] + wi) : 0xffffffffu;
+            }
             // the next window's line of every bitmap towards L1 while this one is processed
             if (((bmask >> lane) & 1u) && base + kMsW < hi)
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(sh.bits[lane] + (base >> 5) + 32));
@@ -279,13 +295,15 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                 sh.cw[t][lane] = w;
                 U |= w;
                 const uint32_t qt = __shfl_sync(0xffffffffu, q, t);
+                const uint32_t ql = __shfl_sync(0xffffffffu, q_lo, t);
                 if (qt >= kMsSat) {  // no usable bound (or no theta yet): every doc of the clause
                     over |= w;
                 } else if (need_scan) {
+                    // every posting adds q_lo; the ones on the high tf-norm plane add the rest of q
                     uint32_t carry = 0u;
 #pragma unroll
                     for (int i = 0; i < kMsPlanes; i++) {
-                        if ((qt >> i) & 1u) {  // warp-uniform
+                        if ((ql >> i) & 1u) {  // warp-uniform
                             const uint32_t x = S[i] ^ w;
                             const uint32_t c2 = (S[i] & w) | (x & carry);
                             S[i] = x ^ carry;
@@ -297,6 +315,25 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                         }
                     }
                     over |= carry;
+                    const uint32_t dq = qt - ql;
+                    if (dq) {  // warp-uniform
+                        const uint32_t wh = w & hv[t];
+                        carry = 0u;
+#pragma unroll
+                        for (int i = 0; i < kMsPlanes; i++) {
+                            if ((dq >> i) & 1u) {
+                                const uint32_t x = S[i] ^ wh;
+                                const uint32_t c2 = (S[i] & wh) | (x & carry);
+                                S[i] = x ^ carry;
+                                carry = c2;
+                            } else {
+                                const uint32_t c2 = S[i] & carry;
+                                S[i] ^= carry;
+                                carry = c2;
+                            }
+                        }
+                        over |= carry;
+                    }
                 }
             }
             E |= over;
@@ -329,102 +366,130 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
         uint32_t lw = 0xffffffffu;
         if (LIVE && seg.live) lw = lmask ? reinterpret_cast<const uint32_t*>(seg.live)[wi] : 0u;
         my_matches += __popc(U & lw);
-        (void)epre;
+        uint32_t hot = 0;
         if (any_e) {
             st_scored++;
             st_edocs += __popc(E);
-            // ---- 3. exact scores, one doc of E per lane: its clauses are visited in clause order
-            // (DisjunctionSumScorer::score_sum, from 0.0f) and summed in registers
-            {   // docs of E in docid order -> sh.edoc (index inside the window)
-                uint32_t w = E, sl = epre;
+            sh.ebits[lane] = E;
+            sh.epre[lane] = epre;
+            __syncwarp();
+            // the column cells this window will read, towards L1 now: the clause-ordered pass below would otherwise
+            // pay one DRAM round trip per column clause, one after the other
+            for (uint32_t m = col_mask; m; m &= m - 1) {
+                const int t = __ffs(m) - 1;
+                uint32_t w = sh.cw[t][lane] & E;
+                const float* col = sh.col[t] + base + 32 * lane;
                 while (w) {
-                    sh.edoc[sl++] = (uint16_t)(32 * lane + __ffs(w) - 1);
+                    const int b = __ffs(w) - 1;
                     w &= w - 1;
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(col + b));
                 }
             }
-            __syncwarp();
+            // ---- 3. exact scores of the docs in E: clauses in clause order (DisjunctionSumScorer::score_sum)
+            for (int t = 0; t < T; t++) {
+                const int kt = __shfl_sync(0xffffffffu, kind, t);
+                if (kt == kKindSparse) {
+                    if (!((act >> t) & 1u)) continue;
+                    const int slot = __popc(stream_mask & ((1u << t) - 1u));
+                    WTerm& tc = sh.term[t];
+                    const int32_t* cd = cdocs + slot * kBlock;
+                    const float* cs = cscores + slot * kBlock;
+                    uint32_t cpos = tc.pos;
+                    const uint32_t n = tc.n;
+                    for (;;) {
+                        const uint32_t i = cpos + lane;
+                        const int d = i < n ? cd[i] : kNoMoreDocs;
+                        const bool in_win = d < win1;
+                        const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, in_win));  // sorted: a prefix
+                        if (in_win) {
+                            const int idx = d - base;
+                            const uint32_t slot = sh.epre[idx >> 5] + __popc(sh.ebits[idx >> 5] & ((1u << (idx & 31)) - 1u));
+                            const float sum = __fadd_rn(sh.acc[slot], cs[i]);
+                            sh.acc[slot] = sum;
+                            if (sum > te) hot |= 1u << (idx >> 5);
+                        }
+                        cpos += cnt;
+                        st_post += cnt;
+                        if (cnt < 32) break;
+                    }
+                    __syncwarp();  // every lane has read this clause's cursor
+                    if (lane == 0) tc.pos = cpos;
+                    if (lane == t) nd = cpos < n ? cd[cpos] : kNoMoreDocs;  // an emptied cache is refilled below
+                    __syncwarp();
+                } else if (kt == kKindCol) {
+                    uint32_t w = sh.cw[t][lane] & E;
+                    if (!__any_sync(0xffffffffu, w != 0u)) continue;
+                    const float* col = sh.col[t] + base + 32 * lane;
+                    while (w) {
+                        const int b = __ffs(w) - 1;
+                        w &= w - 1;
+                        const uint32_t slot = epre + __popc(E & ((1u << b) - 1u));
+                        const float sum = __fadd_rn(sh.acc[slot], __ldg(col + b));
+                        sh.acc[slot] = sum;
+                        st_gather++;
+                        if (sum > te) hot |= 1u << lane;
+                    }
+                    __syncwarp();
+                } else if (kt == kKindBStream) {
+                    // a block stream that does not drive windows: seek to this window, add the postings that fall on E
+                    if (!__any_sync(0xffffffffu, (sh.cw[t][lane] & E) != 0u)) continue;
+                    const int slot = __popc(stream_mask & ((1u << t) - 1u));
+                    WTerm& tc = sh.term[t];
+                    int32_t* cd = cdocs + slot * kBlock;
+                    float* cs = cscores + slot * kBlock;
+                    for (;;) {
+                        uint32_t cpos = tc.pos;
+                        const uint32_t n = tc.n;
+                        if (cpos >= n || cd[n - 1] < win0) {  // nothing cached for this window
+                            if (tc.cur > tc.nb) break;        // exhausted
+                            __syncwarp();                     // every lane has read the cursor
+                            if (lane == 0) tc.cur = lower_bound_gallop(tc.blk_last, min(tc.cur, tc.nb), tc.nb, win0);
+                            __syncwarp();
+                            st_refill++;
+                            if (!stream_refill<false, false, false, false>(seg, p, tc, cd, cs, lo, hi, lane, 0, -2147483647 - 1,
+                                                                          sh.ubits, hot_unused,
+                                                                          mm_unused, INFINITY, mc_unused))
+                                break;
+                            continue;
+                        }
+                        const uint32_t i = cpos + lane;
+                        const int d = i < n ? cd[i] : kNoMoreDocs;
+                        const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, d < win1));  // sorted: a prefix
+                        if (d >= win0 && d < win1) {
+                            const int idx = d - base;
+                            const uint32_t ew = sh.ebits[idx >> 5];
+                            if ((ew >> (idx & 31)) & 1u) {
+                                const uint32_t slot = sh.epre[idx >> 5] + __popc(ew & ((1u << (idx & 31)) - 1u));
+                                const float sum = __fadd_rn(sh.acc[slot], cs[i]);
+                                sh.acc[slot] = sum;
+                                if (sum > te) hot |= 1u << (idx >> 5);
+                            }
+                        }
+                        st_post += cnt;
+                        __syncwarp();  // every lane has read the cursor
+                        if (lane == 0) tc.pos = cpos + cnt;
+                        __syncwarp();
+                        if (cnt < 32 && cpos + cnt < n) break;  // the next cached posting lies beyond the window
+                        // else: 32 more may follow, or the cache is used up and the next block may reach into the window
+                    }
+                    __syncwarp();
+                }
+            }
+            hot = __reduce_or_sync(0xffffffffu, hot);
+        }
+        // ---- 4. candidates: touched docs (bits of E) whose score beats theta, in docid order
+        {
             uint32_t newc_n = 0;
-            for (uint32_t p0 = 0; p0 < n_e; p0 += 32) {
-                const uint32_t i = p0 + lane;
-                const bool has = i < n_e;
-                const int idx = has ? (int)sh.edoc[i] : 0;
-                const int d = base + idx;
-                const int ew = idx >> 5;
-                const uint32_t ebit = 1u << (idx & 31);
-                // the doc's column cells: all loads issued before any use (one DRAM round trip per pass, not per clause)
-                {
-                    float cv[kMaxTerms];
-#pragma unroll
-                    for (int t = 0; t < kMaxTerms; t++) {
-                        cv[t] = 0.0f;
-                        if (((col_mask >> t) & 1u) && has && (sh.cw[t][ew] & ebit)) {
-                            cv[t] = __ldg(sh.col[t] + d);
-                            st_gather++;
-                        }
-                    }
-#pragma unroll
-                    for (int t = 0; t < kMaxTerms; t++)
-                        if ((col_mask >> t) & 1u) sh.cval[t][lane] = cv[t];
-                }
-                const bool in_sparse = has && act && (sh.ubits[ew] & ebit);
-                float sum = 0.0f;
-                for (int t = 0; t < T; t++) {
-                    const int kt = __shfl_sync(0xffffffffu, kind, t);
-                    if (kt == kKindCol) {
-                        if (has && (sh.cw[t][ew] & ebit)) sum = __fadd_rn(sum, sh.cval[t][lane]);
-                    } else if (kt == kKindSparse) {
-                        if (!((act >> t) & 1u)) continue;
-                        if (in_sparse) {  // this window's postings of the stream are cached: binary search for the doc
-                            const int slot = __popc(stream_mask & ((1u << t) - 1u));
-                            const WTerm& tc = sh.term[t];
-                            const int32_t* cd = cdocs + slot * kBlock;
-                            uint32_t l = tc.pos, h = tc.n;
-                            while (l < h) {
-                                const uint32_t m = (l + h) >> 1;
-                                if (cd[m] < d) l = m + 1;
-                                else h = m;
-                            }
-                            if (l < tc.n && cd[l] == d) sum = __fadd_rn(sum, cscores[slot * kBlock + l]);
-                        }
-                    } else if (kt == kKindBStream) {
-                        // a block stream that does not drive windows: decode the blocks that hold this pass's docs
-                        bool pend = has && (sh.cw[t][ew] & ebit);
-                        if (!__any_sync(0xffffffffu, pend)) continue;
-                        const int slot = __popc(stream_mask & ((1u << t) - 1u));
-                        WTerm& tc = sh.term[t];
-                        int32_t* cd = cdocs + slot * kBlock;
-                        float* cs = cscores + slot * kBlock;
-                        for (;;) {
-                            const int dmin = __reduce_min_sync(0xffffffffu, pend ? d : kNoMoreDocs);
-                            if (dmin == kNoMoreDocs) break;
-                            if (tc.pos >= tc.n || cd[tc.n - 1] < dmin) {  // the cached block ends before the doc
-                                if (tc.cur > tc.nb) break;                // (cannot happen: the bitmap says the doc is there)
-                                __syncwarp();                             // every lane has read the cursor
-                                if (lane == 0) tc.cur = lower_bound_gallop(tc.blk_last, min(tc.cur, tc.nb), tc.nb, dmin);
-                                __syncwarp();
-                                st_refill++;
-                                if (!stream_refill<false, false, false, false>(seg, p, tc, cd, cs, lo, hi, lane, 0, -2147483647 - 1,
-                                                                              sh.ubits, hot_unused, mm_unused, INFINITY,
-                                                                              mc_unused))
-                                    break;
-                                continue;
-                            }
-                            if (pend && d <= cd[tc.n - 1]) {  // inside the cached block
-                                uint32_t l = tc.pos, h = tc.n;
-                                while (l < h) {
-                                    const uint32_t m = (l + h) >> 1;
-                                    if (cd[m] < d) l = m + 1;
-                                    else h = m;
-                                }
-                                if (l < tc.n && cd[l] == d) sum = __fadd_rn(sum, cs[l]);
-                                pend = false;
-                                st_post++;
-                            }
-                        }
-                    }
-                }
-                // ---- 4. candidates, in docid order (= lane order)
-                const bool cand = has && (LIVE ? is_live(seg, d) : true) && (open || sum > te);
+            while (hot) {
+                const int s = __ffs(hot) - 1;
+                hot &= hot - 1;
+                const int idx = s * 32 + lane;
+                st_steps++;
+                const uint32_t Es = __shfl_sync(0xffffffffu, E, s);
+                const uint32_t ps = __shfl_sync(0xffffffffu, epre, s);
+                const uint32_t ls = __shfl_sync(0xffffffffu, lw, s);
+                const float sc = ((Es >> lane) & 1u) ? sh.acc[ps + __popc(Es & ((1u << lane) - 1u))] : 0.0f;
+                const bool cand = ((Es & ls) >> lane) & 1u && (open || sc > te);
                 const uint32_t cm = __ballot_sync(0xffffffffu, cand);
                 if (!cm || em.overflow) continue;
                 const uint32_t cn = __popc(cm);
@@ -450,8 +515,8 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                 }
                 if (cand) {
                     const uint32_t r = __popc(cm & ((1u << lane) - 1u));
-                    p.cand_arena[em.run_slot + 1 + em.run_cnt + r] = rg_hit{d + seg.doc_base, sum};
-                    if (newc_n + r < (uint32_t)kNewcW) sh.newc[newc_n + r] = sum;
+                    p.cand_arena[em.run_slot + 1 + em.run_cnt + r] = rg_hit{base + idx + seg.doc_base, sc};
+                    if (newc_n + r < (uint32_t)kNewcW) sh.newc[newc_n + r] = sc;
                 }
                 em.run_cnt += cn;
                 newc_n += cn;
@@ -459,24 +524,12 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                 if (lane == 0) hdr[em.run_slot] = CandRun{kNone, em.run_cnt};
             }
             __syncwarp();
+            // re-arm the accumulator words that were touched (E bits live in the owning lane's word)
+            if ((uint32_t)lane < n_e) sh.acc[lane] = 0.0f;
+            if ((uint32_t)lane + 32u < n_e) sh.acc[lane + 32] = 0.0f;
             wtheta_update(em, p.k, kcap, lane, sh.newc, newc_n, p.item_theta + item_idx);
             __syncwarp();
         }
-        // the sparse streams move past the window: each owner lane finds its first cached posting >= win1
-        if (kind == kKindSparse && nd < win1) {
-            WTerm& tc = sh.term[lane];
-            const int32_t* cd = cdocs + my_slot * kBlock;
-            uint32_t l = tc.pos, h = tc.n;
-            while (l < h) {
-                const uint32_t m = (l + h) >> 1;
-                if (cd[m] < win1) l = m + 1;
-                else h = m;
-            }
-            st_post += l - tc.pos;
-            tc.pos = l;
-            nd = l < tc.n ? cd[l] : kNoMoreDocs;  // an emptied cache is refilled below
-        }
-        __syncwarp();
         pos = win1;
         // ---- 5. refill the sparse streams whose cached block is used up
         {

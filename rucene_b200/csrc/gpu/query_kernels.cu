@@ -810,10 +810,12 @@ k_merge_leaf_records(const uint8_t* __restrict__ records, uint32_t n_leaves, uin
 constexpr int kColWarps = 4;
 // BITMAP = true: the same walk over a term's blocks, but every posting sets its presence bit in the term's
 // bitmap (built once per segment at upload; weight / norms are not touched).
-template <bool BITMAP>
+// MODE 0: score column, 1: presence bitmap, 2: "high tf-norm" plane (bit set when f/(f+norm), rounded up, exceeds tf_low)
+template <int MODE>
 __global__ void __launch_bounds__(kColWarps * 32)
 k_build_columns(const SegDev* __restrict__ segs, const ColumnJob* __restrict__ jobs, uint32_t n_jobs,
-                uint32_t n_units, const float* __restrict__ caches, float k1) {
+                uint32_t n_units, const float* __restrict__ caches, float k1, float tf_low) {
+    constexpr bool BITMAP = MODE == 1;
     __shared__ __align__(16) int32_t s_docs[kColWarps][kBlock];
     __shared__ __align__(16) int32_t s_freqs[kColWarps][kBlock];
     const int lane = lane_id(), warp = threadIdx.x >> 5;
@@ -863,6 +865,18 @@ k_build_columns(const SegDev* __restrict__ segs, const ColumnJob* __restrict__ j
         return;
     }
     const float* cache = caches + (size_t)job.cache_id * 256;
+    if (MODE == 2) {
+        uint32_t* bits = static_cast<uint32_t*>(job.dst);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (d[q] < 0 || d[q] >= seg.max_doc) continue;
+            const float nrm = seg.norms ? __ldg(cache + __ldg(seg.norms + d[q])) : k1;
+            const float fq = (float)f[q];
+            const float t = __fdiv_ru(fq, __fadd_rd(fq, nrm));  // >= the true factor
+            if (!(t <= tf_low)) atomicOr(bits + (d[q] >> 5), 1u << (d[q] & 31));  // NaN counts as high
+        }
+        return;
+    }
     float* col = static_cast<float*>(job.dst);
     const float w1 = __fmul_rn(job.weight, __fadd_rn(k1, 1.0f));  // as k_eval_or computes it
 #pragma unroll
@@ -879,15 +893,21 @@ k_build_columns(const SegDev* __restrict__ segs, const ColumnJob* __restrict__ j
 void launch_build_columns(cudaStream_t st, const SegDev* segs, const ColumnJob* jobs, uint32_t n_jobs,
                           uint32_t n_units, const float* caches, float k1) {
     if (!n_jobs || !n_units) return;
-    k_build_columns<false><<<(n_units + kColWarps - 1) / kColWarps, kColWarps * 32, 0, st>>>(segs, jobs, n_jobs,
-                                                                                             n_units, caches, k1);
+    k_build_columns<0><<<(n_units + kColWarps - 1) / kColWarps, kColWarps * 32, 0, st>>>(segs, jobs, n_jobs, n_units,
+                                                                                         caches, k1, 0.f);
 }
 // seg: device pointer to ONE SegDev (jobs carry seg = 0)
 void launch_build_bitmaps(cudaStream_t st, const SegDev* seg, const ColumnJob* jobs, uint32_t n_jobs,
                           uint32_t n_units) {
     if (!n_jobs || !n_units) return;
-    k_build_columns<true><<<(n_units + kColWarps - 1) / kColWarps, kColWarps * 32, 0, st>>>(seg, jobs, n_jobs,
-                                                                                            n_units, nullptr, 0.f);
+    k_build_columns<1><<<(n_units + kColWarps - 1) / kColWarps, kColWarps * 32, 0, st>>>(seg, jobs, n_jobs, n_units,
+                                                                                         nullptr, 0.f, 0.f);
+}
+void launch_build_tf_planes(cudaStream_t st, const SegDev* segs, const ColumnJob* jobs, uint32_t n_jobs,
+                            uint32_t n_units, const float* caches, float k1, float tf_low) {
+    if (!n_jobs || !n_units) return;
+    k_build_columns<2><<<(n_units + kColWarps - 1) / kColWarps, kColWarps * 32, 0, st>>>(segs, jobs, n_jobs, n_units,
+                                                                                         caches, k1, tf_low);
 }
 template <bool LIVE, bool NOT, bool MSM, bool DMAX>
 static void launch_eval_or_t(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, size_t wb,

@@ -75,7 +75,7 @@ struct HostPlan {
     std::vector<uint32_t> or_ids, ms_ids, and_ids, ro_ids, dpq_ids;
     uint32_t max_dpq_terms = 0;
     std::vector<ColRef> col_refs;
-    std::map<std::pair<uint32_t, uint32_t>, uint32_t> bitmap_refs;  // (leaf, term) -> col_refs entry {null, bits}
+    std::map<std::tuple<uint32_t, uint32_t, uint32_t>, uint32_t> bitmap_refs;  // (leaf, term, cache) -> col_refs entry {null, bits, hi}
     std::vector<std::shared_ptr<ColEntry>> cols;
     uint32_t n_cols_built = 0, max_ms_streams = 0;
     uint64_t col_floats = 0;
@@ -187,6 +187,49 @@ QShape classify(const rg_query& q, const rg_clause* clauses, uint32_t n_clauses_
 // used columns no batch references while over the HBM budget.  RG_CFG_NO_COLUMNS turns the feature off.
 constexpr uint32_t kMatchAllTerm = 0xffffffffu;  // ColKey term of a leaf's MatchAllDocsQuery column
 
+// "High tf-norm" plane of a bitmap term for one (norm cache, k1): built for ALL bitmap terms of the leaf the first
+// time a batch asks (one pass over their postings), kept until the cache changes.  nullptr: none (flag, no bitmap,
+// or no memory) — the kernel then bounds the clause by presence alone.
+const uint32_t* tf_plane(rg_engine* e, uint32_t si, uint32_t term, uint32_t cache_id, float k1) {
+    if (e->cfg.flags & RG_CFG_NO_TFPLANES) return nullptr;
+    Segment& seg = e->segs[si];
+    if (term >= seg.bitmap_slot.size() || seg.bitmap_slot[term] < 0) return nullptr;
+    uint32_t k1bits;
+    memcpy(&k1bits, &k1, 4);
+    const auto key = std::make_pair(cache_id, k1bits);
+    auto it = seg.tf_planes.find(key);
+    if (it == seg.tf_planes.end()) {
+        const size_t n_bm = seg.bitmap_terms.size();
+        TfPlanes tp;
+        if (cudaMalloc(reinterpret_cast<void**>(&tp.bits.p), n_bm * seg.bitmap_words * sizeof(uint32_t)) != cudaSuccess) {
+            cudaGetLastError();
+            tp.bits.p = nullptr;
+            it = seg.tf_planes.emplace(key, std::move(tp)).first;  // remembered as "none": do not retry every batch
+            return nullptr;
+        }
+        tp.bits.n = n_bm * seg.bitmap_words;
+        cudaStream_t st = e->stream;
+        RG_CUDA_CHECK(cudaMemsetAsync(tp.bits.p, 0, tp.bits.bytes(), st));
+        std::vector<ColumnJob> jobs(n_bm);
+        uint32_t units = 0;
+        for (size_t i = 0; i < n_bm; i++) {
+            const uint32_t t = seg.bitmap_terms[i];
+            jobs[i] = ColumnJob{si, t, cache_id, 0.0f, tp.bits.p + i * seg.bitmap_words, units, 0u};
+            units += seg.host_terms[t].n_blocks + (seg.host_terms[t].tail_n ? 1u : 0u);
+        }
+        DevBuf<ColumnJob> d_jobs;
+        d_jobs.alloc(jobs.size());
+        RG_CUDA_CHECK(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(ColumnJob), cudaMemcpyHostToDevice, st));
+        launch_build_tf_planes(st, e->d_segs.p, d_jobs.p, (uint32_t)jobs.size(), units, e->d_caches.p, k1, kTfLow);
+        RG_CUDA_CHECK(cudaGetLastError());
+        RG_CUDA_CHECK(cudaStreamSynchronize(st));
+        e->launches++;
+        it = seg.tf_planes.emplace(key, std::move(tp)).first;
+    }
+    if (!it->second.bits.p) return nullptr;
+    return it->second.bits.p + (size_t)seg.bitmap_slot[term] * seg.bitmap_words;
+}
+
 std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape>& shapes, const rg_clause* clauses,
                                           float k1, HostPlan& hp) {
     std::map<ColKey, uint32_t> chosen;
@@ -226,7 +269,9 @@ std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape
     auto add_ref = [&](const ColKey& key, const std::shared_ptr<ColEntry>& ent) {
         ent->last_use = ++e->col_tick;
         chosen[key] = (uint32_t)hp.col_refs.size();
-        hp.col_refs.push_back(ColRef{ent->col, ent->bits});
+        const uint32_t kterm = std::get<1>(key);
+        hp.col_refs.push_back(ColRef{ent->col, ent->bits,
+                                     kterm == kMatchAllTerm ? nullptr : tf_plane(e, std::get<0>(key), kterm, std::get<3>(key), k1)});
         hp.cols.push_back(ent);
         hp.col_floats += ent->len;
     };
@@ -454,11 +499,12 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                     n_streams++;
                     uint32_t flags = 0;
                     if (use_ms && seg.bitmap_slot[c.term_id] >= 0) {  // a block stream whose presence comes from its bitmap
-                        const auto key = std::make_pair(si, c.term_id);
+                        const auto key = std::make_tuple(si, c.term_id, c.cache_id);
                         auto it = hp.bitmap_refs.find(key);
                         if (it == hp.bitmap_refs.end()) {
                             it = hp.bitmap_refs.emplace(key, (uint32_t)hp.col_refs.size()).first;
-                            hp.col_refs.push_back(ColRef{nullptr, seg.bitmaps.p + (size_t)seg.bitmap_slot[c.term_id] * seg.bitmap_words});
+                            hp.col_refs.push_back(ColRef{nullptr, seg.bitmaps.p + (size_t)seg.bitmap_slot[c.term_id] * seg.bitmap_words,
+                                                         tf_plane(e, si, c.term_id, c.cache_id, k1)});
                         }
                         if (it->second < 65536u) flags = 32u | (boundable ? 0u : 16u) | (it->second << 16);
                     }
