@@ -70,17 +70,20 @@ struct DevBuf {
 struct ColRef {
     const float* col;
     const uint32_t* bits;
-    const uint32_t* hi;   // "high tf-norm" plane of the term for the clause's norm cache (null: none), see TfPlanes
+    const uint32_t* hi1;  // plane "tf-norm factor above tau1" of the term for the clause's norm cache (null: none)
+    const uint32_t* hi2;  // plane "... above tau2" (a subset of hi1)
+    float tau1, tau2;
 };
 
-// BM25's tf-norm factor f/(f+norm) of a posting is <= kTfLow for most postings (f = 1 in an average-length doc gives
-// 0.45).  For every bitmap term one more bit per docid says "this posting's factor is above kTfLow" (for one norm
-// cache and k1: the factor depends on them), so the per-document score bound of k_eval_or_ms can use kTfLow*ub for
-// the others.  One buffer per (segment, cache id, k1), built for all bitmap terms of the segment the first time a
-// batch needs it.
-constexpr float kTfLow = 0.55f;
+// BM25's tf-norm factor f/(f+norm) of most postings is far below 1 (f = 1 in an average-length doc gives 0.45; where
+// norms say "long document" much less).  For every bitmap term two more bits per docid say "this posting's factor is
+// above tau1" / "above tau2", tau1 <= tau2 being the term's 90th and 99th percentile of the factor for one norm cache
+// and k1 (taken from a histogram over a sample of its blocks), so the per-document score bound of k_eval_or_ms can
+// count tau1*ub, tau2*ub or ub.  One buffer per (segment, cache id, k1), built for all bitmap terms of the segment the
+// first time a batch needs it.  ANY thresholds give correct results; the percentiles make the bound tight.
 struct TfPlanes {
-    DevBuf<uint32_t> bits;  // [n bitmap terms][bitmap_words], same slot order as Segment::bitmaps
+    DevBuf<uint32_t> bits;     // [2][n bitmap terms][bitmap_words], slot order of Segment::bitmaps
+    std::vector<float> tau1, tau2;  // per slot
 };
 
 // Persistent score column (engine-owned, LRU): the contributions of one (leaf, term, weight, norm
@@ -184,9 +187,11 @@ void launch_build_columns(cudaStream_t st, const SegDev* segs, const ColumnJob* 
                           uint32_t n_units, const float* caches, float k1);
 void launch_build_bitmaps(cudaStream_t st, const SegDev* seg, const ColumnJob* jobs, uint32_t n_jobs,
                           uint32_t n_units);
-// jobs carry cache_id; a posting sets its bit when its tf-norm factor (rounded up) exceeds tf_low
+// jobs carry cache_id.  hist != null: every 8th block of a job adds its postings' factors (rounded up, 256 bins) to
+// hist[job][256].  Else: a posting sets its bit in job.dst when its factor exceeds job.weight (tau1) and in
+// job.dst + plane_stride when it exceeds job.pad (the bits of tau2).
 void launch_build_tf_planes(cudaStream_t st, const SegDev* segs, const ColumnJob* jobs, uint32_t n_jobs,
-                            uint32_t n_units, const float* caches, float k1, float tf_low);
+                            uint32_t n_units, const float* caches, float k1, uint32_t* hist, size_t plane_stride);
 void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n,
                     uint32_t max_terms, bool has_live, bool has_not, bool has_msm, bool has_dmax);
 // eval_dpq.cu: disjunctions with >= 10 clauses in a leaf (DisiPriorityQueue order), one warp per (query, leaf)

@@ -50,7 +50,8 @@ struct alignas(16) MsWarpShared {  // followed by topk[kcap] floats, then cdocs[
     WTerm term[kMaxTerms];         // block-stream clauses (same cursor as k_eval_or)
     const float* col[kMaxTerms];   // score column (leaf-local docid -> BM25 contribution), column clauses
     const uint32_t* bits[kMaxTerms];  // presence bitmap, column clauses and block streams of dense-enough terms
-    const uint32_t* hi[kMaxTerms];    // "tf-norm factor above kTfLow" plane of the same clauses (null: none)
+    const uint32_t* hi1[kMaxTerms];   // "tf-norm factor above tau1" plane of the same clauses (null: none)
+    const uint32_t* hi2[kMaxTerms];   // "... above tau2" (subset of hi1)
     float newc[kNewcW];
 };
 
@@ -74,6 +75,25 @@ __device__ __forceinline__ uint32_t ms_count_range(const MsWarpShared& sh, uint3
     return cnt;
 }
 
+// S += q on the docs of mask m (bit-sliced, kMsPlanes planes); a carry out of the top plane is sticky in `over`
+__device__ __forceinline__ void ms_add(uint32_t (&S)[kMsPlanes], uint32_t& over, uint32_t m, uint32_t q) {
+    uint32_t carry = 0u;
+#pragma unroll
+    for (int i = 0; i < kMsPlanes; i++) {
+        if ((q >> i) & 1u) {  // warp-uniform
+            const uint32_t x = S[i] ^ m;
+            const uint32_t c2 = (S[i] & m) | (x & carry);
+            S[i] = x ^ carry;
+            carry = c2;
+        } else {
+            const uint32_t c2 = S[i] & carry;
+            S[i] ^= carry;
+            carry = c2;
+        }
+    }
+    over |= carry;
+}
+
 template <bool LIVE>
 __global__ void __launch_bounds__(kMsThreads, 24)
 k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, uint32_t warp_bytes,
@@ -95,6 +115,7 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
     // ---- clauses: lane t < T owns clause t
     int kind = kKindNone;
     float ub = 0.0f;  // score bound of a bitmap clause (INF: no usable bound)
+    float tau1 = 1.0f, tau2 = 1.0f;  // thresholds of the clause's tf-norm planes
     ItemClause c{};
     if (lane < T) {
         c = p.clauses[it.clause_begin + lane];
@@ -111,7 +132,10 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
         const ColRef r = p.cols[c.term_id];
         sh.col[lane] = r.col;
         sh.bits[lane] = r.bits;
-        sh.hi[lane] = r.hi;
+        sh.hi1[lane] = r.hi1;
+        sh.hi2[lane] = r.hi2;
+        tau1 = r.tau1;
+        tau2 = r.tau2;
     } else if (kind != kKindNone) {
         const TermDev td = seg.terms[c.term_id];
         WTerm& tc = sh.term[lane];
@@ -127,18 +151,29 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
         tc.w1 = __fmul_rn(c.weight, __fadd_rn(p.k1, 1.0f));
         tc.is_not = 0;
         sh.col[lane] = nullptr;
-        sh.bits[lane] = kind == kKindBStream ? p.cols[c.flags >> 16].bits : nullptr;
-        sh.hi[lane] = kind == kKindBStream ? p.cols[c.flags >> 16].hi : nullptr;
+        sh.bits[lane] = nullptr;
+        sh.hi1[lane] = sh.hi2[lane] = nullptr;
+        if (kind == kKindBStream) {
+            const ColRef r = p.cols[c.flags >> 16];
+            sh.bits[lane] = r.bits;
+            sh.hi1[lane] = r.hi1;
+            sh.hi2[lane] = r.hi2;
+            tau1 = r.tau1;
+            tau2 = r.tau2;
+        }
     }
-    float ub_lo = 0.0f;  // bound for the postings whose high-tf plane bit is clear
+    // bounds of a posting by its tf-norm planes: neither bit -> factor <= tau1, only hi1 -> <= tau2, hi2 -> <= 1
+    float ub0 = 0.0f, ub1 = 0.0f;
     if ((bmask >> lane) & 1u) {
         const float w1 = __fmul_rn(c.weight, __fadd_rn(p.k1, 1.0f));
         // score = rn(rn(w1*f) / rn(f + norm)) with f >= 1, norm >= 0  =>  score <= nextafter(w1); with a tf-norm factor
-        // (rounded up at build time) <= kTfLow:  score <= w1 * kTfLow * (1 + 4 * 2^-24)
+        // (rounded up at build time) <= tau:  score <= w1 * tau * (1 + 4 * 2^-24)
         ub = (c.flags & 16u) || !(w1 >= 0.0f) || !(w1 < INFINITY) ? INFINITY : __uint_as_float(__float_as_uint(w1) + 1u);
-        ub_lo = sh.hi[lane] && ub < INFINITY ? __fmul_ru(__fmul_ru(w1, kTfLow), 1.000001f) : ub;
+        const bool planes = sh.hi1[lane] != nullptr && ub < INFINITY;
+        ub0 = planes ? fminf(ub, __fmul_ru(__fmul_ru(w1, tau1), 1.000001f)) : ub;
+        ub1 = planes ? fminf(ub, __fmul_ru(__fmul_ru(w1, tau2), 1.000001f)) : ub;
     }
-    const uint32_t hmask = __ballot_sync(0xffffffffu, ((bmask >> lane) & 1u) && sh.hi[lane] != nullptr && ub < INFINITY);
+    const uint32_t hmask = __ballot_sync(0xffffffffu, ((bmask >> lane) & 1u) && sh.hi1[lane] != nullptr && ub < INFINITY);
     sh.acc[lane] = 0.0f;
     sh.acc[lane + 32] = 0.0f;
     __syncwarp();
@@ -176,7 +211,7 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
     // quantised bounds, valid for theta == q_te
     float q_te = NAN;
     uint32_t q = 0;          // lane t: q of clause t (kMsSat: any doc of the clause must be scored)
-    uint32_t q_lo = 0;       // ... of its postings with a low tf-norm factor (== q without a plane)
+    uint32_t q0 = 0, q1 = 0; // ... of its postings with neither / only the first tf-norm plane bit (== q without planes)
     bool prune = false;      // a usable theta exists: docs without a carry are dropped
     bool need_scan = bmask != 0;  // some combination of bitmap clauses can still beat theta
     // RG_CFG_STATS event counters (warp-uniform unless noted)
@@ -208,12 +243,12 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                 const float x = __fmul_ru(ub, scale);
                 q = ((bmask >> lane) & 1u) ? (x < (float)kMsSat ? (uint32_t)ceilf(x) : kMsSat) : 0u;  // NaN -> kMsSat
                 if (((bmask >> lane) & 1u) && q == 0u) q = 1u;
-                const float xl = __fmul_ru(ub_lo, scale);
-                q_lo = ((hmask >> lane) & 1u) ? min(q, max(1u, (uint32_t)ceilf(xl))) : q;
+                q1 = ((hmask >> lane) & 1u) ? min(q, max(1u, (uint32_t)ceilf(__fmul_ru(ub1, scale)))) : q;
+                q0 = ((hmask >> lane) & 1u) ? min(q1, max(1u, (uint32_t)ceilf(__fmul_ru(ub0, scale)))) : q;
                 need_scan = __reduce_add_sync(0xffffffffu, q) >= kMsSat;
             } else {
                 q = ((bmask >> lane) & 1u) ? kMsSat : 0u;
-                q_lo = q;
+                q0 = q1 = q;
                 need_scan = bmask != 0;
             }
         }
@@ -275,11 +310,13 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
         const int wi = (base >> 5) + lane;
         {
             // all words first (independent loads in flight together), then the arithmetic
-            uint32_t wv[kMaxTerms], hv[kMaxTerms];
+            uint32_t wv[kMaxTerms], hv1[kMaxTerms], hv2[kMaxTerms];
 #pragma unroll
             for (int t = 0; t < kMaxTerms; t++) {
                 wv[t] = (((bmask >> t) & 1u) && lmask) ? (__ldg(sh.bits[t] + wi) & lmask) : 0u;
-                hv[t] = (((hmask >> t) & 1u) && lmask && need_scan) ? __ldg(sh.hi[t] + wi) : 0xffffffffu;
+                const bool pl = ((hmask >> t) & 1u) && lmask && need_scan;
+                hv1[t] = pl ? __ldg(sh.hi1[t] + wi) : 0xffffffffu;
+                hv2[t] = pl ? __ldg(sh.hi2[t] + wi) : 0xffffffffu;
             }
             // the next window's line of every bitmap towards L1 while this one is processed
             if (((bmask >> lane) & 1u) && base + kMsW < hi)
@@ -295,45 +332,15 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                 sh.cw[t][lane] = w;
                 U |= w;
                 const uint32_t qt = __shfl_sync(0xffffffffu, q, t);
-                const uint32_t ql = __shfl_sync(0xffffffffu, q_lo, t);
+                const uint32_t qa = __shfl_sync(0xffffffffu, q0, t);
+                const uint32_t qb = __shfl_sync(0xffffffffu, q1, t);
                 if (qt >= kMsSat) {  // no usable bound (or no theta yet): every doc of the clause
                     over |= w;
                 } else if (need_scan) {
-                    // every posting adds q_lo; the ones on the high tf-norm plane add the rest of q
-                    uint32_t carry = 0u;
-#pragma unroll
-                    for (int i = 0; i < kMsPlanes; i++) {
-                        if ((ql >> i) & 1u) {  // warp-uniform
-                            const uint32_t x = S[i] ^ w;
-                            const uint32_t c2 = (S[i] & w) | (x & carry);
-                            S[i] = x ^ carry;
-                            carry = c2;
-                        } else {
-                            const uint32_t c2 = S[i] & carry;
-                            S[i] ^= carry;
-                            carry = c2;
-                        }
-                    }
-                    over |= carry;
-                    const uint32_t dq = qt - ql;
-                    if (dq) {  // warp-uniform
-                        const uint32_t wh = w & hv[t];
-                        carry = 0u;
-#pragma unroll
-                        for (int i = 0; i < kMsPlanes; i++) {
-                            if ((dq >> i) & 1u) {
-                                const uint32_t x = S[i] ^ wh;
-                                const uint32_t c2 = (S[i] & wh) | (x & carry);
-                                S[i] = x ^ carry;
-                                carry = c2;
-                            } else {
-                                const uint32_t c2 = S[i] & carry;
-                                S[i] ^= carry;
-                                carry = c2;
-                            }
-                        }
-                        over |= carry;
-                    }
+                    // every posting adds q0, those on the first plane q1 - q0 more, those on the second the rest of q
+                    ms_add(S, over, w, qa);
+                    if (qb != qa) ms_add(S, over, w & hv1[t], qb - qa);
+                    if (qt != qb) ms_add(S, over, w & hv2[t], qt - qb);
                 }
             }
             E |= over;

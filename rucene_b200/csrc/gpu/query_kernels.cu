@@ -810,11 +810,13 @@ k_merge_leaf_records(const uint8_t* __restrict__ records, uint32_t n_leaves, uin
 constexpr int kColWarps = 4;
 // BITMAP = true: the same walk over a term's blocks, but every posting sets its presence bit in the term's
 // bitmap (built once per segment at upload; weight / norms are not touched).
-// MODE 0: score column, 1: presence bitmap, 2: "high tf-norm" plane (bit set when f/(f+norm), rounded up, exceeds tf_low)
+// MODE 0: score column, 1: presence bitmap, 2: tf-norm planes (bit set when f/(f+norm), rounded up, exceeds the job's
+// tau1 / tau2), 3: histogram of that factor over a sample of the job's blocks
 template <int MODE>
 __global__ void __launch_bounds__(kColWarps * 32)
 k_build_columns(const SegDev* __restrict__ segs, const ColumnJob* __restrict__ jobs, uint32_t n_jobs,
-                uint32_t n_units, const float* __restrict__ caches, float k1, float tf_low) {
+                uint32_t n_units, const float* __restrict__ caches, float k1, uint32_t* __restrict__ hist,
+                size_t plane_stride) {
     constexpr bool BITMAP = MODE == 1;
     __shared__ __align__(16) int32_t s_docs[kColWarps][kBlock];
     __shared__ __align__(16) int32_t s_freqs[kColWarps][kBlock];
@@ -831,6 +833,7 @@ k_build_columns(const SegDev* __restrict__ segs, const ColumnJob* __restrict__ j
     const SegDev seg = segs[job.seg];
     const TermDev td = seg.terms[job.term_id];
     const uint32_t b = unit - job.unit_begin;
+    if (MODE == 3 && (b & 7u) != 0u && b < td.n_blocks) return;  // a sample: every 8th block (and the tail)
     int4 docs, freqs = make_int4(1, 1, 1, 1);
     if (b < td.n_blocks) {
         const BlockDesc bd = seg.blk_desc[td.blk_begin + b];
@@ -865,15 +868,22 @@ k_build_columns(const SegDev* __restrict__ segs, const ColumnJob* __restrict__ j
         return;
     }
     const float* cache = caches + (size_t)job.cache_id * 256;
-    if (MODE == 2) {
+    if (MODE == 2 || MODE == 3) {
         uint32_t* bits = static_cast<uint32_t*>(job.dst);
+        const float tau1 = job.weight, tau2 = __uint_as_float(job.pad);
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             if (d[q] < 0 || d[q] >= seg.max_doc) continue;
             const float nrm = seg.norms ? __ldg(cache + __ldg(seg.norms + d[q])) : k1;
             const float fq = (float)f[q];
             const float t = __fdiv_ru(fq, __fadd_rd(fq, nrm));  // >= the true factor
-            if (!(t <= tf_low)) atomicOr(bits + (d[q] >> 5), 1u << (d[q] & 31));  // NaN counts as high
+            if (MODE == 3) {
+                const int bin = t > 0.0f ? min(255, (int)ceilf(t * 256.0f) - 1) : 0;  // bin i <=> factor <= (i+1)/256; NaN -> 0..255 clamp
+                atomicAdd(hist + (size_t)jl * 256 + (t <= 1.0f ? bin : 255), 1u);
+            } else {
+                if (!(t <= tau1)) atomicOr(bits + (d[q] >> 5), 1u << (d[q] & 31));  // NaN counts as high
+                if (!(t <= tau2)) atomicOr(bits + plane_stride + (d[q] >> 5), 1u << (d[q] & 31));
+            }
         }
         return;
     }
@@ -894,20 +904,21 @@ void launch_build_columns(cudaStream_t st, const SegDev* segs, const ColumnJob* 
                           uint32_t n_units, const float* caches, float k1) {
     if (!n_jobs || !n_units) return;
     k_build_columns<0><<<(n_units + kColWarps - 1) / kColWarps, kColWarps * 32, 0, st>>>(segs, jobs, n_jobs, n_units,
-                                                                                         caches, k1, 0.f);
+                                                                                         caches, k1, nullptr, 0);
 }
 // seg: device pointer to ONE SegDev (jobs carry seg = 0)
 void launch_build_bitmaps(cudaStream_t st, const SegDev* seg, const ColumnJob* jobs, uint32_t n_jobs,
                           uint32_t n_units) {
     if (!n_jobs || !n_units) return;
     k_build_columns<1><<<(n_units + kColWarps - 1) / kColWarps, kColWarps * 32, 0, st>>>(seg, jobs, n_jobs, n_units,
-                                                                                         nullptr, 0.f, 0.f);
+                                                                                         nullptr, 0.f, nullptr, 0);
 }
 void launch_build_tf_planes(cudaStream_t st, const SegDev* segs, const ColumnJob* jobs, uint32_t n_jobs,
-                            uint32_t n_units, const float* caches, float k1, float tf_low) {
+                            uint32_t n_units, const float* caches, float k1, uint32_t* hist, size_t plane_stride) {
     if (!n_jobs || !n_units) return;
-    k_build_columns<2><<<(n_units + kColWarps - 1) / kColWarps, kColWarps * 32, 0, st>>>(segs, jobs, n_jobs, n_units,
-                                                                                         caches, k1, tf_low);
+    const uint32_t ctas = (n_units + kColWarps - 1) / kColWarps;
+    if (hist) k_build_columns<3><<<ctas, kColWarps * 32, 0, st>>>(segs, jobs, n_jobs, n_units, caches, k1, hist, 0);
+    else k_build_columns<2><<<ctas, kColWarps * 32, 0, st>>>(segs, jobs, n_jobs, n_units, caches, k1, nullptr, plane_stride);
 }
 template <bool LIVE, bool NOT, bool MSM, bool DMAX>
 static void launch_eval_or_t(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, size_t wb,

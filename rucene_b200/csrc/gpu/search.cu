@@ -187,47 +187,86 @@ QShape classify(const rg_query& q, const rg_clause* clauses, uint32_t n_clauses_
 // used columns no batch references while over the HBM budget.  RG_CFG_NO_COLUMNS turns the feature off.
 constexpr uint32_t kMatchAllTerm = 0xffffffffu;  // ColKey term of a leaf's MatchAllDocsQuery column
 
-// "High tf-norm" plane of a bitmap term for one (norm cache, k1): built for ALL bitmap terms of the leaf the first
-// time a batch asks (one pass over their postings), kept until the cache changes.  nullptr: none (flag, no bitmap,
-// or no memory) — the kernel then bounds the clause by presence alone.
-const uint32_t* tf_plane(rg_engine* e, uint32_t si, uint32_t term, uint32_t cache_id, float k1) {
-    if (e->cfg.flags & RG_CFG_NO_TFPLANES) return nullptr;
+// tf-norm planes of a bitmap term for one (norm cache, k1) — see TfPlanes: built for ALL bitmap terms of the leaf the
+// first time a batch asks (a histogram pass over a sample of their blocks picks tau1/tau2, one more pass sets the
+// bits), kept until the cache changes.  Fills ref.hi1/hi2/tau1/tau2; leaves them null when there is none (flag, no
+// bitmap, no memory) — the kernel then bounds the clause by presence alone.
+void tf_planes_of(rg_engine* e, uint32_t si, uint32_t term, uint32_t cache_id, float k1, ColRef& ref) {
+    ref.hi1 = ref.hi2 = nullptr;
+    ref.tau1 = ref.tau2 = 1.0f;
+    if (e->cfg.flags & RG_CFG_NO_TFPLANES) return;
     Segment& seg = e->segs[si];
-    if (term >= seg.bitmap_slot.size() || seg.bitmap_slot[term] < 0) return nullptr;
+    if (term >= seg.bitmap_slot.size() || seg.bitmap_slot[term] < 0) return;
     uint32_t k1bits;
     memcpy(&k1bits, &k1, 4);
     const auto key = std::make_pair(cache_id, k1bits);
     auto it = seg.tf_planes.find(key);
+    const size_t n_bm = seg.bitmap_terms.size();
+    const size_t stride = n_bm * seg.bitmap_words;
     if (it == seg.tf_planes.end()) {
-        const size_t n_bm = seg.bitmap_terms.size();
         TfPlanes tp;
-        if (cudaMalloc(reinterpret_cast<void**>(&tp.bits.p), n_bm * seg.bitmap_words * sizeof(uint32_t)) != cudaSuccess) {
+        if (cudaMalloc(reinterpret_cast<void**>(&tp.bits.p), 2 * stride * sizeof(uint32_t)) != cudaSuccess) {
             cudaGetLastError();
             tp.bits.p = nullptr;
-            it = seg.tf_planes.emplace(key, std::move(tp)).first;  // remembered as "none": do not retry every batch
-            return nullptr;
+            seg.tf_planes.emplace(key, std::move(tp));  // remembered as "none": do not retry every batch
+            return;
         }
-        tp.bits.n = n_bm * seg.bitmap_words;
+        tp.bits.n = 2 * stride;
         cudaStream_t st = e->stream;
         RG_CUDA_CHECK(cudaMemsetAsync(tp.bits.p, 0, tp.bits.bytes(), st));
         std::vector<ColumnJob> jobs(n_bm);
         uint32_t units = 0;
         for (size_t i = 0; i < n_bm; i++) {
             const uint32_t t = seg.bitmap_terms[i];
-            jobs[i] = ColumnJob{si, t, cache_id, 0.0f, tp.bits.p + i * seg.bitmap_words, units, 0u};
+            jobs[i] = ColumnJob{si, t, cache_id, 1.0f, tp.bits.p + i * seg.bitmap_words, units, 0u};
             units += seg.host_terms[t].n_blocks + (seg.host_terms[t].tail_n ? 1u : 0u);
         }
         DevBuf<ColumnJob> d_jobs;
-        d_jobs.alloc(jobs.size());
-        RG_CUDA_CHECK(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(ColumnJob), cudaMemcpyHostToDevice, st));
-        launch_build_tf_planes(st, e->d_segs.p, d_jobs.p, (uint32_t)jobs.size(), units, e->d_caches.p, k1, kTfLow);
+        DevBuf<uint32_t> d_hist;
+        d_jobs.alloc(n_bm);
+        d_hist.alloc(n_bm * 256);
+        RG_CUDA_CHECK(cudaMemsetAsync(d_hist.p, 0, d_hist.bytes(), st));
+        RG_CUDA_CHECK(cudaMemcpyAsync(d_jobs.p, jobs.data(), n_bm * sizeof(ColumnJob), cudaMemcpyHostToDevice, st));
+        launch_build_tf_planes(st, e->d_segs.p, d_jobs.p, (uint32_t)n_bm, units, e->d_caches.p, k1, d_hist.p, 0);
+        RG_CUDA_CHECK(cudaGetLastError());
+        std::vector<uint32_t> hist(n_bm * 256);
+        RG_CUDA_CHECK(cudaMemcpyAsync(hist.data(), d_hist.p, hist.size() * 4, cudaMemcpyDeviceToHost, st));
+        RG_CUDA_CHECK(cudaStreamSynchronize(st));
+        tp.tau1.assign(n_bm, 1.0f);
+        tp.tau2.assign(n_bm, 1.0f);
+        for (size_t i = 0; i < n_bm; i++) {  // 90th / 99th percentile bin edges of the sampled factor
+            uint64_t total = 0, cum = 0;
+            for (int b = 0; b < 256; b++) total += hist[i * 256 + b];
+            bool have1 = false;
+            for (int b = 0; b < 256 && total; b++) {
+                cum += hist[i * 256 + b];
+                if (!have1 && cum * 10 >= total * 9) {
+                    tp.tau1[i] = (float)(b + 1) / 256.0f;
+                    have1 = true;
+                }
+                if (cum * 100 >= total * 99) {
+                    tp.tau2[i] = (float)(b + 1) / 256.0f;
+                    break;
+                }
+            }
+            uint32_t t2bits;
+            memcpy(&t2bits, &tp.tau2[i], 4);
+            jobs[i].weight = tp.tau1[i];
+            jobs[i].pad = t2bits;
+        }
+        RG_CUDA_CHECK(cudaMemcpyAsync(d_jobs.p, jobs.data(), n_bm * sizeof(ColumnJob), cudaMemcpyHostToDevice, st));
+        launch_build_tf_planes(st, e->d_segs.p, d_jobs.p, (uint32_t)n_bm, units, e->d_caches.p, k1, nullptr, stride);
         RG_CUDA_CHECK(cudaGetLastError());
         RG_CUDA_CHECK(cudaStreamSynchronize(st));
-        e->launches++;
+        e->launches += 2;
         it = seg.tf_planes.emplace(key, std::move(tp)).first;
     }
-    if (!it->second.bits.p) return nullptr;
-    return it->second.bits.p + (size_t)seg.bitmap_slot[term] * seg.bitmap_words;
+    if (!it->second.bits.p) return;
+    const size_t slot = (size_t)seg.bitmap_slot[term];
+    ref.hi1 = it->second.bits.p + slot * seg.bitmap_words;
+    ref.hi2 = ref.hi1 + stride;
+    ref.tau1 = it->second.tau1[slot];
+    ref.tau2 = it->second.tau2[slot];
 }
 
 std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape>& shapes, const rg_clause* clauses,
@@ -269,9 +308,9 @@ std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape
     auto add_ref = [&](const ColKey& key, const std::shared_ptr<ColEntry>& ent) {
         ent->last_use = ++e->col_tick;
         chosen[key] = (uint32_t)hp.col_refs.size();
-        const uint32_t kterm = std::get<1>(key);
-        hp.col_refs.push_back(ColRef{ent->col, ent->bits,
-                                     kterm == kMatchAllTerm ? nullptr : tf_plane(e, std::get<0>(key), kterm, std::get<3>(key), k1)});
+        ColRef ref{ent->col, ent->bits, nullptr, nullptr, 1.0f, 1.0f};
+        if (std::get<1>(key) != kMatchAllTerm) tf_planes_of(e, std::get<0>(key), std::get<1>(key), std::get<3>(key), k1, ref);
+        hp.col_refs.push_back(ref);
         hp.cols.push_back(ent);
         hp.col_floats += ent->len;
     };
@@ -503,8 +542,10 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                         auto it = hp.bitmap_refs.find(key);
                         if (it == hp.bitmap_refs.end()) {
                             it = hp.bitmap_refs.emplace(key, (uint32_t)hp.col_refs.size()).first;
-                            hp.col_refs.push_back(ColRef{nullptr, seg.bitmaps.p + (size_t)seg.bitmap_slot[c.term_id] * seg.bitmap_words,
-                                                         tf_plane(e, si, c.term_id, c.cache_id, k1)});
+                            ColRef ref{nullptr, seg.bitmaps.p + (size_t)seg.bitmap_slot[c.term_id] * seg.bitmap_words, nullptr, nullptr,
+                                       1.0f, 1.0f};
+                            tf_planes_of(e, si, c.term_id, c.cache_id, k1, ref);
+                            hp.col_refs.push_back(ref);
                         }
                         if (it->second < 65536u) flags = 32u | (boundable ? 0u : 16u) | (it->second << 16);
                     }
