@@ -243,8 +243,9 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                 const float x = __fmul_ru(ub, scale);
                 q = ((bmask >> lane) & 1u) ? (x < (float)kMsSat ? (uint32_t)ceilf(x) : kMsSat) : 0u;  // NaN -> kMsSat
                 if (((bmask >> lane) & 1u) && q == 0u) q = 1u;
-                q1 = ((hmask >> lane) & 1u) ? min(q, max(1u, (uint32_t)ceilf(__fmul_ru(ub1, scale)))) : q;
-                q0 = ((hmask >> lane) & 1u) ? min(q1, max(1u, (uint32_t)ceilf(__fmul_ru(ub0, scale)))) : q;
+                const float x1 = __fmul_ru(ub1, scale), x0 = __fmul_ru(ub0, scale);
+                q1 = ((hmask >> lane) & 1u) ? min(q, max(1u, x1 < (float)kMsSat ? (uint32_t)ceilf(x1) : kMsSat)) : q;
+                q0 = ((hmask >> lane) & 1u) ? min(q1, max(1u, x0 < (float)kMsSat ? (uint32_t)ceilf(x0) : kMsSat)) : q;
                 need_scan = __reduce_add_sync(0xffffffffu, q) >= kMsSat;
             } else {
                 q = ((bmask >> lane) & 1u) ? kMsSat : 0u;
@@ -334,13 +335,22 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                 const uint32_t qt = __shfl_sync(0xffffffffu, q, t);
                 const uint32_t qa = __shfl_sync(0xffffffffu, q0, t);
                 const uint32_t qb = __shfl_sync(0xffffffffu, q1, t);
-                if (qt >= kMsSat) {  // no usable bound (or no theta yet): every doc of the clause
+                // every posting adds q0, those on the first tf-norm plane q1 - q0 more, those on the second the rest of q;
+                // a level whose bound alone beats theta (q >= kMsSat; also: no theta yet / no usable bound) puts its
+                // docs into E directly
+                if (qa >= kMsSat) {
                     over |= w;
                 } else if (need_scan) {
-                    // every posting adds q0, those on the first plane q1 - q0 more, those on the second the rest of q
                     ms_add(S, over, w, qa);
-                    if (qb != qa) ms_add(S, over, w & hv1[t], qb - qa);
-                    if (qt != qb) ms_add(S, over, w & hv2[t], qt - qb);
+                    const uint32_t w1 = w & hv1[t];
+                    if (qb >= kMsSat) {
+                        over |= w1;
+                    } else {
+                        if (qb != qa) ms_add(S, over, w1, qb - qa);
+                        const uint32_t w2 = w & hv2[t];
+                        if (qt >= kMsSat) over |= w2;
+                        else if (qt != qb) ms_add(S, over, w2, qt - qb);
+                    }
                 }
             }
             E |= over;
