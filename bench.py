@@ -72,6 +72,7 @@ def parse_args():
     ap.add_argument("--no-extra", action="store_true", help="skip the C3 / C5 legs and the A/B legs of the default run")
     ap.add_argument("--no-columns", action="store_true",
                     help="RG_CFG_NO_COLUMNS: evaluate every clause from its block stream (A/B runs)")
+    ap.add_argument("--tf-planes", action="store_true", help="RG_CFG_TFPLANES: three-level per-document bound (A/B runs)")
     ap.add_argument("--stats", action="store_true", help="RG_CFG_STATS: event counters of k_eval_or_ms in the line")
     ap.add_argument("--no-maxscore", action="store_true",
                     help="RG_CFG_NO_MAXSCORE: exhaustive disjunction kernel only (A/B runs)")
@@ -666,7 +667,7 @@ def main():
     ctx.traffic = {} if args.scaled else {n: tr.get(n) for n in WORKLOADS}
 
     flags = ((engine.CFG_NO_COLUMNS if args.no_columns else 0) | (engine.CFG_NO_MAXSCORE if args.no_maxscore else 0) |
-             (engine.CFG_STATS if args.stats else 0))
+             (engine.CFG_STATS if args.stats else 0) | (engine.CFG_TFPLANES if args.tf_planes else 0))
     name, w = args.workload, args.w
     main_res = run_workload(ctx, name, w, args, args.steps, args.warmup, args.cpu_sample, args.cpu_seconds, flags=flags)
     eng, batch = ctx.last_engine, ctx.last_batch
@@ -680,7 +681,8 @@ def main():
     if not args.no_extra and not args.scaled and name == "c4" and (flags & ~engine.CFG_STATS) == 0:
         # A/B legs on the same workload: what the other evaluation routes deliver (2 steps each)
         for label, fl in (("block_streams_only", engine.CFG_NO_COLUMNS | engine.CFG_NO_MAXSCORE),
-                          ("columns_exhaustive_kernel", engine.CFG_NO_MAXSCORE)):
+                          ("columns_exhaustive_kernel", engine.CFG_NO_MAXSCORE),
+                          ("bitmaps_with_tf_planes", engine.CFG_TFPLANES)):
             r = run_workload(ctx, name, w, args, 2, 1, 0, 0, flags=fl, light=True)
             ab[label] = {"queries_per_s": r["value"], "ms_per_step": r["ms_per_step"]}
         if ctx.world == 1:

@@ -38,7 +38,10 @@ extern "C" {
 #define RG_CFG_EAGER_COLUMNS 2u /* a column for every disjunction clause with df >= max_doc/64 (tests) */
 #define RG_CFG_NO_BITMAPS 4u    /* no presence bitmaps at upload (and therefore no score columns) */
 #define RG_CFG_NO_MAXSCORE 8u   /* evaluate every disjunction with the exhaustive kernel (A/B runs, tests) */
-#define RG_CFG_NO_TFPLANES 32u  /* no "high tf-norm" planes: the per-document score bound uses presence only (A/B runs) */
+#define RG_CFG_TFPLANES 32u     /* build and use tf-norm planes: the per-document score bound of k_eval_or_ms then knows three
+                                   levels of a posting's BM25 tf-norm factor instead of presence only.  Cuts the docs it has
+                                   to score ~16x, but scanning three planes costs more than it saves on the benchmark index
+                                   (DESIGN.md section 6); off by default */
 #define RG_CFG_STATS 16u        /* count events inside k_eval_or_ms (rg_batch_debug); costs a few atomics per work item */
 
 typedef struct rg_engine rg_engine;

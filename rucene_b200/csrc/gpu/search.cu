@@ -194,7 +194,7 @@ constexpr uint32_t kMatchAllTerm = 0xffffffffu;  // ColKey term of a leaf's Matc
 void tf_planes_of(rg_engine* e, uint32_t si, uint32_t term, uint32_t cache_id, float k1, ColRef& ref) {
     ref.hi1 = ref.hi2 = nullptr;
     ref.tau1 = ref.tau2 = 1.0f;
-    if (e->cfg.flags & RG_CFG_NO_TFPLANES) return;
+    if (!(e->cfg.flags & RG_CFG_TFPLANES)) return;
     Segment& seg = e->segs[si];
     if (term >= seg.bitmap_slot.size() || seg.bitmap_slot[term] < 0) return;
     uint32_t k1bits;

@@ -1,0 +1,13 @@
+#!/bin/bash
+# Multi-GPU validation (run under gpurun --gpus N): the N>1 parity tests, the bench line with its parity verdict,
+# BASELINE config 5 across the ranks, the reference arm.
+set -u
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+TAG=${1:-mg}
+N=${2:-2}
+( timeout 900 python -m pytest tests/test_gpu_sharded.py -x -q 2>&1 | tail -15 ) > gpurun_out/${TAG}_pytest.log
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
+timeout 900 $TR bench.py --gpus $N --steps 3 --warmup 3 --no-decode --cpu-sample 128 --cpu-seconds 6 > gpurun_out/${TAG}_c4_n$N.json 2> gpurun_out/${TAG}_c4_n$N.err
+timeout 900 $TR bench.py --gpus $N --workload c5 --steps 3 --warmup 3 --no-decode --no-extra --cpu-sample 128 --cpu-seconds 6 > gpurun_out/${TAG}_c5_n$N.json 2> gpurun_out/${TAG}_c5_n$N.err
+echo done > gpurun_out/${TAG}_done

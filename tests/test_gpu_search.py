@@ -34,11 +34,11 @@ def _run_both(segs, specs, k, mode=0, range_postings=0, threads=4, extra_flags=0
     q, c = ob.make_queries(specs)
     want = ix.search_batch(q, c, k, parallel_mode=mode, n_threads=threads)
     # every evaluation route must equal the oracle: a score column for every clause of df >= max_doc/64
-    # (k_eval_or_ms: presence bitmaps + non-essential clauses), the same columns read by the exhaustive kernel,
-    # no bitmaps / columns at all (block streams only), and the planner's own choice
+    # (k_eval_or_ms: presence bitmaps + bit-sliced per-document bound), the same with tf-norm planes, the same
+    # columns read by the exhaustive kernel, no bitmaps / columns at all (block streams only), the planner's choice
     got = None
-    for flags in (engine.CFG_EAGER_COLUMNS, engine.CFG_EAGER_COLUMNS | engine.CFG_NO_MAXSCORE,
-                  engine.CFG_NO_BITMAPS, 0):
+    for flags in (engine.CFG_EAGER_COLUMNS, engine.CFG_EAGER_COLUMNS | engine.CFG_TFPLANES,
+                  engine.CFG_EAGER_COLUMNS | engine.CFG_NO_MAXSCORE, engine.CFG_NO_BITMAPS, 0):
         s = search.GpuIndexSearcher(search.IndexReader(segs), range_postings=range_postings,
                                     flags=flags | extra_flags)
         try:
