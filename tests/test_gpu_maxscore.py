@@ -199,3 +199,39 @@ def test_device_terms_dictionary_resolves_a_batch():
     finally:
         dev.engine.close()
         host.engine.close()
+
+
+def test_abi_rejects_bad_clause_and_corrupt_index_fields():
+    """The C ABI validates what the kernels later use as indices: a MUST_NOT clause with an unset norm cache id
+    (kernels form cache pointers from it even though the clause never scores) and index fields that point outside
+    the segment are RG_EINVAL, not out-of-bounds device accesses."""
+    rng = np.random.default_rng(3)
+    seg, _ = helpers.build_segment(rng, 20000, [5000, 900, 1])
+    eng = engine.Engine()
+    try:
+        eng.upload_segment(seg)
+        eng.set_norm_cache(0, codec.bm25_norm_cache(1.2, 0.75, 100.0))
+        q = np.zeros(1, engine.QUERY_DTYPE)
+        q["n_clauses"], q["flags"] = 2, engine.Q_BOOLEAN
+        c = np.zeros(2, engine.CLAUSE_DTYPE)
+        c["occur"] = [engine.SHOULD, engine.MUST_NOT]
+        c["term_id"] = [0, 1]
+        c["weight"] = 1.0
+        c["cache_id"] = [0, 0x7FFFFFFF]      # garbage on the clause that "does not score"
+        with pytest.raises(engine.EngineError):
+            eng.search_batch(q, c, 10)
+        c["cache_id"] = [0, 0]
+        eng.search_batch(q, c, 10)
+        # corrupt BlockTermState rows
+        bad = np.array(seg.terms, copy=True)
+        bad["singleton_doc_id"][2] = 20000          # singleton docid == max_doc
+        e2 = engine.Engine()
+        try:
+            with pytest.raises(engine.EngineError):
+                e2.upload_segment(type("S", (), dict(terms=bad, doc_file=seg.doc_file, norms=seg.norms, live_docs=None, max_doc=20000))())
+            with pytest.raises(engine.EngineError):    # max_doc smaller than the docids in the file
+                e2.upload_segment(type("S", (), dict(terms=seg.terms, doc_file=seg.doc_file, norms=seg.norms[:6000], live_docs=None, max_doc=6000))())
+        finally:
+            e2.close()
+    finally:
+        eng.close()
