@@ -199,7 +199,7 @@ void launch_eval_dpq(cudaStream_t st, const EvalParams& p, const uint32_t* item_
                      bool has_live);
 // eval_or_ms.cu: pure-SHOULD sum disjunctions whose dense clauses all have a score column + bitmap
 void launch_eval_or_ms(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n,
-                       uint32_t max_streams, bool has_live);
+                       uint32_t max_streams, bool has_live, bool planes);
 void launch_eval_and(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, bool req_opt,
                      bool has_other_enc);
 

@@ -94,7 +94,8 @@ __device__ __forceinline__ void ms_add(uint32_t (&S)[kMsPlanes], uint32_t& over,
     over |= carry;
 }
 
-template <bool LIVE>
+// PLANES: the batch uses tf-norm planes (RG_CFG_TFPLANES): three-level bound, two more words per clause and window
+template <bool LIVE, bool PLANES>
 __global__ void __launch_bounds__(kMsThreads, 24)
 k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, uint32_t warp_bytes,
              uint32_t kcap) {
@@ -169,11 +170,12 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
         // score = rn(rn(w1*f) / rn(f + norm)) with f >= 1, norm >= 0  =>  score <= nextafter(w1); with a tf-norm factor
         // (rounded up at build time) <= tau:  score <= w1 * tau * (1 + 4 * 2^-24)
         ub = (c.flags & 16u) || !(w1 >= 0.0f) || !(w1 < INFINITY) ? INFINITY : __uint_as_float(__float_as_uint(w1) + 1u);
-        const bool planes = sh.hi1[lane] != nullptr && ub < INFINITY;
+        const bool planes = PLANES && sh.hi1[lane] != nullptr && ub < INFINITY;
         ub0 = planes ? fminf(ub, __fmul_ru(__fmul_ru(w1, tau1), 1.000001f)) : ub;
         ub1 = planes ? fminf(ub, __fmul_ru(__fmul_ru(w1, tau2), 1.000001f)) : ub;
     }
-    const uint32_t hmask = __ballot_sync(0xffffffffu, ((bmask >> lane) & 1u) && sh.hi1[lane] != nullptr && ub < INFINITY);
+    const uint32_t hmask = !PLANES ? 0u
+                                   : __ballot_sync(0xffffffffu, ((bmask >> lane) & 1u) && sh.hi1[lane] != nullptr && ub < INFINITY);
     sh.acc[lane] = 0.0f;
     sh.acc[lane + 32] = 0.0f;
     __syncwarp();
@@ -311,13 +313,15 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
         const int wi = (base >> 5) + lane;
         {
             // all words first (independent loads in flight together), then the arithmetic
-            uint32_t wv[kMaxTerms], hv1[kMaxTerms], hv2[kMaxTerms];
+            uint32_t wv[kMaxTerms], hv1[PLANES ? kMaxTerms : 1], hv2[PLANES ? kMaxTerms : 1];
 #pragma unroll
             for (int t = 0; t < kMaxTerms; t++) {
                 wv[t] = (((bmask >> t) & 1u) && lmask) ? (__ldg(sh.bits[t] + wi) & lmask) : 0u;
-                const bool pl = ((hmask >> t) & 1u) && lmask && need_scan;
-                hv1[t] = pl ? __ldg(sh.hi1[t] + wi) : 0xffffffffu;
-                hv2[t] = pl ? __ldg(sh.hi2[t] + wi) : 0xffffffffu;
+                if (PLANES) {
+                    const bool pl = ((hmask >> t) & 1u) && lmask && need_scan;
+                    hv1[t] = pl ? __ldg(sh.hi1[t] + wi) : 0xffffffffu;
+                    hv2[t] = pl ? __ldg(sh.hi2[t] + wi) : 0xffffffffu;
+                }
             }
             // the next window's line of every bitmap towards L1 while this one is processed
             if (((bmask >> lane) & 1u) && base + kMsW < hi)
@@ -342,14 +346,16 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
                     over |= w;
                 } else if (need_scan) {
                     ms_add(S, over, w, qa);
-                    const uint32_t w1 = w & hv1[t];
-                    if (qb >= kMsSat) {
-                        over |= w1;
-                    } else {
-                        if (qb != qa) ms_add(S, over, w1, qb - qa);
-                        const uint32_t w2 = w & hv2[t];
-                        if (qt >= kMsSat) over |= w2;
-                        else if (qt != qb) ms_add(S, over, w2, qt - qb);
+                    if (PLANES) {
+                        const uint32_t w1 = w & hv1[t];
+                        if (qb >= kMsSat) {
+                            over |= w1;
+                        } else {
+                            if (qb != qa) ms_add(S, over, w1, qb - qa);
+                            const uint32_t w2 = w & hv2[t];
+                            if (qt >= kMsSat) over |= w2;
+                            else if (qt != qb) ms_add(S, over, w2, qt - qb);
+                        }
                     }
                 }
             }
@@ -584,24 +590,26 @@ k_eval_or_ms(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids
     }
 }
 
-template <bool LIVE>
+template <bool LIVE, bool PLANES>
 static void launch_eval_or_ms_t(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, size_t wb,
                                 uint32_t kcap) {
     const size_t smem = wb * kMsWarps;
     // per launch, not cached: the attribute is per device and engines may live on several
-    cudaFuncSetAttribute(k_eval_or_ms<LIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_eval_or_ms<LIVE, PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const uint32_t ctas = (n + kMsWarps - 1) / kMsWarps;
-    k_eval_or_ms<LIVE><<<ctas, kMsThreads, smem, st>>>(p, item_ids, n, (uint32_t)wb, kcap);
+    k_eval_or_ms<LIVE, PLANES><<<ctas, kMsThreads, smem, st>>>(p, item_ids, n, (uint32_t)wb, kcap);
 }
 
 void launch_eval_or_ms(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n,
-                       uint32_t max_streams, bool has_live) {
+                       uint32_t max_streams, bool has_live, bool planes) {
     if (!n) return;
     const uint32_t kcap = (std::min<uint32_t>(p.k, kMaxK) + 31u) & ~31u;
     size_t wb = sizeof(MsWarpShared) + (size_t)kcap * sizeof(float) + (size_t)max_streams * kBlock * 8;
     wb = (wb + 15) & ~size_t(15);
-    if (has_live) launch_eval_or_ms_t<true>(st, p, item_ids, n, wb, kcap);
-    else launch_eval_or_ms_t<false>(st, p, item_ids, n, wb, kcap);
+    if (has_live && planes) launch_eval_or_ms_t<true, true>(st, p, item_ids, n, wb, kcap);
+    else if (has_live) launch_eval_or_ms_t<true, false>(st, p, item_ids, n, wb, kcap);
+    else if (planes) launch_eval_or_ms_t<false, true>(st, p, item_ids, n, wb, kcap);
+    else launch_eval_or_ms_t<false, false>(st, p, item_ids, n, wb, kcap);
 }
 
 }  // namespace rg

@@ -44,6 +44,7 @@ struct rg_batch {
     Span<uint32_t> ms_ids;           // OR work items evaluated by k_eval_or_ms (bitmaps + non-essential clauses)
     Span<uint32_t> dpq_ids;          // disjunctions with >= 10 clauses in the leaf (k_eval_dpq), one per (query, leaf)
     uint32_t n_dpq = 0, max_dpq_terms = 0;
+    bool uses_planes = false;        // some column / bitmap reference of this batch carries tf-norm planes
     Span<uint32_t> ro_ids;           // MUST+SHOULD (ReqOptScorer) work items: one per (query, leaf)
     Span<ColRef> col_refs;           // score columns this batch reads (ItemClause.term_id indexes it)
     std::vector<std::shared_ptr<ColEntry>> cols;  // keeps them alive (the engine's LRU may drop them meanwhile)
@@ -693,6 +694,7 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     b->col_floats = hp.col_floats;
     b->n_ms = (uint32_t)hp.ms_ids.size();
     b->max_ms_streams = hp.max_ms_streams;
+    for (const ColRef& r : hp.col_refs) b->uses_planes = b->uses_planes || r.hi1 != nullptr;
     b->n_dpq = (uint32_t)hp.dpq_ids.size();
     b->max_dpq_terms = hp.max_dpq_terms;
     b->n_queries = n_queries;
@@ -821,7 +823,7 @@ int rg_batch_run(rg_engine* e, rg_batch* b) {
         has_live = has_live || sg.live.p != nullptr;
         has_other = has_other || sg.has_other_enc;
     }
-    launch_eval_or_ms(st, ep, b->ms_ids.p, b->n_ms, b->max_ms_streams, has_live);
+    launch_eval_or_ms(st, ep, b->ms_ids.p, b->n_ms, b->max_ms_streams, has_live, b->uses_planes);
     RG_CUDA_CHECK(cudaGetLastError());
     launch_eval_or(st, ep, b->or_ids.p, b->n_or, b->max_or_terms, has_live, b->or_has_not, b->or_has_msm, b->or_has_dmax);
     RG_CUDA_CHECK(cudaGetLastError());
