@@ -74,8 +74,8 @@ def parse_args():
                     help="RG_CFG_NO_COLUMNS: evaluate every clause from its block stream (A/B runs)")
     ap.add_argument("--tf-planes", action="store_true", help="RG_CFG_TFPLANES: three-level per-document bound (A/B runs)")
     ap.add_argument("--stats", action="store_true", help="RG_CFG_STATS: event counters of k_eval_or_ms in the line")
-    ap.add_argument("--no-maxscore", action="store_true",
-                    help="RG_CFG_NO_MAXSCORE: exhaustive disjunction kernel only (A/B runs)")
+    ap.add_argument("--maxscore", action="store_true",
+                    help="RG_CFG_MAXSCORE: disjunctions through k_eval_or_ms (bitmaps + per-document bound) (A/B runs)")
     a = ap.parse_args()
     w = dict(WORKLOADS[a.workload])
     for key in ("docs", "terms", "batch", "k"):
@@ -513,17 +513,16 @@ def run_workload(ctx, name, w, args, steps, warmup, cpu_queries, cpu_seconds, fl
             upper_bytes, algo_bytes = algo_bytes, dbg_all["and_touched_bytes"] + nq * k * 8
         achieved = algo_bytes / (eval_ms / 1e3) / 1e9 if eval_ms > 0 else 0.0
         out["roofline"] = {
-            "bound": "hbm", "kernel": "k_eval_and" if name == "c3" else "k_eval_or_ms (+ k_eval_or for the items it does not take)",
+            "bound": "hbm", "kernel": "k_eval_and" if name == "c3" else ("k_eval_or_ms (+ k_eval_or)" if flags & engine.CFG_MAXSCORE else "k_eval_or"),
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ctx.traffic.get(name),
             "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "upper_bound_bytes_all_lists": upper_bytes,
             "kernel_ms": eval_ms,
             "replay_ms": replay_ms, "postings_per_launch": bstats["postings"], "work_items": bstats["items"],
             "candidate_slots": bstats["candidate_slots"],
             "note": "algorithmic bytes = SURVEY 8d: every clause's encoded blocks + tails + 12 B/block of tables + one "
-                    "norm byte per posting (for AND: lead list + upper bound of the touched blocks).  k_eval_or_ms does "
-                    "not read most of them: non-essential clauses are only counted from presence bitmaps, so achieved "
-                    "can exceed what a kernel that decodes every posting could reach; traffic = DRAM bytes actually "
-                    "moved (ncu, profiles/)",
+                    "norm byte per posting (conjunctions: the bytes the kernel itself counted — lead list + touched "
+                    "blocks / table entries / column cells).  Dense clauses that have a score column are read from it "
+                    "(4 B per docid) instead of being decoded; traffic = DRAM bytes actually moved (ncu, profiles/)",
             "score_columns": {"n": n_cols, "bytes": col_bytes, "built_by_first_batch": col_stats_cold["built"],
                               "engine_cache": eng.column_stats(),
                               "note": "persistent across batches (LRU, <= 1/3 of the free HBM); the timed steps hit the "
@@ -666,7 +665,7 @@ def main():
     tr = load_traffic()
     ctx.traffic = {} if args.scaled else {n: tr.get(n) for n in WORKLOADS}
 
-    flags = ((engine.CFG_NO_COLUMNS if args.no_columns else 0) | (engine.CFG_NO_MAXSCORE if args.no_maxscore else 0) |
+    flags = ((engine.CFG_NO_COLUMNS if args.no_columns else 0) | (engine.CFG_MAXSCORE if (args.maxscore or args.tf_planes) else 0) |
              (engine.CFG_STATS if args.stats else 0) | (engine.CFG_TFPLANES if args.tf_planes else 0))
     name, w = args.workload, args.w
     main_res = run_workload(ctx, name, w, args, args.steps, args.warmup, args.cpu_sample, args.cpu_seconds, flags=flags)
@@ -680,9 +679,9 @@ def main():
     ab = {}
     if not args.no_extra and not args.scaled and name == "c4" and (flags & ~engine.CFG_STATS) == 0:
         # A/B legs on the same workload: what the other evaluation routes deliver (2 steps each)
-        for label, fl in (("block_streams_only", engine.CFG_NO_COLUMNS | engine.CFG_NO_MAXSCORE),
-                          ("columns_exhaustive_kernel", engine.CFG_NO_MAXSCORE),
-                          ("bitmaps_with_tf_planes", engine.CFG_TFPLANES)):
+        for label, fl in (("block_streams_only", engine.CFG_NO_COLUMNS),
+                          ("bitmaps_per_document_bound", engine.CFG_MAXSCORE),
+                          ("bitmaps_bound_with_tf_planes", engine.CFG_MAXSCORE | engine.CFG_TFPLANES)):
             r = run_workload(ctx, name, w, args, 2, 1, 0, 0, flags=fl, light=True)
             ab[label] = {"queries_per_s": r["value"], "ms_per_step": r["ms_per_step"]}
         if ctx.world == 1:

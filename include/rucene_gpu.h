@@ -29,16 +29,19 @@ extern "C" {
 
 #define RG_NO_MORE_DOCS 0x7fffffff /* search/mod.rs:59 */
 
-/* rg_config.flags.  Presence bitmaps: every term with df >= max_doc/64 (largest first, within a byte
- * budget) gets a bitmap over the leaf's docids at upload.  Score columns: the BM25 contributions of
+/* rg_config.flags.  Presence bitmaps: every term with df >= max_doc/64 (max_doc/1024 when the engine is created
+ * with RG_CFG_MAXSCORE; largest first, within a byte budget) gets a bitmap over the leaf's docids at upload.  Score columns: the BM25 contributions of
  * such a term for one (weight, norm cache, k1) are materialised into a docid-indexed f32 column (the
  * same f32 values the per-query path computes) the first time two clauses of a batch share them, kept
  * across batches (LRU within 1/3 of the free HBM) and read from there. */
 #define RG_CFG_NO_COLUMNS 1u    /* never materialise score columns */
 #define RG_CFG_EAGER_COLUMNS 2u /* a column for every disjunction clause with df >= max_doc/64 (tests) */
 #define RG_CFG_NO_BITMAPS 4u    /* no presence bitmaps at upload (and therefore no score columns) */
-#define RG_CFG_NO_MAXSCORE 8u   /* evaluate every disjunction with the exhaustive kernel (A/B runs, tests) */
-#define RG_CFG_TFPLANES 32u     /* build and use tf-norm planes: the per-document score bound of k_eval_or_ms then knows three
+#define RG_CFG_MAXSCORE 8u      /* plain sum disjunctions that have a bitmap clause go to k_eval_or_ms (presence bitmaps for
+                                   df >= max_doc/1024, bit-sliced per-document score bound) instead of the exhaustive
+                                   k_eval_or.  On the benchmark index the two are equally fast on one GPU and the exhaustive
+                                   kernel scales better to small leaves; off by default */
+#define RG_CFG_TFPLANES 32u     /* (with RG_CFG_MAXSCORE) build and use tf-norm planes: the per-document score bound of k_eval_or_ms then knows three
                                    levels of a posting's BM25 tf-norm factor instead of presence only.  Cuts the docs it has
                                    to score ~16x, but scanning three planes costs more than it saves on the benchmark index
                                    (DESIGN.md section 6); off by default */

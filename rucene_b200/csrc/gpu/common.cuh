@@ -11,7 +11,7 @@ constexpr int kBlock = 128;           // codec/postings/posting_format.rs BLOCK_
 constexpr int kMaxTerms = 9;          // DisjunctionSumScorer SimpleQueue regime (< 10 children)
 constexpr int kDpqMaxTerms = 32;      // widest disjunction the DisiPriorityQueue kernel takes (>= 10 clauses in a leaf)
 constexpr int kNoMoreDocs = 0x7fffffff;
-constexpr int kBitmapDen = 1024;      // terms with df >= max_doc / 1024 get a presence bitmap at upload (within a budget)
+constexpr int kBitmapDen = 1024;      // RG_CFG_MAXSCORE: terms with df >= max_doc / 1024 get a presence bitmap at upload (within a budget)
 constexpr int kColumnDen = 64;        // terms with df >= max_doc / 64 may also get a score column (per weight, on demand)
 
 // ------------------------------------------------------------------ index image in HBM

@@ -614,9 +614,11 @@ void build_segment(rg_engine* e, Segment& seg, int32_t doc_base, int32_t max_doc
     // ---- presence bitmaps of the dense terms (device-side: one warp per block sets 128 bits)
     seg.bitmap_slot.assign(n_terms, -1);
     if (!(e->cfg.flags & RG_CFG_NO_BITMAPS)) {
+        // score columns need the bitmaps of the terms with df >= max_doc/64 only; k_eval_or_ms wants them down to /1024
+        const uint64_t bitmap_den = (e->cfg.flags & RG_CFG_MAXSCORE) ? kBitmapDen : kColumnDen;
         std::vector<uint32_t> dense;
         for (uint32_t t = 0; t < n_terms; t++)
-            if ((uint64_t)std::max(terms[t].doc_freq, 0) * kBitmapDen >= (uint64_t)max_doc && terms[t].doc_freq >= 2)
+            if ((uint64_t)std::max(terms[t].doc_freq, 0) * bitmap_den >= (uint64_t)max_doc && terms[t].doc_freq >= 2)
                 dense.push_back(t);
         std::sort(dense.begin(), dense.end(), [&](uint32_t a, uint32_t b) {
             return terms[a].doc_freq != terms[b].doc_freq ? terms[a].doc_freq > terms[b].doc_freq : a < b;

@@ -195,7 +195,7 @@ constexpr uint32_t kMatchAllTerm = 0xffffffffu;  // ColKey term of a leaf's Matc
 void tf_planes_of(rg_engine* e, uint32_t si, uint32_t term, uint32_t cache_id, float k1, ColRef& ref) {
     ref.hi1 = ref.hi2 = nullptr;
     ref.tau1 = ref.tau2 = 1.0f;
-    if (!(e->cfg.flags & RG_CFG_TFPLANES)) return;
+    if ((e->cfg.flags & (RG_CFG_TFPLANES | RG_CFG_MAXSCORE)) != (RG_CFG_TFPLANES | RG_CFG_MAXSCORE)) return;
     Segment& seg = e->segs[si];
     if (term >= seg.bitmap_slot.size() || seg.bitmap_slot[term] < 0) return;
     uint32_t k1bits;
@@ -285,19 +285,22 @@ std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape
         if (cols_off) continue;
         for (uint32_t si = 0; si < e->segs.size(); si++) {
             const Segment& seg = e->segs[si];
-            auto count = [&](uint32_t ci) {
+            // a column pays where it is read: the exhaustive disjunction kernel scans it docid by docid (df >= max_doc/8),
+            // k_eval_or_ms and the conjunction kernel gather single cells (df >= max_doc/64)
+            auto count = [&](uint32_t ci, uint64_t den) {
                 const rg_clause& c = clauses[ci];
                 if (c.term_id >= seg.host_terms.size() || seg.bitmap_slot[c.term_id] < 0) return;
-                if ((uint64_t)seg.host_terms[c.term_id].doc_freq * kColumnDen < (uint64_t)seg.max_doc) return;
+                if ((uint64_t)seg.host_terms[c.term_id].doc_freq * den < (uint64_t)seg.max_doc) return;
                 const float w = clause_weight(c);
                 uint32_t wbits;
                 memcpy(&wbits, &w, 4);
                 uses[ColKey(si, c.term_id, wbits, c.cache_id, k1bits)]++;
             };
-            for (uint32_t ci : sh.clause_idx) count(ci);
+            const uint64_t or_den = ((e->cfg.flags & RG_CFG_MAXSCORE) || eager) ? (uint64_t)kColumnDen : 8u;
+            for (uint32_t ci : sh.clause_idx) count(ci, sh.type == kTypeOr ? or_den : (uint64_t)kColumnDen);
             // conjunctions probe the columns of their non-lead clauses (which clause leads depends on the leaf;
             // the lead's use is counted too and simply stays unused)
-            for (uint32_t ci : sh.opt_idx) count(ci);
+            for (uint32_t ci : sh.opt_idx) count(ci, (uint64_t)kColumnDen);
         }
     }
     if (uses.empty() && !any_match_all) return chosen;
@@ -423,7 +426,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
     const std::map<ColKey, uint32_t> columns = choose_columns(e, shapes, clauses, k1, hp);
     uint32_t k1bits;
     memcpy(&k1bits, &k1, 4);
-    const bool no_ms = (e->cfg.flags & RG_CFG_NO_MAXSCORE) != 0;
+    const bool no_ms = (e->cfg.flags & RG_CFG_MAXSCORE) == 0;
     for (uint32_t qi = 0; qi < n_queries; qi++) {
         const QShape& shape = shapes[qi];
         bool group_open = false;

@@ -15,7 +15,7 @@ MUST, SHOULD, MUST_NOT, FILTER = 0, 1, 2, 3
 Q_BOOLEAN = 1
 Q_DISMAX = 2    # rg_query.flags: DisjunctionMaxQuery; min_should_match = bits of the f32 tie breaker
 MODE_SEARCH, MODE_SEARCH_PARALLEL = 0, 1
-CFG_NO_COLUMNS, CFG_EAGER_COLUMNS, CFG_NO_BITMAPS, CFG_NO_MAXSCORE, CFG_STATS, CFG_TFPLANES = 1, 2, 4, 8, 16, 32   # rg_config.flags (include/rucene_gpu.h)
+CFG_NO_COLUMNS, CFG_EAGER_COLUMNS, CFG_NO_BITMAPS, CFG_MAXSCORE, CFG_STATS, CFG_TFPLANES = 1, 2, 4, 8, 16, 32   # rg_config.flags (include/rucene_gpu.h)
 NO_MORE_DOCS = 0x7FFFFFFF
 
 TERM_STATE_DTYPE = np.dtype([("doc_freq", "<i4"), ("singleton_doc_id", "<i4"),

@@ -36,7 +36,7 @@ def test_zipf_disjunctions_all_routes(k):
     ix = helpers.oracle_index([seg])
     rng = np.random.default_rng(20 + k)
     specs = _or_specs(rng, 4000, 70) + [("term", 0), ("term", 7), ("term", 300)]
-    for flags in (engine.CFG_EAGER_COLUMNS, engine.CFG_TFPLANES, 0):
+    for flags in (engine.CFG_EAGER_COLUMNS | engine.CFG_MAXSCORE, engine.CFG_MAXSCORE | engine.CFG_TFPLANES, engine.CFG_MAXSCORE, 0):
         for rp in (0, 6000):
             s = search.GpuIndexSearcher(search.IndexReader([seg]), range_postings=rp, flags=flags)
             try:
@@ -55,7 +55,7 @@ def test_boosts_change_the_essential_order_and_negative_boost_is_never_pruned():
     specs += [("bool", [(ob.SHOULD, 0, -1.0), (ob.SHOULD, 3), (ob.SHOULD, 40)], 0),
               ("bool", [(ob.SHOULD, 1, 0.0), (ob.SHOULD, 2), (ob.SHOULD, 900)], 0),
               ("bool", [(ob.SHOULD, 0), (ob.SHOULD, 1), (ob.SHOULD, 2), (ob.SHOULD, 3), (ob.SHOULD, 4)], 0)]
-    s = search.GpuIndexSearcher(search.IndexReader([seg]), range_postings=8000, flags=engine.CFG_EAGER_COLUMNS | engine.CFG_TFPLANES)
+    s = search.GpuIndexSearcher(search.IndexReader([seg]), range_postings=8000, flags=engine.CFG_EAGER_COLUMNS | engine.CFG_MAXSCORE | engine.CFG_TFPLANES)
     try:
         for k in (5, 50):
             _check(s, ix, specs, k, "boosts k=%d" % k)
@@ -94,7 +94,7 @@ def test_leaves_live_docs_and_clustered_streams(mode):
     for i in range(60):
         t = int(rng.integers(2, 7))
         specs.append(("bool", [(ob.SHOULD, int(x)) for x in rng.choice(9, size=t, replace=False)], 0))
-    for flags in (engine.CFG_EAGER_COLUMNS | engine.CFG_TFPLANES, 0):
+    for flags in (engine.CFG_EAGER_COLUMNS | engine.CFG_MAXSCORE | engine.CFG_TFPLANES, engine.CFG_MAXSCORE, 0):
         s = search.GpuIndexSearcher(search.IndexReader(segs), range_postings=4000, flags=flags)
         try:
             for k in (3, 100):

@@ -37,8 +37,8 @@ def _run_both(segs, specs, k, mode=0, range_postings=0, threads=4, extra_flags=0
     # (k_eval_or_ms: presence bitmaps + bit-sliced per-document bound), the same with tf-norm planes, the same
     # columns read by the exhaustive kernel, no bitmaps / columns at all (block streams only), the planner's choice
     got = None
-    for flags in (engine.CFG_EAGER_COLUMNS, engine.CFG_EAGER_COLUMNS | engine.CFG_TFPLANES,
-                  engine.CFG_EAGER_COLUMNS | engine.CFG_NO_MAXSCORE, engine.CFG_NO_BITMAPS, 0):
+    for flags in (engine.CFG_EAGER_COLUMNS | engine.CFG_MAXSCORE, engine.CFG_EAGER_COLUMNS | engine.CFG_MAXSCORE | engine.CFG_TFPLANES,
+                  engine.CFG_EAGER_COLUMNS, engine.CFG_NO_BITMAPS, engine.CFG_MAXSCORE, 0):
         s = search.GpuIndexSearcher(search.IndexReader(segs), range_postings=range_postings,
                                     flags=flags | extra_flags)
         try:
