@@ -406,9 +406,10 @@ def run_workload(ctx, name, w, args, steps, warmup, cpu_queries, cpu_seconds, fl
 
     def one_step(fetch=False):
         batch.run()
-        if world > 1:
+        if world > 1:  # kernels -> one all-gather -> leaf-order merge, all on one stream; the copy back only on request
             dist.all_gather_into_tensor(gathered, local_rec)
-            return eng.merge_leaf_records(gathered.data_ptr(), n_seg, nq, k)
+            eng.merge_leaf_records_device(gathered.data_ptr(), n_seg, nq, k)
+            return eng.merge_fetch() if fetch else None
         return batch.fetch() if fetch else None
 
     for _ in range(warmup):

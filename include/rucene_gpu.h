@@ -213,6 +213,12 @@ int rg_merge_leaf_records(rg_engine* e, const void* dev_records_all, uint32_t n_
                           uint32_t n_queries, uint32_t k, rg_hit* out_hits, uint32_t* out_counts,
                           uint64_t* out_total_hits);
 
+/* The same merge without the copy back: the result stays in engine memory (asynchronous on the stream) until
+ * rg_merge_fetch — a serving loop can launch the next batch before it reads this one's TopDocs. */
+int rg_merge_leaf_records_device(rg_engine* e, const void* dev_records_all, uint32_t n_leaves,
+                                 uint32_t n_queries, uint32_t k);
+int rg_merge_fetch(rg_engine* e, rg_hit* out_hits, uint32_t* out_counts, uint64_t* out_total_hits);
+
 /* The whole sharded step behind one call, for a host that holds an ncclComm_t (no Python / torch needed):
  * runs the prepared RG_MODE_SEARCH_PARALLEL batch, all-gathers every rank's leaf records with ncclAllGather on the
  * engine's stream and replays finish_parallel in leaf order (rank r holds leaves [r*L, (r+1)*L), L = segments

@@ -254,6 +254,7 @@ struct rg_engine {
     std::vector<uint8_t> cache_nonneg;  // per norm cache: every entry >= 0 (MaxScore bound needs it)
     rg::DevBuf<uint8_t> merge_scratch;  // rg_merge_leaf_records outputs (grow-only)
     rg::DevBuf<uint8_t> gather_scratch; // rg_batch_run_sharded: all ranks' leaf records (grow-only)
+    uint32_t merged_queries = 0, merged_k = 0;  // shape of the result sitting in merge_scratch
     rg::DevBuf<uint8_t> spare_slab;  // device slab of the last destroyed rg_batch, reused by the next
     uint64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;

@@ -13,6 +13,8 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <tuple>
 #include <type_traits>
 
@@ -427,7 +429,12 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
     uint32_t k1bits;
     memcpy(&k1bits, &k1, 4);
     const bool no_ms = (e->cfg.flags & RG_CFG_MAXSCORE) == 0;
-    for (uint32_t qi = 0; qi < n_queries; qi++) {
+    // Queries are planned in parallel: contiguous chunks, one HostPlan each, concatenated in query order (item order
+    // is collection order, so the result equals the serial plan).
+    std::mutex refs_mutex;
+    const uint32_t n_threads = n_queries >= 512 ? std::min<uint32_t>(16u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+    auto plan_range = [&](uint32_t q_begin, uint32_t q_end, HostPlan& lp) {
+    for (uint32_t qi = q_begin; qi < q_end; qi++) {
         const QShape& shape = shapes[qi];
         bool group_open = false;
         uint32_t chain_pos = 0;
@@ -493,9 +500,9 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 total_df = cost;
             }
             for (uint32_t ci : nots) bytes += seg.host_terms[clauses[ci].term_id].enc_bytes;
-            hp.postings += total_df;
-            hp.algo_bytes += bytes;
-            const uint32_t clause_begin = (uint32_t)hp.clauses.size();
+            lp.postings += total_df;
+            lp.algo_bytes += bytes;
+            const uint32_t clause_begin = (uint32_t)lp.clauses.size();
             // score column of a clause in this leaf (-1: none)
             auto col_of = [&](uint32_t ci) -> int64_t {
                 if (columns.empty()) return -1;
@@ -513,9 +520,9 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 // the leaf's match-all column (every docid present, score 0) + the MUST_NOT streams: k_eval_or<NOT>
                 const auto it = columns.find(ColKey(si, kMatchAllTerm, 0u, 0u, 0u));
                 if (it == columns.end()) throw Unsupported("no memory for the MatchAllDocsQuery column");
-                hp.clauses.push_back(ItemClause{it->second, 0.0f, 0u, 4u | 16u});
+                lp.clauses.push_back(ItemClause{it->second, 0.0f, 0u, 4u | 16u});
             } else if (leaf_dpq) {
-                for (uint32_t ci : present) hp.clauses.push_back(ItemClause{clauses[ci].term_id, clause_weight(clauses[ci]), clauses[ci].cache_id, 0});
+                for (uint32_t ci : present) lp.clauses.push_back(ItemClause{clauses[ci].term_id, clause_weight(clauses[ci]), clauses[ci].cache_id, 0});
             } else if (shape.type == kTypeOr) {
                 // A disjunction goes to k_eval_or_ms (presence bitmaps, non-essential clauses are only counted)
                 // when it is a plain sum of SHOULD clauses, reads at least one score column, and none of its
@@ -536,13 +543,14 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                                            c.cache_id < e->cache_nonneg.size() && e->cache_nonneg[c.cache_id];
                     // the exhaustive kernel scans a column docid by docid: that only pays for df >= max_doc/8
                     if (col >= 0 && (use_ms || df_of(ci) * 8u >= (uint64_t)seg.max_doc)) {
-                        hp.clauses.push_back(ItemClause{(uint32_t)col, w, c.cache_id, 4u | (boundable ? 0u : 16u)});
+                        lp.clauses.push_back(ItemClause{(uint32_t)col, w, c.cache_id, 4u | (boundable ? 0u : 16u)});
                         continue;
                     }
                     n_streams++;
                     uint32_t flags = 0;
                     if (use_ms && seg.bitmap_slot[c.term_id] >= 0) {  // a block stream whose presence comes from its bitmap
                         const auto key = std::make_tuple(si, c.term_id, c.cache_id);
+                        std::lock_guard<std::mutex> lock(refs_mutex);  // the reference table is shared by the planner threads
                         auto it = hp.bitmap_refs.find(key);
                         if (it == hp.bitmap_refs.end()) {
                             it = hp.bitmap_refs.emplace(key, (uint32_t)hp.col_refs.size()).first;
@@ -553,7 +561,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                         }
                         if (it->second < 65536u) flags = 32u | (boundable ? 0u : 16u) | (it->second << 16);
                     }
-                    hp.clauses.push_back(ItemClause{c.term_id, w, c.cache_id, flags});
+                    lp.clauses.push_back(ItemClause{c.term_id, w, c.cache_id, flags});
                 }
             } else {
                 // conjunction: the lead (cheapest) clause is a block stream; every other clause that has a score
@@ -561,25 +569,25 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 for (size_t i = 0; i < present.size(); i++) {
                     const rg_clause& c = clauses[present[i]];
                     const int64_t col = i == 0 ? -1 : col_of(present[i]);
-                    if (col >= 0) hp.clauses.push_back(ItemClause{(uint32_t)col, clause_weight(c), c.cache_id, 4u});
-                    else hp.clauses.push_back(ItemClause{c.term_id, clause_weight(c), c.cache_id, 0});
+                    if (col >= 0) lp.clauses.push_back(ItemClause{(uint32_t)col, clause_weight(c), c.cache_id, 4u});
+                    else lp.clauses.push_back(ItemClause{c.term_id, clause_weight(c), c.cache_id, 0});
                 }
             }
             for (uint32_t ci : nots) {
                 const int64_t col = shape.type == kTypeOr ? -1 : col_of(ci);  // conjunctions: any column of the term will do
-                if (col >= 0) hp.clauses.push_back(ItemClause{(uint32_t)col, 0.0f, clauses[ci].cache_id, 1u | 4u});
-                else hp.clauses.push_back(ItemClause{clauses[ci].term_id, 0.0f, clauses[ci].cache_id, 1u});
+                if (col >= 0) lp.clauses.push_back(ItemClause{(uint32_t)col, 0.0f, clauses[ci].cache_id, 1u | 4u});
+                else lp.clauses.push_back(ItemClause{clauses[ci].term_id, 0.0f, clauses[ci].cache_id, 1u});
             }
             for (uint32_t ci : opts) {
                 const int64_t col = col_of(ci);
-                if (col >= 0) hp.clauses.push_back(ItemClause{(uint32_t)col, clauses[ci].weight, clauses[ci].cache_id, 2u | 4u});
-                else hp.clauses.push_back(ItemClause{clauses[ci].term_id, clauses[ci].weight, clauses[ci].cache_id, 2u});
+                if (col >= 0) lp.clauses.push_back(ItemClause{(uint32_t)col, clauses[ci].weight, clauses[ci].cache_id, 2u | 4u});
+                else lp.clauses.push_back(ItemClause{clauses[ci].term_id, clauses[ci].weight, clauses[ci].cache_id, 2u});
             }
             const uint32_t n_item_terms = (uint32_t)(present.size() + (shape.match_all ? 1 : 0) + nots.size() + opts.size());
             // DisjunctionMaxWeight::create_scorer (disjunction_max_query.rs:135-155): one scorer in this
             // leaf is that scorer; otherwise the tie breaker rides in a meta clause after the item's
             const bool leaf_dismax = shape.dismax && present.size() > 1;
-            if (leaf_dismax) hp.clauses.push_back(ItemClause{0u, shape.tie, 0u, 8u});
+            if (leaf_dismax) lp.clauses.push_back(ItemClause{0u, shape.tie, 0u, 8u});
             // ranges of ~range_postings postings, at most 256 per (query, leaf): long lists get
             // longer ranges (a range is one warp's sequential job; there are thousands of warps)
             uint64_t R = (cost + range_postings - 1) / range_postings;
@@ -588,7 +596,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
             if (leaf_type == (int)kTypeReqOpt || leaf_dpq) R = 1;  // sequential scorer state: one item per leaf
             if (new_group) {
                 // SEARCH: one heap per query over all its leaves; SEARCH_PARALLEL: one per leaf
-                hp.group_out.push_back(mode == RG_MODE_SEARCH_PARALLEL ? si * n_queries + qi : qi);
+                lp.group_out.push_back(mode == RG_MODE_SEARCH_PARALLEL ? si * n_queries + qi : qi);
                 group_open = true;
             }
             for (uint64_t r = 0; r < R; r++) {
@@ -602,29 +610,76 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 it.clause_begin = clause_begin;
                 it.chain_pos = (r == 0 && new_group) ? 0u : chain_pos;
                 chain_pos = it.chain_pos + 1;
-                const uint32_t idx = (uint32_t)hp.items.size();
-                hp.items.push_back(it);
+                const uint32_t idx = (uint32_t)lp.items.size();
+                lp.items.push_back(it);
                 if (leaf_dpq) {
-                    hp.dpq_ids.push_back(idx);
-                    hp.max_dpq_terms = std::max<uint32_t>(hp.max_dpq_terms, n_item_terms);
+                    lp.dpq_ids.push_back(idx);
+                    lp.max_dpq_terms = std::max<uint32_t>(lp.max_dpq_terms, n_item_terms);
                 } else if (leaf_type == (int)kTypeReqOpt) {
-                    hp.ro_ids.push_back(idx);
+                    lp.ro_ids.push_back(idx);
                 } else if (leaf_type == (int)kTypeAnd) {
-                    hp.and_ids.push_back(idx);
-                    hp.and_rank.push_back((uint32_t)r);
+                    lp.and_ids.push_back(idx);
+                    lp.and_rank.push_back((uint32_t)r);
                 } else if (use_ms) {
-                    hp.ms_ids.push_back(idx);
-                    hp.ms_rank.push_back((uint32_t)r);
-                    hp.max_ms_streams = std::max<uint32_t>(hp.max_ms_streams, n_streams);
+                    lp.ms_ids.push_back(idx);
+                    lp.ms_rank.push_back((uint32_t)r);
+                    lp.max_ms_streams = std::max<uint32_t>(lp.max_ms_streams, n_streams);
                 } else {
-                    hp.or_ids.push_back(idx);
-                    hp.or_rank.push_back((uint32_t)r);
-                    hp.max_or_terms = std::max<uint32_t>(hp.max_or_terms, n_item_terms);
-                    if (!nots.empty()) hp.or_has_not = true;
-                    if (shape.msm) hp.or_has_msm = true;
-                    if (leaf_dismax) hp.or_has_dmax = true;
+                    lp.or_ids.push_back(idx);
+                    lp.or_rank.push_back((uint32_t)r);
+                    lp.max_or_terms = std::max<uint32_t>(lp.max_or_terms, n_item_terms);
+                    if (!nots.empty()) lp.or_has_not = true;
+                    if (shape.msm) lp.or_has_msm = true;
+                    if (leaf_dismax) lp.or_has_dmax = true;
                 }
             }
+        }
+    }
+    };
+    if (n_threads <= 1) {
+        plan_range(0, n_queries, hp);
+    } else {
+        std::vector<HostPlan> parts(n_threads);
+        std::vector<std::exception_ptr> errs(n_threads);
+        std::vector<std::thread> ths;
+        for (uint32_t t = 0; t < n_threads; t++)
+            ths.emplace_back([&, t] {
+                try {
+                    plan_range((uint32_t)((uint64_t)n_queries * t / n_threads), (uint32_t)((uint64_t)n_queries * (t + 1) / n_threads), parts[t]);
+                } catch (...) {
+                    errs[t] = std::current_exception();
+                }
+            });
+        for (auto& th : ths) th.join();
+        for (auto& ep : errs)
+            if (ep) std::rethrow_exception(ep);
+        for (HostPlan& lp : parts) {
+            const uint32_t item_off = (uint32_t)hp.items.size(), clause_off = (uint32_t)hp.clauses.size();
+            for (WorkItem it : lp.items) {
+                it.clause_begin += clause_off;
+                hp.items.push_back(it);
+            }
+            hp.clauses.insert(hp.clauses.end(), lp.clauses.begin(), lp.clauses.end());
+            auto append_ids = [&](std::vector<uint32_t>& dst, const std::vector<uint32_t>& src) {
+                for (uint32_t id : src) dst.push_back(id + item_off);
+            };
+            append_ids(hp.or_ids, lp.or_ids);
+            append_ids(hp.ms_ids, lp.ms_ids);
+            append_ids(hp.and_ids, lp.and_ids);
+            append_ids(hp.ro_ids, lp.ro_ids);
+            append_ids(hp.dpq_ids, lp.dpq_ids);
+            hp.or_rank.insert(hp.or_rank.end(), lp.or_rank.begin(), lp.or_rank.end());
+            hp.ms_rank.insert(hp.ms_rank.end(), lp.ms_rank.begin(), lp.ms_rank.end());
+            hp.and_rank.insert(hp.and_rank.end(), lp.and_rank.begin(), lp.and_rank.end());
+            hp.group_out.insert(hp.group_out.end(), lp.group_out.begin(), lp.group_out.end());
+            hp.postings += lp.postings;
+            hp.algo_bytes += lp.algo_bytes;
+            hp.max_or_terms = std::max(hp.max_or_terms, lp.max_or_terms);
+            hp.max_ms_streams = std::max(hp.max_ms_streams, lp.max_ms_streams);
+            hp.max_dpq_terms = std::max(hp.max_dpq_terms, lp.max_dpq_terms);
+            hp.or_has_not = hp.or_has_not || lp.or_has_not;
+            hp.or_has_msm = hp.or_has_msm || lp.or_has_msm;
+            hp.or_has_dmax = hp.or_has_dmax || lp.or_has_dmax;
         }
     }
     // Launch order: all first ranges, then all second ranges, ... so that by the time range r of a
@@ -955,11 +1010,8 @@ int rg_batch_leaf_records(rg_engine* e, rg_batch* b, void** dev_ptr, size_t* rec
     RG_CATCH
 }
 
-int rg_merge_leaf_records(rg_engine* e, const void* dev_records_all, uint32_t n_leaves,
-                          uint32_t n_queries, uint32_t k, rg_hit* out_hits, uint32_t* out_counts,
-                          uint64_t* out_total_hits) {
-    RG_TRY
-    if (!e || !dev_records_all || !out_hits || !out_counts || !out_total_hits) throw ArgError("null argument");
+// finish_parallel on the device into the engine's merge scratch; nothing is copied back and nothing waits
+static void merge_on_device(rg_engine* e, const void* dev_records_all, uint32_t n_leaves, uint32_t n_queries, uint32_t k) {
     if (k == 0 || k > 1024) throw ArgError("k out of range");
     RG_CUDA_CHECK(cudaSetDevice(e->device));
     cudaStream_t st = e->stream;
@@ -969,19 +1021,49 @@ int rg_merge_leaf_records(rg_engine* e, const void* dev_records_all, uint32_t n_
     const size_t counts_b = (nq * 4 + 255) & ~(size_t)255;
     const size_t total_b = nq * 8;
     if (e->merge_scratch.n < hits_b + counts_b + total_b) e->merge_scratch.alloc(hits_b + counts_b + total_b);
-    Span<rg_hit> d_hits{reinterpret_cast<rg_hit*>(e->merge_scratch.p), nq * k};
-    Span<uint32_t> d_counts{reinterpret_cast<uint32_t*>(e->merge_scratch.p + hits_b), nq};
-    Span<unsigned long long> d_total{reinterpret_cast<unsigned long long*>(e->merge_scratch.p + hits_b + counts_b), nq};
-    RG_CUDA_CHECK(cudaMemsetAsync(d_hits.p, 0, d_hits.bytes(), st));
-    launch_merge_leaf_records(st, static_cast<const uint8_t*>(dev_records_all), n_leaves, n_queries, k,
-                              d_hits.p, d_counts.p, d_total.p);
+    rg_hit* d_hits = reinterpret_cast<rg_hit*>(e->merge_scratch.p);
+    uint32_t* d_counts = reinterpret_cast<uint32_t*>(e->merge_scratch.p + hits_b);
+    unsigned long long* d_total = reinterpret_cast<unsigned long long*>(e->merge_scratch.p + hits_b + counts_b);
+    RG_CUDA_CHECK(cudaMemsetAsync(d_hits, 0, nq * k * sizeof(rg_hit), st));
+    launch_merge_leaf_records(st, static_cast<const uint8_t*>(dev_records_all), n_leaves, n_queries, k, d_hits, d_counts, d_total);
     RG_CUDA_CHECK(cudaGetLastError());
     e->launches++;
-    RG_CUDA_CHECK(cudaMemcpyAsync(out_hits, d_hits.p, (size_t)n_queries * k * sizeof(rg_hit), cudaMemcpyDeviceToHost, st));
-    RG_CUDA_CHECK(cudaMemcpyAsync(out_counts, d_counts.p, (size_t)n_queries * 4, cudaMemcpyDeviceToHost, st));
-    RG_CUDA_CHECK(cudaMemcpyAsync(out_total_hits, d_total.p, (size_t)n_queries * 8, cudaMemcpyDeviceToHost, st));
+    e->merged_queries = n_queries;
+    e->merged_k = k;
+}
+
+int rg_merge_leaf_records_device(rg_engine* e, const void* dev_records_all, uint32_t n_leaves, uint32_t n_queries, uint32_t k) {
+    RG_TRY
+    if (!e || !dev_records_all) throw ArgError("null argument");
+    merge_on_device(e, dev_records_all, n_leaves, n_queries, k);
+    return RG_OK;
+    RG_CATCH
+}
+
+int rg_merge_fetch(rg_engine* e, rg_hit* out_hits, uint32_t* out_counts, uint64_t* out_total_hits) {
+    RG_TRY
+    if (!e || !out_hits || !out_counts || !out_total_hits) throw ArgError("null argument");
+    if (!e->merged_k) throw ArgError("rg_merge_fetch before a merge");
+    RG_CUDA_CHECK(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    const size_t nq = std::max<uint32_t>(1, e->merged_queries), k = e->merged_k;
+    const size_t hits_b = (nq * k * sizeof(rg_hit) + 255) & ~(size_t)255;
+    const size_t counts_b = (nq * 4 + 255) & ~(size_t)255;
+    RG_CUDA_CHECK(cudaMemcpyAsync(out_hits, e->merge_scratch.p, (size_t)e->merged_queries * k * sizeof(rg_hit), cudaMemcpyDeviceToHost, st));
+    RG_CUDA_CHECK(cudaMemcpyAsync(out_counts, e->merge_scratch.p + hits_b, (size_t)e->merged_queries * 4, cudaMemcpyDeviceToHost, st));
+    RG_CUDA_CHECK(cudaMemcpyAsync(out_total_hits, e->merge_scratch.p + hits_b + counts_b, (size_t)e->merged_queries * 8, cudaMemcpyDeviceToHost, st));
     RG_CUDA_CHECK(cudaStreamSynchronize(st));
     return RG_OK;
+    RG_CATCH
+}
+
+int rg_merge_leaf_records(rg_engine* e, const void* dev_records_all, uint32_t n_leaves,
+                          uint32_t n_queries, uint32_t k, rg_hit* out_hits, uint32_t* out_counts,
+                          uint64_t* out_total_hits) {
+    RG_TRY
+    if (!e || !dev_records_all || !out_hits || !out_counts || !out_total_hits) throw ArgError("null argument");
+    merge_on_device(e, dev_records_all, n_leaves, n_queries, k);
+    return rg_merge_fetch(e, out_hits, out_counts, out_total_hits);
     RG_CATCH
 }
 

@@ -91,6 +91,8 @@ def lib():
     L.rg_batch_columns.argtypes = [vp, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
     L.rg_batch_leaf_records.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.rg_batch_run_sharded.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, vp]
+    L.rg_merge_leaf_records_device.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.rg_merge_fetch.argtypes = [vp, vp, vp, vp]
     L.rg_merge_leaf_records.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp]
     L.rg_segment_decode.argtypes = [vp, C.c_uint32, C.c_uint64, C.c_uint64, vp, vp]
     L.rg_forutil_decode.argtypes = [vp, vp, C.c_size_t, vp, C.c_uint32, C.c_int, vp, vp]
@@ -326,6 +328,19 @@ class Engine:
         total = np.zeros(n_queries, np.uint64)
         _check(lib().rg_merge_leaf_records(self.h, dev_ptr, n_leaves, n_queries, k, _p(hits),
                                            _p(counts), _p(total)), self.h)
+        return hits, counts, total
+
+    def merge_leaf_records_device(self, dev_ptr, n_leaves, n_queries, k):
+        """finish_parallel on the device; the result stays there until merge_fetch()."""
+        _check(lib().rg_merge_leaf_records_device(self.h, dev_ptr, n_leaves, n_queries, k), self.h)
+        self._merged = (n_queries, k)
+
+    def merge_fetch(self):
+        n_queries, k = self._merged
+        hits = np.zeros((n_queries, k), HIT_DTYPE)
+        counts = np.zeros(n_queries, np.uint32)
+        total = np.zeros(n_queries, np.uint64)
+        _check(lib().rg_merge_fetch(self.h, _p(hits), _p(counts), _p(total)), self.h)
         return hits, counts, total
 
     # ---- block codec ----
