@@ -45,6 +45,10 @@ extern "C" {
                                    levels of a posting's BM25 tf-norm factor instead of presence only.  Cuts the docs it has
                                    to score ~16x, but scanning three planes costs more than it saves on the benchmark index
                                    (DESIGN.md section 6); off by default */
+#define RG_CFG_NO_LISTS 64u     /* never materialise scored posting lists: a disjunction clause (df >= 4096) that two clauses of a batch share
+                                   is decoded and BM25-scored ONCE into (docid, f32 score) pairs, 1 KB per 128-posting block, kept
+                                   across batches in the same LRU budget as the score columns; k_eval_or then streams the pairs
+                                   instead of unpacking, prefix-summing, gathering norms and dividing per query */
 #define RG_CFG_STATS 16u        /* count events inside k_eval_or_ms (rg_batch_debug); costs a few atomics per work item */
 
 typedef struct rg_engine rg_engine;
@@ -133,6 +137,8 @@ int rg_engine_set_flags(rg_engine* e, uint32_t flags);
 /* Persistent score columns: [0]=columns cached, [1]=their bytes in HBM, [2]=columns built so far,
  * [3]=cache hits so far. */
 int rg_engine_column_stats(rg_engine* e, uint64_t out[4]);
+/* Persistent scored posting lists (see RG_CFG_NO_LISTS), same four figures. */
+int rg_engine_list_stats(rg_engine* e, uint64_t out[4]);
 /* Number of this library's kernels launched so far (bench.py's gpu_launches). */
 uint64_t rg_engine_launch_count(rg_engine* e);
 /* Device-side timing of the last rg_batch_run / rg_blockset_decode, CUDA events on the launch

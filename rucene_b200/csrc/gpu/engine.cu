@@ -587,7 +587,10 @@ void build_segment(rg_engine* e, Segment& seg, int32_t doc_base, int32_t max_doc
     upload(seg.blk_desc, h_desc.data(), h_desc.size(), st);
     upload(seg.tails, h_tails.data(), h_tails.size(), st);
     upload(seg.terms, h_terms.data(), h_terms.size(), st);
-    if (norms) upload(seg.norms, norms, (size_t)max_doc, st);
+    if (norms) {
+        upload(seg.norms, norms, (size_t)max_doc, st);
+        for (int64_t i = 0; i < (int64_t)max_doc; i++) seg.norm_seen[norms[i]] = 1;
+    }
     if (live) upload(seg.live, live, ((size_t)max_doc + 63) / 64, st);
     RG_CUDA_CHECK(cudaStreamSynchronize(st));
     for (const Chunk& ch : chunks)
@@ -653,6 +656,18 @@ void build_segment(rg_engine* e, Segment& seg, int32_t doc_base, int32_t max_doc
     }
     seg.device_bytes = seg.arena.bytes() + seg.blk_last.bytes() + seg.blk_desc.bytes() + seg.tails.bytes() +
                        seg.terms.bytes() + seg.norms.bytes() + seg.live.bytes() + seg.bitmaps.bytes();
+}
+
+// Lucene's norm table maps byte 0 to an infinite length, so a norm cache usually holds +inf at [0]: what matters is the
+// entries that norm bytes of the leaf actually select (f / (f + inf) would be a score of exactly 0).
+void refresh_cache_small(rg_engine* e) {
+    const size_t n_caches = e->h_caches.size() / 256;
+    for (Segment& sg : e->segs) {
+        sg.cache_small.assign(n_caches, 1);
+        for (size_t c = 0; c < n_caches; c++)
+            for (int i = 0; i < 256; i++)
+                if (sg.norm_seen[i] && !(e->h_caches[c * 256 + i] >= 0.0f && e->h_caches[c * 256 + i] <= 1e10f)) sg.cache_small[c] = 0;
+    }
 }
 
 }  // namespace rg
@@ -772,6 +787,17 @@ int rg_engine_column_stats(rg_engine* e, uint64_t out[4]) {
     RG_CATCH
 }
 
+int rg_engine_list_stats(rg_engine* e, uint64_t out[4]) {
+    RG_TRY
+    if (!e || !out) throw ArgError("null argument");
+    out[0] = e->list_cache.size();
+    out[1] = e->list_floats * sizeof(float);
+    out[2] = e->list_builds;
+    out[3] = e->list_hits;
+    return RG_OK;
+    RG_CATCH
+}
+
 float rg_engine_last_kernel_ms(rg_engine* e, const char* which) {
     if (!e || !which) return -1.f;
     std::string w(which);
@@ -803,6 +829,7 @@ int rg_segment_upload(rg_engine* e, uint32_t seg_ord, int32_t doc_base, int32_t 
     e->segs.push_back(std::move(seg));
     e->segs_dirty = true;
     e->generation++;  // batches prepared before this upload are stale (rg_batch_run checks)
+    refresh_cache_small(e);
     return RG_OK;
     RG_CATCH
 }
@@ -819,14 +846,23 @@ int rg_norm_cache_set(rg_engine* e, uint32_t cache_id, const float cache[256]) {
     bool nonneg = true;
     for (int i = 0; i < 256; i++) nonneg = nonneg && cache[i] >= 0.0f;  // false for NaN as well
     e->cache_nonneg[cache_id] = nonneg ? 1 : 0;
+    refresh_cache_small(e);
     for (Segment& sg : e->segs)  // and so are the high tf-norm planes of this cache
         for (auto it = sg.tf_planes.begin(); it != sg.tf_planes.end();)
             it = it->first.first == cache_id ? sg.tf_planes.erase(it) : std::next(it);
-    // score columns computed with the previous contents of this cache are no longer valid
+    // score columns / scored lists computed with the previous contents of this cache are no longer valid
     for (auto it = e->col_cache.begin(); it != e->col_cache.end();) {
         if (std::get<3>(it->first) == cache_id) {
             e->col_floats -= it->second->len;
             it = e->col_cache.erase(it);
+        } else {
+            ++it;
+        }
+    }
+    for (auto it = e->list_cache.begin(); it != e->list_cache.end();) {
+        if (std::get<3>(it->first) == cache_id) {
+            e->list_floats -= it->second->len;
+            it = e->list_cache.erase(it);
         } else {
             ++it;
         }

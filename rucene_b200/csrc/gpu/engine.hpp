@@ -65,7 +65,7 @@ struct DevBuf {
     size_t bytes() const { return n * sizeof(T); }
 };
 
-// A score column as the kernels see it: f32 BM25 contribution per leaf-local docid (0xffffffff = no
+// A score column as the kernels see it: f32 BM25 contribution per leaf-local docid (+0.0f = no
 // posting) + the term's presence bitmap (null when the term has none).
 struct ColRef {
     const float* col;
@@ -130,6 +130,8 @@ struct Segment {
     DevBuf<uint32_t> bitmaps;
     uint64_t bitmap_words = 0;
     std::vector<int32_t> bitmap_slot;  // per term: index of its bitmap, -1 = none
+    uint8_t norm_seen[256] = {0};      // norm byte values that occur in this leaf (all zero: the leaf has no norms)
+    std::vector<uint8_t> cache_small;  // per norm cache: every entry a norm byte of this leaf selects is in [0, 1e10]
     std::vector<uint32_t> bitmap_terms;  // slot -> term id
     std::map<std::pair<uint32_t, uint32_t>, TfPlanes> tf_planes;  // (cache id, k1 bits) -> high tf-norm planes
     std::vector<TermHost> host_terms;
@@ -185,6 +187,9 @@ struct ColumnJob {
 };
 void launch_build_columns(cudaStream_t st, const SegDev* segs, const ColumnJob* jobs, uint32_t n_jobs,
                           uint32_t n_units, const float* caches, float k1);
+// scored posting lists: job.dst = uint4[units * 64], unit = block or vint tail of the job's term
+void launch_build_lists(cudaStream_t st, const SegDev* segs, const ColumnJob* jobs, uint32_t n_jobs, uint32_t n_units,
+                        const float* caches, float k1);
 void launch_build_bitmaps(cudaStream_t st, const SegDev* seg, const ColumnJob* jobs, uint32_t n_jobs,
                           uint32_t n_units);
 // jobs carry cache_id.  hist != null: every 8th block of a job adds its postings' factors (rounded up, 256 bins) to
@@ -192,8 +197,10 @@ void launch_build_bitmaps(cudaStream_t st, const SegDev* seg, const ColumnJob* j
 // job.dst + plane_stride when it exceeds job.pad (the bits of tau2).
 void launch_build_tf_planes(cudaStream_t st, const SegDev* segs, const ColumnJob* jobs, uint32_t n_jobs,
                             uint32_t n_units, const float* caches, float k1, uint32_t* hist, size_t plane_stride);
+// recompute Segment::cache_small for every (leaf, norm cache) — after an upload and after rg_norm_cache_set
+void refresh_cache_small(rg_engine* e);
 void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n,
-                    uint32_t max_terms, bool has_live, bool has_not, bool has_msm, bool has_dmax);
+                    uint32_t max_terms, bool has_live, bool has_not, bool has_msm, bool has_dmax, bool all_pos);
 // eval_dpq.cu: disjunctions with >= 10 clauses in a leaf (DisiPriorityQueue order), one warp per (query, leaf)
 void launch_eval_dpq(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, uint32_t max_terms,
                      bool has_live);
@@ -250,6 +257,9 @@ struct rg_engine {
     uint64_t col_floats = 0;            // floats held by map-resident entries
     uint64_t col_budget_floats = 0;     // 0 = not computed yet (reset by rg_segment_upload)
     uint64_t col_tick = 0, col_builds = 0, col_hits = 0;
+    // persistent scored posting lists (same key, same budget and LRU clock as the columns)
+    std::map<rg::ColKey, std::shared_ptr<rg::ColEntry>> list_cache;
+    uint64_t list_floats = 0, list_builds = 0, list_hits = 0;
     uint64_t generation = 1;            // bumped by rg_segment_upload / rg_norm_cache_set (stale-batch check)
     std::vector<uint8_t> cache_nonneg;  // per norm cache: every entry >= 0 (MaxScore bound needs it)
     rg::DevBuf<uint8_t> merge_scratch;  // rg_merge_leaf_records outputs (grow-only)

@@ -117,6 +117,7 @@ k_eval_dpq(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, 
         const TermDev td = seg.terms[c.term_id];
         WTerm& tc = sh.term[lane];
         tc.is_col = 0;
+        tc.pre = nullptr;
         tc.blk_last = seg.blk_last + td.blk_begin;
         tc.blk_desc = seg.blk_desc + td.blk_begin;
         tc.cache = p.caches + (size_t)c.cache_id * 256;

@@ -276,6 +276,7 @@ struct WTerm {
     float w1;           // weight * (k1 + 1)
     uint32_t is_not;    // MUST_NOT clause: its postings exclude docs (search/scorer/req_not_scorer.rs)
     uint32_t is_col;    // score column: blk_last is really a const float* indexed by docid (see k_build_columns)
+    const uint4* pre;   // scored posting list (k_build_columns<4>): 1 KB per block = 128 docids + 128 f32 scores; null = decode
 };
 
 // One posting of a clause lands on window slot idx.  SHOULD clause: clause-order f32 add, first
@@ -290,10 +291,19 @@ struct MsmCtx {
     uint32_t msm;
     float* mx;     // [kWw] per-doc maximum clause score (DMAX variant only)
 };
-template <bool NOT, bool MSM, bool DMAX>
+// POS (only with !NOT, !MSM, !DMAX): every clause score of the launch is > 0, so "no posting yet" is simply
+// the sum +0.0f — the add needs no select, a doc matched iff its sum is non-zero (counted when the window is
+// re-armed), and te is the caller's max(theta, 0).
+template <bool NOT, bool MSM, bool DMAX, bool POS = false>
 __device__ __forceinline__ void accumulate_posting(uint32_t* acc, int idx, float s, bool is_not, bool live,
                                                    float te, uint32_t& hot, uint32_t& my_matches,
                                                    const MsmCtx& mc) {
+    if (POS) {
+        const float sum = __fadd_rn(__uint_as_float(acc[idx]), s);
+        acc[idx] = __float_as_uint(sum);
+        hot |= sum > te ? 1u << (idx >> 5) : 0u;
+        return;
+    }
     const uint32_t old = acc[idx];
     if (!NOT || !is_not) {
         const float sum = __fadd_rn(old == kSent ? 0.0f : __uint_as_float(old), s);
@@ -445,7 +455,7 @@ __device__ __forceinline__ void wtheta_inherit(WEmit& em, const EvalParams& p, u
 // list is exhausted.  Warp-cooperative; all lanes must call it.
 // When called while clause t is being drained into the window [win0, win1) the new block's
 // postings below win1 are accumulated straight from registers (no round trip through the cache).
-template <bool LIVE, bool NOT, bool MSM, bool DMAX>
+template <bool LIVE, bool NOT, bool MSM, bool DMAX, bool POS = false>
 __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParams& p, WTerm& tc, int32_t* cd,
                                            float* cs, int lo, int hi, int lane, int win0, int win1,
                                            uint32_t* acc, uint32_t& hot, uint32_t& my_matches, float te,
@@ -458,7 +468,33 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
         uint32_t next_off16 = 0;  // payload of the block after this one (0: none) — prefetched below
         bool interior = false;    // every posting of the block lies inside [lo, hi)
         bool all_direct = false;  // ... and inside the window being drained
-        if (b < tc.nb) {
+        float sc[4];
+        const uint4* pre = tc.pre;
+        if (pre) {
+            // the clause's postings were decoded and scored once for all batches (scored list): two 16-byte loads
+            // per lane replace unpack + scan + norm gather + division; entries past the end hold kNoMoreDocs
+            if (b < tc.nb) {
+                const int base = b == 0 ? 0 : __ldg(tc.blk_last + b - 1);
+                const int last = __ldg(tc.blk_last + b);
+                interior = (b == 0 ? lo == 0 : base >= lo) && last < hi;
+                all_direct = interior && last < win1;
+            } else {
+                n_in = seg.terms[tc.term_id].tail_n;
+                if (n_in == 0) {
+                    if (lane == 0) tc.cur = tc.nb + 1;
+                    __syncwarp();
+                    return false;
+                }
+            }
+            const uint4* blk = pre + (size_t)b * 64;
+            const uint4 dv = __ldg(blk + lane), sv = __ldg(blk + 32 + lane);
+            docs = make_int4((int)dv.x, (int)dv.y, (int)dv.z, (int)dv.w);
+            sc[0] = __uint_as_float(sv.x);
+            sc[1] = __uint_as_float(sv.y);
+            sc[2] = __uint_as_float(sv.z);
+            sc[3] = __uint_as_float(sv.w);
+            if (b < tc.nb && lane < 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + 64 + lane * 8));
+        } else if (b < tc.nb) {
             const BlockDesc bd = tc.blk_desc[b];
             const int base = b == 0 ? 0 : __ldg(tc.blk_last + b - 1);
             const int last = __ldg(tc.blk_last + b);
@@ -505,8 +541,6 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
             __syncwarp();
         }
         const int d[4] = {docs.x, docs.y, docs.z, docs.w};
-        const int f[4] = {freqs.x, freqs.y, freqs.z, freqs.w};
-        float sc[4];
         uint32_t below = 0, inside = 0, direct = 0;
         const float w1 = tc.w1;
         const float* cache = tc.cache;
@@ -527,18 +561,21 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
                 inside += ok[q];
             }
         }
-        if (norms) {
-            uint32_t nb8[4];
+        if (!pre) {
+            const int f[4] = {freqs.x, freqs.y, freqs.z, freqs.w};
+            if (norms) {
+                uint32_t nb8[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) nb8[q] = __ldg(norms + (ok[q] ? d[q] : lo));
+                for (int q = 0; q < 4; q++) nb8[q] = __ldg(norms + (ok[q] ? d[q] : lo));
 #pragma unroll
-            for (int q = 0; q < 4; q++) nrm[q] = __ldg(cache + nb8[q]);
-        } else {
+                for (int q = 0; q < 4; q++) nrm[q] = __ldg(cache + nb8[q]);
+            } else {
 #pragma unroll
-            for (int q = 0; q < 4; q++) nrm[q] = p.k1;
+                for (int q = 0; q < 4; q++) nrm[q] = p.k1;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) sc[q] = bm25_score(w1, (float)f[q], nrm[q]);
         }
-#pragma unroll
-        for (int q = 0; q < 4; q++) sc[q] = bm25_score(w1, (float)f[q], nrm[q]);
         // pull the next block's payload towards L1 while this one is accumulated (dense clauses come
         // straight back for it).  Prefetching the norm bytes the next block will probably hit, or
         // carrying the next descriptor in shared memory, both measured slower.
@@ -549,7 +586,7 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
         if (all_direct) {  // the common case for dense clauses: nothing to cache, no cursor arithmetic
 #pragma unroll
             for (int q = 0; q < 4; q++)
-                accumulate_posting<NOT, MSM, DMAX>(acc, d[q] - win0, sc[q], neg, LIVE ? is_live(seg, d[q]) : true,
+                accumulate_posting<NOT, MSM, DMAX, POS>(acc, d[q] - win0, sc[q], neg, (LIVE && !POS) ? is_live(seg, d[q]) : true,
                                                    te, hot, my_matches, mc);
             __syncwarp();  // every lane has read tc.cur / tc.nb above
             if (lane == 0) {
@@ -562,7 +599,7 @@ __device__ __forceinline__ bool stream_refill(const SegDev& seg, const EvalParam
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             if (ok[q] && d[q] < win1) {  // still inside the window being drained: accumulate now
-                accumulate_posting<NOT, MSM, DMAX>(acc, d[q] - win0, sc[q], neg, LIVE ? is_live(seg, d[q]) : true,
+                accumulate_posting<NOT, MSM, DMAX, POS>(acc, d[q] - win0, sc[q], neg, (LIVE && !POS) ? is_live(seg, d[q]) : true,
                                                    te, hot, my_matches, mc);
                 direct++;
             }

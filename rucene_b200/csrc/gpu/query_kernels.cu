@@ -36,7 +36,53 @@
 namespace rg {
 
 
-template <bool LIVE, bool NOT, bool MSM, bool DMAX>
+// One score column over one accumulator window: four adjacent docids per lane, one 16-byte
+// read-modify-write of the window per step (no MUST_NOT marker can be present yet: those clauses are
+// drained last).  A column cell is the clause's BM25 contribution, +0.0f where the term has no posting
+// (columns are only built for clauses whose every score is > 0).  Branch-free; only the first and the
+// last window of a range (EDGE) clip by position.
+// POS (every clause score of the launch > 0, plain sum): the window holds +0.0f for "no posting yet", so a
+// column is just added — absent cells add +0.0f — and matches are counted when the window is re-armed.
+template <bool LIVE, bool EDGE, bool POS>
+__device__ __forceinline__ void column_window(uint32_t* acc, const float* __restrict__ col, bool every_doc,
+                                              const SegDev& seg, int win0, int wlen, int first_in, float te, int lane,
+                                              uint32_t& hot, uint32_t& my_matches) {
+#pragma unroll 2
+    for (int i = lane * 4; i < wlen; i += 128) {
+        const int d0 = win0 + i;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(col + d0));
+        float sv[4] = {v.x, v.y, v.z, v.w};
+        const uint4 o4 = *reinterpret_cast<const uint4*>(acc + i);
+        uint32_t o[4] = {o4.x, o4.y, o4.z, o4.w};
+        bool any_hot = false;
+        if (POS) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (EDGE) sv[q] = (i + q >= first_in && i + q < wlen) ? sv[q] : 0.0f;
+                const float sum = __fadd_rn(__uint_as_float(o[q]), sv[q]);
+                o[q] = __float_as_uint(sum);
+                any_hot |= sum > te;
+            }
+        } else {
+            uint32_t live4 = 0xfu;
+            if (LIVE && seg.live) live4 = (uint32_t)(seg.live[d0 >> 6] >> (d0 & 63)) & 0xfu;  // d0 % 4 == 0
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                bool present = every_doc || sv[q] != 0.0f;  // every_doc: the MatchAllDocsQuery column (all cells 0)
+                if (EDGE) present = present && i + q >= first_in && i + q < wlen;
+                const bool fresh = o[q] == kSent;
+                const float sum = __fadd_rn(fresh ? 0.0f : __uint_as_float(o[q]), sv[q]);
+                o[q] = present ? __float_as_uint(sum) : o[q];
+                my_matches += (fresh && present && (!LIVE || ((live4 >> q) & 1u))) ? 1u : 0u;
+                any_hot |= present && sum > te;
+            }
+        }
+        *reinterpret_cast<uint4*>(acc + i) = make_uint4(o[0], o[1], o[2], o[3]);
+        hot |= any_hot ? 1u << (i >> 5) : 0u;
+    }
+}
+
+template <bool LIVE, bool NOT, bool MSM, bool DMAX, bool POS>
 __global__ void __launch_bounds__(kOrThreads, 24)
 k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, uint32_t warp_bytes,
           uint32_t kcap) {
@@ -55,7 +101,7 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
     const int lo = it.lo, hi = it.hi;
     float* cscores = reinterpret_cast<float*>(cdocs + T * kBlock);
 
-    for (int i = lane; i < kWw; i += 32) sh.acc[i] = kSent;
+    for (int i = lane; i < kWw; i += 32) sh.acc[i] = POS ? 0u : kSent;
     MsmCtx mc;
     mc.cnt = reinterpret_cast<uint8_t*>(cscores + T * kBlock);  // MSM variants reserve kWw more bytes
     mc.msm = max(1u, (uint32_t)it.type >> 4);  // items without min_should_match in an MSM launch: 1
@@ -81,12 +127,14 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
         tc.term_id = c.term_id;
         tc.w1 = 0.0f;
         tc.is_not = 0;
-        tc.is_col = 1;
+        tc.is_col = (c.flags & 64u) ? 2 : 1;  // 2: every docid present (MatchAllDocsQuery), cells all 0
+        tc.pre = nullptr;
     } else if (lane < T) {
         const ItemClause c = p.clauses[it.clause_begin + lane];
         const TermDev td = seg.terms[c.term_id];
         WTerm& tc = sh.term[lane];
         tc.is_col = 0;
+        tc.pre = (c.flags & 128u) ? reinterpret_cast<const uint4*>(p.cols[c.flags >> 16].col) : nullptr;
         tc.blk_last = seg.blk_last + td.blk_begin;
         tc.blk_desc = seg.blk_desc + td.blk_begin;
         tc.cache = p.caches + (size_t)c.cache_id * 256;
@@ -102,7 +150,7 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
     uint32_t hot = 0, my_matches = 0;
     int nd = kNoMoreDocs;  // lane t: next cached docid of clause t (kNoMoreDocs = exhausted)
     for (int t = 0; t < T; t++) {
-        if (stream_refill<LIVE, NOT, MSM, DMAX>(seg, p, sh.term[t], cdocs + t * kBlock, cscores + t * kBlock, lo, hi,
+        if (stream_refill<LIVE, NOT, MSM, DMAX, POS>(seg, p, sh.term[t], cdocs + t * kBlock, cscores + t * kBlock, lo, hi,
                                                 lane, 0, -2147483647 - 1, sh.acc, hot, my_matches, INFINITY, mc)) {
             const int first = cdocs[t * kBlock + sh.term[t].pos];
             if (lane == t) nd = first;
@@ -147,7 +195,8 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
         }
         float te = em.theta_local;
         if (em.theta_in > kOrderedNegInf) te = fmaxf(te, ordered_to_float(em.theta_in));
-        const bool open = te == -INFINITY;
+        const bool open = !POS && te == -INFINITY;
+        if (POS) te = fmaxf(te, 0.0f);  // every match scores > 0: "heap still open" needs no case of its own
         // ---- clauses with a posting in this window, in clause order: drain each stream up to the
         // window end (a sparse clause sits out most windows)
         uint32_t active = __ballot_sync(0xffffffffu, nd < win1);
@@ -163,41 +212,24 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                 if (lane < kWw / 32 && win1 + lane * 32 < hi)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(col + win1 + lane * 32));
                 const int first_in = lo - win0;  // > 0 only in the first window of a range
-#pragma unroll 2
-                for (int i = lane * 4; i < wlen; i += 128) {
-                    const int d0 = win0 + i;
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(col + d0));
-                    const float sv[4] = {v.x, v.y, v.z, v.w};
-                    if (MSM || DMAX) {  // per-doc clause counters / maxima: the scalar path
+                const bool every_doc = tc.is_col == 2;
+                if (MSM || DMAX) {  // per-doc clause counters / maxima: the scalar path
+                    for (int i = lane * 4; i < wlen; i += 128) {
+                        const int d0 = win0 + i;
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(col + d0));
+                        const float sv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                         for (int q = 0; q < 4; q++) {
                             const int d = d0 + q;
-                            if (__float_as_uint(sv[q]) != 0xffffffffu && d >= lo && d < win1)
+                            if ((every_doc || sv[q] != 0.0f) && d >= lo && d < win1)
                                 accumulate_posting<NOT, MSM, DMAX>(sh.acc, i + q, sv[q], false,
                                                                    LIVE ? is_live(seg, d) : true, te, hot, my_matches, mc);
                         }
-                        continue;
                     }
-                    // four adjacent docids per lane: one 16-byte read-modify-write of the accumulator window
-                    // (no MUST_NOT marker can be present yet: those clauses are drained last)
-                    uint4 o4 = *reinterpret_cast<const uint4*>(sh.acc + i);
-                    uint32_t o[4] = {o4.x, o4.y, o4.z, o4.w};
-                    uint32_t live4 = 0xfu;
-                    if (LIVE && seg.live) live4 = (uint32_t)(seg.live[d0 >> 6] >> (d0 & 63)) & 0xfu;  // d0 % 4 == 0
-                    bool any_hot = false;
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const bool present = __float_as_uint(sv[q]) != 0xffffffffu && i + q >= first_in && i + q < wlen;
-                        const bool fresh = o[q] == kSent;
-                        const float sum = __fadd_rn(fresh ? 0.0f : __uint_as_float(o[q]), sv[q]);
-                        if (present) {
-                            o[q] = __float_as_uint(sum);
-                            if (fresh && ((live4 >> q) & 1u)) my_matches++;
-                            any_hot |= sum > te;
-                        }
-                    }
-                    *reinterpret_cast<uint4*>(sh.acc + i) = make_uint4(o[0], o[1], o[2], o[3]);
-                    if (any_hot) hot |= 1u << (i >> 5);
+                } else if (first_in > 0 || (wlen & 3)) {  // warp-uniform: first / last window of a range
+                    column_window<LIVE, true, POS>(sh.acc, col, every_doc, seg, win0, wlen, first_in, te, lane, hot, my_matches);
+                } else {
+                    column_window<LIVE, false, POS>(sh.acc, col, every_doc, seg, win0, wlen, first_in, te, lane, hot, my_matches);
                 }
                 if (lane == t) nd = win1 < hi ? win1 : kNoMoreDocs;
                 __syncwarp();
@@ -212,7 +244,7 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                     __syncwarp();  // every lane has read tc.pos / tc.n / tc.cur
                     if (lane == 0) tc.pos = pos;
                     __syncwarp();
-                    if (!stream_refill<LIVE, NOT, MSM, DMAX>(seg, p, tc, cdocs + t * kBlock, cscores + t * kBlock, lo, hi,
+                    if (!stream_refill<LIVE, NOT, MSM, DMAX, POS>(seg, p, tc, cdocs + t * kBlock, cscores + t * kBlock, lo, hi,
                                                              lane, win0, win1, sh.acc, hot, my_matches, te, mc)) {
                         pos = n = 0;
                         break;
@@ -225,8 +257,8 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                 const bool in_win = d < win1;
                 const uint32_t c = __popc(__ballot_sync(0xffffffffu, in_win));  // sorted: a prefix
                 if (in_win)
-                    accumulate_posting<NOT, MSM, DMAX>(sh.acc, d - win0, cs[i], NOT && tc.is_not != 0,
-                                                       LIVE ? is_live(seg, d) : true, te, hot, my_matches, mc);
+                    accumulate_posting<NOT, MSM, DMAX, POS>(sh.acc, d - win0, cs[i], NOT && tc.is_not != 0,
+                                                            (LIVE && !POS) ? is_live(seg, d) : true, te, hot, my_matches, mc);
                 pos += c;
                 if (c < 32 && pos < n) break;  // next cached doc is beyond this window
             }
@@ -256,8 +288,9 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                     const float m = mc.mx[idx];
                     sc = __fadd_rn(m, __fmul_rn(__fsub_rn(sc, m), tie));
                 }
-                const bool cand = v != kSent && (!NOT || v != kExcl) && (open || sc > te) &&
-                                  (!MSM || mc.cnt[idx] >= mc.msm) && (LIVE ? is_live(seg, win0 + idx) : true);
+                const bool cand = POS ? (sc > te && (LIVE ? is_live(seg, win0 + idx) : true))
+                                      : (v != kSent && (!NOT || v != kExcl) && (open || sc > te) &&
+                                         (!MSM || mc.cnt[idx] >= mc.msm) && (LIVE ? is_live(seg, win0 + idx) : true));
                 const uint32_t cm = __ballot_sync(0xffffffffu, cand);
                 if (!cm || em.overflow) continue;
                 const uint32_t c = __popc(cm);
@@ -291,9 +324,27 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                 if (lane == 0) hdr[em.run_slot] = CandRun{kNone, em.run_cnt};
             }
             __syncwarp();
+            if (POS) {
+                // re-arm and count in one pass: a doc of the window matched iff its sum is non-zero
 #pragma unroll
-            for (int g = 0; g < kWw / 128; g++)
-                reinterpret_cast<uint4*>(sh.acc)[g * 32 + lane] = make_uint4(kSent, kSent, kSent, kSent);
+                for (int g = 0; g < kWw / 128; g++) {
+                    const uint4 o = reinterpret_cast<const uint4*>(sh.acc)[g * 32 + lane];
+                    reinterpret_cast<uint4*>(sh.acc)[g * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+                    uint32_t m4 = (o.x != 0u ? 1u : 0u) | (o.y != 0u ? 2u : 0u) | (o.z != 0u ? 4u : 0u) | (o.w != 0u ? 8u : 0u);
+                    if (LIVE && seg.live && m4) {
+                        const int d0 = win0 + (g * 32 + lane) * 4;
+                        uint32_t l4 = 0;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) l4 |= is_live(seg, d0 + q) ? 1u << q : 0u;
+                        m4 &= l4;
+                    }
+                    my_matches += __popc(m4);
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < kWw / 128; g++)
+                    reinterpret_cast<uint4*>(sh.acc)[g * 32 + lane] = make_uint4(kSent, kSent, kSent, kSent);
+            }
             if (MSM) {
                 for (int i = lane; i < kWw / 16; i += 32) reinterpret_cast<uint4*>(mc.cnt)[i] = make_uint4(0, 0, 0, 0);
             }
@@ -471,7 +522,7 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
             const bool neg = sh.is_not[t] != 0;
             const bool opt = REQOPT && sh.is_opt[t] != 0;
             if (const float* col = sh.colp[t]) {
-                // the clause's BM25 contributions sit in a docid-indexed column (0xffffffff = no posting): no skip
+                // the clause's BM25 contributions sit in a docid-indexed column (+0.0f = no posting): no skip
                 // search, no block decode — the same f32 value the stream path would compute
 #pragma unroll
                 for (int r = 0; r < kAndSteps; r++) {
@@ -480,7 +531,7 @@ k_eval_and(EvalParams p, const uint32_t* __restrict__ item_ids) {
                     if (d == kNoMoreDocs) continue;
                     const float v = __ldg(col + d);
                     touched += 4u;
-                    if (__float_as_uint(v) != 0xffffffffu) {
+                    if (v != 0.0f) {
                         if (neg) {
                             sh.ldoc[slot] = kNoMoreDocs;  // ReqNotScorer: excluded
                         } else if (opt) {
@@ -804,12 +855,13 @@ k_merge_leaf_records(const uint8_t* __restrict__ records, uint32_t n_leaves, uin
 // k_build_columns — batch-level common subexpression: the BM25 contributions of a hot, dense
 // (term, weight, norm cache) are the same f32 values for every query of the batch that carries
 // the clause, so they are decoded / gathered / divided ONCE into a docid-indexed f32 column
-// (0xffffffff = no posting) that k_eval_or then reads with 16-byte loads.  One warp per
+// (+0.0f = no posting; only clauses whose every score is > 0 get one) that k_eval_or then reads with 16-byte loads.  One warp per
 // 128-posting block (or vint tail) of a job's term.
 // ------------------------------------------------------------------------------------------
 constexpr int kColWarps = 4;
 // BITMAP = true: the same walk over a term's blocks, but every posting sets its presence bit in the term's
 // bitmap (built once per segment at upload; weight / norms are not touched).
+// MODE 4: scored posting list — per block 128 docids + 128 BM25 scores (1 KB), what stream_refill would compute.
 // MODE 0: score column, 1: presence bitmap, 2: tf-norm planes (bit set when f/(f+norm), rounded up, exceeds the job's
 // tau1 / tau2), 3: histogram of that factor over a sample of the job's blocks
 template <int MODE>
@@ -889,6 +941,20 @@ k_build_columns(const SegDev* __restrict__ segs, const ColumnJob* __restrict__ j
     }
     float* col = static_cast<float*>(job.dst);
     const float w1 = __fmul_rn(job.weight, __fadd_rn(k1, 1.0f));  // as k_eval_or computes it
+    if (MODE == 4) {  // scored list: the block's 128 docids, then its 128 scores (entries past the end: kNoMoreDocs, 0)
+        uint32_t dv[4], sv[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const bool ok = d[q] >= 0 && d[q] < seg.max_doc;
+            const float nrm = seg.norms ? __ldg(cache + __ldg(seg.norms + (ok ? d[q] : 0))) : k1;
+            dv[q] = ok ? (uint32_t)d[q] : (uint32_t)kNoMoreDocs;
+            sv[q] = ok ? __float_as_uint(bm25_score(w1, (float)f[q], nrm)) : 0u;
+        }
+        uint4* blk = static_cast<uint4*>(job.dst) + (size_t)b * 64;
+        blk[lane] = make_uint4(dv[0], dv[1], dv[2], dv[3]);
+        blk[32 + lane] = make_uint4(sv[0], sv[1], sv[2], sv[3]);
+        return;
+    }
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         if (d[q] < 0 || d[q] >= seg.max_doc) continue;
@@ -906,6 +972,12 @@ void launch_build_columns(cudaStream_t st, const SegDev* segs, const ColumnJob* 
     k_build_columns<0><<<(n_units + kColWarps - 1) / kColWarps, kColWarps * 32, 0, st>>>(segs, jobs, n_jobs, n_units,
                                                                                          caches, k1, nullptr, 0);
 }
+void launch_build_lists(cudaStream_t st, const SegDev* segs, const ColumnJob* jobs, uint32_t n_jobs, uint32_t n_units,
+                        const float* caches, float k1) {
+    if (!n_jobs || !n_units) return;
+    k_build_columns<4><<<(n_units + kColWarps - 1) / kColWarps, kColWarps * 32, 0, st>>>(segs, jobs, n_jobs, n_units,
+                                                                                         caches, k1, nullptr, 0);
+}
 // seg: device pointer to ONE SegDev (jobs carry seg = 0)
 void launch_build_bitmaps(cudaStream_t st, const SegDev* seg, const ColumnJob* jobs, uint32_t n_jobs,
                           uint32_t n_units) {
@@ -920,18 +992,19 @@ void launch_build_tf_planes(cudaStream_t st, const SegDev* segs, const ColumnJob
     if (hist) k_build_columns<3><<<ctas, kColWarps * 32, 0, st>>>(segs, jobs, n_jobs, n_units, caches, k1, hist, 0);
     else k_build_columns<2><<<ctas, kColWarps * 32, 0, st>>>(segs, jobs, n_jobs, n_units, caches, k1, nullptr, plane_stride);
 }
-template <bool LIVE, bool NOT, bool MSM, bool DMAX>
+template <bool LIVE, bool NOT, bool MSM, bool DMAX, bool POS = false>
 static void launch_eval_or_t(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n, size_t wb,
                              uint32_t kcap) {
     const size_t smem = wb * kOrWarps;
     // per launch, not cached: the attribute is per device and engines may live on several
-    cudaFuncSetAttribute(k_eval_or<LIVE, NOT, MSM, DMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_eval_or<LIVE, NOT, MSM, DMAX, POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const uint32_t ctas = (n + kOrWarps - 1) / kOrWarps;
-    k_eval_or<LIVE, NOT, MSM, DMAX><<<ctas, kOrThreads, smem, st>>>(p, item_ids, n, (uint32_t)wb, kcap);
+    k_eval_or<LIVE, NOT, MSM, DMAX, POS><<<ctas, kOrThreads, smem, st>>>(p, item_ids, n, (uint32_t)wb, kcap);
 }
-// has_live: some leaf has deleted docs; has_not: some item of the launch carries a MUST_NOT clause
+// has_live: some leaf has deleted docs; has_not: some item of the launch carries a MUST_NOT clause;
+// all_pos: every clause score of every item of the launch is > 0 (the planner checked weights and norm caches)
 void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_ids, uint32_t n,
-                    uint32_t max_terms, bool has_live, bool has_not, bool has_msm, bool has_dmax) {
+                    uint32_t max_terms, bool has_live, bool has_not, bool has_msm, bool has_dmax, bool all_pos) {
     if (!n) return;
     const uint32_t kcap = (std::min<uint32_t>(p.k, kMaxK) + 31u) & ~31u;
     size_t wb = sizeof(WarpShared) + (size_t)kcap * sizeof(float) + (size_t)max_terms * kBlock * 8;
@@ -945,8 +1018,10 @@ void launch_eval_or(cudaStream_t st, const EvalParams& p, const uint32_t* item_i
         wb = (wb + 15) & ~size_t(15);
         launch_eval_or_t<true, true, true, false>(st, p, item_ids, n, wb, kcap);
     } else if (has_live && has_not) launch_eval_or_t<true, true, false, false>(st, p, item_ids, n, wb, kcap);
-    else if (has_live) launch_eval_or_t<true, false, false, false>(st, p, item_ids, n, wb, kcap);
     else if (has_not) launch_eval_or_t<false, true, false, false>(st, p, item_ids, n, wb, kcap);
+    else if (has_live && all_pos) launch_eval_or_t<true, false, false, false, true>(st, p, item_ids, n, wb, kcap);
+    else if (all_pos) launch_eval_or_t<false, false, false, false, true>(st, p, item_ids, n, wb, kcap);
+    else if (has_live) launch_eval_or_t<true, false, false, false>(st, p, item_ids, n, wb, kcap);
     else launch_eval_or_t<false, false, false, false>(st, p, item_ids, n, wb, kcap);
 }
 template <bool REQOPT, bool OTHER>

@@ -50,8 +50,10 @@ struct rg_batch {
     Span<uint32_t> ro_ids;           // MUST+SHOULD (ReqOptScorer) work items: one per (query, leaf)
     Span<ColRef> col_refs;           // score columns this batch reads (ItemClause.term_id indexes it)
     std::vector<std::shared_ptr<ColEntry>> cols;  // keeps them alive (the engine's LRU may drop them meanwhile)
+    std::vector<std::shared_ptr<ColEntry>> lists; // scored posting lists this batch streams, likewise
     uint32_t n_cols_built = 0;       // columns materialised by this rg_batch_prepare (the others were cached)
-    uint64_t col_floats = 0;
+    uint32_t n_lists_built = 0;
+    uint64_t col_floats = 0, list_floats = 0;
     Span<uint32_t> group_item_begin, group_out;
     Span<uint32_t> item_head, item_matches, item_theta, item_topk_n;
     Span<float> item_topk;  // [n_items][kcap] (not zeroed: item_topk_n says what is valid)
@@ -66,7 +68,7 @@ struct rg_batch {
     size_t zero_bytes = 0;
     uint64_t postings = 0, algo_bytes = 0, h2d_bytes = 0;
     uint32_t kernels_per_run = 0;
-    bool or_has_not = false, or_has_msm = false, or_has_dmax = false;
+    bool or_has_not = false, or_has_msm = false, or_has_dmax = false, or_nonpos = false;
     bool ran = false;
 };
 
@@ -79,14 +81,14 @@ struct HostPlan {
     uint32_t max_dpq_terms = 0;
     std::vector<ColRef> col_refs;
     std::map<std::tuple<uint32_t, uint32_t, uint32_t>, uint32_t> bitmap_refs;  // (leaf, term, cache) -> col_refs entry {null, bits, hi}
-    std::vector<std::shared_ptr<ColEntry>> cols;
-    uint32_t n_cols_built = 0, max_ms_streams = 0;
-    uint64_t col_floats = 0;
+    std::vector<std::shared_ptr<ColEntry>> cols, lists;
+    uint32_t n_cols_built = 0, n_lists_built = 0, max_ms_streams = 0;
+    uint64_t col_floats = 0, list_floats = 0;
     std::vector<uint32_t> or_rank, ms_rank, and_rank;  // range index of each id (launch-order key)
     std::vector<uint32_t> group_item_begin, group_out;
     uint64_t postings = 0, algo_bytes = 0;
     uint32_t max_or_terms = 1;
-    bool or_has_not = false, or_has_msm = false, or_has_dmax = false;
+    bool or_has_not = false, or_has_msm = false, or_has_dmax = false, or_nonpos = false;
 };
 
 struct QShape {
@@ -272,6 +274,40 @@ void tf_planes_of(rg_engine* e, uint32_t si, uint32_t term, uint32_t cache_id, f
     ref.tau2 = it->second.tau2[slot];
 }
 
+// Every BM25 contribution w*(k1+1)*f / (f + cache[norm]) of the clause is a finite-or-infinite f32 > 0 (no zero, no
+// negative, no NaN): weight well inside the normal range, 0 <= k1 <= 1e6, the norm cache entries
+// that norm bytes of the leaf select in [0, 1e10] (Segment::cache_small).  Score columns store
+// +0.0f for "no posting", and the plain-sum disjunction kernel tells a match from its non-zero sum.
+static bool scores_positive(const Segment& seg, float w, uint32_t cache_id, float k1) {
+    return w >= 1e-20f && w <= 1e30f && k1 >= 0.0f && k1 <= 1e6f && cache_id < seg.cache_small.size() && seg.cache_small[cache_id];
+}
+
+static void ensure_budget(rg_engine* e) {
+    if (e->col_budget_floats) return;  // once per index state (cudaMemGetInfo costs milliseconds)
+    size_t free_b = 0, total_b = 0;
+    RG_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    e->col_budget_floats = std::max<uint64_t>(1, ((uint64_t)free_b / sizeof(float) + e->col_floats + e->list_floats) / 3);
+}
+
+// Score columns and scored lists share one HBM budget and one LRU clock: drop the least recently used entries no
+// batch references until `len` more floats fit.  (cudaFree synchronises, which also orders it after running kernels.)
+static bool make_room(rg_engine* e, uint64_t len) {
+    while (e->col_floats + e->list_floats + len > e->col_budget_floats) {
+        std::map<ColKey, std::shared_ptr<ColEntry>>* from = nullptr;
+        std::map<ColKey, std::shared_ptr<ColEntry>>::iterator victim;
+        for (auto* m : {&e->col_cache, &e->list_cache})
+            for (auto it = m->begin(); it != m->end(); ++it)
+                if (it->second.use_count() == 1 && (!from || it->second->last_use < victim->second->last_use)) {
+                    from = m;
+                    victim = it;
+                }
+        if (!from) return false;
+        (from == &e->col_cache ? e->col_floats : e->list_floats) -= victim->second->len;
+        from->erase(victim);
+    }
+    return true;
+}
+
 std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape>& shapes, const rg_clause* clauses,
                                           float k1, HostPlan& hp) {
     std::map<ColKey, uint32_t> chosen;
@@ -294,6 +330,7 @@ std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape
                 if (c.term_id >= seg.host_terms.size() || seg.bitmap_slot[c.term_id] < 0) return;
                 if ((uint64_t)seg.host_terms[c.term_id].doc_freq * den < (uint64_t)seg.max_doc) return;
                 const float w = clause_weight(c);
+                if (!scores_positive(seg, w, c.cache_id, k1)) return;  // a column cell of +0.0f means "no posting"
                 uint32_t wbits;
                 memcpy(&wbits, &w, 4);
                 uses[ColKey(si, c.term_id, wbits, c.cache_id, k1bits)]++;
@@ -306,11 +343,7 @@ std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape
         }
     }
     if (uses.empty() && !any_match_all) return chosen;
-    if (e->col_budget_floats == 0) {  // once per index state (cudaMemGetInfo costs milliseconds)
-        size_t free_b = 0, total_b = 0;
-        RG_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-        e->col_budget_floats = std::max<uint64_t>(1, ((uint64_t)free_b / sizeof(float) + e->col_floats) / 3);
-    }
+    ensure_budget(e);
     auto add_ref = [&](const ColKey& key, const std::shared_ptr<ColEntry>& ent) {
         ent->last_use = ++e->col_tick;
         chosen[key] = (uint32_t)hp.col_refs.size();
@@ -360,16 +393,7 @@ std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape
         if (hp.col_refs.size() >= 4096) break;
         const Segment& seg = e->segs[std::get<0>(r.second)];
         const uint64_t len = ((uint64_t)seg.max_doc + 1024 + 3) & ~3ull;  // windows read past max_doc
-        while (e->col_floats + len > e->col_budget_floats) {  // evict the least recently used unreferenced column
-            auto victim = e->col_cache.end();
-            for (auto it = e->col_cache.begin(); it != e->col_cache.end(); ++it)
-                if (it->second.use_count() == 1 && (victim == e->col_cache.end() || it->second->last_use < victim->second->last_use))
-                    victim = it;
-            if (victim == e->col_cache.end()) break;
-            e->col_floats -= victim->second->len;
-            e->col_cache.erase(victim);  // cudaFree: synchronises, which also orders it after running kernels
-        }
-        if (e->col_floats + len > e->col_budget_floats) break;
+        if (!make_room(e, len)) break;
         auto ent = std::make_shared<ColEntry>();
         ent->key = r.second;
         ent->len = len;
@@ -380,7 +404,7 @@ std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape
         }
         const TermHost& th = seg.host_terms[std::get<1>(r.second)];
         ent->bits = seg.bitmaps.p + (size_t)seg.bitmap_slot[std::get<1>(r.second)] * seg.bitmap_words;
-        RG_CUDA_CHECK(cudaMemsetAsync(ent->col, 0xff, len * sizeof(float), st));
+        RG_CUDA_CHECK(cudaMemsetAsync(ent->col, 0, len * sizeof(float), st));
         ColumnJob job{};
         job.seg = std::get<0>(r.second);
         job.term_id = std::get<1>(r.second);
@@ -409,6 +433,111 @@ std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape
     return chosen;
 }
 
+// Scored posting lists.  A disjunction clause that stays a block stream costs, per query that carries it: unpack the
+// doc and freq blocks, a warp scan, one norm-byte gather + one cache load + one IEEE division per posting.  None of
+// that depends on the query beyond (term, weight, norm cache, k1) — so a clause two queries of a batch share (or that
+// an earlier batch left behind) is decoded and scored ONCE into (docid, f32 score) pairs, 1 KB per 128-posting block in
+// block order, and k_eval_or streams those: two 16-byte loads per lane and block.  Exactly the values stream_refill
+// would compute (same instructions, same order), so the results do not change.  8 bytes per posting: the whole
+// 100 M-doc benchmark index would be 10.7 GB; the budget / LRU is the columns'.  RG_CFG_NO_LISTS turns it off.
+constexpr uint32_t kListMinDf = 4096;  // shorter lists are a few blocks per query: not worth a cache entry (eager: 256)
+std::map<ColKey, uint32_t> choose_lists(rg_engine* e, const std::vector<QShape>& shapes, const rg_clause* clauses, float k1,
+                                        const std::map<ColKey, uint32_t>& columns, HostPlan& hp) {
+    std::map<ColKey, uint32_t> chosen;
+    if (e->cfg.flags & (RG_CFG_NO_LISTS | RG_CFG_MAXSCORE)) return chosen;  // (k_eval_or_ms seeks inside blocks: not wired)
+    const bool eager = (e->cfg.flags & RG_CFG_EAGER_COLUMNS) != 0;
+    const uint32_t min_uses = eager ? 1u : 2u;
+    const uint64_t min_df = eager ? 256u : kListMinDf;
+    uint32_t k1bits;
+    memcpy(&k1bits, &k1, 4);
+    std::map<ColKey, uint32_t> uses;
+    for (const QShape& sh : shapes) {
+        if (sh.type != kTypeOr || sh.match_all || sh.clause_idx.size() >= 10) continue;  // (>= 10: k_eval_dpq)
+        for (uint32_t si = 0; si < e->segs.size(); si++) {
+            const Segment& seg = e->segs[si];
+            for (uint32_t ci : sh.clause_idx) {
+                const rg_clause& c = clauses[ci];
+                if (c.term_id >= seg.host_terms.size()) continue;
+                const uint64_t df = (uint64_t)seg.host_terms[c.term_id].doc_freq;
+                if (df < min_df) continue;
+                const float w = clause_weight(c);
+                uint32_t wbits;
+                memcpy(&wbits, &w, 4);
+                const ColKey key(si, c.term_id, wbits, c.cache_id, k1bits);
+                if (df * 8u >= (uint64_t)seg.max_doc && columns.count(key)) continue;  // read from its score column
+                uses[key]++;
+            }
+        }
+    }
+    if (uses.empty()) return chosen;
+    ensure_budget(e);
+    auto add_ref = [&](const ColKey& key, const std::shared_ptr<ColEntry>& ent) {
+        if (hp.col_refs.size() >= 65536) return;  // ItemClause.flags carries the reference in 16 bits
+        ent->last_use = ++e->col_tick;
+        chosen[key] = (uint32_t)hp.col_refs.size();
+        hp.col_refs.push_back(ColRef{ent->col, nullptr, nullptr, nullptr, 1.0f, 1.0f});
+        hp.lists.push_back(ent);
+        hp.list_floats += ent->len;
+    };
+    std::vector<std::pair<uint64_t, ColKey>> to_build;
+    for (const auto& kv : uses) {
+        const auto it = e->list_cache.find(kv.first);
+        if (it != e->list_cache.end()) {
+            e->list_hits++;
+            add_ref(kv.first, it->second);
+        } else if (kv.second >= min_uses) {
+            const Segment& seg = e->segs[std::get<0>(kv.first)];
+            to_build.emplace_back((uint64_t)kv.second * (uint64_t)seg.host_terms[std::get<1>(kv.first)].doc_freq, kv.first);
+        }
+    }
+    std::sort(to_build.begin(), to_build.end(), [](const auto& x, const auto& y) { return x.first > y.first; });
+    std::vector<ColumnJob> jobs;
+    uint32_t n_units = 0;
+    cudaStream_t st = e->stream;
+    for (const auto& r : to_build) {
+        if (hp.col_refs.size() >= 65536) break;
+        const Segment& seg = e->segs[std::get<0>(r.second)];
+        const TermHost& th = seg.host_terms[std::get<1>(r.second)];
+        const uint32_t units = th.n_blocks + 1u;  // + the vint tail (or an unused unit the last block's prefetch may touch)
+        const uint64_t len = (uint64_t)units * 256u;
+        if ((uint64_t)n_units + units > 0x7fffffffu) break;
+        if (!make_room(e, len)) break;
+        auto ent = std::make_shared<ColEntry>();
+        ent->key = r.second;
+        ent->len = len;
+        if (cudaMalloc(reinterpret_cast<void**>(&ent->col), len * sizeof(float)) != cudaSuccess) {
+            cudaGetLastError();
+            ent->col = nullptr;
+            break;
+        }
+        ColumnJob job{};
+        job.seg = std::get<0>(r.second);
+        job.term_id = std::get<1>(r.second);
+        const uint32_t wbits = std::get<2>(r.second);
+        memcpy(&job.weight, &wbits, 4);
+        job.cache_id = std::get<3>(r.second);
+        job.dst = ent->col;
+        job.unit_begin = n_units;
+        n_units += th.n_blocks + (th.tail_n ? 1u : 0u);
+        jobs.push_back(job);
+        e->list_cache[r.second] = ent;
+        e->list_floats += len;
+        e->list_builds++;
+        add_ref(r.second, ent);
+    }
+    if (!jobs.empty()) {
+        DevBuf<ColumnJob> d_jobs;
+        d_jobs.alloc(jobs.size());
+        RG_CUDA_CHECK(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(ColumnJob), cudaMemcpyHostToDevice, st));
+        launch_build_lists(st, e->d_segs.p, d_jobs.p, (uint32_t)jobs.size(), n_units, e->d_caches.p, k1);
+        RG_CUDA_CHECK(cudaGetLastError());
+        RG_CUDA_CHECK(cudaStreamSynchronize(st));  // d_jobs goes out of scope
+        e->launches++;
+        hp.n_lists_built = (uint32_t)jobs.size();
+    }
+    return chosen;
+}
+
 void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const rg_clause* clauses,
                 uint32_t n_clauses, uint32_t mode, float k1, HostPlan& hp) {
     const uint32_t n_caches = (uint32_t)(e->h_caches.size() / 256);
@@ -426,6 +555,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
             if (clauses[ci].cache_id >= n_caches) throw ArgError("clause refers to an unset norm cache");
     }
     const std::map<ColKey, uint32_t> columns = choose_columns(e, shapes, clauses, k1, hp);
+    const std::map<ColKey, uint32_t> lists = choose_lists(e, shapes, clauses, k1, columns, hp);
     uint32_t k1bits;
     memcpy(&k1bits, &k1, 4);
     const bool no_ms = (e->cfg.flags & RG_CFG_MAXSCORE) == 0;
@@ -516,11 +646,13 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
             auto df_of = [&](uint32_t ci) { return (uint64_t)seg.host_terms[clauses[ci].term_id].doc_freq; };
             bool use_ms = false;
             uint32_t n_streams = 0;
+            bool item_pos = !shape.match_all;  // every clause score > 0: the plain-sum kernel variant applies
+            for (uint32_t ci : present) item_pos = item_pos && scores_positive(seg, clause_weight(clauses[ci]), clauses[ci].cache_id, k1);
             if (shape.match_all) {
                 // the leaf's match-all column (every docid present, score 0) + the MUST_NOT streams: k_eval_or<NOT>
                 const auto it = columns.find(ColKey(si, kMatchAllTerm, 0u, 0u, 0u));
                 if (it == columns.end()) throw Unsupported("no memory for the MatchAllDocsQuery column");
-                lp.clauses.push_back(ItemClause{it->second, 0.0f, 0u, 4u | 16u});
+                lp.clauses.push_back(ItemClause{it->second, 0.0f, 0u, 4u | 16u | 64u});  // 64: every docid present
             } else if (leaf_dpq) {
                 for (uint32_t ci : present) lp.clauses.push_back(ItemClause{clauses[ci].term_id, clause_weight(clauses[ci]), clauses[ci].cache_id, 0});
             } else if (shape.type == kTypeOr) {
@@ -548,6 +680,12 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                     }
                     n_streams++;
                     uint32_t flags = 0;
+                    if (!use_ms && !lists.empty()) {  // a scored list of this clause: streamed instead of decoded
+                        uint32_t wbits;
+                        memcpy(&wbits, &w, 4);
+                        const auto lt = lists.find(ColKey(si, c.term_id, wbits, c.cache_id, k1bits));
+                        if (lt != lists.end()) flags = 128u | (lt->second << 16);
+                    }
                     if (use_ms && seg.bitmap_slot[c.term_id] >= 0) {  // a block stream whose presence comes from its bitmap
                         const auto key = std::make_tuple(si, c.term_id, c.cache_id);
                         std::lock_guard<std::mutex> lock(refs_mutex);  // the reference table is shared by the planner threads
@@ -629,6 +767,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                     lp.or_rank.push_back((uint32_t)r);
                     lp.max_or_terms = std::max<uint32_t>(lp.max_or_terms, n_item_terms);
                     if (!nots.empty()) lp.or_has_not = true;
+                    if (!item_pos) lp.or_nonpos = true;
                     if (shape.msm) lp.or_has_msm = true;
                     if (leaf_dismax) lp.or_has_dmax = true;
                 }
@@ -678,6 +817,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
             hp.max_ms_streams = std::max(hp.max_ms_streams, lp.max_ms_streams);
             hp.max_dpq_terms = std::max(hp.max_dpq_terms, lp.max_dpq_terms);
             hp.or_has_not = hp.or_has_not || lp.or_has_not;
+            hp.or_nonpos = hp.or_nonpos || lp.or_nonpos;
             hp.or_has_msm = hp.or_has_msm || lp.or_has_msm;
             hp.or_has_dmax = hp.or_has_dmax || lp.or_has_dmax;
         }
@@ -748,7 +888,10 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     std::unique_ptr<rg_batch> b(new rg_batch());
     b->generation = e->generation;
     b->cols = std::move(hp.cols);
+    b->lists = std::move(hp.lists);
     b->n_cols_built = hp.n_cols_built;
+    b->n_lists_built = hp.n_lists_built;
+    b->list_floats = hp.list_floats;
     b->col_floats = hp.col_floats;
     b->n_ms = (uint32_t)hp.ms_ids.size();
     b->max_ms_streams = hp.max_ms_streams;
@@ -766,6 +909,7 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     b->n_groups = (uint32_t)hp.group_out.size();
     b->max_or_terms = hp.max_or_terms;
     b->or_has_not = hp.or_has_not;
+    b->or_nonpos = hp.or_nonpos;
     b->or_has_msm = hp.or_has_msm;
     b->or_has_dmax = hp.or_has_dmax;
     b->n_leaves = (uint32_t)e->segs.size();
@@ -883,7 +1027,8 @@ int rg_batch_run(rg_engine* e, rg_batch* b) {
     }
     launch_eval_or_ms(st, ep, b->ms_ids.p, b->n_ms, b->max_ms_streams, has_live, b->uses_planes);
     RG_CUDA_CHECK(cudaGetLastError());
-    launch_eval_or(st, ep, b->or_ids.p, b->n_or, b->max_or_terms, has_live, b->or_has_not, b->or_has_msm, b->or_has_dmax);
+    launch_eval_or(st, ep, b->or_ids.p, b->n_or, b->max_or_terms, has_live, b->or_has_not, b->or_has_msm, b->or_has_dmax,
+                   !b->or_nonpos);
     RG_CUDA_CHECK(cudaGetLastError());
     launch_eval_dpq(st, ep, b->dpq_ids.p, b->n_dpq, b->max_dpq_terms, has_live);
     RG_CUDA_CHECK(cudaGetLastError());

@@ -15,7 +15,7 @@ MUST, SHOULD, MUST_NOT, FILTER = 0, 1, 2, 3
 Q_BOOLEAN = 1
 Q_DISMAX = 2    # rg_query.flags: DisjunctionMaxQuery; min_should_match = bits of the f32 tie breaker
 MODE_SEARCH, MODE_SEARCH_PARALLEL = 0, 1
-CFG_NO_COLUMNS, CFG_EAGER_COLUMNS, CFG_NO_BITMAPS, CFG_MAXSCORE, CFG_STATS, CFG_TFPLANES = 1, 2, 4, 8, 16, 32   # rg_config.flags (include/rucene_gpu.h)
+CFG_NO_COLUMNS, CFG_EAGER_COLUMNS, CFG_NO_BITMAPS, CFG_MAXSCORE, CFG_STATS, CFG_TFPLANES, CFG_NO_LISTS = 1, 2, 4, 8, 16, 32, 64   # rg_config.flags (include/rucene_gpu.h)
 NO_MORE_DOCS = 0x7FFFFFFF
 
 TERM_STATE_DTYPE = np.dtype([("doc_freq", "<i4"), ("singleton_doc_id", "<i4"),
@@ -67,6 +67,7 @@ def lib():
     L.rg_engine_set_stream.argtypes = [vp, vp]
     L.rg_engine_set_flags.argtypes = [vp, C.c_uint32]
     L.rg_engine_column_stats.argtypes = [vp, vp]
+    L.rg_engine_list_stats.argtypes = [vp, vp]
     L.rg_engine_launch_count.restype = C.c_uint64
     L.rg_engine_launch_count.argtypes = [vp]
     L.rg_engine_last_kernel_ms.restype = C.c_float
@@ -244,6 +245,12 @@ class Engine:
     def column_stats(self):
         out = np.zeros(4, np.uint64)
         _check(lib().rg_engine_column_stats(self.h, _p(out)), self.h)
+        return {"cached": int(out[0]), "bytes": int(out[1]), "built": int(out[2]), "hits": int(out[3])}
+
+    def list_stats(self):
+        """persistent scored posting lists (RG_CFG_NO_LISTS turns them off)"""
+        out = np.zeros(4, np.uint64)
+        _check(lib().rg_engine_list_stats(self.h, _p(out)), self.h)
         return {"cached": int(out[0]), "bytes": int(out[1]), "built": int(out[2]), "hits": int(out[3])}
 
     def launch_count(self):

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Join an ncu report's per-instruction stall samples with source lines (-lineinfo).
-usage: ncu_hotspots.py <report.ncu-rep> <lib.so> <kernel-substring> [top_n]
+usage: ncu_hotspots.py <report.ncu-rep> <lib.so> <substring of the MANGLED kernel name, e.g. 9k_eval_orILb0ELb0E> [top_n]
 Prints the source lines with the most stall samples / executed instructions."""
 import csv
 import io

@@ -117,6 +117,8 @@ def test_columns_persist_across_batches_and_follow_the_norm_cache():
         _check(s, ix, b, 10, "second batch")
         st2 = s.engine.column_stats()
         assert st2["hits"] > st1["hits"]          # columns of the first batch were reused
+        l1 = s.engine.list_stats()
+        assert l1["built"] > 0 and l1["hits"] > 0  # and so were the scored posting lists of its mid-frequency clauses
         # a batch prepared before the cache changes must not run afterwards
         q, c = s.compile_batch(helpers.to_queries(a))
         stale = s.engine.prepare(q, c, 10)
@@ -127,8 +129,10 @@ def test_columns_persist_across_batches_and_follow_the_norm_cache():
             stale.run()
         stale.close()
         assert s.engine.column_stats()["cached"] == 0
+        assert s.engine.list_stats()["cached"] == 0
         ix2 = helpers.oracle_index([seg], b=0.3)
         _check(s, ix2, b, 10, "after the norm cache changed")
+        assert s.engine.list_stats()["cached"] > 0
     finally:
         s.engine.close()
 
@@ -235,3 +239,57 @@ def test_abi_rejects_bad_clause_and_corrupt_index_fields():
             e2.close()
     finally:
         eng.close()
+
+
+def test_zero_score_matches_stay_on_the_general_disjunction_kernel():
+    """Lucene's norm table maps norm byte 0 to an infinite field length, so such a doc's BM25 contribution is exactly
+    0f32: it still matches (total_hits, and it is collected while the heap is not full).  The plain-sum kernel
+    variant tells matches by a non-zero sum and score columns use +0.0f for "no posting" — both must step aside for a
+    leaf whose norms select such a cache entry, and for zero / negative boosts."""
+    seg = codec.synth_segment(0x5EED0077, 120000, 1500, doc_version=1)
+    seg.norms[::5] = 0
+    ix = helpers.oracle_index([seg])
+    rng = np.random.default_rng(77)
+    specs = _or_specs(rng, 1500, 40) + [("term", 0), ("term", 900),
+                                         ("bool", [(ob.SHOULD, 0, 0.0), (ob.SHOULD, 5, 0.0)], 0),
+                                         ("bool", [(ob.SHOULD, 2, 1e-30), (ob.SHOULD, 700, 1e-30)], 0)]
+    for flags in (0, engine.CFG_EAGER_COLUMNS, engine.CFG_EAGER_COLUMNS | engine.CFG_MAXSCORE):
+        s = search.GpuIndexSearcher(search.IndexReader([seg]), range_postings=5000, flags=flags)
+        try:
+            for k in (3, 1000):
+                _check(s, ix, specs, k, "zero scores flags=%d k=%d" % (flags, k))
+            assert s.engine.column_stats()["cached"] == 0  # no clause of this leaf is provably positive
+        finally:
+            s.engine.close()
+    # the same queries over a leaf with ordinary norms: columns are built and the plain-sum variant runs
+    seg2 = codec.synth_segment(0x5EED0077, 120000, 1500, doc_version=1)
+    ix2 = helpers.oracle_index([seg2])
+    s = search.GpuIndexSearcher(search.IndexReader([seg2]), range_postings=5000, flags=engine.CFG_EAGER_COLUMNS)
+    try:
+        _check(s, ix2, specs, 10, "ordinary norms")
+        assert s.engine.column_stats()["cached"] > 0
+    finally:
+        s.engine.close()
+
+
+def test_scored_lists_every_block_layout_and_tails():
+    """Scored posting lists (k_build_columns<4>) must reproduce stream_refill for PF / EF / BITSET doc blocks, both
+    .doc versions, vint tails, docid ranges that cut blocks, live docs and several leaves; with and without them the
+    TopDocs are the oracle's."""
+    rng = np.random.default_rng(404)
+    dfs = [40000, 25000, 12000, 6000, 3000, 1500, 700, 385, 300, 129, 128, 127, 5]
+    for version, use_ef in ((1, False), (0, False), (1, True)):
+        segs = []
+        for i in range(2):
+            seg, _ = helpers.build_segment(rng, 50000, dfs, doc_version=version, use_ef=use_ef, live_fraction=0.9 if i else None)
+            segs.append(seg)
+        ix = helpers.oracle_index(segs)
+        specs = [("term", t) for t in range(len(dfs))] + _or_specs(rng, len(dfs), 60, 2, 6)
+        for flags in (engine.CFG_EAGER_COLUMNS, engine.CFG_EAGER_COLUMNS | engine.CFG_NO_COLUMNS, engine.CFG_NO_LISTS):
+            for mode in (0, 1):
+                s = search.GpuIndexSearcher(search.IndexReader(segs), range_postings=3000, flags=flags)
+                try:
+                    _check(s, ix, specs, 20, "lists v%d ef%d flags=%d mode=%d" % (version, use_ef, flags, mode), mode=mode)
+                    assert (s.engine.list_stats()["cached"] > 0) == (not flags & engine.CFG_NO_LISTS)
+                finally:
+                    s.engine.close()

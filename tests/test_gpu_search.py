@@ -35,10 +35,12 @@ def _run_both(segs, specs, k, mode=0, range_postings=0, threads=4, extra_flags=0
     want = ix.search_batch(q, c, k, parallel_mode=mode, n_threads=threads)
     # every evaluation route must equal the oracle: a score column for every clause of df >= max_doc/64
     # (k_eval_or_ms: presence bitmaps + bit-sliced per-document bound), the same with tf-norm planes, the same
-    # columns read by the exhaustive kernel, no bitmaps / columns at all (block streams only), the planner's choice
+    # columns read by the exhaustive kernel (every other disjunction clause of df >= 256 streamed from its scored
+    # list), the same without lists, no bitmaps / columns / lists at all (block streams only), the planner's choice
     got = None
     for flags in (engine.CFG_EAGER_COLUMNS | engine.CFG_MAXSCORE, engine.CFG_EAGER_COLUMNS | engine.CFG_MAXSCORE | engine.CFG_TFPLANES,
-                  engine.CFG_EAGER_COLUMNS, engine.CFG_NO_BITMAPS, engine.CFG_MAXSCORE, 0):
+                  engine.CFG_EAGER_COLUMNS, engine.CFG_EAGER_COLUMNS | engine.CFG_NO_LISTS,
+                  engine.CFG_NO_BITMAPS | engine.CFG_NO_LISTS, engine.CFG_MAXSCORE, 0):
         s = search.GpuIndexSearcher(search.IndexReader(segs), range_postings=range_postings,
                                     flags=flags | extra_flags)
         try:
