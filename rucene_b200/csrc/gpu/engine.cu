@@ -740,6 +740,7 @@ int rg_engine_create(const rg_config* cfg, rg_engine** out) {
     RG_CUDA_CHECK(cudaEventCreate(&e->ev2));
     RG_CUDA_CHECK(cudaEventCreate(&e->ev3));
     if (e->cfg.range_postings == 0) e->cfg.range_postings = 1u << 15;  // one warp per work item
+    if (const char* v = getenv("RG_OR_COL_DEN")) e->or_col_den = std::max(1, atoi(v));  // tuning knob (bench sweeps)
     *out = e.release();
     return RG_OK;
     RG_CATCH

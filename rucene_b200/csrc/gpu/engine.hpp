@@ -260,6 +260,9 @@ struct rg_engine {
     // persistent scored posting lists (same key, same budget and LRU clock as the columns)
     std::map<rg::ColKey, std::shared_ptr<rg::ColEntry>> list_cache;
     uint64_t list_floats = 0, list_builds = 0, list_hits = 0;
+    // the exhaustive disjunction kernel scans a score column docid by docid: that beats streaming the clause's postings
+    // only for df >= max_doc / or_col_den
+    uint64_t or_col_den = 8;
     uint64_t generation = 1;            // bumped by rg_segment_upload / rg_norm_cache_set (stale-batch check)
     std::vector<uint8_t> cache_nonneg;  // per norm cache: every entry >= 0 (MaxScore bound needs it)
     rg::DevBuf<uint8_t> merge_scratch;  // rg_merge_leaf_records outputs (grow-only)

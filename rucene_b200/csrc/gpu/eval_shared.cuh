@@ -292,16 +292,14 @@ struct MsmCtx {
     float* mx;     // [kWw] per-doc maximum clause score (DMAX variant only)
 };
 // POS (only with !NOT, !MSM, !DMAX): every clause score of the launch is > 0, so "no posting yet" is simply
-// the sum +0.0f — the add needs no select, a doc matched iff its sum is non-zero (counted when the window is
-// re-armed), and te is the caller's max(theta, 0).
+// the sum +0.0f — the add needs no select; a doc matched iff its sum is non-zero, and the window epilogue counts
+// the matches and finds the sums above theta in one pass over the finished window.
 template <bool NOT, bool MSM, bool DMAX, bool POS = false>
 __device__ __forceinline__ void accumulate_posting(uint32_t* acc, int idx, float s, bool is_not, bool live,
                                                    float te, uint32_t& hot, uint32_t& my_matches,
                                                    const MsmCtx& mc) {
     if (POS) {
-        const float sum = __fadd_rn(__uint_as_float(acc[idx]), s);
-        acc[idx] = __float_as_uint(sum);
-        hot |= sum > te ? 1u << (idx >> 5) : 0u;
+        acc[idx] = __float_as_uint(__fadd_rn(__uint_as_float(acc[idx]), s));
         return;
     }
     const uint32_t old = acc[idx];

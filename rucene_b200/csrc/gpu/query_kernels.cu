@@ -42,11 +42,29 @@ namespace rg {
 // (columns are only built for clauses whose every score is > 0).  Branch-free; only the first and the
 // last window of a range (EDGE) clip by position.
 // POS (every clause score of the launch > 0, plain sum): the window holds +0.0f for "no posting yet", so a
-// column is just added — absent cells add +0.0f — and matches are counted when the window is re-armed.
+// column is just added — absent cells add +0.0f; matches are counted and the docs above theta found by the
+// window epilogue.
 template <bool LIVE, bool EDGE, bool POS>
 __device__ __forceinline__ void column_window(uint32_t* acc, const float* __restrict__ col, bool every_doc,
                                               const SegDev& seg, int win0, int wlen, int first_in, float te, int lane,
                                               uint32_t& hot, uint32_t& my_matches) {
+    if (POS && !EDGE && wlen == kWw) {
+        // a whole window: three 16-byte column loads of the lane are in flight before the first is used (the column
+        // comes from L2 / HBM; six at once would spill)
+#pragma unroll
+        for (int h = 0; h < kWw / 128; h += 3) {
+            float4 v[3];
+#pragma unroll
+            for (int j = 0; j < 3; j++) v[j] = __ldg(reinterpret_cast<const float4*>(col + win0 + lane * 4 + (h + j) * 128));
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                float4* a = reinterpret_cast<float4*>(acc + lane * 4 + (h + j) * 128);
+                const float4 o = *a;
+                *a = make_float4(__fadd_rn(o.x, v[j].x), __fadd_rn(o.y, v[j].y), __fadd_rn(o.z, v[j].z), __fadd_rn(o.w, v[j].w));
+            }
+        }
+        return;
+    }
 #pragma unroll 2
     for (int i = lane * 4; i < wlen; i += 128) {
         const int d0 = win0 + i;
@@ -55,13 +73,11 @@ __device__ __forceinline__ void column_window(uint32_t* acc, const float* __rest
         const uint4 o4 = *reinterpret_cast<const uint4*>(acc + i);
         uint32_t o[4] = {o4.x, o4.y, o4.z, o4.w};
         bool any_hot = false;
-        if (POS) {
+        if (POS) {  // (the window epilogue finds the docs above theta)
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 if (EDGE) sv[q] = (i + q >= first_in && i + q < wlen) ? sv[q] : 0.0f;
-                const float sum = __fadd_rn(__uint_as_float(o[q]), sv[q]);
-                o[q] = __float_as_uint(sum);
-                any_hot |= sum > te;
+                o[q] = __float_as_uint(__fadd_rn(__uint_as_float(o[q]), sv[q]));
             }
         } else {
             uint32_t live4 = 0xfu;
@@ -78,7 +94,7 @@ __device__ __forceinline__ void column_window(uint32_t* acc, const float* __rest
             }
         }
         *reinterpret_cast<uint4*>(acc + i) = make_uint4(o[0], o[1], o[2], o[3]);
-        hot |= any_hot ? 1u << (i >> 5) : 0u;
+        if (!POS) hot |= any_hot ? 1u << (i >> 5) : 0u;
     }
 }
 
@@ -272,10 +288,32 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
             __syncwarp();
         }
         const int next_doc = __reduce_min_sync(0xffffffffu, nd);
+        if (POS) {
+            // one pass over the finished window: a doc matched iff its sum is non-zero (every clause score is > 0), and
+            // a 32-doc step is scanned for candidates iff one of its sums beats theta
+            hot = 0;
+#pragma unroll
+            for (int g = 0; g < kWw / 128; g++) {
+                const uint4 o = reinterpret_cast<const uint4*>(sh.acc)[g * 32 + lane];
+                if (LIVE && seg.live) {
+                    uint32_t m4 = (o.x != 0u ? 1u : 0u) | (o.y != 0u ? 2u : 0u) | (o.z != 0u ? 4u : 0u) | (o.w != 0u ? 8u : 0u);
+                    if (m4) {
+                        const int d0 = win0 + (g * 32 + lane) * 4;
+                        uint32_t l4 = 0;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) l4 |= is_live(seg, d0 + q) ? 1u << q : 0u;
+                        m4 &= l4;
+                    }
+                    my_matches += __popc(m4);
+                } else {
+                    my_matches += min(o.x, 1u) + min(o.y, 1u) + min(o.z, 1u) + min(o.w, 1u);
+                }
+                const float mx = fmaxf(fmaxf(__uint_as_float(o.x), __uint_as_float(o.y)),
+                                       fmaxf(__uint_as_float(o.z), __uint_as_float(o.w)));
+                hot |= mx > te ? 1u << (g * 4 + (lane >> 3)) : 0u;
+            }
+        }
         hot = __reduce_or_sync(0xffffffffu, hot);
-        // ---- window epilogue.  Matches were counted when a doc was first touched; only 32-doc
-        // steps holding a doc whose (partial) sum exceeded theta are scanned for candidates, then
-        // the whole window is re-armed with eight 16-byte stores per lane.
         {
             uint32_t newc_n = 0;
             while (hot) {
@@ -324,26 +362,10 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                 if (lane == 0) hdr[em.run_slot] = CandRun{kNone, em.run_cnt};
             }
             __syncwarp();
-            if (POS) {
-                // re-arm and count in one pass: a doc of the window matched iff its sum is non-zero
 #pragma unroll
-                for (int g = 0; g < kWw / 128; g++) {
-                    const uint4 o = reinterpret_cast<const uint4*>(sh.acc)[g * 32 + lane];
-                    reinterpret_cast<uint4*>(sh.acc)[g * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
-                    uint32_t m4 = (o.x != 0u ? 1u : 0u) | (o.y != 0u ? 2u : 0u) | (o.z != 0u ? 4u : 0u) | (o.w != 0u ? 8u : 0u);
-                    if (LIVE && seg.live && m4) {
-                        const int d0 = win0 + (g * 32 + lane) * 4;
-                        uint32_t l4 = 0;
-#pragma unroll
-                        for (int q = 0; q < 4; q++) l4 |= is_live(seg, d0 + q) ? 1u << q : 0u;
-                        m4 &= l4;
-                    }
-                    my_matches += __popc(m4);
-                }
-            } else {
-#pragma unroll
-                for (int g = 0; g < kWw / 128; g++)
-                    reinterpret_cast<uint4*>(sh.acc)[g * 32 + lane] = make_uint4(kSent, kSent, kSent, kSent);
+            for (int g = 0; g < kWw / 128; g++) {
+                const uint32_t z = POS ? 0u : kSent;
+                reinterpret_cast<uint4*>(sh.acc)[g * 32 + lane] = make_uint4(z, z, z, z);
             }
             if (MSM) {
                 for (int i = lane; i < kWw / 16; i += 32) reinterpret_cast<uint4*>(mc.cnt)[i] = make_uint4(0, 0, 0, 0);

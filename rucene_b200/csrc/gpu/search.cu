@@ -335,7 +335,7 @@ std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape
                 memcpy(&wbits, &w, 4);
                 uses[ColKey(si, c.term_id, wbits, c.cache_id, k1bits)]++;
             };
-            const uint64_t or_den = ((e->cfg.flags & RG_CFG_MAXSCORE) || eager) ? (uint64_t)kColumnDen : 8u;
+            const uint64_t or_den = ((e->cfg.flags & RG_CFG_MAXSCORE) || eager) ? (uint64_t)kColumnDen : (uint64_t)e->or_col_den;
             for (uint32_t ci : sh.clause_idx) count(ci, sh.type == kTypeOr ? or_den : (uint64_t)kColumnDen);
             // conjunctions probe the columns of their non-lead clauses (which clause leads depends on the leaf;
             // the lead's use is counted too and simply stays unused)
@@ -464,7 +464,7 @@ std::map<ColKey, uint32_t> choose_lists(rg_engine* e, const std::vector<QShape>&
                 uint32_t wbits;
                 memcpy(&wbits, &w, 4);
                 const ColKey key(si, c.term_id, wbits, c.cache_id, k1bits);
-                if (df * 8u >= (uint64_t)seg.max_doc && columns.count(key)) continue;  // read from its score column
+                if (df * e->or_col_den >= (uint64_t)seg.max_doc && columns.count(key)) continue;  // read from its score column
                 uses[key]++;
             }
         }
@@ -674,7 +674,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                     const bool boundable = w >= 0.0f && w < INFINITY && k1 >= 0.0f &&
                                            c.cache_id < e->cache_nonneg.size() && e->cache_nonneg[c.cache_id];
                     // the exhaustive kernel scans a column docid by docid: that only pays for df >= max_doc/8
-                    if (col >= 0 && (use_ms || df_of(ci) * 8u >= (uint64_t)seg.max_doc)) {
+                    if (col >= 0 && (use_ms || df_of(ci) * e->or_col_den >= (uint64_t)seg.max_doc)) {
                         lp.clauses.push_back(ItemClause{(uint32_t)col, w, c.cache_id, 4u | (boundable ? 0u : 16u)});
                         continue;
                     }

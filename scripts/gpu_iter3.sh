@@ -1,0 +1,11 @@
+#!/bin/bash
+# GPU parity tests, then C4 with scored lists at several column density thresholds, and without lists.
+set -u
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+TAG=${1:-it}
+( timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -30 ) > gpurun_out/${TAG}_pytest.log
+for den in 8 3 2; do
+  RG_OR_COL_DEN=$den timeout 900 python bench.py --steps 3 --warmup 3 --no-decode --no-extra --cpu-sample 128 --cpu-seconds 6 > gpurun_out/${TAG}_c4_den${den}.json 2> gpurun_out/${TAG}_c4_den${den}.err
+done
+echo done > gpurun_out/${TAG}_done

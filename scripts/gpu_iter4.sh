@@ -1,0 +1,12 @@
+#!/bin/bash
+set -u
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+TAG=${1:-it}
+S="--docs 10000000 --terms 100000 --batch 1024 --cpu-sample 16 --cpu-seconds 2 --no-decode --no-extra"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_eval_or$' -s 1 -c 1 -o gpurun_out/${TAG}_eval_or_scaled \
+  python bench.py $S --steps 1 --warmup 1 > gpurun_out/${TAG}_ncu_or.log 2>&1
+for den in 16 32; do
+  RG_OR_COL_DEN=$den timeout 900 python bench.py --steps 3 --warmup 3 --no-decode --no-extra --cpu-sample 128 --cpu-seconds 6 > gpurun_out/${TAG}_c4_den${den}.json 2> gpurun_out/${TAG}_c4_den${den}.err
+done
+echo done > gpurun_out/${TAG}_done
