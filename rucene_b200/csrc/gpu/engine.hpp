@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <deque>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -92,12 +93,13 @@ struct TfPlanes {
 using ColKey = std::tuple<uint32_t, uint32_t, uint32_t, uint32_t, uint32_t>;  // leaf, term, weight bits, cache, k1 bits
 struct ColEntry {
     ColKey key;
-    float* col = nullptr;  // cudaMalloc'ed, len floats
+    float* col = nullptr;  // len floats: its own cudaMalloc (score column) or a piece of the engine's list arena
+    bool in_arena = false;
     const uint32_t* bits = nullptr;
     uint64_t len = 0;
     uint64_t last_use = 0;
     ~ColEntry() {
-        if (col) cudaFree(col);
+        if (col && !in_arena) cudaFree(col);
     }
 };
 
@@ -260,6 +262,18 @@ struct rg_engine {
     // persistent scored posting lists (same key, same budget and LRU clock as the columns)
     std::map<rg::ColKey, std::shared_ptr<rg::ColEntry>> list_cache;
     uint64_t list_floats = 0, list_builds = 0, list_hits = 0;
+    rg::DevBuf<rg::ColumnJob> list_jobs;  // grow-only: the build kernel reads it in stream order, no synchronise needed
+    // The lists live in one arena allocated at first need (a cudaMalloc per batch costs more than building the lists):
+    // a ring of slabs, one per rg_batch_prepare that built something; space is reclaimed oldest slab first, and only
+    // when no batch still references one of its lists.
+    struct ListSlab {
+        uint64_t off, len;
+        std::vector<std::shared_ptr<rg::ColEntry>> entries;
+    };
+    rg::DevBuf<float> list_arena;
+    uint64_t list_head = 0;  // next free float of the ring
+    std::deque<ListSlab> list_slabs;
+    bool list_arena_tried = false;
     // the exhaustive disjunction kernel scans a score column docid by docid: that beats streaming the clause's postings
     // only for df >= max_doc / or_col_den
     uint64_t or_col_den = 8;

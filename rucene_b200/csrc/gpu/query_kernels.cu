@@ -98,6 +98,64 @@ __device__ __forceinline__ void column_window(uint32_t* acc, const float* __rest
     }
 }
 
+// Plain-sum variant, four finished sums of the window (docids win0 + 4 * (g * 32 + lane) ..): count the matches
+// (a sum is non-zero iff some clause matched: every clause score is > 0) and flag the 32-doc step if one beats theta.
+template <bool LIVE>
+__device__ __forceinline__ void count_and_flag(const uint4 o, int g, int lane, const uint64_t* __restrict__ live, int win0,
+                                               float te, uint32_t& matches, uint32_t& hot) {
+    if (LIVE && live) {
+        uint32_t m4 = (o.x != 0u ? 1u : 0u) | (o.y != 0u ? 2u : 0u) | (o.z != 0u ? 4u : 0u) | (o.w != 0u ? 8u : 0u);
+        if (m4) {
+            const int d0 = win0 + (g * 32 + lane) * 4;
+            uint32_t l4 = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) l4 |= ((live[(d0 + q) >> 6] >> ((d0 + q) & 63)) & 1ull) ? 1u << q : 0u;
+            m4 &= l4;
+        }
+        matches += __popc(m4);
+    } else {
+        matches += min(o.x, 1u) + min(o.y, 1u) + min(o.z, 1u) + min(o.w, 1u);
+    }
+    const float mx = fmaxf(fmaxf(__uint_as_float(o.x), __uint_as_float(o.y)), fmaxf(__uint_as_float(o.z), __uint_as_float(o.w)));
+    hot |= mx > te ? 1u << (g * 4 + (lane >> 3)) : 0u;
+}
+
+// A whole window in which only score columns have postings (plain-sum variant): their sums are formed in registers, in
+// clause order from +0.0f exactly like the accumulator would, counted and compared with theta — the window in shared
+// memory is neither read nor written.  Returns 0xffffffff when some doc beats theta (the caller then runs the general
+// path to scan the window), else this lane's number of matches.  Not inlined: its 24 live float registers must not weigh on the
+// register allocation of the stream loops.
+template <bool LIVE>
+__device__ __noinline__ uint32_t columns_only_window(const WTerm* term, uint32_t active, const uint64_t* __restrict__ live,
+                                                     int win0, int hi, float te, int lane) {
+    uint32_t hotf = 0, c = 0;
+    const int win1 = win0 + kWw;
+#pragma unroll
+    for (int h = 0; h < kWw / 128; h += 3) {
+        float4 s3[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) s3[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (uint32_t m = active; m; m &= m - 1) {
+            const float* col = reinterpret_cast<const float*>(term[__ffs(m) - 1].blk_last) + win0 + lane * 4;
+            float4 v[3];
+#pragma unroll
+            for (int j = 0; j < 3; j++) v[j] = __ldg(reinterpret_cast<const float4*>(col + (h + j) * 128));
+            if (h == 0 && lane < kWw / 32 && win1 + lane * 32 < hi)  // next window's slice towards L2
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(col - lane * 4 + kWw + lane * 32));
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+                s3[j] = make_float4(__fadd_rn(s3[j].x, v[j].x), __fadd_rn(s3[j].y, v[j].y), __fadd_rn(s3[j].z, v[j].z),
+                                    __fadd_rn(s3[j].w, v[j].w));
+        }
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            count_and_flag<LIVE>(make_uint4(__float_as_uint(s3[j].x), __float_as_uint(s3[j].y), __float_as_uint(s3[j].z),
+                                            __float_as_uint(s3[j].w)),
+                                 h + j, lane, live, win0, te, c, hotf);
+    }
+    return __any_sync(0xffffffffu, hotf != 0u) ? 0xffffffffu : c;
+}
+
 template <bool LIVE, bool NOT, bool MSM, bool DMAX, bool POS>
 __global__ void __launch_bounds__(kOrThreads, 24)
 k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, uint32_t warp_bytes,
@@ -163,6 +221,7 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
         tc.is_not = c.flags & 1u;
     }
     __syncwarp();
+    const uint32_t col_mask = __ballot_sync(0xffffffffu, lane < T && sh.term[lane < T ? lane : 0].is_col != 0);
     uint32_t hot = 0, my_matches = 0;
     int nd = kNoMoreDocs;  // lane t: next cached docid of clause t (kNoMoreDocs = exhausted)
     for (int t = 0; t < T; t++) {
@@ -216,6 +275,19 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
         // ---- clauses with a posting in this window, in clause order: drain each stream up to the
         // window end (a sparse clause sits out most windows)
         uint32_t active = __ballot_sync(0xffffffffu, nd < win1);
+        if (POS && active && (active & ~col_mask) == 0u && win1 - win0 == kWw && win0 >= lo) {
+            // Only score columns have postings in this (whole) window: see columns_only_window.  Only if a doc beats
+            // theta (rare) the general path below redoes the window to scan it.
+            const uint32_t cnt = columns_only_window<LIVE>(sh.term, active, seg.live, win0, hi, te, lane);
+            if (cnt != 0xffffffffu) {
+                my_matches += cnt;
+                if ((active >> lane) & 1u) nd = win1 < hi ? win1 : kNoMoreDocs;
+                const int next_doc = __reduce_min_sync(0xffffffffu, nd);
+                if (next_doc == kNoMoreDocs) break;
+                w0 = next_doc;
+                continue;
+            }
+        }
         while (active) {
             const int t = __ffs(active) - 1;
             active &= active - 1;
@@ -293,25 +365,8 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
             // a 32-doc step is scanned for candidates iff one of its sums beats theta
             hot = 0;
 #pragma unroll
-            for (int g = 0; g < kWw / 128; g++) {
-                const uint4 o = reinterpret_cast<const uint4*>(sh.acc)[g * 32 + lane];
-                if (LIVE && seg.live) {
-                    uint32_t m4 = (o.x != 0u ? 1u : 0u) | (o.y != 0u ? 2u : 0u) | (o.z != 0u ? 4u : 0u) | (o.w != 0u ? 8u : 0u);
-                    if (m4) {
-                        const int d0 = win0 + (g * 32 + lane) * 4;
-                        uint32_t l4 = 0;
-#pragma unroll
-                        for (int q = 0; q < 4; q++) l4 |= is_live(seg, d0 + q) ? 1u << q : 0u;
-                        m4 &= l4;
-                    }
-                    my_matches += __popc(m4);
-                } else {
-                    my_matches += min(o.x, 1u) + min(o.y, 1u) + min(o.z, 1u) + min(o.w, 1u);
-                }
-                const float mx = fmaxf(fmaxf(__uint_as_float(o.x), __uint_as_float(o.y)),
-                                       fmaxf(__uint_as_float(o.z), __uint_as_float(o.w)));
-                hot |= mx > te ? 1u << (g * 4 + (lane >> 3)) : 0u;
-            }
+            for (int g = 0; g < kWw / 128; g++)
+                count_and_flag<LIVE>(reinterpret_cast<const uint4*>(sh.acc)[g * 32 + lane], g, lane, seg.live, win0, te, my_matches, hot);
         }
         hot = __reduce_or_sync(0xffffffffu, hot);
         {

@@ -9,11 +9,14 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <tuple>
 #include <type_traits>
@@ -73,6 +76,24 @@ struct rg_batch {
 };
 
 namespace {
+
+// RG_PLAN_TIMING=1: where rg_batch_prepare's host time goes, one line per call on stderr
+struct PlanTimer {
+    bool on = getenv("RG_PLAN_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    std::string line;
+    void mark(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        char buf[96];
+        snprintf(buf, sizeof buf, " %s=%.2f", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        line += buf;
+        t0 = t1;
+    }
+    ~PlanTimer() {
+        if (on && !line.empty()) fprintf(stderr, "[rg plan ms]%s\n", line.c_str());
+    }
+};
 
 struct HostPlan {
     std::vector<WorkItem> items;
@@ -286,26 +307,85 @@ static void ensure_budget(rg_engine* e) {
     if (e->col_budget_floats) return;  // once per index state (cudaMemGetInfo costs milliseconds)
     size_t free_b = 0, total_b = 0;
     RG_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-    e->col_budget_floats = std::max<uint64_t>(1, ((uint64_t)free_b / sizeof(float) + e->col_floats + e->list_floats) / 3);
+    e->col_budget_floats = std::max<uint64_t>(1, ((uint64_t)free_b / sizeof(float) + e->col_floats) / 3);
 }
 
-// Score columns and scored lists share one HBM budget and one LRU clock: drop the least recently used entries no
-// batch references until `len` more floats fit.  (cudaFree synchronises, which also orders it after running kernels.)
+// Drop the least recently used score columns no batch references until `len` more floats fit the column budget.
+// (cudaFree synchronises, which also orders it after running kernels.)
 static bool make_room(rg_engine* e, uint64_t len) {
-    while (e->col_floats + e->list_floats + len > e->col_budget_floats) {
-        std::map<ColKey, std::shared_ptr<ColEntry>>* from = nullptr;
-        std::map<ColKey, std::shared_ptr<ColEntry>>::iterator victim;
-        for (auto* m : {&e->col_cache, &e->list_cache})
-            for (auto it = m->begin(); it != m->end(); ++it)
-                if (it->second.use_count() == 1 && (!from || it->second->last_use < victim->second->last_use)) {
-                    from = m;
-                    victim = it;
-                }
-        if (!from) return false;
-        (from == &e->col_cache ? e->col_floats : e->list_floats) -= victim->second->len;
-        from->erase(victim);
+    while (e->col_floats + len > e->col_budget_floats) {
+        auto victim = e->col_cache.end();
+        for (auto it = e->col_cache.begin(); it != e->col_cache.end(); ++it)
+            if (it->second.use_count() == 1 && (victim == e->col_cache.end() || it->second->last_use < victim->second->last_use))
+                victim = it;
+        if (victim == e->col_cache.end()) return false;
+        e->col_floats -= victim->second->len;
+        e->col_cache.erase(victim);
     }
     return true;
+}
+
+// The scored lists' arena: one cudaMalloc at first need (a sixth of the free HBM, at most 24 GiB), used as a ring of
+// slabs — one per rg_batch_prepare that built lists.  Space is reclaimed oldest slab first and only when no batch
+// still references one of its lists; a list that is evicted while still popular is simply rebuilt by the next batch
+// that shares it (one pass over its postings).  Returns the offset of `len` contiguous floats, or ~0 if there is none.
+static uint64_t list_arena_alloc(rg_engine* e, uint64_t len) {
+    constexpr uint64_t kNoRoom = ~0ull;
+    if (!e->list_arena.p) {
+        if (e->list_arena_tried) return kNoRoom;
+        e->list_arena_tried = true;
+        size_t free_b = 0, total_b = 0;
+        RG_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+        uint64_t want = std::min<uint64_t>((uint64_t)free_b / 6, 24ull << 30) / sizeof(float);
+        for (; want >= (16ull << 20); want /= 2) {
+            float* p = nullptr;
+            if (cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(float)) == cudaSuccess) {
+                e->list_arena.p = p;
+                e->list_arena.n = want;
+                break;
+            }
+            cudaGetLastError();
+        }
+        if (!e->list_arena.p) return kNoRoom;
+    }
+    const uint64_t size = e->list_arena.n;
+    if (len > size / 2) return kNoRoom;
+    auto evict_front = [&]() {
+        auto& sl = e->list_slabs.front();
+        auto cached = [&](const std::shared_ptr<ColEntry>& ent) {
+            const auto it = e->list_cache.find(ent->key);
+            return it != e->list_cache.end() && it->second == ent;
+        };
+        for (const auto& ent : sl.entries)
+            if (ent.use_count() > (cached(ent) ? 2 : 1)) return false;  // a prepared batch still streams it
+        for (const auto& ent : sl.entries)
+            if (cached(ent)) {
+                e->list_floats -= ent->len;
+                e->list_cache.erase(ent->key);
+            }
+        e->list_slabs.pop_front();
+        return true;
+    };
+    for (;;) {
+        if (e->list_slabs.empty()) {
+            e->list_head = 0;
+            break;
+        }
+        const uint64_t tail = e->list_slabs.front().off, head = e->list_head;
+        if (head > tail) {  // in use: [tail, head)
+            if (size - head >= len) break;
+            if (tail >= len) {  // wrap around; [head, size) stays unused until the ring comes round again
+                e->list_head = 0;
+                break;
+            }
+        } else if (tail - head >= len) {  // in use: [tail, end) and [0, head)
+            break;
+        }
+        if (!evict_front()) return kNoRoom;
+    }
+    const uint64_t off = e->list_head;
+    e->list_head += len;
+    return off;
 }
 
 std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape>& shapes, const rg_clause* clauses,
@@ -439,7 +519,8 @@ std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape
 // an earlier batch left behind) is decoded and scored ONCE into (docid, f32 score) pairs, 1 KB per 128-posting block in
 // block order, and k_eval_or streams those: two 16-byte loads per lane and block.  Exactly the values stream_refill
 // would compute (same instructions, same order), so the results do not change.  8 bytes per posting: the whole
-// 100 M-doc benchmark index would be 10.7 GB; the budget / LRU is the columns'.  RG_CFG_NO_LISTS turns it off.
+// 100 M-doc benchmark index would be 10.7 GB; they live in the engine's list arena (list_arena_alloc).
+// RG_CFG_NO_LISTS turns the feature off.
 constexpr uint32_t kListMinDf = 4096;  // shorter lists are a few blocks per query: not worth a cache entry (eager: 256)
 std::map<ColKey, uint32_t> choose_lists(rg_engine* e, const std::vector<QShape>& shapes, const rg_clause* clauses, float k1,
                                         const std::map<ColKey, uint32_t>& columns, HostPlan& hp) {
@@ -491,55 +572,68 @@ std::map<ColKey, uint32_t> choose_lists(rg_engine* e, const std::vector<QShape>&
         }
     }
     std::sort(to_build.begin(), to_build.end(), [](const auto& x, const auto& y) { return x.first > y.first; });
-    std::vector<ColumnJob> jobs;
-    uint32_t n_units = 0;
-    cudaStream_t st = e->stream;
+    // one piece of the arena for everything this call builds
+    struct Pick { ColKey key; uint64_t len, off; uint32_t units; };
+    std::vector<Pick> picks;
+    uint64_t total = 0, n_units64 = 0;
+    const uint64_t room = e->list_arena.p ? e->list_arena.n / 2 : (e->list_arena_tried ? 0 : ~0ull);
     for (const auto& r : to_build) {
-        if (hp.col_refs.size() >= 65536) break;
+        if (hp.col_refs.size() + picks.size() >= 65536) break;
         const Segment& seg = e->segs[std::get<0>(r.second)];
         const TermHost& th = seg.host_terms[std::get<1>(r.second)];
         const uint32_t units = th.n_blocks + 1u;  // + the vint tail (or an unused unit the last block's prefetch may touch)
         const uint64_t len = (uint64_t)units * 256u;
-        if ((uint64_t)n_units + units > 0x7fffffffu) break;
-        if (!make_room(e, len)) break;
+        if (n_units64 + units > 0x7fffffffu || total + len > room) break;
+        picks.push_back(Pick{r.second, len, total, th.n_blocks + (th.tail_n ? 1u : 0u)});
+        total += len;
+        n_units64 += units;
+    }
+    if (picks.empty()) return chosen;
+    uint64_t at = list_arena_alloc(e, total);
+    while (at == ~0ull && picks.size() > 1) {  // (first call: the arena turned out smaller than hoped) build the most valuable half
+        picks.resize(picks.size() / 2);
+        total = picks.back().off + picks.back().len;
+        at = list_arena_alloc(e, total);
+    }
+    if (at == ~0ull) return chosen;
+    float* base = e->list_arena.p + at;
+    e->list_slabs.push_back(rg_engine::ListSlab{at, total, {}});
+    std::vector<ColumnJob> jobs;
+    uint32_t n_units = 0;
+    cudaStream_t st = e->stream;
+    for (const Pick& pk : picks) {
         auto ent = std::make_shared<ColEntry>();
-        ent->key = r.second;
-        ent->len = len;
-        if (cudaMalloc(reinterpret_cast<void**>(&ent->col), len * sizeof(float)) != cudaSuccess) {
-            cudaGetLastError();
-            ent->col = nullptr;
-            break;
-        }
+        ent->key = pk.key;
+        ent->len = pk.len;
+        ent->col = base + pk.off;
+        ent->in_arena = true;
+        e->list_slabs.back().entries.push_back(ent);
         ColumnJob job{};
-        job.seg = std::get<0>(r.second);
-        job.term_id = std::get<1>(r.second);
-        const uint32_t wbits = std::get<2>(r.second);
+        job.seg = std::get<0>(pk.key);
+        job.term_id = std::get<1>(pk.key);
+        const uint32_t wbits = std::get<2>(pk.key);
         memcpy(&job.weight, &wbits, 4);
-        job.cache_id = std::get<3>(r.second);
+        job.cache_id = std::get<3>(pk.key);
         job.dst = ent->col;
         job.unit_begin = n_units;
-        n_units += th.n_blocks + (th.tail_n ? 1u : 0u);
+        n_units += pk.units;
         jobs.push_back(job);
-        e->list_cache[r.second] = ent;
-        e->list_floats += len;
+        e->list_cache[pk.key] = ent;
+        e->list_floats += pk.len;
         e->list_builds++;
-        add_ref(r.second, ent);
+        add_ref(pk.key, ent);
     }
-    if (!jobs.empty()) {
-        DevBuf<ColumnJob> d_jobs;
-        d_jobs.alloc(jobs.size());
-        RG_CUDA_CHECK(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(ColumnJob), cudaMemcpyHostToDevice, st));
-        launch_build_lists(st, e->d_segs.p, d_jobs.p, (uint32_t)jobs.size(), n_units, e->d_caches.p, k1);
-        RG_CUDA_CHECK(cudaGetLastError());
-        RG_CUDA_CHECK(cudaStreamSynchronize(st));  // d_jobs goes out of scope
-        e->launches++;
-        hp.n_lists_built = (uint32_t)jobs.size();
-    }
+    if (e->list_jobs.n < jobs.size()) e->list_jobs.alloc(jobs.size() + jobs.size() / 2 + 64);
+    RG_CUDA_CHECK(cudaMemcpyAsync(e->list_jobs.p, jobs.data(), jobs.size() * sizeof(ColumnJob), cudaMemcpyHostToDevice, st));
+    launch_build_lists(st, e->d_segs.p, e->list_jobs.p, (uint32_t)jobs.size(), n_units, e->d_caches.p, k1);
+    RG_CUDA_CHECK(cudaGetLastError());
+    e->launches++;
+    hp.n_lists_built = (uint32_t)jobs.size();
     return chosen;
 }
 
 void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const rg_clause* clauses,
-                uint32_t n_clauses, uint32_t mode, float k1, HostPlan& hp) {
+                uint32_t n_clauses, uint32_t mode, float k1, HostPlan& hp, PlanTimer& tm) {
     const uint32_t n_caches = (uint32_t)(e->h_caches.size() / 256);
     const uint64_t range_postings = e->cfg.range_postings;
     const uint32_t n_segs = (uint32_t)e->segs.size();
@@ -554,8 +648,11 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
         for (uint32_t ci : shapes[qi].not_idx)
             if (clauses[ci].cache_id >= n_caches) throw ArgError("clause refers to an unset norm cache");
     }
+    tm.mark("classify");
     const std::map<ColKey, uint32_t> columns = choose_columns(e, shapes, clauses, k1, hp);
+    tm.mark("columns");
     const std::map<ColKey, uint32_t> lists = choose_lists(e, shapes, clauses, k1, columns, hp);
+    tm.mark("lists");
     uint32_t k1bits;
     memcpy(&k1bits, &k1, 4);
     const bool no_ms = (e->cfg.flags & RG_CFG_MAXSCORE) == 0;
@@ -777,6 +874,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
     };
     if (n_threads <= 1) {
         plan_range(0, n_queries, hp);
+        tm.mark("plan");
     } else {
         std::vector<HostPlan> parts(n_threads);
         std::vector<std::exception_ptr> errs(n_threads);
@@ -790,27 +888,17 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                 }
             });
         for (auto& th : ths) th.join();
+        tm.mark("plan_threads");
         for (auto& ep : errs)
             if (ep) std::rethrow_exception(ep);
-        for (HostPlan& lp : parts) {
-            const uint32_t item_off = (uint32_t)hp.items.size(), clause_off = (uint32_t)hp.clauses.size();
-            for (WorkItem it : lp.items) {
-                it.clause_begin += clause_off;
-                hp.items.push_back(it);
-            }
-            hp.clauses.insert(hp.clauses.end(), lp.clauses.begin(), lp.clauses.end());
-            auto append_ids = [&](std::vector<uint32_t>& dst, const std::vector<uint32_t>& src) {
-                for (uint32_t id : src) dst.push_back(id + item_off);
-            };
-            append_ids(hp.or_ids, lp.or_ids);
-            append_ids(hp.ms_ids, lp.ms_ids);
-            append_ids(hp.and_ids, lp.and_ids);
-            append_ids(hp.ro_ids, lp.ro_ids);
-            append_ids(hp.dpq_ids, lp.dpq_ids);
-            hp.or_rank.insert(hp.or_rank.end(), lp.or_rank.begin(), lp.or_rank.end());
-            hp.ms_rank.insert(hp.ms_rank.end(), lp.ms_rank.begin(), lp.ms_rank.end());
-            hp.and_rank.insert(hp.and_rank.end(), lp.and_rank.begin(), lp.and_rank.end());
-            hp.group_out.insert(hp.group_out.end(), lp.group_out.begin(), lp.group_out.end());
+        // concatenate in query order: offsets first, then every part is copied by its own thread
+        struct Off { size_t items, clauses, or_ids, ms_ids, and_ids, ro_ids, dpq_ids, groups; };
+        std::vector<Off> off(n_threads + 1, Off{0, 0, 0, 0, 0, 0, 0, 0});
+        for (uint32_t t = 0; t < n_threads; t++) {
+            const HostPlan& lp = parts[t];
+            off[t + 1] = Off{off[t].items + lp.items.size(), off[t].clauses + lp.clauses.size(), off[t].or_ids + lp.or_ids.size(),
+                             off[t].ms_ids + lp.ms_ids.size(), off[t].and_ids + lp.and_ids.size(), off[t].ro_ids + lp.ro_ids.size(),
+                             off[t].dpq_ids + lp.dpq_ids.size(), off[t].groups + lp.group_out.size()};
             hp.postings += lp.postings;
             hp.algo_bytes += lp.algo_bytes;
             hp.max_or_terms = std::max(hp.max_or_terms, lp.max_or_terms);
@@ -821,7 +909,46 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
             hp.or_has_msm = hp.or_has_msm || lp.or_has_msm;
             hp.or_has_dmax = hp.or_has_dmax || lp.or_has_dmax;
         }
+        const Off& end = off[n_threads];
+        hp.items.resize(end.items);
+        hp.clauses.resize(end.clauses);
+        hp.or_ids.resize(end.or_ids);
+        hp.or_rank.resize(end.or_ids);
+        hp.ms_ids.resize(end.ms_ids);
+        hp.ms_rank.resize(end.ms_ids);
+        hp.and_ids.resize(end.and_ids);
+        hp.and_rank.resize(end.and_ids);
+        hp.ro_ids.resize(end.ro_ids);
+        hp.dpq_ids.resize(end.dpq_ids);
+        hp.group_out.resize(end.groups);
+        ths.clear();
+        for (uint32_t t = 0; t < n_threads; t++)
+            ths.emplace_back([&, t] {
+                const HostPlan& lp = parts[t];
+                const Off& o = off[t];
+                const uint32_t item_off = (uint32_t)o.items, clause_off = (uint32_t)o.clauses;
+                for (size_t i = 0; i < lp.items.size(); i++) {
+                    WorkItem it = lp.items[i];
+                    it.clause_begin += clause_off;
+                    hp.items[o.items + i] = it;
+                }
+                std::copy(lp.clauses.begin(), lp.clauses.end(), hp.clauses.begin() + o.clauses);
+                auto put_ids = [&](std::vector<uint32_t>& dst, size_t at, const std::vector<uint32_t>& src) {
+                    for (size_t i = 0; i < src.size(); i++) dst[at + i] = src[i] + item_off;
+                };
+                put_ids(hp.or_ids, o.or_ids, lp.or_ids);
+                put_ids(hp.ms_ids, o.ms_ids, lp.ms_ids);
+                put_ids(hp.and_ids, o.and_ids, lp.and_ids);
+                put_ids(hp.ro_ids, o.ro_ids, lp.ro_ids);
+                put_ids(hp.dpq_ids, o.dpq_ids, lp.dpq_ids);
+                std::copy(lp.or_rank.begin(), lp.or_rank.end(), hp.or_rank.begin() + o.or_ids);
+                std::copy(lp.ms_rank.begin(), lp.ms_rank.end(), hp.ms_rank.begin() + o.ms_ids);
+                std::copy(lp.and_rank.begin(), lp.and_rank.end(), hp.and_rank.begin() + o.and_ids);
+                std::copy(lp.group_out.begin(), lp.group_out.end(), hp.group_out.begin() + o.groups);
+            });
+        for (auto& th : ths) th.join();
     }
+    tm.mark("merge");
     // Launch order: all first ranges, then all second ranges, ... so that by the time range r of a
     // query starts, its range r-1 has (almost always) finished and published theta; candidate
     // lists then stay ~k*ln(n) per query instead of per range.  Item order itself is untouched.
@@ -844,6 +971,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
         if (hp.items[i].chain_pos == 0) hp.group_item_begin.push_back(i);
     hp.group_item_begin.push_back((uint32_t)hp.items.size());
     if (hp.group_item_begin.size() != hp.group_out.size() + 1) throw ArgError("internal: group bookkeeping mismatch");
+    tm.mark("order");
 }
 
 template <class T>
@@ -881,10 +1009,12 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     if (p->mode != RG_MODE_SEARCH && p->mode != RG_MODE_SEARCH_PARALLEL) throw ArgError("bad mode");
     if (e->segs.empty()) throw ArgError("no segment uploaded");
     RG_CUDA_CHECK(cudaSetDevice(e->device));
+    PlanTimer tm;
     e->sync_tables();
     ensure_arena(e);
+    tm.mark("tables");
     HostPlan hp;
-    plan_batch(e, queries, n_queries, clauses, n_clauses, p->mode, p->k1, hp);
+    plan_batch(e, queries, n_queries, clauses, n_clauses, p->mode, p->k1, hp, tm);
     std::unique_ptr<rg_batch> b(new rg_batch());
     b->generation = e->generation;
     b->cols = std::move(hp.cols);
@@ -916,6 +1046,7 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     b->postings = hp.postings;
     b->algo_bytes = hp.algo_bytes + (uint64_t)n_queries * p->k * sizeof(rg_hit);
     cudaStream_t st = e->stream;
+    tm.mark("fields");
     // carve the slab
     size_t off = 0;
     auto carve = [&](auto& span, size_t count) {
@@ -983,7 +1114,9 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
                    hp.col_refs.size() * sizeof(ColRef);
     b->kernels_per_run = (b->n_ms ? 1 : 0) + (b->n_dpq ? 1 : 0) + (b->n_or ? 1 : 0) + (b->n_and ? 1 : 0) + (b->n_ro ? 1 : 0) + (b->n_groups ? 1 : 0) +
                          (p->mode == RG_MODE_SEARCH_PARALLEL ? 1 : 0);
+    tm.mark("alloc_copy_issue");
     RG_CUDA_CHECK(cudaStreamSynchronize(st));
+    tm.mark("sync");
     *out = b.release();
     return RG_OK;
     RG_CATCH
