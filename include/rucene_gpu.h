@@ -186,7 +186,11 @@ int rg_search_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries,
                     const rg_clause* clauses, uint32_t n_clauses, const rg_search_params* p,
                     rg_hit* out_hits, uint32_t* out_counts, uint64_t* out_total_hits);
 
-/* The same in three steps, so the evaluation can be timed with inputs resident in HBM. */
+/* The same in three steps, so the evaluation can be timed with inputs resident in HBM — and so that batches can be
+ * pipelined: calls are made from one thread at a time, but several batches may be in flight.  rg_batch_prepare
+ * (host planning + plan upload on the engine's copy stream) does not wait for a batch that is running,
+ * rg_batch_run queues the kernels on the engine stream behind the previous run, rg_batch_fetch waits for ITS
+ * batch only.  The usual loop: run(i); prepare(i+1); fetch(i); destroy(i). */
 int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
                      const rg_clause* clauses, uint32_t n_clauses, const rg_search_params* p,
                      rg_batch** out);

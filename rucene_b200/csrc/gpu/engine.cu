@@ -735,6 +735,8 @@ int rg_engine_create(const rg_config* cfg, rg_engine** out) {
     e->device = dev;
     RG_CUDA_CHECK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     e->stream = e->own_stream;
+    RG_CUDA_CHECK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (auto& ev : e->list_jobs_done) RG_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     RG_CUDA_CHECK(cudaEventCreate(&e->ev0));
     RG_CUDA_CHECK(cudaEventCreate(&e->ev1));
     RG_CUDA_CHECK(cudaEventCreate(&e->ev2));
@@ -754,6 +756,9 @@ void rg_engine_destroy(rg_engine* e) {
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev2) cudaEventDestroy(e->ev2);
     if (e->ev3) cudaEventDestroy(e->ev3);
+    for (auto& ev : e->list_jobs_done)
+        if (ev) cudaEventDestroy(ev);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }

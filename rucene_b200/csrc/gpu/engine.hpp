@@ -9,6 +9,7 @@
 #include <stdexcept>
 #include <string>
 #include <tuple>
+#include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
@@ -91,6 +92,14 @@ struct TfPlanes {
 // cache, k1) are the same f32 values for every query that carries the clause, in this batch and in
 // later ones, so they are materialised once and kept while HBM allows.
 using ColKey = std::tuple<uint32_t, uint32_t, uint32_t, uint32_t, uint32_t>;  // leaf, term, weight bits, cache, k1 bits
+struct ColKeyHash {
+    size_t operator()(const ColKey& k) const {
+        uint64_t h = ((uint64_t)std::get<0>(k) << 32 | std::get<1>(k)) * 0x9e3779b97f4a7c15ull;
+        h ^= ((uint64_t)std::get<2>(k) << 32 | std::get<3>(k)) * 0xc2b2ae3d27d4eb4full + (h >> 29);
+        h ^= (uint64_t)std::get<4>(k) * 0x165667b19e3779f9ull + (h >> 31);
+        return (size_t)(h ^ (h >> 32));
+    }
+};
 struct ColEntry {
     ColKey key;
     float* col = nullptr;  // len floats: its own cudaMalloc (score column) or a piece of the engine's list arena
@@ -243,6 +252,7 @@ int translate_exception();  // maps the in-flight exception to an RG_E* code + g
 struct rg_engine {
     int device = 0;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // plan uploads and result fetches: they must not queue behind a running batch
     cudaStream_t stream = nullptr;
     rg_config cfg{};
     std::vector<rg::Segment> segs;
@@ -262,7 +272,9 @@ struct rg_engine {
     // persistent scored posting lists (same key, same budget and LRU clock as the columns)
     std::map<rg::ColKey, std::shared_ptr<rg::ColEntry>> list_cache;
     uint64_t list_floats = 0, list_builds = 0, list_hits = 0;
-    rg::DevBuf<rg::ColumnJob> list_jobs;  // grow-only: the build kernel reads it in stream order, no synchronise needed
+    rg::DevBuf<rg::ColumnJob> list_jobs[4];  // grow-only, round robin: the build kernel reads one in stream order
+    cudaEvent_t list_jobs_done[4] = {nullptr, nullptr, nullptr, nullptr};  // ... and this says when it is done with it
+    uint32_t list_jobs_next = 0;
     // The lists live in one arena allocated at first need (a cudaMalloc per batch costs more than building the lists):
     // a ring of slabs, one per rg_batch_prepare that built something; space is reclaimed oldest slab first, and only
     // when no batch still references one of its lists.
@@ -282,7 +294,7 @@ struct rg_engine {
     rg::DevBuf<uint8_t> merge_scratch;  // rg_merge_leaf_records outputs (grow-only)
     rg::DevBuf<uint8_t> gather_scratch; // rg_batch_run_sharded: all ranks' leaf records (grow-only)
     uint32_t merged_queries = 0, merged_k = 0;  // shape of the result sitting in merge_scratch
-    rg::DevBuf<uint8_t> spare_slab;  // device slab of the last destroyed rg_batch, reused by the next
+    std::vector<rg::DevBuf<uint8_t>> spare_slabs;  // device slabs of destroyed batches (at most 3), reused by the next ones
     uint64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     float last_decode_ms = -1.f, last_eval_ms = -1.f, last_replay_ms = -1.f, last_run_ms = -1.f;

@@ -99,10 +99,16 @@ __device__ __forceinline__ void column_window(uint32_t* acc, const float* __rest
 }
 
 // Plain-sum variant, four finished sums of the window (docids win0 + 4 * (g * 32 + lane) ..): count the matches
-// (a sum is non-zero iff some clause matched: every clause score is > 0) and flag the 32-doc step if one beats theta.
+// (a sum is non-zero iff some clause matched: every clause score is > 0) and keep the lane's running maximum.
+// min.u32 through asm: the compiler would otherwise turn min(x, 1) into a compare + a select per element, chained.
+__device__ __forceinline__ uint32_t min1(uint32_t x) {
+    uint32_t r;
+    asm("min.u32 %0, %1, 1;" : "=r"(r) : "r"(x));
+    return r;
+}
 template <bool LIVE>
-__device__ __forceinline__ void count_and_flag(const uint4 o, int g, int lane, const uint64_t* __restrict__ live, int win0,
-                                               float te, uint32_t& matches, uint32_t& hot) {
+__device__ __forceinline__ void count_and_max(const uint4 o, int g, int lane, const uint64_t* __restrict__ live, int win0,
+                                              uint32_t& matches, float& mx) {
     if (LIVE && live) {
         uint32_t m4 = (o.x != 0u ? 1u : 0u) | (o.y != 0u ? 2u : 0u) | (o.z != 0u ? 4u : 0u) | (o.w != 0u ? 8u : 0u);
         if (m4) {
@@ -114,10 +120,9 @@ __device__ __forceinline__ void count_and_flag(const uint4 o, int g, int lane, c
         }
         matches += __popc(m4);
     } else {
-        matches += min(o.x, 1u) + min(o.y, 1u) + min(o.z, 1u) + min(o.w, 1u);
+        matches += (min1(o.x) + min1(o.y)) + (min1(o.z) + min1(o.w));
     }
-    const float mx = fmaxf(fmaxf(__uint_as_float(o.x), __uint_as_float(o.y)), fmaxf(__uint_as_float(o.z), __uint_as_float(o.w)));
-    hot |= mx > te ? 1u << (g * 4 + (lane >> 3)) : 0u;
+    mx = fmaxf(fmaxf(mx, __uint_as_float(o.x)), fmaxf(fmaxf(__uint_as_float(o.y), __uint_as_float(o.z)), __uint_as_float(o.w)));
 }
 
 // A whole window in which only score columns have postings (plain-sum variant): their sums are formed in registers, in
@@ -128,7 +133,8 @@ __device__ __forceinline__ void count_and_flag(const uint4 o, int g, int lane, c
 template <bool LIVE>
 __device__ __noinline__ uint32_t columns_only_window(const WTerm* term, uint32_t active, const uint64_t* __restrict__ live,
                                                      int win0, int hi, float te, int lane) {
-    uint32_t hotf = 0, c = 0;
+    uint32_t c = 0;
+    float mx = 0.0f;
     const int win1 = win0 + kWw;
 #pragma unroll
     for (int h = 0; h < kWw / 128; h += 3) {
@@ -149,11 +155,11 @@ __device__ __noinline__ uint32_t columns_only_window(const WTerm* term, uint32_t
         }
 #pragma unroll
         for (int j = 0; j < 3; j++)
-            count_and_flag<LIVE>(make_uint4(__float_as_uint(s3[j].x), __float_as_uint(s3[j].y), __float_as_uint(s3[j].z),
-                                            __float_as_uint(s3[j].w)),
-                                 h + j, lane, live, win0, te, c, hotf);
+            count_and_max<LIVE>(make_uint4(__float_as_uint(s3[j].x), __float_as_uint(s3[j].y), __float_as_uint(s3[j].z),
+                                           __float_as_uint(s3[j].w)),
+                                h + j, lane, live, win0, c, mx);
     }
-    return __any_sync(0xffffffffu, hotf != 0u) ? 0xffffffffu : c;
+    return __any_sync(0xffffffffu, mx > te) ? 0xffffffffu : c;
 }
 
 template <bool LIVE, bool NOT, bool MSM, bool DMAX, bool POS>
@@ -329,9 +335,7 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
             for (;;) {
                 if (pos >= n) {
                     if (tc.cur > tc.nb) break;  // exhausted
-                    __syncwarp();  // every lane has read tc.pos / tc.n / tc.cur
-                    if (lane == 0) tc.pos = pos;
-                    __syncwarp();
+                    __syncwarp();  // every lane has read tc.pos / tc.n / tc.cur before lane 0 rewrites them in there
                     if (!stream_refill<LIVE, NOT, MSM, DMAX, POS>(seg, p, tc, cdocs + t * kBlock, cscores + t * kBlock, lo, hi,
                                                              lane, win0, win1, sh.acc, hot, my_matches, te, mc)) {
                         pos = n = 0;
@@ -350,23 +354,30 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                 pos += c;
                 if (c < 32 && pos < n) break;  // next cached doc is beyond this window
             }
-            __syncwarp();  // every lane has read this clause's cursor
-            if (lane == 0) {
-                tc.pos = pos;
-                tc.n = n;
-            }
+            // every lane stores the same cursor: each later reads back (at least) its own store (stream_refill, which
+            // lets lane 0 write, synchronises on its own)
+            tc.pos = pos;
+            tc.n = n;
             const int nx = pos < n ? cd[pos] : kNoMoreDocs;
             if (lane == t) nd = nx;
-            __syncwarp();
+            __syncwarp();  // the next clause's lanes read window slots other lanes have just written
         }
         const int next_doc = __reduce_min_sync(0xffffffffu, nd);
         if (POS) {
             // one pass over the finished window: a doc matched iff its sum is non-zero (every clause score is > 0), and
             // a 32-doc step is scanned for candidates iff one of its sums beats theta
             hot = 0;
+            float mx = 0.0f;
 #pragma unroll
             for (int g = 0; g < kWw / 128; g++)
-                count_and_flag<LIVE>(reinterpret_cast<const uint4*>(sh.acc)[g * 32 + lane], g, lane, seg.live, win0, te, my_matches, hot);
+                count_and_max<LIVE>(reinterpret_cast<const uint4*>(sh.acc)[g * 32 + lane], g, lane, seg.live, win0, my_matches, mx);
+            if (__any_sync(0xffffffffu, mx > te)) {  // a few percent of the windows: which 32-doc steps hold such a sum
+#pragma unroll
+                for (int g = 0; g < kWw / 128; g++) {
+                    const float4 o = reinterpret_cast<const float4*>(sh.acc)[g * 32 + lane];
+                    hot |= fmaxf(fmaxf(o.x, o.y), fmaxf(o.z, o.w)) > te ? 1u << (g * 4 + (lane >> 3)) : 0u;
+                }
+            }
         }
         hot = __reduce_or_sync(0xffffffffu, hot);
         {

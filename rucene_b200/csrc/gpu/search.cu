@@ -73,6 +73,14 @@ struct rg_batch {
     uint32_t kernels_per_run = 0;
     bool or_has_not = false, or_has_msm = false, or_has_dmax = false, or_nonpos = false;
     bool ran = false;
+    // two batches may be in flight (prepare the next while one runs): the plan goes up on the engine's copy stream,
+    // the run waits for `uploaded`, the fetch waits for `done` on the copy stream; timing events are the batch's own
+    cudaEvent_t uploaded = nullptr, done = nullptr, ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool synced = false;  // the host has waited for `done`
+    ~rg_batch() {
+        for (cudaEvent_t x : {uploaded, done, ev[0], ev[1], ev[2], ev[3]})
+            if (x) cudaEventDestroy(x);
+    }
 };
 
 namespace {
@@ -310,6 +318,21 @@ static void ensure_budget(rg_engine* e) {
     e->col_budget_floats = std::max<uint64_t>(1, ((uint64_t)free_b / sizeof(float) + e->col_floats) / 3);
 }
 
+// Job table of a column / list build: uploaded on the copy stream (the engine stream may be busy with a running
+// batch) into one of four grow-only device tables; the build kernel is launched on the engine stream — ordered before
+// the run of the batch being prepared — and the caller records list_jobs_done[slot] behind it, which is what the
+// table's next reuse waits for.  No stream is synchronised beyond the copy itself.
+static const ColumnJob* stage_jobs(rg_engine* e, const std::vector<ColumnJob>& jobs, uint32_t& slot) {
+    slot = e->list_jobs_next;
+    e->list_jobs_next = (e->list_jobs_next + 1u) & 3u;
+    RG_CUDA_CHECK(cudaEventSynchronize(e->list_jobs_done[slot]));  // the build that last read this table has finished
+    if (e->list_jobs[slot].n < jobs.size()) e->list_jobs[slot].alloc(jobs.size() + jobs.size() / 2 + 64);
+    RG_CUDA_CHECK(cudaMemcpyAsync(e->list_jobs[slot].p, jobs.data(), jobs.size() * sizeof(ColumnJob), cudaMemcpyHostToDevice,
+                                  e->copy_stream));
+    RG_CUDA_CHECK(cudaStreamSynchronize(e->copy_stream));
+    return e->list_jobs[slot].p;
+}
+
 // Drop the least recently used score columns no batch references until `len` more floats fit the column budget.
 // (cudaFree synchronises, which also orders it after running kernels.)
 static bool make_room(rg_engine* e, uint64_t len) {
@@ -396,7 +419,7 @@ std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape
     const uint32_t min_uses = eager ? 1u : 2u;
     uint32_t k1bits;
     memcpy(&k1bits, &k1, 4);
-    std::map<ColKey, uint32_t> uses;
+    std::unordered_map<ColKey, uint32_t, ColKeyHash> uses;
     bool any_match_all = false;
     for (const QShape& sh : shapes) {
         any_match_all = any_match_all || sh.match_all;
@@ -444,7 +467,7 @@ std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape
             to_build.emplace_back((uint64_t)kv.second * (uint64_t)seg.host_terms[std::get<1>(kv.first)].doc_freq, kv.first);
         }
     }
-    std::sort(to_build.begin(), to_build.end(), [](const auto& x, const auto& y) { return x.first > y.first; });
+    std::sort(to_build.begin(), to_build.end(), [](const auto& x, const auto& y) { return x.first != y.first ? x.first > y.first : x.second < y.second; });
     std::vector<ColumnJob> jobs;
     uint32_t n_units = 0;
     cudaStream_t st = e->stream;
@@ -501,12 +524,11 @@ std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape
         add_ref(r.second, ent);
     }
     if (!jobs.empty()) {
-        DevBuf<ColumnJob> d_jobs;
-        d_jobs.alloc(jobs.size());
-        RG_CUDA_CHECK(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(ColumnJob), cudaMemcpyHostToDevice, st));
-        launch_build_columns(st, e->d_segs.p, d_jobs.p, (uint32_t)jobs.size(), n_units, e->d_caches.p, k1);
+        uint32_t jb = 0;
+        const ColumnJob* d_jobs = stage_jobs(e, jobs, jb);
+        launch_build_columns(st, e->d_segs.p, d_jobs, (uint32_t)jobs.size(), n_units, e->d_caches.p, k1);
         RG_CUDA_CHECK(cudaGetLastError());
-        RG_CUDA_CHECK(cudaStreamSynchronize(st));  // d_jobs goes out of scope
+        RG_CUDA_CHECK(cudaEventRecord(e->list_jobs_done[jb], st));
         e->launches++;
         hp.n_cols_built = (uint32_t)jobs.size();
     }
@@ -531,7 +553,7 @@ std::map<ColKey, uint32_t> choose_lists(rg_engine* e, const std::vector<QShape>&
     const uint64_t min_df = eager ? 256u : kListMinDf;
     uint32_t k1bits;
     memcpy(&k1bits, &k1, 4);
-    std::map<ColKey, uint32_t> uses;
+    std::unordered_map<ColKey, uint32_t, ColKeyHash> uses;
     for (const QShape& sh : shapes) {
         if (sh.type != kTypeOr || sh.match_all || sh.clause_idx.size() >= 10) continue;  // (>= 10: k_eval_dpq)
         for (uint32_t si = 0; si < e->segs.size(); si++) {
@@ -571,7 +593,7 @@ std::map<ColKey, uint32_t> choose_lists(rg_engine* e, const std::vector<QShape>&
             to_build.emplace_back((uint64_t)kv.second * (uint64_t)seg.host_terms[std::get<1>(kv.first)].doc_freq, kv.first);
         }
     }
-    std::sort(to_build.begin(), to_build.end(), [](const auto& x, const auto& y) { return x.first > y.first; });
+    std::sort(to_build.begin(), to_build.end(), [](const auto& x, const auto& y) { return x.first != y.first ? x.first > y.first : x.second < y.second; });
     // one piece of the arena for everything this call builds
     struct Pick { ColKey key; uint64_t len, off; uint32_t units; };
     std::vector<Pick> picks;
@@ -623,9 +645,10 @@ std::map<ColKey, uint32_t> choose_lists(rg_engine* e, const std::vector<QShape>&
         e->list_builds++;
         add_ref(pk.key, ent);
     }
-    if (e->list_jobs.n < jobs.size()) e->list_jobs.alloc(jobs.size() + jobs.size() / 2 + 64);
-    RG_CUDA_CHECK(cudaMemcpyAsync(e->list_jobs.p, jobs.data(), jobs.size() * sizeof(ColumnJob), cudaMemcpyHostToDevice, st));
-    launch_build_lists(st, e->d_segs.p, e->list_jobs.p, (uint32_t)jobs.size(), n_units, e->d_caches.p, k1);
+    uint32_t jb = 0;
+    const ColumnJob* d_jobs = stage_jobs(e, jobs, jb);
+    launch_build_lists(st, e->d_segs.p, d_jobs, (uint32_t)jobs.size(), n_units, e->d_caches.p, k1);
+    RG_CUDA_CHECK(cudaEventRecord(e->list_jobs_done[jb], st));
     RG_CUDA_CHECK(cudaGetLastError());
     e->launches++;
     hp.n_lists_built = (uint32_t)jobs.size();
@@ -1083,10 +1106,22 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     carve(b->out_total, n_queries);
     if (p->mode == RG_MODE_SEARCH_PARALLEL)
         carve(b->leaf_records, (size_t)b->n_leaves * std::max<uint32_t>(1, n_queries) * leaf_record_bytes(p->k));
-    if (e->spare_slab.n >= off) b->slab = std::move(e->spare_slab);
-    else {
-        e->spare_slab.release();
-        b->slab.alloc(off);
+    {   // the smallest spare slab that fits, else a new one (a cudaMalloc + cudaFree per batch costs milliseconds)
+        int best = -1;
+        for (size_t i = 0; i < e->spare_slabs.size(); i++)
+            if (e->spare_slabs[i].n >= off && (best < 0 || e->spare_slabs[i].n < e->spare_slabs[best].n)) best = (int)i;
+        if (best >= 0) {
+            b->slab = std::move(e->spare_slabs[best]);
+            e->spare_slabs.erase(e->spare_slabs.begin() + best);
+        } else {
+            if (e->spare_slabs.size() >= 3) {  // none fits: drop the smallest to bound what idle slabs hold
+                size_t sm = 0;
+                for (size_t i = 1; i < e->spare_slabs.size(); i++)
+                    if (e->spare_slabs[i].n < e->spare_slabs[sm].n) sm = i;
+                e->spare_slabs.erase(e->spare_slabs.begin() + sm);
+            }
+            b->slab.alloc(off + off / 8);  // some headroom: the next batch of the same shape will fit
+        }
     }
     auto rebase = [&](auto& span) {
         using T = std::remove_reference_t<decltype(*span.p)>;
@@ -1099,23 +1134,28 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     if (p->mode == RG_MODE_SEARCH_PARALLEL) rebase(b->leaf_records);
     b->zero_begin = b->slab.p + zero_off;
     b->zero_bytes = off - zero_off;
-    up(b->items, hp.items, st);
-    up(b->clauses, hp.clauses, st);
-    up(b->or_ids, hp.or_ids, st);
-    up(b->and_ids, hp.and_ids, st);
-    up(b->ms_ids, hp.ms_ids, st);
-    up(b->dpq_ids, hp.dpq_ids, st);
-    up(b->ro_ids, hp.ro_ids, st);
-    up(b->col_refs, hp.col_refs, st);
-    up(b->group_item_begin, hp.group_item_begin, st);
-    up(b->group_out, hp.group_out, st);
+    cudaStream_t cs = e->copy_stream;
+    up(b->items, hp.items, cs);
+    up(b->clauses, hp.clauses, cs);
+    up(b->or_ids, hp.or_ids, cs);
+    up(b->and_ids, hp.and_ids, cs);
+    up(b->ms_ids, hp.ms_ids, cs);
+    up(b->dpq_ids, hp.dpq_ids, cs);
+    up(b->ro_ids, hp.ro_ids, cs);
+    up(b->col_refs, hp.col_refs, cs);
+    up(b->group_item_begin, hp.group_item_begin, cs);
+    up(b->group_out, hp.group_out, cs);
+    RG_CUDA_CHECK(cudaEventCreateWithFlags(&b->uploaded, cudaEventDisableTiming));
+    RG_CUDA_CHECK(cudaEventCreateWithFlags(&b->done, cudaEventDisableTiming));
+    for (auto& x : b->ev) RG_CUDA_CHECK(cudaEventCreate(&x));
+    RG_CUDA_CHECK(cudaEventRecord(b->uploaded, cs));
     b->h2d_bytes = (hp.items.size() * sizeof(WorkItem)) + hp.clauses.size() * sizeof(ItemClause) +
                    4 * (hp.or_ids.size() + hp.ms_ids.size() + hp.dpq_ids.size() + hp.and_ids.size() + hp.ro_ids.size() + hp.group_item_begin.size() + hp.group_out.size()) +
                    hp.col_refs.size() * sizeof(ColRef);
     b->kernels_per_run = (b->n_ms ? 1 : 0) + (b->n_dpq ? 1 : 0) + (b->n_or ? 1 : 0) + (b->n_and ? 1 : 0) + (b->n_ro ? 1 : 0) + (b->n_groups ? 1 : 0) +
                          (p->mode == RG_MODE_SEARCH_PARALLEL ? 1 : 0);
     tm.mark("alloc_copy_issue");
-    RG_CUDA_CHECK(cudaStreamSynchronize(st));
+    RG_CUDA_CHECK(cudaStreamSynchronize(cs));  // the host vectors go out of scope (a running batch is not waited for)
     tm.mark("sync");
     *out = b.release();
     return RG_OK;
@@ -1129,7 +1169,8 @@ int rg_batch_run(rg_engine* e, rg_batch* b) {
         throw ArgError("stale batch: a segment was uploaded or a norm cache changed after rg_batch_prepare");
     RG_CUDA_CHECK(cudaSetDevice(e->device));
     cudaStream_t st = e->stream;
-    RG_CUDA_CHECK(cudaEventRecord(e->ev0, st));
+    RG_CUDA_CHECK(cudaStreamWaitEvent(st, b->uploaded, 0));
+    RG_CUDA_CHECK(cudaEventRecord(b->ev[0], st));
     RG_CUDA_CHECK(cudaMemsetAsync(b->item_head.p, 0xff, b->item_head.bytes(), st));
     RG_CUDA_CHECK(cudaMemsetAsync(b->zero_begin, 0, b->zero_bytes, st));
     EvalParams ep{};
@@ -1151,7 +1192,7 @@ int rg_batch_run(rg_engine* e, rg_batch* b) {
     ep.error_flag = reinterpret_cast<uint32_t*>(b->arena_next.p + 1);
     ep.dbg = (e->cfg.flags & RG_CFG_STATS) ? b->dbg.p : nullptr;
     ep.touched = b->dbg.p + 15;
-    RG_CUDA_CHECK(cudaEventRecord(e->ev2, st));
+    RG_CUDA_CHECK(cudaEventRecord(b->ev[2], st));
     ep.cols = b->col_refs.p;
     bool has_live = false, has_other = false;
     for (const Segment& sg : e->segs) {
@@ -1169,7 +1210,7 @@ int rg_batch_run(rg_engine* e, rg_batch* b) {
     RG_CUDA_CHECK(cudaGetLastError());
     launch_eval_and(st, ep, b->ro_ids.p, b->n_ro, true, has_other);
     RG_CUDA_CHECK(cudaGetLastError());
-    RG_CUDA_CHECK(cudaEventRecord(e->ev3, st));
+    RG_CUDA_CHECK(cudaEventRecord(b->ev[3], st));
     ReplayParams rp{};
     rp.cand_arena = e->cand_arena.p;
     rp.item_head = b->item_head.p;
@@ -1190,8 +1231,10 @@ int rg_batch_run(rg_engine* e, rg_batch* b) {
         RG_CUDA_CHECK(cudaGetLastError());
     }
     e->launches += b->kernels_per_run;
-    RG_CUDA_CHECK(cudaEventRecord(e->ev1, st));
+    RG_CUDA_CHECK(cudaEventRecord(b->ev[1], st));
+    RG_CUDA_CHECK(cudaEventRecord(b->done, st));
     b->ran = true;
+    b->synced = false;
     return RG_OK;
     RG_CATCH
 }
@@ -1202,16 +1245,18 @@ int rg_batch_fetch(rg_engine* e, rg_batch* b, rg_hit* out_hits, uint32_t* out_co
     if (!e || !b || !out_hits || !out_counts || !out_total_hits) throw ArgError("null argument");
     if (!b->ran) throw ArgError("rg_batch_fetch before rg_batch_run");
     RG_CUDA_CHECK(cudaSetDevice(e->device));
-    cudaStream_t st = e->stream;
+    cudaStream_t st = e->copy_stream;  // not the engine stream: the next batch may already be running there
+    RG_CUDA_CHECK(cudaStreamWaitEvent(st, b->done, 0));
     unsigned long long flags[2] = {0, 0};
     RG_CUDA_CHECK(cudaMemcpyAsync(out_hits, b->out_hits.p, (size_t)b->n_queries * b->k * sizeof(rg_hit), cudaMemcpyDeviceToHost, st));
     RG_CUDA_CHECK(cudaMemcpyAsync(out_counts, b->out_counts.p, (size_t)b->n_queries * 4, cudaMemcpyDeviceToHost, st));
     RG_CUDA_CHECK(cudaMemcpyAsync(out_total_hits, b->out_total.p, (size_t)b->n_queries * 8, cudaMemcpyDeviceToHost, st));
     RG_CUDA_CHECK(cudaMemcpyAsync(flags, b->arena_next.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
     RG_CUDA_CHECK(cudaStreamSynchronize(st));
-    cudaEventElapsedTime(&e->last_run_ms, e->ev0, e->ev1);
-    cudaEventElapsedTime(&e->last_eval_ms, e->ev2, e->ev3);
-    cudaEventElapsedTime(&e->last_replay_ms, e->ev3, e->ev1);
+    b->synced = true;
+    cudaEventElapsedTime(&e->last_run_ms, b->ev[0], b->ev[1]);
+    cudaEventElapsedTime(&e->last_eval_ms, b->ev[2], b->ev[3]);
+    cudaEventElapsedTime(&e->last_replay_ms, b->ev[3], b->ev[1]);
     cudaGetLastError();
     if (flags[1] & 1ull) throw OutOfArena("candidate arena exhausted: split the batch or raise cand_arena_bytes");
     return RG_OK;
@@ -1220,8 +1265,18 @@ int rg_batch_fetch(rg_engine* e, rg_batch* b, rg_hit* out_hits, uint32_t* out_co
 
 void rg_batch_destroy(rg_engine* e, rg_batch* b) {
     if (!b) return;
-    // hand the slab back for the next batch (stream-ordered reuse: same engine stream)
-    if (e && b->slab.n > e->spare_slab.n) e->spare_slab = std::move(b->slab);
+    // hand the slab back for the next batch — whose plan goes up on the copy stream, so this batch's kernels must be over
+    if (e && b->ran && !b->synced) cudaEventSynchronize(b->done);
+    if (e && b->slab.p) {
+        if (e->spare_slabs.size() < 3) {
+            e->spare_slabs.push_back(std::move(b->slab));
+        } else {
+            size_t sm = 0;
+            for (size_t i = 1; i < e->spare_slabs.size(); i++)
+                if (e->spare_slabs[i].n < e->spare_slabs[sm].n) sm = i;
+            if (e->spare_slabs[sm].n < b->slab.n) e->spare_slabs[sm] = std::move(b->slab);
+        }
+    }
     delete b;
 }
 

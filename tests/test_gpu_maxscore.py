@@ -293,3 +293,42 @@ def test_scored_lists_every_block_layout_and_tails():
                     assert (s.engine.list_stats()["cached"] > 0) == (not flags & engine.CFG_NO_LISTS)
                 finally:
                     s.engine.close()
+
+
+def test_two_batches_in_flight():
+    """rg_batch_prepare of the next batch while one runs (plan uploads and result fetches ride the copy stream): both
+    orders of fetching, a batch closed without being fetched, and scored lists built by the second prepare while
+    the first batch is still queued."""
+    seg = codec.synth_segment(0x5EED0099, 200000, 2000, doc_version=1)
+    ix = helpers.oracle_index([seg])
+    rng = np.random.default_rng(99)
+    sets = [_or_specs(rng, 2000, 50, 2, 6) for _ in range(4)]
+    want = []
+    for sp in sets:
+        q, c = ob.make_queries(sp)
+        want.append(ix.search_batch(q, c, 10, parallel_mode=0, n_threads=4))
+    s = search.GpuIndexSearcher(search.IndexReader([seg]), range_postings=4000, flags=engine.CFG_EAGER_COLUMNS)
+    try:
+        arrays = [s.compile_batch(helpers.to_queries(sp)) for sp in sets]
+        k1 = s.similarity.k1
+        a = s.engine.prepare(arrays[0][0], arrays[0][1], 10, k1=k1)
+        a.run()
+        b = s.engine.prepare(arrays[1][0], arrays[1][1], 10, k1=k1)   # planned while a is (possibly) still running
+        b.run()
+        c = s.engine.prepare(arrays[2][0], arrays[2][1], 10, k1=k1)
+        c.run()
+        d = s.engine.prepare(arrays[3][0], arrays[3][1], 10, k1=k1)
+        c.close()                                                     # never fetched
+        got_b = b.fetch()                                             # out of order
+        got_a = a.fetch()
+        d.run()
+        got_d = d.fetch()
+        got_a2 = a.fetch()                                            # a second fetch of a finished batch
+        for x in (a, b, d):
+            x.close()
+        helpers.assert_same_topdocs(got_a, want[0], "in flight: a")
+        helpers.assert_same_topdocs(got_a2, want[0], "in flight: a again")
+        helpers.assert_same_topdocs(got_b, want[1], "in flight: b")
+        helpers.assert_same_topdocs(got_d, want[3], "in flight: d")
+    finally:
+        s.engine.close()
