@@ -58,7 +58,8 @@ typedef struct rg_blockset rg_blockset;
 typedef struct {
     int32_t device;            /* CUDA ordinal; -1 = current device */
     uint64_t cand_arena_bytes; /* candidate arena for exact top-k replay; 0 = default */
-    uint32_t range_postings;   /* target postings per (query, docid-range) work item; 0 = default */
+    uint32_t range_postings;   /* target postings per (query, docid-range) work item; 0 = the planner chooses per batch
+                                  (32 K for conjunctions, 8 K..128 K for disjunctions depending on the batch's size) */
     uint32_t flags;            /* RG_CFG_* */
 } rg_config;
 

@@ -741,7 +741,8 @@ int rg_engine_create(const rg_config* cfg, rg_engine** out) {
     RG_CUDA_CHECK(cudaEventCreate(&e->ev1));
     RG_CUDA_CHECK(cudaEventCreate(&e->ev2));
     RG_CUDA_CHECK(cudaEventCreate(&e->ev3));
-    if (e->cfg.range_postings == 0) e->cfg.range_postings = 1u << 15;  // one warp per work item
+    e->range_postings_set = e->cfg.range_postings != 0;  // else the planner picks per batch (plan_batch)
+    if (e->cfg.range_postings == 0) e->cfg.range_postings = 1u << 15;
     if (const char* v = getenv("RG_OR_COL_DEN")) e->or_col_den = std::max(1, atoi(v));  // tuning knob (bench sweeps)
     *out = e.release();
     return RG_OK;

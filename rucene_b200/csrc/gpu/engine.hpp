@@ -287,13 +287,15 @@ struct rg_engine {
     std::deque<ListSlab> list_slabs;
     bool list_arena_tried = false;
     // the exhaustive disjunction kernel scans a score column docid by docid: that beats streaming the clause's postings
-    // only for df >= max_doc / or_col_den
-    uint64_t or_col_den = 8;
+    // (scored list) for df >= max_doc / or_col_den; measured on C4: 1/8 342 ms, 1/16 331, 1/32 336, 1/64 351
+    uint64_t or_col_den = 16;
+    bool range_postings_set = false;  // rg_config.range_postings was given (else the planner chooses per batch)
     uint64_t generation = 1;            // bumped by rg_segment_upload / rg_norm_cache_set (stale-batch check)
     std::vector<uint8_t> cache_nonneg;  // per norm cache: every entry >= 0 (MaxScore bound needs it)
     rg::DevBuf<uint8_t> merge_scratch;  // rg_merge_leaf_records outputs (grow-only)
     rg::DevBuf<uint8_t> gather_scratch; // rg_batch_run_sharded: all ranks' leaf records (grow-only)
     uint32_t merged_queries = 0, merged_k = 0;  // shape of the result sitting in merge_scratch
+    std::shared_ptr<void> plan_scratch;  // host-side plan buffers kept between rg_batch_prepare calls (search.cu: PlanScratch)
     std::vector<rg::DevBuf<uint8_t>> spare_slabs;  // device slabs of destroyed batches (at most 3), reused by the next ones
     uint64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;

@@ -118,6 +118,23 @@ struct HostPlan {
     uint64_t postings = 0, algo_bytes = 0;
     uint32_t max_or_terms = 1;
     bool or_has_not = false, or_has_msm = false, or_has_dmax = false, or_nonpos = false;
+    // back to the empty plan, keeping the vectors' storage (a plan is tens of MB: fresh vectors would be page-faulted
+    // in by every rg_batch_prepare)
+    void reset() {
+        items.clear(); clauses.clear(); or_ids.clear(); ms_ids.clear(); and_ids.clear(); ro_ids.clear(); dpq_ids.clear();
+        col_refs.clear(); bitmap_refs.clear(); cols.clear(); lists.clear(); or_rank.clear(); ms_rank.clear(); and_rank.clear();
+        group_item_begin.clear(); group_out.clear();
+        max_dpq_terms = n_cols_built = n_lists_built = max_ms_streams = 0;
+        col_floats = list_floats = postings = algo_bytes = 0;
+        max_or_terms = 1;
+        or_has_not = or_has_msm = or_has_dmax = or_nonpos = false;
+    }
+};
+// the engine keeps one of these between calls (rg_engine::plan_scratch)
+struct PlanScratch {
+    HostPlan hp;
+    std::vector<HostPlan> parts;
+    std::vector<uint32_t> sort_tmp;
 };
 
 struct QShape {
@@ -360,7 +377,12 @@ static uint64_t list_arena_alloc(rg_engine* e, uint64_t len) {
         size_t free_b = 0, total_b = 0;
         RG_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
         uint64_t want = std::min<uint64_t>((uint64_t)free_b / 6, 24ull << 30) / sizeof(float);
-        for (; want >= (16ull << 20); want /= 2) {
+        uint64_t least = 16ull << 20;
+        if (const char* v = getenv("RG_LIST_ARENA_KB")) {  // tests: a small arena, so that the ring wraps and reclaims
+            want = std::max<uint64_t>(64, strtoull(v, nullptr, 10)) * 1024 / sizeof(float);
+            least = want;
+        }
+        for (; want >= least; want /= 2) {
             float* p = nullptr;
             if (cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(float)) == cudaSuccess) {
                 e->list_arena.p = p;
@@ -412,7 +434,7 @@ static uint64_t list_arena_alloc(rg_engine* e, uint64_t len) {
 }
 
 std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape>& shapes, const rg_clause* clauses,
-                                          float k1, HostPlan& hp) {
+                                          float k1, HostPlan& hp, PlanTimer& tm) {
     std::map<ColKey, uint32_t> chosen;
     const bool cols_off = (e->cfg.flags & (RG_CFG_NO_COLUMNS | RG_CFG_NO_BITMAPS)) != 0;  // (a match-all column is not optional)
     const bool eager = (e->cfg.flags & RG_CFG_EAGER_COLUMNS) != 0;
@@ -445,8 +467,10 @@ std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape
             for (uint32_t ci : sh.opt_idx) count(ci, (uint64_t)kColumnDen);
         }
     }
+    tm.mark("col_uses");
     if (uses.empty() && !any_match_all) return chosen;
     ensure_budget(e);
+    tm.mark("col_budget");
     auto add_ref = [&](const ColKey& key, const std::shared_ptr<ColEntry>& ent) {
         ent->last_use = ++e->col_tick;
         chosen[key] = (uint32_t)hp.col_refs.size();
@@ -468,6 +492,7 @@ std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape
         }
     }
     std::sort(to_build.begin(), to_build.end(), [](const auto& x, const auto& y) { return x.first != y.first ? x.first > y.first : x.second < y.second; });
+    tm.mark("col_cached");
     std::vector<ColumnJob> jobs;
     uint32_t n_units = 0;
     cudaStream_t st = e->stream;
@@ -523,9 +548,11 @@ std::map<ColKey, uint32_t> choose_columns(rg_engine* e, const std::vector<QShape
         e->col_builds++;
         add_ref(r.second, ent);
     }
+    tm.mark("col_alloc");
     if (!jobs.empty()) {
         uint32_t jb = 0;
         const ColumnJob* d_jobs = stage_jobs(e, jobs, jb);
+        tm.mark("col_stage");
         launch_build_columns(st, e->d_segs.p, d_jobs, (uint32_t)jobs.size(), n_units, e->d_caches.p, k1);
         RG_CUDA_CHECK(cudaGetLastError());
         RG_CUDA_CHECK(cudaEventRecord(e->list_jobs_done[jb], st));
@@ -605,7 +632,8 @@ std::map<ColKey, uint32_t> choose_lists(rg_engine* e, const std::vector<QShape>&
         const TermHost& th = seg.host_terms[std::get<1>(r.second)];
         const uint32_t units = th.n_blocks + 1u;  // + the vint tail (or an unused unit the last block's prefetch may touch)
         const uint64_t len = (uint64_t)units * 256u;
-        if (n_units64 + units > 0x7fffffffu || total + len > room) break;
+        if (n_units64 + units > 0x7fffffffu) break;
+        if (total + len > room) continue;  // does not fit next to the more valuable ones: it stays a decoded stream
         picks.push_back(Pick{r.second, len, total, th.n_blocks + (th.tail_n ? 1u : 0u)});
         total += len;
         n_units64 += units;
@@ -656,9 +684,8 @@ std::map<ColKey, uint32_t> choose_lists(rg_engine* e, const std::vector<QShape>&
 }
 
 void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const rg_clause* clauses,
-                uint32_t n_clauses, uint32_t mode, float k1, HostPlan& hp, PlanTimer& tm) {
+                uint32_t n_clauses, uint32_t mode, float k1, HostPlan& hp, PlanTimer& tm, PlanScratch& scratch) {
     const uint32_t n_caches = (uint32_t)(e->h_caches.size() / 256);
-    const uint64_t range_postings = e->cfg.range_postings;
     const uint32_t n_segs = (uint32_t)e->segs.size();
     std::vector<QShape> shapes(n_queries);
     for (uint32_t qi = 0; qi < n_queries; qi++) {
@@ -671,8 +698,22 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
         for (uint32_t ci : shapes[qi].not_idx)
             if (clauses[ci].cache_id >= n_caches) throw ArgError("clause refers to an unset norm cache");
     }
+    // Postings per work item.  A caller's rg_config.range_postings is taken as is.  By default conjunction items (one CTA
+    // each) get 32 K; disjunction items (one warp each) get up to 128 K — fewer, longer ranges cost less setup and
+    // keep theta chains short — but never so few that the batch has under ~32 K of them (1 K resident warps x waves).
+    uint64_t and_rp = e->cfg.range_postings, or_rp = e->cfg.range_postings;
+    if (!e->range_postings_set) {
+        uint64_t or_cost = 0;
+        for (const QShape& sh : shapes)
+            if (sh.type == kTypeOr)
+                for (const Segment& seg : e->segs)
+                    for (uint32_t ci : sh.clause_idx)
+                        if (clauses[ci].term_id < seg.host_terms.size()) or_cost += (uint64_t)seg.host_terms[clauses[ci].term_id].doc_freq;
+        and_rp = 1u << 15;
+        or_rp = std::min<uint64_t>(1u << 17, std::max<uint64_t>(1u << 13, or_cost >> 15));
+    }
     tm.mark("classify");
-    const std::map<ColKey, uint32_t> columns = choose_columns(e, shapes, clauses, k1, hp);
+    const std::map<ColKey, uint32_t> columns = choose_columns(e, shapes, clauses, k1, hp, tm);
     tm.mark("columns");
     const std::map<ColKey, uint32_t> lists = choose_lists(e, shapes, clauses, k1, columns, hp);
     tm.mark("lists");
@@ -848,6 +889,7 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
             if (leaf_dismax) lp.clauses.push_back(ItemClause{0u, shape.tie, 0u, 8u});
             // ranges of ~range_postings postings, at most 256 per (query, leaf): long lists get
             // longer ranges (a range is one warp's sequential job; there are thousands of warps)
+            const uint64_t range_postings = leaf_type == (int)kTypeOr ? or_rp : and_rp;
             uint64_t R = (cost + range_postings - 1) / range_postings;
             R = std::min<uint64_t>(R, 256);
             R = std::max<uint64_t>(1, std::min<uint64_t>(R, (uint64_t)(seg.max_doc + kBlock - 1) / kBlock));
@@ -899,7 +941,9 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
         plan_range(0, n_queries, hp);
         tm.mark("plan");
     } else {
-        std::vector<HostPlan> parts(n_threads);
+        std::vector<HostPlan>& parts = scratch.parts;
+        parts.resize(n_threads);
+        for (HostPlan& lp : parts) lp.reset();
         std::vector<std::exception_ptr> errs(n_threads);
         std::vector<std::thread> ths;
         for (uint32_t t = 0; t < n_threads; t++)
@@ -975,14 +1019,15 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
     // Launch order: all first ranges, then all second ranges, ... so that by the time range r of a
     // query starts, its range r-1 has (almost always) finished and published theta; candidate
     // lists then stay ~k*ln(n) per query instead of per range.  Item order itself is untouched.
-    auto by_rank = [](std::vector<uint32_t>& ids, const std::vector<uint32_t>& rank) {
+    auto by_rank = [&scratch](std::vector<uint32_t>& ids, const std::vector<uint32_t>& rank) {
         // stable counting sort on the range index (<= 256 distinct values)
         uint32_t max_rank = 0;
         for (uint32_t r : rank) max_rank = std::max(max_rank, r);
         std::vector<uint32_t> start(max_rank + 2, 0);
         for (uint32_t r : rank) start[r + 1]++;
         for (uint32_t r = 0; r <= max_rank; r++) start[r + 1] += start[r];
-        std::vector<uint32_t> out(ids.size());
+        std::vector<uint32_t>& out = scratch.sort_tmp;
+        out.resize(ids.size());
         for (size_t i = 0; i < ids.size(); i++) out[start[rank[i]]++] = ids[i];
         ids.swap(out);
     };
@@ -1036,8 +1081,11 @@ int rg_batch_prepare(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     e->sync_tables();
     ensure_arena(e);
     tm.mark("tables");
-    HostPlan hp;
-    plan_batch(e, queries, n_queries, clauses, n_clauses, p->mode, p->k1, hp, tm);
+    if (!e->plan_scratch) e->plan_scratch = std::make_shared<PlanScratch>();
+    PlanScratch& scratch = *static_cast<PlanScratch*>(e->plan_scratch.get());
+    HostPlan& hp = scratch.hp;
+    hp.reset();
+    plan_batch(e, queries, n_queries, clauses, n_clauses, p->mode, p->k1, hp, tm, scratch);
     std::unique_ptr<rg_batch> b(new rg_batch());
     b->generation = e->generation;
     b->cols = std::move(hp.cols);

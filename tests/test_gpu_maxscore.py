@@ -332,3 +332,35 @@ def test_two_batches_in_flight():
         helpers.assert_same_topdocs(got_d, want[3], "in flight: d")
     finally:
         s.engine.close()
+
+
+def test_scored_list_arena_wraps_and_reclaims(monkeypatch):
+    """A list arena of 768 KB: successive batches over different terms fill it, the ring wraps, the oldest slabs are
+    reclaimed (their lists leave the cache), a slab a prepared batch still references is never reclaimed — and every
+    batch equals the oracle throughout."""
+    monkeypatch.setenv("RG_LIST_ARENA_KB", "768")
+    seg = codec.synth_segment(0x5EED00AA, 150000, 3000, doc_version=1)
+    ix = helpers.oracle_index([seg])
+    rng = np.random.default_rng(170)
+    s = search.GpuIndexSearcher(search.IndexReader([seg]), range_postings=6000, flags=engine.CFG_EAGER_COLUMNS | engine.CFG_NO_COLUMNS)
+    try:
+        k1 = s.similarity.k1
+        first = _or_specs(rng, 3000, 12, 2, 4)
+        qa, ca = s.compile_batch(helpers.to_queries(first))
+        pinned = s.engine.prepare(qa, ca, 10, k1=k1)           # holds its lists (the first slab) until closed
+        seen_max, reclaimed = 0, False
+        for i in range(40):
+            specs = _or_specs(rng, 3000, 12, 2, 4)
+            _check(s, ix, specs, 10, "arena round %d" % i)
+            st = s.engine.list_stats()
+            assert st["bytes"] <= 768 * 1024
+            reclaimed = reclaimed or st["cached"] < seen_max
+            seen_max = max(seen_max, st["cached"])
+            if i == 20:                                          # the ring may now pass the first slab
+                pinned.run()
+                helpers.assert_same_topdocs(pinned.fetch(), ix.search_batch(*ob.make_queries(first), 10, parallel_mode=0, n_threads=2), "pinned batch")
+                pinned.close()
+        assert s.engine.list_stats()["built"] > seen_max        # more lists were built than ever fit: space was reused
+        assert reclaimed
+    finally:
+        s.engine.close()
