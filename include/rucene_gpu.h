@@ -51,6 +51,11 @@ extern "C" {
                                    instead of unpacking, prefix-summing, gathering norms and dividing per query */
 #define RG_CFG_STATS 16u        /* count events inside k_eval_or_ms (rg_batch_debug); costs a few atomics per work item */
 
+/* Environment variables read by the library (diagnostics / tuning sweeps; none is needed in production):
+ * RG_PLAN_TIMING=1 prints where rg_batch_prepare's host time goes; RG_OR_COL_DEN=n reads a disjunction clause from its
+ * score column when df >= max_doc/n (default 16); RG_MAX_RANGES=n caps the docid ranges per (query, leaf) (default 128);
+ * RG_LIST_ARENA_KB=n sizes the scored-list arena (default: a sixth of the free HBM, at most 24 GiB). */
+
 typedef struct rg_engine rg_engine;
 typedef struct rg_batch rg_batch;
 typedef struct rg_blockset rg_blockset;

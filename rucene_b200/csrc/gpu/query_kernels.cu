@@ -346,10 +346,11 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                 }
                 const uint32_t i = pos + lane;
                 const int d = i < n ? cd[i] : kNoMoreDocs;
+                const float sv = i < n ? cs[i] : 0.0f;  // (loaded next to the docid, not behind the vote)
                 const bool in_win = d < win1;
                 const uint32_t c = __popc(__ballot_sync(0xffffffffu, in_win));  // sorted: a prefix
                 if (in_win)
-                    accumulate_posting<NOT, MSM, DMAX, POS>(sh.acc, d - win0, cs[i], NOT && tc.is_not != 0,
+                    accumulate_posting<NOT, MSM, DMAX, POS>(sh.acc, d - win0, sv, NOT && tc.is_not != 0,
                                                             (LIVE && !POS) ? is_live(seg, d) : true, te, hot, my_matches, mc);
                 pos += c;
                 if (c < 32 && pos < n) break;  // next cached doc is beyond this window

@@ -701,6 +701,11 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
     // Postings per work item.  A caller's rg_config.range_postings is taken as is.  By default conjunction items (one CTA
     // each) get 32 K; disjunction items (one warp each) get up to 128 K — fewer, longer ranges cost less setup and
     // keep theta chains short — but never so few that the batch has under ~32 K of them (1 K resident warps x waves).
+    // At most 128 ranges per (query, leaf): the expensive queries of a batch then all cut the leaf at the same docids,
+    // and since items are launched range-major the warps in flight read the same region of columns, lists and norms
+    // through L2 (measured on C4, one 100 M-doc leaf: 128 ranges 318 ms, 256 324, 512 334; ranges of unequal count
+    // per query 343).
+    static const uint64_t max_ranges = getenv("RG_MAX_RANGES") ? std::max(1, atoi(getenv("RG_MAX_RANGES"))) : 128;  // tuning knob
     uint64_t and_rp = e->cfg.range_postings, or_rp = e->cfg.range_postings;
     if (!e->range_postings_set) {
         uint64_t or_cost = 0;
@@ -887,11 +892,11 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
             // leaf is that scorer; otherwise the tie breaker rides in a meta clause after the item's
             const bool leaf_dismax = shape.dismax && present.size() > 1;
             if (leaf_dismax) lp.clauses.push_back(ItemClause{0u, shape.tie, 0u, 8u});
-            // ranges of ~range_postings postings, at most 256 per (query, leaf): long lists get
+            // ranges of ~range_postings postings, at most max_ranges per (query, leaf): long lists get
             // longer ranges (a range is one warp's sequential job; there are thousands of warps)
             const uint64_t range_postings = leaf_type == (int)kTypeOr ? or_rp : and_rp;
             uint64_t R = (cost + range_postings - 1) / range_postings;
-            R = std::min<uint64_t>(R, 256);
+            R = std::min<uint64_t>(R, max_ranges);
             R = std::max<uint64_t>(1, std::min<uint64_t>(R, (uint64_t)(seg.max_doc + kBlock - 1) / kBlock));
             if (leaf_type == (int)kTypeReqOpt || leaf_dpq) R = 1;  // sequential scorer state: one item per leaf
             if (new_group) {
