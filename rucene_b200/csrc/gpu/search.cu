@@ -698,24 +698,38 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
         for (uint32_t ci : shapes[qi].not_idx)
             if (clauses[ci].cache_id >= n_caches) throw ArgError("clause refers to an unset norm cache");
     }
-    // Postings per work item.  A caller's rg_config.range_postings is taken as is.  By default conjunction items (one CTA
-    // each) get 32 K; disjunction items (one warp each) get up to 128 K — fewer, longer ranges cost less setup and
-    // keep theta chains short — but never so few that the batch has under ~32 K of them (1 K resident warps x waves).
-    // At most 128 ranges per (query, leaf): the expensive queries of a batch then all cut the leaf at the same docids,
-    // and since items are launched range-major the warps in flight read the same region of columns, lists and norms
-    // through L2 (measured on C4, one 100 M-doc leaf: 128 ranges 318 ms, 256 324, 512 334; ranges of unequal count
-    // per query 343).
+    // Docid ranges (= work items) per (query, leaf).  A caller's rg_config.range_postings is taken as is: ~that many
+    // postings per range.  By default conjunction items (one CTA each) get 32 K postings; disjunctions (one warp each)
+    // are cut on a GRID THE WHOLE BATCH SHARES: per leaf a power of two R_leaf <= 128 of equal docid ranges, sized so that
+    // an average query's range holds ~128 K postings (longer ranges cost less setup and keep theta chains short) but the
+    // batch still has ~32 K items; an inexpensive query takes R_leaf / 2^j of them (>= 8 K postings each).  Items are
+    // launched in order of their range's start on that grid, so the warps in flight read the same region of the
+    // columns, lists and norms through L2 — measured on C4 (one 100 M-doc leaf): 128 equal ranges 318 ms, 256 324,
+    // 512 334, and 343 with range counts that differ from query to query.
     static const uint64_t max_ranges = getenv("RG_MAX_RANGES") ? std::max(1, atoi(getenv("RG_MAX_RANGES"))) : 128;  // tuning knob
     uint64_t and_rp = e->cfg.range_postings, or_rp = e->cfg.range_postings;
+    std::vector<uint32_t> or_grid(n_segs, 0);  // R_leaf; 0 = per-query ranges of or_rp postings (explicit range_postings)
     if (!e->range_postings_set) {
-        uint64_t or_cost = 0;
-        for (const QShape& sh : shapes)
-            if (sh.type == kTypeOr)
-                for (const Segment& seg : e->segs)
-                    for (uint32_t ci : sh.clause_idx)
-                        if (clauses[ci].term_id < seg.host_terms.size()) or_cost += (uint64_t)seg.host_terms[clauses[ci].term_id].doc_freq;
         and_rp = 1u << 15;
-        or_rp = std::min<uint64_t>(1u << 17, std::max<uint64_t>(1u << 13, or_cost >> 15));
+        uint64_t n_or = 0;
+        std::vector<uint64_t> leaf_cost(n_segs, 0);
+        for (const QShape& sh : shapes)
+            if (sh.type == kTypeOr) {
+                n_or++;
+                for (uint32_t si = 0; si < n_segs; si++)
+                    for (uint32_t ci : sh.clause_idx)
+                        if (clauses[ci].term_id < e->segs[si].host_terms.size())
+                            leaf_cost[si] += (uint64_t)e->segs[si].host_terms[clauses[ci].term_id].doc_freq;
+            }
+        uint64_t total = 0;
+        for (uint64_t c : leaf_cost) total += c;
+        const uint64_t per_range = std::min<uint64_t>(1u << 17, std::max<uint64_t>(1u << 13, total >> 15));
+        for (uint32_t si = 0; si < n_segs; si++) {
+            const uint64_t mean = n_or ? leaf_cost[si] / n_or : 0;
+            uint32_t g = 1;
+            while (g < max_ranges && (uint64_t)g * per_range < mean) g <<= 1;
+            or_grid[si] = std::min<uint32_t>(g, (uint32_t)max_ranges);
+        }
     }
     tm.mark("classify");
     const std::map<ColKey, uint32_t> columns = choose_columns(e, shapes, clauses, k1, hp, tm);
@@ -897,6 +911,14 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
             const uint64_t range_postings = leaf_type == (int)kTypeOr ? or_rp : and_rp;
             uint64_t R = (cost + range_postings - 1) / range_postings;
             R = std::min<uint64_t>(R, max_ranges);
+            uint32_t rank_step = 1;  // launch-order key of range r = r * rank_step (its start on the leaf's grid)
+            if (leaf_type == (int)kTypeOr && or_grid[si]) {
+                R = or_grid[si];
+                while (R > 1 && cost / R < (1u << 13)) {
+                    R >>= 1;
+                    rank_step <<= 1;
+                }
+            }
             R = std::max<uint64_t>(1, std::min<uint64_t>(R, (uint64_t)(seg.max_doc + kBlock - 1) / kBlock));
             if (leaf_type == (int)kTypeReqOpt || leaf_dpq) R = 1;  // sequential scorer state: one item per leaf
             if (new_group) {
@@ -927,11 +949,11 @@ void plan_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries, const
                     lp.and_rank.push_back((uint32_t)r);
                 } else if (use_ms) {
                     lp.ms_ids.push_back(idx);
-                    lp.ms_rank.push_back((uint32_t)r);
+                    lp.ms_rank.push_back((uint32_t)r * rank_step);
                     lp.max_ms_streams = std::max<uint32_t>(lp.max_ms_streams, n_streams);
                 } else {
                     lp.or_ids.push_back(idx);
-                    lp.or_rank.push_back((uint32_t)r);
+                    lp.or_rank.push_back((uint32_t)r * rank_step);
                     lp.max_or_terms = std::max<uint32_t>(lp.max_or_terms, n_item_terms);
                     if (!nots.empty()) lp.or_has_not = true;
                     if (!item_pos) lp.or_nonpos = true;
