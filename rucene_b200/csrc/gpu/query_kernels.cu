@@ -47,19 +47,7 @@ namespace rg {
 template <bool LIVE, bool EDGE, bool POS>
 __device__ __forceinline__ void column_window(uint32_t* acc, const float* __restrict__ col, bool every_doc,
                                               const SegDev& seg, int win0, int wlen, int first_in, float te, int lane,
-                                              uint32_t& hot, uint32_t& my_matches, bool untouched) {
-    if (POS && !EDGE && wlen == kWw && untouched) {
-        // the first clause of the window: +0.0f + cell == cell, so the window is written without being read
-#pragma unroll
-        for (int h = 0; h < kWw / 128; h += 3) {
-            float4 v[3];
-#pragma unroll
-            for (int j = 0; j < 3; j++) v[j] = __ldg(reinterpret_cast<const float4*>(col + win0 + lane * 4 + (h + j) * 128));
-#pragma unroll
-            for (int j = 0; j < 3; j++) *reinterpret_cast<float4*>(acc + lane * 4 + (h + j) * 128) = v[j];
-        }
-        return;
-    }
+                                              uint32_t& hot, uint32_t& my_matches) {
     if (POS && !EDGE && wlen == kWw) {
         // a whole window: three 16-byte column loads of the lane are in flight before the first is used (the column
         // comes from L2 / HBM; six at once would spill)
@@ -174,39 +162,6 @@ __device__ __noinline__ uint32_t columns_only_window(const WTerm* term, uint32_t
     return __any_sync(0xffffffffu, mx > te) ? 0xffffffffu : c;
 }
 
-// The score column that is the LAST clause with postings in a whole window (plain-sum variant) closes the window in
-// registers: sum = window slot + column cell (or the cell alone when no clause has touched the window yet), counted and
-// compared with theta right there, and the window is re-armed — instead of a read-modify-write pass, a second read by
-// the epilogue and the re-arming stores.  Shared memory is the kernel's scarcest resource (its LSU wavefronts run at
-// 80 % of peak): this saves 48 of the ~170 wavefronts such a window costs.  Returns 0xffffffff, with the window
-// untouched, when some doc beats theta (the caller then takes the general path), else this lane's number of matches.
-template <bool LIVE>
-__device__ __noinline__ uint32_t column_closes_window(uint32_t* acc, const float* __restrict__ col, const uint64_t* __restrict__ live,
-                                                      int win0, float te, int lane, bool untouched) {
-    uint32_t c = 0;
-    float mx = 0.0f;
-#pragma unroll
-    for (int h = 0; h < kWw / 128; h += 3) {
-        float4 v[3];
-#pragma unroll
-        for (int j = 0; j < 3; j++) v[j] = __ldg(reinterpret_cast<const float4*>(col + win0 + lane * 4 + (h + j) * 128));
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (!untouched) o = *reinterpret_cast<const float4*>(acc + lane * 4 + (h + j) * 128);
-            count_and_max<LIVE>(make_uint4(__float_as_uint(__fadd_rn(o.x, v[j].x)), __float_as_uint(__fadd_rn(o.y, v[j].y)),
-                                           __float_as_uint(__fadd_rn(o.z, v[j].z)), __float_as_uint(__fadd_rn(o.w, v[j].w))),
-                                h + j, lane, live, win0, c, mx);
-        }
-    }
-    if (__any_sync(0xffffffffu, mx > te)) return 0xffffffffu;
-    if (!untouched) {
-#pragma unroll
-        for (int g = 0; g < kWw / 128; g++) reinterpret_cast<uint4*>(acc)[g * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    return c;
-}
-
 template <bool LIVE, bool NOT, bool MSM, bool DMAX, bool POS>
 __global__ void __launch_bounds__(kOrThreads, 24)
 k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, uint32_t warp_bytes,
@@ -302,14 +257,13 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
     // max(own, inherited)), re-read every 8 windows
     const bool lb_ok = (uint32_t)lane < it.chain_pos;
     const uint32_t* theta_lb = p.item_theta + item_idx - 1 - (lb_ok ? lane : 0);
-    int next_lookback = -2147483647 - 1;  // docid from which the look-back is read again (every ~8 windows)
+    uint32_t win_no = 0;
 
     while (w0 < hi) {
         const int win0 = (int)w0;
         const int win1 = (int)min((long long)hi, w0 + kWw);
         uint32_t inherited = 0;
-        if (win0 >= next_lookback && it.chain_pos) {
-            next_lookback = win0 + 8 * kWw;
+        if ((win_no++ & 7u) == 0 && it.chain_pos) {
             inherited = lb_ok ? ld_volatile_u32(theta_lb) : 0u;
             inherited = __reduce_max_sync(0xffffffffu, inherited);
         }
@@ -327,8 +281,6 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
         // ---- clauses with a posting in this window, in clause order: drain each stream up to the
         // window end (a sparse clause sits out most windows)
         uint32_t active = __ballot_sync(0xffffffffu, nd < win1);
-        bool untouched = true;  // no clause has written the accumulator window yet (it holds the re-armed +0.0f)
-        bool closed = false;    // column_closes_window has finished the window: nothing left for the epilogue
         if (POS && active && (active & ~col_mask) == 0u && win1 - win0 == kWw && win0 >= lo) {
             // Only score columns have postings in this (whole) window: see columns_only_window.  Only if a doc beats
             // theta (rare) the general path below redoes the window to scan it.
@@ -369,19 +321,10 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
                         }
                     }
                 } else if (first_in > 0 || (wlen & 3)) {  // warp-uniform: first / last window of a range
-                    column_window<LIVE, true, POS>(sh.acc, col, every_doc, seg, win0, wlen, first_in, te, lane, hot, my_matches, false);
-                } else if (POS && active == 0u && wlen == kWw) {  // no further clause has a posting in this window
-                    const uint32_t cnt = column_closes_window<LIVE>(sh.acc, col, seg.live, win0, te, lane, untouched);
-                    if (cnt != 0xffffffffu) {
-                        my_matches += cnt;
-                        closed = true;
-                    } else {
-                        column_window<LIVE, false, POS>(sh.acc, col, every_doc, seg, win0, wlen, first_in, te, lane, hot, my_matches, untouched);
-                    }
+                    column_window<LIVE, true, POS>(sh.acc, col, every_doc, seg, win0, wlen, first_in, te, lane, hot, my_matches);
                 } else {
-                    column_window<LIVE, false, POS>(sh.acc, col, every_doc, seg, win0, wlen, first_in, te, lane, hot, my_matches, untouched);
+                    column_window<LIVE, false, POS>(sh.acc, col, every_doc, seg, win0, wlen, first_in, te, lane, hot, my_matches);
                 }
-                untouched = false;
                 if (lane == t) nd = win1 < hi ? win1 : kNoMoreDocs;
                 __syncwarp();
                 continue;
@@ -418,15 +361,9 @@ k_eval_or(EvalParams p, const uint32_t* __restrict__ item_ids, uint32_t n_ids, u
             tc.n = n;
             const int nx = pos < n ? cd[pos] : kNoMoreDocs;
             if (lane == t) nd = nx;
-            untouched = false;
             __syncwarp();  // the next clause's lanes read window slots other lanes have just written
         }
         const int next_doc = __reduce_min_sync(0xffffffffu, nd);
-        if (POS && closed) {  // counted, compared with theta and re-armed by column_closes_window
-            if (next_doc == kNoMoreDocs) break;
-            w0 = next_doc;
-            continue;
-        }
         if (POS) {
             // one pass over the finished window: a doc matched iff its sum is non-zero (every clause score is > 0), and
             // a 32-doc step is scanned for candidates iff one of its sums beats theta
