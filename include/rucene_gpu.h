@@ -25,7 +25,8 @@ extern "C" {
 #define RG_ECUDA (-3)       /* CUDA runtime error */
 #define RG_EUNSUPPORTED (-4)/* plan shape outside the accelerated path: caller falls back to
                                DefaultIndexSearcher (searcher.rs:487-525) */
-#define RG_ENOMEM (-5)      /* candidate arena exhausted: split the batch */
+#define RG_ENOMEM (-5)      /* candidate arena exhausted: split the batch (rg_search_batch does so itself; the split
+                               calls rg_batch_prepare/run/fetch report it to the caller) */
 
 #define RG_NO_MORE_DOCS 0x7fffffff /* search/mod.rs:59 */
 

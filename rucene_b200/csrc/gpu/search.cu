@@ -1384,6 +1384,15 @@ int rg_search_batch(rg_engine* e, const rg_query* queries, uint32_t n_queries,
     rc = rg_batch_run(e, b);
     if (rc == RG_OK) rc = rg_batch_fetch(e, b, out_hits, out_counts, out_total_hits);
     rg_batch_destroy(e, b);
+    if (rc == RG_ENOMEM && n_queries > 1 && p && p->k) {
+        // the candidate arena overflowed: the two halves of the batch, one after the other (queries are independent and
+        // refer to `clauses` by absolute index, so a half is just a sub-array of `queries`); recursively if need be
+        const uint32_t h = n_queries / 2;
+        rc = rg_search_batch(e, queries, h, clauses, n_clauses, p, out_hits, out_counts, out_total_hits);
+        if (rc == RG_OK)
+            rc = rg_search_batch(e, queries + h, n_queries - h, clauses, n_clauses, p, out_hits + (size_t)h * p->k, out_counts + h,
+                                 out_total_hits + h);
+    }
     return rc;
 }
 

@@ -413,3 +413,26 @@ def test_reference_style_api():
             search.BooleanQuery.build([], [], [], [], 0)
     finally:
         searcher.engine.close()
+
+
+def test_candidate_arena_overflow_splits_the_batch():
+    """A 1 MB candidate arena cannot hold a 300-query, k=1000 batch: rg_search_batch halves the batch (recursively) on
+    its own and still equals the oracle; the split calls report RG_ENOMEM to the caller."""
+    rng = np.random.default_rng(4242)
+    seg, _ = helpers.build_segment(rng, 150000, [60000, 40000, 25000, 12000, 8000, 5000, 3000, 2000, 900, 400])
+    ix = helpers.oracle_index([seg])
+    specs = _mixed_specs(rng, 10, 300, kinds=("or",))
+    q, c = ob.make_queries(specs)
+    want = ix.search_batch(q, c, 1000, parallel_mode=0, n_threads=4)
+    s = search.GpuIndexSearcher(search.IndexReader([seg]), cand_arena_bytes=1 << 20)
+    try:
+        got = s.search_batch(helpers.to_queries(specs), 1000)
+        helpers.assert_same_topdocs(got, want, "auto split")
+        qa, ca = s.compile_batch(helpers.to_queries(specs))
+        b = s.engine.prepare(qa, ca, 1000, k1=s.similarity.k1)
+        b.run()
+        with pytest.raises(engine.EngineError):
+            b.fetch()
+        b.close()
+    finally:
+        s.engine.close()
