@@ -569,7 +569,7 @@ def run_workload(ctx, name, w, args, steps, warmup, cpu_queries, cpu_seconds, fl
                     "blocks / table entries / column cells).  Dense clauses that have a score column are read from it "
                     "(4 B per docid) instead of being decoded; traffic = DRAM bytes actually moved (ncu, profiles/)",
             "scored_lists": dict(eng.list_stats(), note="(docid, f32 score) pairs of disjunction clauses two queries of a batch share, "
-                                 "1 KB per 128-posting block; same LRU budget as the columns"),
+                                 "1 KB per 128-posting block; kept across batches in the engine's list arena (a ring of slabs, <= 1/6 of the free HBM)"),
             "score_columns": {"n": n_cols, "bytes": col_bytes, "built_by_first_batch": col_stats_cold["built"],
                               "engine_cache": eng.column_stats(),
                               "note": "persistent across batches (LRU, <= 1/3 of the free HBM); the timed steps hit the "

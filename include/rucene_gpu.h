@@ -48,7 +48,7 @@ extern "C" {
                                    (DESIGN.md section 6); off by default */
 #define RG_CFG_NO_LISTS 64u     /* never materialise scored posting lists: a disjunction clause (df >= 4096) that two clauses of a batch share
                                    is decoded and BM25-scored ONCE into (docid, f32 score) pairs, 1 KB per 128-posting block, kept
-                                   across batches in the same LRU budget as the score columns; k_eval_or then streams the pairs
+                                   across batches in the engine's list arena (a sixth of the free HBM, reclaimed oldest first); k_eval_or then streams the pairs
                                    instead of unpacking, prefix-summing, gathering norms and dividing per query */
 #define RG_CFG_STATS 16u        /* count events inside k_eval_or_ms (rg_batch_debug); costs a few atomics per work item */
 

@@ -600,7 +600,6 @@ std::map<ColKey, uint32_t> choose_lists(rg_engine* e, const std::vector<QShape>&
         }
     }
     if (uses.empty()) return chosen;
-    ensure_budget(e);
     auto add_ref = [&](const ColKey& key, const std::shared_ptr<ColEntry>& ent) {
         if (hp.col_refs.size() >= 65536) return;  // ItemClause.flags carries the reference in 16 bits
         ent->last_use = ++e->col_tick;
