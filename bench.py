@@ -748,6 +748,12 @@ def main():
                 "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"],
                 "roofline": main_res.get("roofline"), "cpu_baseline": main_res.get("cpu_baseline"),
                 "first_batch_ms": main_res["first_batch_ms"], "per_rank_eval_ms": main_res["per_rank_eval_ms"],
+                "step_breakdown": {"slowest_rank_eval_kernels_ms": max(main_res["per_rank_eval_ms"]),
+                                   "rank_skew_ms": max(main_res["per_rank_eval_ms"]) - min(main_res["per_rank_eval_ms"]),
+                                   "outside_eval_kernels_ms": main_res["ms_per_step"] - max(main_res["per_rank_eval_ms"]),
+                                   "note": "ms_per_step = slowest rank's evaluation kernels + heap replay (+ all-gather and "
+                                           "leaf-order merge at N > 1); against N = 1 the remainder is the per-leaf "
+                                           "collectors' weaker theta (search_parallel semantics), not the exchange"},
                 "kernel_events": main_res.get("kernel_events"),
                 "forutil_decode": decode, "ab": ab or None, "workloads": extra or None, "setup": main_res["setup"]}
         print(json.dumps(line))
